@@ -1,0 +1,228 @@
+/* isg.h — C ABI of libisg.so: the B200 (sm_100a) kernels behind the ISubGVQA hot path.
+ *
+ * The reference (DigitalPhonetics/Intrinsic-Subgraph-Generation-for-VQA) has no FFI layer: its
+ * hot path reaches native code only through torch_geometric / torch_scatter / ATen from the
+ * Python modules cited at each entry point below (paths relative to the reference root).  This
+ * header is what a maintainer binds with ctypes to replace those call sites.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all
+ *     memory (outputs and workspaces are caller-allocated; the library never allocates,
+ *     frees or retains device memory and keeps no global state);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and never
+ *     synchronises the host;
+ *   - return value: 0 = ok, negative = ISG_E* (bad argument / unsupported shape), positive =
+ *     cudaError_t of a failed launch.  Nothing throws, nothing exits;
+ *   - feature tensors are row-major; `dtype` selects their storage type: ISG_F32 (parity
+ *     configuration) or ISG_BF16 (storage only, fp32 accumulation).  Indices are int32
+ *     internally; the int64 COO of PyG is converted once by isg_csr_build;
+ *   - H = heads, C = channels per head (C % 4 == 0, C <= 512), HC = H*C.
+ */
+#ifndef ISG_H_
+#define ISG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISG_OK 0
+#define ISG_EINVAL (-1)      /* null pointer / negative size / inconsistent argument */
+#define ISG_EUNSUPPORTED (-2) /* shape or dtype outside what the kernels are built for */
+#define ISG_EWORKSPACE (-3)  /* workspace too small */
+
+#define ISG_F32 0
+#define ISG_BF16 1
+
+#define ISG_ACT_NONE 0
+#define ISG_ACT_GELU 1 /* exact erf GELU, torch.nn.GELU() default */
+
+int isg_version(void);
+const char* isg_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------
+ * (a) destination-sorted (and source-sorted) CSR rebuild of the COO edge_index.
+ * No reference counterpart: the reference keeps COO and lets PyG's propagate() gather /
+ * index_add_ (models/mgat_v2_conv.py:215; torch_geometric MessagePassing).  Result ==
+ * stable sort of edge ids by key:  *_ptr [N+1], *_eid [E] (original edge id of the p-th
+ * sorted edge), *_nbr [E] (the other endpoint: source for the dst ordering, destination for
+ * the src ordering).  `status` (1 int32, device) is set to the number of out-of-range indices.
+ * ------------------------------------------------------------------------------------- */
+size_t isg_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int isg_csr_build(const int64_t* edge_index /* [2,E] */, int64_t num_edges, int64_t num_nodes,
+                  int32_t* dst_ptr, int32_t* dst_nbr, int32_t* dst_eid,
+                  int32_t* src_ptr, int32_t* src_nbr, int32_t* src_eid,
+                  int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* graph_ptr [B+1] from the sorted `batch` vector [N] int64 (replaces the count/cumsum inside
+ * torch_geometric.utils.to_dense_batch, models/masking.py:162, and GraphNorm's int(batch.max())).
+ * Also writes batch32 [N] (int32 copy) and nmax (1 int32: max nodes per graph). */
+int isg_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
+                  int32_t* graph_ptr, int32_t* batch32, int32_t* nmax, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (b) fused edge kernel = MaskingGATv2Conv.message (models/mgat_v2_conv.py:243-279) + PyG
+ * propagate gathers + torch_geometric.utils.softmax (:272) + sum aggregation + bias (:231-232).
+ *   s = x_r[dst] + x_l[src] + e_proj[e];  u = s*m;  v = leaky_relu(u, slope);  w = v*m
+ *   logit[e,h] = sum_c w*att[h,c];  alpha = exp(l - max_dst) / (sum_dst + 1e-16)
+ *   out[dst,h,:] = sum_e x_l[src,h,:] * alpha*m  + bias
+ * x_l / x_r: [N, HC] with row pitch ld_x elements (they may be the two halves of one fused
+ * projection); e_proj [E,HC] dense, ORIGINAL edge order; edge_mask [E] fp32 or NULL;
+ * out [N,HC] pitch ld_out; alpha [E,H] fp32 in ORIGINAL edge order.
+ * ------------------------------------------------------------------------------------- */
+int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj,
+                     const float* att /* [H*C] */, const float* bias /* [H*C] or NULL */,
+                     const float* edge_mask,
+                     const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
+                     void* out, int64_t ld_out, float* alpha,
+                     int64_t num_nodes, int64_t num_edges, int heads, int channels,
+                     float negative_slope, int dtype, void* stream);
+
+/* Backward of the above (the reference gets it from autograd through message()/softmax).
+ * Inputs: g_out [N,HC] pitch ld_g; saved x_l,x_r,e_proj,att,bias,edge_mask,alpha,out.
+ * Outputs: g_xl,g_xr [N,HC] pitch ld_gx; g_eproj [E,HC]; g_att [H*C] fp32;
+ *          g_edge_mask [E] fp32 (NULL iff edge_mask NULL).
+ * Two deterministic passes: dst-major (g_eproj, g_xr, g_att, g_edge_mask) then src-major
+ * (g_xl) — no floating-point atomics. */
+size_t isg_gat_edge_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int heads, int channels);
+int isg_gat_edge_bwd(const void* g_out, int64_t ld_g,
+                     const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj,
+                     const float* att, const float* bias, const float* edge_mask,
+                     const float* alpha, const void* out, int64_t ld_out,
+                     const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
+                     const int32_t* src_ptr, const int32_t* src_nbr, const int32_t* src_eid,
+                     void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj,
+                     float* g_att, float* g_edge_mask,
+                     int64_t num_nodes, int64_t num_edges, int heads, int channels,
+                     float negative_slope, int dtype,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* NodeMaskToEdgeMask (sampling/node_edge_masks.py:5-19).
+ * fwd: edge_mask[e] = mask[src]*mask[dst] (fp32).  bwd (the reference's custom, non-true
+ * gradient): g_mask[i] = sum over edges with dst == i of g_edge_mask[e]. */
+int isg_node_edge_mask_fwd(const float* node_mask, const int64_t* edge_index, int64_t num_edges,
+                           float* edge_mask, void* stream);
+int isg_node_edge_mask_bwd(const float* g_edge_mask, const int32_t* dst_ptr, const int32_t* dst_eid,
+                           int64_t num_nodes, float* g_node_mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (c) perturb-and-MAP top-k samplers.  Dense layout = torch_geometric.utils.to_dense_batch
+ * (models/masking.py:162): graph b owns slots [b*Nmax, (b+1)*Nmax), real nodes first, pads 0.0
+ * (pads COMPETE in top-k).  nb_samples S = 1.
+ * MAP = select_from_edge_candidates (sampling/methods/deterministic_scheme.py:36-43):
+ *   k >= Nmax -> all ones; else mask = score >= (k-th largest score), ties give > k ones.
+ * ------------------------------------------------------------------------------------- */
+
+/* IMLE/AIMLE forward (sampling/methods/wrapper.py:75-121, aimle.py:83-138):
+ * z = MAP(theta_dense + noise*tau).  theta [N] ragged; noise [B,Nmax] or NULL (=0);
+ * outputs: mask [N] ragged (z[valid]) and z_dense [B,Nmax] (saved for backward). */
+int isg_topk_mask_fwd(const float* theta, const float* noise, const int32_t* graph_ptr,
+                      int64_t num_graphs, int nmax, int k, float tau,
+                      float* mask, float* z_dense, void* stream);
+
+/* IMLE backward (wrapper.py:124-172, target.py:44-48):
+ * z' = MAP(alpha*theta - beta*dy + noise*tau_target);  g_theta = z - z'   (ragged [N]). */
+int isg_imle_bwd(const float* dy, const float* theta, const float* noise, const float* z_dense,
+                 const int32_t* graph_ptr, int64_t num_graphs, int nmax, int k,
+                 float alpha, float beta, float tau_target, float* g_theta, void* stream);
+
+/* AIMLE backward with the adaptive target (aimle.py:141-243, target_aimle.py:87-162),
+ * symmetric perturbation.  `state` is 8 doubles on the device, updated in place with no host
+ * sync: [0] beta, [1] grad_norm (fp32 value), [2] previous_beta_update, [3] alpha,
+ * [4] beta_update_step, [5] grad_norm_decay_rate, [6] target_norm, [7] beta_update_momentum.
+ * adaptive = 0 gives the fixed TargetDistribution(alpha,beta) of the validation scheme.
+ * workspace: isg_aimle_workspace_bytes(). */
+size_t isg_aimle_workspace_bytes(void);
+int isg_aimle_bwd(const float* dy, const float* theta, const float* noise,
+                  const int32_t* graph_ptr, int64_t num_nodes, int64_t num_graphs, int nmax, int k,
+                  float tau_target, int adaptive, double* state, float* g_theta,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gumbel relaxed top-k with straight-through (sampling/methods/gumbel_scheme.py:26-107,
+ * policy edge_candid, tau 0.1, hard=True).  gumbel [B,Nmax] = Gumbel(0,1) noise.
+ * fwd: mask [N] ragged = (hard - khot) + khot; saves khot-rounds in `saved`
+ * [B, k, Nmax] (softmax one-hot approximations).  bwd: g_theta [N]. */
+int isg_gumbel_topk_fwd(const float* theta, const float* gumbel, const int32_t* graph_ptr,
+                        int64_t num_graphs, int nmax, int k, float tau,
+                        float* mask, float* saved, void* stream);
+int isg_gumbel_topk_bwd(const float* dy, const float* saved, const int32_t* graph_ptr,
+                        int64_t num_graphs, int nmax, int k, float tau,
+                        float* g_theta, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * node-side fused segment ops
+ * ------------------------------------------------------------------------------------- */
+
+/* instruction gating  y = gelu(x * ins[batch])  (models/mgat_v2_conv.py:156-157).
+ * bwd: g_x [N,D] and g_ins [B,D] (segmented sum per graph, deterministic). */
+int isg_instr_gate_fwd(const float* x, const float* ins, const int32_t* batch32,
+                       int64_t num_nodes, int dim, float* y, void* stream);
+int isg_instr_gate_bwd(const float* g_y, const float* x, const float* ins,
+                       const int32_t* graph_ptr, int64_t num_graphs, int dim,
+                       float* g_x, float* g_ins, void* stream);
+
+/* gate logits (models/masking.py:151-155).  double_gather = 1: q is [B,D] (one row per graph) and
+ * theta[n] = gelu(<xn[n], q[batch[batch[n]]]> / sqrt(D)) — the double gather that results from
+ * models/mgat_v2_conv.py:166-168 passing imle_att[batch] into a forward that indexes [batch] again.
+ * double_gather = 0: q is [N,D] and theta[n] = gelu(<xn[n], q[batch[n]]> / sqrt(D)) (MaskingModel.forward
+ * called directly with a per-node u).  bwd: g_xn [N,D], g_q (same shape as q). */
+int isg_gate_theta_fwd(const float* xn, const float* q, const int32_t* batch32,
+                       int64_t num_nodes, int dim, int double_gather, float* theta, void* stream);
+int isg_gate_theta_bwd(const float* g_theta, const float* xn, const float* q,
+                       const int32_t* batch32, const int32_t* graph_ptr,
+                       int64_t num_nodes, int64_t num_graphs, int dim, int double_gather,
+                       float* g_xn, float* g_q, float* scratch /* [N] */, void* stream);
+
+/* scatter-SDPA + GraphNorm + residual (models/mgat.py:168-172; utils/scatter_scaled_dot_product.py:6-15;
+ * torch_geometric GraphNorm eps 1e-5):
+ *   a = softmax_graph(<ins[b], v_n>/sqrt(D)); y = a*v; o = y - mean*mean_scale;
+ *   h_out = weight*o*rsqrt(mean(o^2)+eps) + bias + h_in.
+ * saves a [N], mean [B,D], rstd [B,D].  bwd returns g_v [N,D], g_ins [B,D] and per-graph
+ * partials gw_part/gb_part/gms_part [B,D] (column-summed by isg_colsum). g_h_in == g_out. */
+int isg_sdpa_graphnorm_fwd(const float* v, const float* ins, const float* h_in,
+                           const float* weight, const float* bias, const float* mean_scale,
+                           const int32_t* graph_ptr, int64_t num_graphs, int dim, int nmax, float eps,
+                           float* h_out, float* a, float* mean, float* rstd, void* stream);
+int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const float* ins,
+                           const float* weight, const float* mean_scale,
+                           const float* a, const float* mean, const float* rstd,
+                           const int32_t* graph_ptr, int64_t num_graphs, int dim, int nmax,
+                           float* g_v, float* g_ins, float* gw_part, float* gb_part, float* gms_part,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (d) dense projections (lin_l / lin_r / lin_edge models/mgat_v2_conv.py:63-103,177,181,259;
+ * x_proj models/mgat.py:79-89,156; node_nn / ques_nn models/masking.py:82-87,137,152).
+ *   fwd:   y = act(x W^T + b);  optionally also writes the pre-activation z (for backward)
+ *   dgrad: g_x = (g_y W) [* gelu'(z_prev) if z_prev != NULL]
+ *   wgrad: g_W = g_y^T x (deterministic split over M; bias gradient = isg_colsum(g_y))
+ * x [M,K] pitch ldx; W [Nout,K] dense; y [M,Nout] pitch ldy.
+ * `mode`: 0 = fp32 FFMA (parity), 1 = tcgen05 3xTF32 split (fp32-grade), 2 = tcgen05 bf16.
+ * ------------------------------------------------------------------------------------- */
+int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
+                   void* y, int64_t ldy, void* z_pre /* or NULL */, int64_t ldz,
+                   int64_t M, int Nout, int K, int act, int mode, int dtype, void* stream);
+int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w,
+                     const void* z_prev /* or NULL */, int64_t ldz,
+                     void* g_x, int64_t ldgx, int accumulate,
+                     int64_t M, int Nout, int K, int mode, int dtype, void* stream);
+size_t isg_linear_wgrad_workspace_bytes(int64_t M, int Nout, int K);
+int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int64_t ldx,
+                     float* g_w /* [Nout,K] */, float* g_b /* reserved: use isg_colsum(g_y) */,
+                     int64_t M, int Nout, int K, int mode, int dtype,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* g = g_y * gelu'(z)  elementwise (backward of a GELU that closes a projection). */
+int isg_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_t n, void* stream);
+
+/* out[c] = sum_r in[r, c]  (deterministic two-stage column sum; rows x cols fp32, pitch ld). */
+size_t isg_colsum_workspace_bytes(int64_t rows, int cols);
+int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, float* out,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISG_H_ */

@@ -1,0 +1,246 @@
+// csr.cu — kernel (a): destination-sorted and source-sorted CSR rebuild of the COO edge_index,
+// plus graph_ptr from the sorted batch vector.  Integer-only, HBM/latency-bound work.
+//
+// Definition (oracle/isg_oracle.py::csr_build): stable sort of edge ids by key.  Implemented as
+//   histogram (int atomics) -> exclusive scan -> unordered placement (int atomic cursor)
+//   -> per-segment ascending sort of the edge ids.
+// Edge ids are unique, so sorting each segment ascending yields exactly the stable order and
+// the result is deterministic although the placement itself is not.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void csr_hist_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t N,
+                                int* __restrict__ deg_dst, int* __restrict__ deg_src,
+                                int* __restrict__ status) {
+  int bad = 0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = ei[e], d = ei[E + e];
+    if (s < 0 || s >= N || d < 0 || d >= N) {
+      ++bad;
+      continue;
+    }
+    atomicAdd(&deg_dst[d], 1);
+    atomicAdd(&deg_src[s], 1);
+  }
+  if (bad) atomicAdd(status, bad);
+}
+
+// grid = (tiles, 2): y selects the array.  Phase 1: per-tile totals.
+__global__ void scan_tile_sums_kernel(const int* __restrict__ a0, const int* __restrict__ a1,
+                                      int64_t N, int* __restrict__ tile_sums, int tiles) {
+  __shared__ float red_unused[1];
+  (void)red_unused;
+  __shared__ int sred[32];
+  const int* a = blockIdx.y ? a1 : a0;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int s = 0;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_THREADS) {
+    const int64_t idx = base + i;
+    if (idx < N) s += a[idx];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(ISG_FULL_MASK, s, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int r = threadIdx.x < (SCAN_THREADS / 32) ? sred[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(ISG_FULL_MASK, r, o);
+    if (threadIdx.x == 0) tile_sums[blockIdx.y * tiles + blockIdx.x] = r;
+  }
+}
+
+// Phase 2: in-place exclusive scan of a[0..N) -> a[0..N], a[N] = total.
+__global__ void scan_apply_kernel(int* __restrict__ a0, int* __restrict__ a1, int64_t N,
+                                  const int* __restrict__ tile_sums, int tiles) {
+  __shared__ int sred[32];
+  __shared__ int s_tile_off;
+  __shared__ int s_warp_off[SCAN_THREADS / 32];
+  int* a = blockIdx.y ? a1 : a0;
+  const int* ts = tile_sums + blockIdx.y * tiles;
+  // offset of this tile = sum of previous tile totals
+  int part = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += SCAN_THREADS) part += ts[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(ISG_FULL_MASK, part, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int r = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) r += sred[w];
+    s_tile_off = r;
+  }
+  __syncthreads();
+
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int tsum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const int64_t idx = base + i;
+    v[i] = (idx < N) ? a[idx] : 0;
+    tsum += v[i];
+  }
+  // exclusive scan of per-thread sums across the block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(ISG_FULL_MASK, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp_off[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+      const int t = s_warp_off[w];
+      s_warp_off[w] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  int off = s_tile_off + s_warp_off[warp] + (incl - tsum);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    const int64_t idx = base + i;
+    if (idx < N) a[idx] = off;
+    off += v[i];
+    if (idx == N - 1) a[N] = off;
+  }
+  if (N == 0 && blockIdx.x == 0 && threadIdx.x == 0) a[0] = 0;
+}
+
+__global__ void csr_place_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t N,
+                                 const int* __restrict__ dst_ptr, const int* __restrict__ src_ptr,
+                                 int* __restrict__ cur_dst, int* __restrict__ cur_src,
+                                 int* __restrict__ dst_eid, int* __restrict__ src_eid) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = ei[e], d = ei[E + e];
+    if (s < 0 || s >= N || d < 0 || d >= N) continue;
+    dst_eid[dst_ptr[d] + atomicAdd(&cur_dst[d], 1)] = (int)e;
+    src_eid[src_ptr[s] + atomicAdd(&cur_src[s], 1)] = (int)e;
+  }
+}
+
+// One thread per segment: ascending insertion sort of the edge ids (segments are node degrees:
+// ~7.5 on GQA graphs, nearly sorted already for the source ordering), then emit the neighbour.
+__global__ void csr_sort_segments_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t N,
+                                         const int* __restrict__ dst_ptr, const int* __restrict__ src_ptr,
+                                         int* __restrict__ dst_eid, int* __restrict__ src_eid,
+                                         int* __restrict__ dst_nbr, int* __restrict__ src_nbr) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= 2 * N) return;
+  const bool by_src = t >= N;
+  const int64_t node = by_src ? t - N : t;
+  const int* ptr = by_src ? src_ptr : dst_ptr;
+  int* eid = by_src ? src_eid : dst_eid;
+  int* nbr = by_src ? src_nbr : dst_nbr;
+  const int64_t* other = by_src ? ei + E : ei;  // src ordering stores dst, dst ordering stores src
+  const int beg = ptr[node], end = ptr[node + 1];
+  for (int i = beg + 1; i < end; ++i) {
+    const int key = eid[i];
+    int j = i - 1;
+    while (j >= beg && eid[j] > key) {
+      eid[j + 1] = eid[j];
+      --j;
+    }
+    eid[j + 1] = key;
+  }
+  for (int i = beg; i < end; ++i) nbr[i] = (int)other[eid[i]];
+}
+
+__global__ void graph_ptr_kernel(const int64_t* __restrict__ batch, int64_t N, int64_t B,
+                                 int* __restrict__ graph_ptr, int* __restrict__ batch32,
+                                 int* __restrict__ nmax) {
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n == 0) *nmax = 0;
+  if (n > N) return;
+  int64_t prev = (n > 0) ? batch[n - 1] : -1;
+  int64_t cur = (n < N) ? batch[n] : B;
+  if (n < N) batch32[n] = (int)cur;
+  if (prev < -1) prev = -1;
+  if (cur > B) cur = B;
+  for (int64_t b = prev + 1; b <= cur; ++b) graph_ptr[b] = (int)n;
+}
+
+__global__ void graph_nmax_kernel(const int* __restrict__ graph_ptr, int64_t B, int* __restrict__ nmax) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int v = (b < B) ? graph_ptr[b + 1] - graph_ptr[b] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(ISG_FULL_MASK, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(nmax, v);
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t isg_csr_workspace_bytes(int64_t N, int64_t E) {
+  (void)E;
+  const int tiles = isg::ceil_div(N > 0 ? N : 1, SCAN_TILE);
+  return align256((size_t)2 * (size_t)N * sizeof(int)) + align256((size_t)2 * tiles * sizeof(int));
+}
+
+extern "C" int isg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* dst_ptr,
+                             int32_t* dst_nbr, int32_t* dst_eid, int32_t* src_ptr, int32_t* src_nbr,
+                             int32_t* src_eid, int32_t* status, void* workspace, size_t ws_bytes,
+                             void* stream_) {
+  if (E < 0 || N < 0 || E >= (int64_t)INT32_MAX || N >= (int64_t)INT32_MAX) return ISG_EINVAL;
+  if (!dst_ptr || !src_ptr || !status || (E > 0 && (!edge_index || !dst_nbr || !dst_eid || !src_nbr || !src_eid)))
+    return ISG_EINVAL;
+  if (ws_bytes < isg_csr_workspace_bytes(N, E) || (!workspace && N > 0)) return ISG_EWORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int tiles = isg::ceil_div(N > 0 ? N : 1, SCAN_TILE);
+  int* cur_dst = (int*)workspace;
+  int* cur_src = cur_dst + N;
+  int* tile_sums = (int*)((char*)workspace + align256((size_t)2 * (size_t)N * sizeof(int)));
+
+  cudaError_t err;
+  if ((err = cudaMemsetAsync(dst_ptr, 0, (size_t)(N + 1) * sizeof(int), stream)) != cudaSuccess) return (int)err;
+  if ((err = cudaMemsetAsync(src_ptr, 0, (size_t)(N + 1) * sizeof(int), stream)) != cudaSuccess) return (int)err;
+  if ((err = cudaMemsetAsync(status, 0, sizeof(int), stream)) != cudaSuccess) return (int)err;
+  if (N > 0 && (err = cudaMemsetAsync(workspace, 0, (size_t)2 * N * sizeof(int), stream)) != cudaSuccess)
+    return (int)err;
+  if (N == 0) return ISG_OK;
+
+  const int eblocks = (int)min((int64_t)ISG_NUM_SMS * 8, (int64_t)isg::ceil_div(E > 0 ? E : 1, 256));
+  if (E > 0) {
+    csr_hist_kernel<<<eblocks, 256, 0, stream>>>(edge_index, E, N, dst_ptr, src_ptr, status);
+    ISG_CHECK_LAUNCH();
+  }
+  scan_tile_sums_kernel<<<dim3(tiles, 2), SCAN_THREADS, 0, stream>>>(dst_ptr, src_ptr, N, tile_sums, tiles);
+  ISG_CHECK_LAUNCH();
+  scan_apply_kernel<<<dim3(tiles, 2), SCAN_THREADS, 0, stream>>>(dst_ptr, src_ptr, N, tile_sums, tiles);
+  ISG_CHECK_LAUNCH();
+  if (E > 0) {
+    csr_place_kernel<<<eblocks, 256, 0, stream>>>(edge_index, E, N, dst_ptr, src_ptr, cur_dst, cur_src,
+                                                  dst_eid, src_eid);
+    ISG_CHECK_LAUNCH();
+    csr_sort_segments_kernel<<<isg::ceil_div(2 * N, 128), 128, 0, stream>>>(
+        edge_index, E, N, dst_ptr, src_ptr, dst_eid, src_eid, dst_nbr, src_nbr);
+    ISG_CHECK_LAUNCH();
+  }
+  return ISG_OK;
+}
+
+extern "C" int isg_graph_ptr(const int64_t* batch, int64_t N, int64_t B, int32_t* graph_ptr,
+                             int32_t* batch32, int32_t* nmax, void* stream_) {
+  if (N < 0 || B < 0 || !graph_ptr || !nmax || (N > 0 && (!batch || !batch32))) return ISG_EINVAL;
+  if (N >= (int64_t)INT32_MAX) return ISG_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  graph_ptr_kernel<<<isg::ceil_div(N + 1, 256), 256, 0, stream>>>(batch, N, B, graph_ptr, batch32, nmax);
+  ISG_CHECK_LAUNCH();
+  if (B > 0) {
+    graph_nmax_kernel<<<isg::ceil_div(B, 256), 256, 0, stream>>>(graph_ptr, B, nmax);
+    ISG_CHECK_LAUNCH();
+  }
+  return ISG_OK;
+}

@@ -1,0 +1,560 @@
+// edge.cu — kernel (b): fused GATv2 edge attention (forward + backward) and NodeMaskToEdgeMask.
+//
+// Restates MaskingGATv2Conv.message + PyG propagate/softmax/aggregate
+// (reference models/mgat_v2_conv.py:243-279, :215, :231-232) as ONE pass over a dst-sorted CSR:
+// a warp owns one (destination node, head) pair, keeps x_r[dst,h,:], att[h,:] and the output
+// accumulator in registers, streams x_l[src,h,:] (gathered, L2-resident) and e_proj[e,h,:]
+// (read-once, HBM) with 16-byte loads, reduces the per-edge logit with warp shuffles and folds
+// it into an online segment softmax.  PyG materialises ~8 [E,H,C] tensors for the same work.
+//
+// HBM-bound: algorithmic bytes per layer (fp32) = 4*HC*(E + 3N) + 4*E*H (+4E mask) + CSR ints
+// (SURVEY.md §8d).  No tensor-core work here by design.
+#include "common.cuh"
+
+namespace {
+
+using namespace isg;
+
+constexpr int EDGE_WARPS = 4;  // warps per CTA (128 threads)
+
+// lane `lane` owns float4 slots v = lane + 32*k (k < VPL) of a C-wide head row, valid if v < C/4.
+template <typename T, int VPL>
+__device__ __forceinline__ void load_row(const T* __restrict__ row, int lane, int c4, float4 (&r)[VPL]) {
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    r[k] = (v < c4) ? Vec4<T>::ld(row + 4 * v) : f4_zero();
+  }
+}
+template <typename T, int VPL>
+__device__ __forceinline__ void load_row_stream(const T* __restrict__ row, int lane, int c4, float4 (&r)[VPL]) {
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    r[k] = (v < c4) ? Vec4<T>::ld_stream(row + 4 * v) : f4_zero();
+  }
+}
+template <int VPL>
+__device__ __forceinline__ void load_row_f32(const float* __restrict__ row, int lane, int c4, float4 (&r)[VPL]) {
+  load_row<float, VPL>(row, lane, c4, r);
+}
+
+__device__ __forceinline__ float leaky(float u, float slope) { return u > 0.f ? u : slope * u; }
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <typename T, int VPL>
+__global__ void __launch_bounds__(EDGE_WARPS * 32)
+gat_edge_fwd_kernel(const T* __restrict__ xl, const T* __restrict__ xr, int64_t ld_x,
+                    const T* __restrict__ ep, const float* __restrict__ att,
+                    const float* __restrict__ bias, const float* __restrict__ emask,
+                    const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                    const int* __restrict__ eid, T* __restrict__ out, int64_t ld_out,
+                    float* __restrict__ alpha, int64_t NH, int H, int C, float slope) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + (threadIdx.x >> 5);
+  if (wid >= NH) return;
+  const int64_t node = wid / H;
+  const int head = (int)(wid - node * H);
+  const int c4 = C >> 2;
+  const int64_t HC = (int64_t)H * C;
+  const int hoff = head * C;
+
+  float4 xr_v[VPL], att_v[VPL], acc[VPL];
+  load_row<T, VPL>(xr + node * ld_x + hoff, lane, c4, xr_v);
+  load_row_f32<VPL>(att + hoff, lane, c4, att_v);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
+
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  float m_run = -INFINITY, s_run = 0.f;
+
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    int my_src = 0, my_eid = 0;
+    float my_m = 1.f, my_logit = 0.f;
+    if (lane < cnt) {
+      my_src = nbr[base + lane];
+      my_eid = eid[base + lane];
+      if (emask != nullptr) my_m = emask[my_eid];
+    }
+    // two edges per iteration: both rows' loads are issued before either reduction
+    for (int t = 0; t < cnt; t += 2) {
+      const bool has2 = (t + 1) < cnt;
+      const int j0 = __shfl_sync(ISG_FULL_MASK, my_src, t);
+      const int e0 = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+      const float m0 = __shfl_sync(ISG_FULL_MASK, my_m, t);
+      const int j1 = __shfl_sync(ISG_FULL_MASK, my_src, has2 ? t + 1 : t);
+      const int e1 = __shfl_sync(ISG_FULL_MASK, my_eid, has2 ? t + 1 : t);
+      const float m1 = __shfl_sync(ISG_FULL_MASK, my_m, has2 ? t + 1 : t);
+      float4 x0[VPL], p0[VPL], x1[VPL], p1[VPL];
+      load_row<T, VPL>(xl + (int64_t)j0 * ld_x + hoff, lane, c4, x0);
+      load_row_stream<T, VPL>(ep + (int64_t)e0 * HC + hoff, lane, c4, p0);
+      if (has2) {
+        load_row<T, VPL>(xl + (int64_t)j1 * ld_x + hoff, lane, c4, x1);
+        load_row_stream<T, VPL>(ep + (int64_t)e1 * HC + hoff, lane, c4, p1);
+      }
+      float part0 = 0.f, part1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        float4 s = f4_add(f4_add(xr_v[k], x0[k]), p0[k]);
+        float4 w;
+        w.x = leaky(s.x * m0, slope) * m0;
+        w.y = leaky(s.y * m0, slope) * m0;
+        w.z = leaky(s.z * m0, slope) * m0;
+        w.w = leaky(s.w * m0, slope) * m0;
+        part0 += f4_dot(w, att_v[k]);
+      }
+      if (has2) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          float4 s = f4_add(f4_add(xr_v[k], x1[k]), p1[k]);
+          float4 w;
+          w.x = leaky(s.x * m1, slope) * m1;
+          w.y = leaky(s.y * m1, slope) * m1;
+          w.z = leaky(s.z * m1, slope) * m1;
+          w.w = leaky(s.w * m1, slope) * m1;
+          part1 += f4_dot(w, att_v[k]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        part0 += __shfl_xor_sync(ISG_FULL_MASK, part0, o);
+        part1 += __shfl_xor_sync(ISG_FULL_MASK, part1, o);
+      }
+      {  // online softmax update, edge t
+        const float m_new = fmaxf(m_run, part0);
+        const float sc = expf(m_run - m_new);
+        const float p = expf(part0 - m_new);
+        s_run = s_run * sc + p;
+        const float pm = p * m0;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = f4_fma(x0[k], pm, f4_scale(acc[k], sc));
+        m_run = m_new;
+        if (lane == t) my_logit = part0;
+      }
+      if (has2) {
+        const float m_new = fmaxf(m_run, part1);
+        const float sc = expf(m_run - m_new);
+        const float p = expf(part1 - m_new);
+        s_run = s_run * sc + p;
+        const float pm = p * m1;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = f4_fma(x1[k], pm, f4_scale(acc[k], sc));
+        m_run = m_new;
+        if (lane == t + 1) my_logit = part1;
+      }
+    }
+    if (lane < cnt) alpha[(int64_t)my_eid * H + head] = my_logit;  // raw logit, normalised below
+  }
+
+  const float inv = 1.f / (s_run + 1e-16f);  // PyG softmax epsilon (mgat_v2_conv.py:272)
+  T* orow = out + node * ld_out + hoff;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < c4) {
+      float4 o = f4_scale(acc[k], inv);
+      if (bias != nullptr) o = f4_add(o, Vec4<float>::ld(bias + hoff + 4 * v));
+      Vec4<T>::st(orow + 4 * v, o);
+    }
+  }
+  // same lane wrote the raw logit above -> program order makes it visible here
+  for (int base = beg; base < end; base += 32) {
+    if (base + lane < end) {
+      const int64_t idx = (int64_t)eid[base + lane] * H + head;
+      alpha[idx] = expf(alpha[idx] - m_run) * inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, pass 1 (dst-major): g_eproj, g_xr, g_att partials, per-head g_edge_mask terms.
+// Uses the identity  sum_e a_e * (m_e t_e) = <G[i,h,:], out[i,h,:] - bias[h,:]>  so every edge
+// is independent given one per-(node,head) dot product — a single sweep over the in-edges.
+// Persistent over (node, head) pairs with the head fixed per warp so the g_att partial lives
+// in registers; partials are reduced by gat_att_reduce_kernel in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------
+template <typename T, int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32)
+gat_edge_bwd_dst_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __restrict__ xl,
+                        const T* __restrict__ xr, int64_t ld_x, const T* __restrict__ ep,
+                        const float* __restrict__ att, const float* __restrict__ bias,
+                        const float* __restrict__ emask, const float* __restrict__ alpha,
+                        const T* __restrict__ out, int64_t ld_out,
+                        const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                        const int* __restrict__ eid, T* __restrict__ g_xr, int64_t ld_gx,
+                        T* __restrict__ g_ep, float* __restrict__ gatt_part,
+                        float* __restrict__ gm_h, int64_t N, int H, int C, float slope) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid0 = (int64_t)blockIdx.x * EDGE_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * EDGE_WARPS;  // multiple of H by construction
+  const int head = (int)(wid0 % H);
+  const int c4 = C >> 2;
+  const int64_t HC = (int64_t)H * C;
+  const int hoff = head * C;
+
+  float4 att_v[VPL], gatt[VPL], bias_v[VPL];
+  load_row_f32<VPL>(att + hoff, lane, c4, att_v);
+  if (bias != nullptr) {
+    load_row_f32<VPL>(bias + hoff, lane, c4, bias_v);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) bias_v[k] = f4_zero();
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) gatt[k] = f4_zero();
+
+  for (int64_t node = wid0 / H; node < N; node += nwarps / H) {
+    float4 G[VPL], xr_v[VPL], gxr[VPL];
+    load_row<T, VPL>(gout + node * ld_g + hoff, lane, c4, G);
+    load_row<T, VPL>(xr + node * ld_x + hoff, lane, c4, xr_v);
+    float dpart = 0.f;
+    {
+      float4 o[VPL];
+      load_row<T, VPL>(out + node * ld_out + hoff, lane, c4, o);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        dpart += G[k].x * (o[k].x - bias_v[k].x) + G[k].y * (o[k].y - bias_v[k].y) +
+                 G[k].z * (o[k].z - bias_v[k].z) + G[k].w * (o[k].w - bias_v[k].w);
+        gxr[k] = f4_zero();
+      }
+    }
+    const float dot = warp_sum(dpart);
+
+    const int beg = rowptr[node], end = rowptr[node + 1];
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_src = 0, my_eid = 0;
+      float my_m = 1.f, my_a = 0.f, my_gm = 0.f;
+      if (lane < cnt) {
+        my_src = nbr[base + lane];
+        my_eid = eid[base + lane];
+        if (MASKED) my_m = emask[my_eid];
+        my_a = alpha[(int64_t)my_eid * H + head];
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+        const float a = __shfl_sync(ISG_FULL_MASK, my_a, t);
+        float4 xv[VPL], pv[VPL];
+        load_row<T, VPL>(xl + (int64_t)j * ld_x + hoff, lane, c4, xv);
+        load_row_stream<T, VPL>(ep + (int64_t)e * HC + hoff, lane, c4, pv);
+        float tpart = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) tpart += f4_dot(G[k], xv[k]);
+        const float tt = warp_sum(tpart);
+        const float gl = a * (m * tt - dot);  // d loss / d logit[e,h]
+        float gmpart = 0.f;
+        T* gerow = g_ep + (int64_t)e * HC + hoff;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const float sx[4] = {xr_v[k].x + xv[k].x + pv[k].x, xr_v[k].y + xv[k].y + pv[k].y,
+                               xr_v[k].z + xv[k].z + pv[k].z, xr_v[k].w + xv[k].w + pv[k].w};
+          const float at[4] = {att_v[k].x, att_v[k].y, att_v[k].z, att_v[k].w};
+          float gs[4], ga[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float u = sx[q] * m;
+            const float lk = u > 0.f ? 1.f : slope;
+            const float v = u * lk;
+            const float gw = gl * at[q];
+            const float gu = gw * m * lk;
+            gs[q] = gu * m;
+            ga[q] = gl * (v * m);
+            if (MASKED) gmpart += gw * v + gu * sx[q];
+          }
+          gatt[k].x += ga[0]; gatt[k].y += ga[1]; gatt[k].z += ga[2]; gatt[k].w += ga[3];
+          gxr[k].x += gs[0]; gxr[k].y += gs[1]; gxr[k].z += gs[2]; gxr[k].w += gs[3];
+          const int v4 = lane + 32 * k;
+          if (v4 < c4) Vec4<T>::st_stream(gerow + 4 * v4, make_float4(gs[0], gs[1], gs[2], gs[3]));
+        }
+        if (MASKED) {
+          const float gm = warp_sum(gmpart) + tt * a;
+          if (lane == t) my_gm = gm;
+        }
+      }
+      if (MASKED && lane < cnt) gm_h[(int64_t)my_eid * H + head] = my_gm;
+    }
+    T* grow = g_xr + node * ld_gx + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v4 = lane + 32 * k;
+      if (v4 < c4) Vec4<T>::st(grow + 4 * v4, gxr[k]);
+    }
+  }
+  float* prow = gatt_part + wid0 * C;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v4 = lane + 32 * k;
+    if (v4 < c4) Vec4<float>::st(prow + 4 * v4, gatt[k]);
+  }
+}
+
+// g_att[h*C + c] = sum over warps w with (w % H == h) of part[w, c], fixed order.
+__global__ void gat_att_reduce_kernel(const float* __restrict__ part, int64_t nwarps, int H, int C,
+                                      float* __restrict__ g_att) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * C) return;
+  const int h = idx / C, c = idx - h * C;
+  float s = 0.f;
+  for (int64_t w = h; w < nwarps; w += H) s += part[w * C + c];
+  g_att[idx] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, pass 2 (src-major): g_xl[j] = sum_{e: src = j} ( g_eproj[e] + G[dst_e] * alpha*m ).
+// ------------------------------------------------------------------------------------------
+template <typename T, int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32)
+gat_edge_bwd_src_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __restrict__ g_ep,
+                        const float* __restrict__ emask, const float* __restrict__ alpha,
+                        const int* __restrict__ colptr, const int* __restrict__ nbr,
+                        const int* __restrict__ eid, T* __restrict__ g_xl, int64_t ld_gx,
+                        int64_t NH, int H, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + (threadIdx.x >> 5);
+  if (wid >= NH) return;
+  const int64_t node = wid / H;
+  const int head = (int)(wid - node * H);
+  const int c4 = C >> 2;
+  const int64_t HC = (int64_t)H * C;
+  const int hoff = head * C;
+  float4 acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
+  const int beg = colptr[node], end = colptr[node + 1];
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    int my_dst = 0, my_eid = 0;
+    float my_am = 0.f;
+    if (lane < cnt) {
+      my_dst = nbr[base + lane];
+      my_eid = eid[base + lane];
+      my_am = alpha[(int64_t)my_eid * H + head];
+      if (MASKED) my_am *= emask[my_eid];
+    }
+    for (int t = 0; t < cnt; ++t) {
+      const int i = __shfl_sync(ISG_FULL_MASK, my_dst, t);
+      const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+      const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+      float4 gv[VPL], Gv[VPL];
+      load_row_stream<T, VPL>(g_ep + (int64_t)e * HC + hoff, lane, c4, gv);
+      load_row<T, VPL>(gout + (int64_t)i * ld_g + hoff, lane, c4, Gv);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) acc[k] = f4_add(acc[k], f4_fma(Gv[k], am, gv[k]));
+    }
+  }
+  T* grow = g_xl + node * ld_gx + hoff;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v4 = lane + 32 * k;
+    if (v4 < c4) Vec4<T>::st(grow + 4 * v4, acc[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NodeMaskToEdgeMask (reference sampling/node_edge_masks.py:5-19)
+// ------------------------------------------------------------------------------------------
+__global__ void node_edge_mask_fwd_kernel(const float* __restrict__ m, const int64_t* __restrict__ ei,
+                                          int64_t E, float* __restrict__ em) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < E) em[e] = __fmul_rn(m[ei[e]], m[ei[E + e]]);
+}
+
+// g_mask[i] = sum_{e -> i} g_em[e]  (custom backward: dst only).  g_em [E] in original order.
+__global__ void node_edge_mask_bwd_kernel(const float* __restrict__ g_em, const int* __restrict__ rowptr,
+                                          const int* __restrict__ eid, int64_t N, float* __restrict__ g_m) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float s = 0.f;
+  for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) s += g_em[eid[p]];
+  g_m[i] = s;
+}
+
+// g_edge_mask[e] = sum_h gm_h[e,h]
+__global__ void gm_head_sum_kernel(const float* __restrict__ gm_h, int64_t E, int H, float* __restrict__ g_em) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float s = 0.f;
+  for (int h = 0; h < H; ++h) s += gm_h[e * H + h];
+  g_em[e] = s;
+}
+
+inline int bwd_grid_blocks(int64_t N, int H) {
+  // persistent grid: CTAs hold EDGE_WARPS warps; total warps must be a multiple of H
+  int64_t want = (N * H + EDGE_WARPS - 1) / EDGE_WARPS;
+  int64_t cap = (int64_t)ISG_NUM_SMS * 4;  // 4 CTAs of 128 threads per SM at ~100 regs
+  int64_t blocks = want < cap ? want : cap;
+  if (blocks < 1) blocks = 1;
+  while ((blocks * EDGE_WARPS) % H != 0) ++blocks;
+  return (int)blocks;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <typename T, int VPL>
+int launch_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj, const float* att,
+               const float* bias, const float* emask, const int* dst_ptr, const int* dst_nbr,
+               const int* dst_eid, void* out, int64_t ld_out, float* alpha, int64_t N, int H, int C,
+               float slope, cudaStream_t stream) {
+  const int64_t NH = N * H;
+  const int blocks = ceil_div(NH, EDGE_WARPS);
+  gat_edge_fwd_kernel<T, VPL><<<blocks, EDGE_WARPS * 32, 0, stream>>>(
+      (const T*)x_l, (const T*)x_r, ld_x, (const T*)e_proj, att, bias, emask, dst_ptr, dst_nbr, dst_eid,
+      (T*)out, ld_out, alpha, NH, H, C, slope);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+template <typename T, int VPL, bool MASKED>
+int launch_bwd(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r, int64_t ld_x,
+               const void* e_proj, const float* att, const float* bias, const float* emask,
+               const float* alpha, const void* out, int64_t ld_out, const int* dst_ptr,
+               const int* dst_nbr, const int* dst_eid, const int* src_ptr, const int* src_nbr,
+               const int* src_eid, void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att,
+               float* g_emask, int64_t N, int64_t E, int H, int C, float slope, float* gatt_part,
+               float* gm_h, cudaStream_t stream) {
+  const int blocks = bwd_grid_blocks(N, H);
+  gat_edge_bwd_dst_kernel<T, VPL, MASKED><<<blocks, EDGE_WARPS * 32, 0, stream>>>(
+      (const T*)g_out, ld_g, (const T*)x_l, (const T*)x_r, ld_x, (const T*)e_proj, att, bias, emask, alpha,
+      (const T*)out, ld_out, dst_ptr, dst_nbr, dst_eid, (T*)g_xr, ld_gx, (T*)g_eproj, gatt_part, gm_h, N, H,
+      C, slope);
+  ISG_CHECK_LAUNCH();
+  gat_att_reduce_kernel<<<ceil_div(H * C, 128), 128, 0, stream>>>(gatt_part, (int64_t)blocks * EDGE_WARPS, H,
+                                                                  C, g_att);
+  ISG_CHECK_LAUNCH();
+  const int64_t NH = N * H;
+  gat_edge_bwd_src_kernel<T, VPL, MASKED><<<ceil_div(NH, EDGE_WARPS), EDGE_WARPS * 32, 0, stream>>>(
+      (const T*)g_out, ld_g, (const T*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, (T*)g_xl, ld_gx, NH,
+      H, C);
+  ISG_CHECK_LAUNCH();
+  if (MASKED && E > 0) {
+    gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
+    ISG_CHECK_LAUNCH();
+  }
+  return ISG_OK;
+}
+
+inline int vpl_for(int C) { return (C / 4 + 31) / 32; }
+
+}  // namespace
+
+extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj,
+                                const float* att, const float* bias, const float* edge_mask,
+                                const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
+                                void* out, int64_t ld_out, float* alpha, int64_t N, int64_t E, int H, int C,
+                                float slope, int dtype, void* stream_) {
+  if (N < 0 || E < 0 || H <= 0 || C <= 0) return ISG_EINVAL;
+  if (C % 4 != 0 || C > 512 || ld_x % 4 != 0 || ld_out % 4 != 0) return ISG_EUNSUPPORTED;
+  if (N == 0) return ISG_OK;
+  if (!x_l || !x_r || !att || !dst_ptr || !out || (E > 0 && (!e_proj || !dst_nbr || !dst_eid || !alpha)))
+    return ISG_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+#define ISG_FWD_CASE(T, V)                                                                              \
+  return launch_fwd<T, V>(x_l, x_r, ld_x, e_proj, att, bias, edge_mask, dst_ptr, dst_nbr, dst_eid, out, \
+                          ld_out, alpha, N, H, C, slope, stream)
+  const int vpl = vpl_for(C);
+  if (dtype == ISG_F32) {
+    switch (vpl) {
+      case 1: ISG_FWD_CASE(float, 1);
+      case 2: ISG_FWD_CASE(float, 2);
+      case 3: ISG_FWD_CASE(float, 3);
+      case 4: ISG_FWD_CASE(float, 4);
+    }
+  } else if (dtype == ISG_BF16) {
+    switch (vpl) {
+      case 1: ISG_FWD_CASE(__nv_bfloat16, 1);
+      case 2: ISG_FWD_CASE(__nv_bfloat16, 2);
+      case 3: ISG_FWD_CASE(__nv_bfloat16, 3);
+      case 4: ISG_FWD_CASE(__nv_bfloat16, 4);
+    }
+  }
+#undef ISG_FWD_CASE
+  return ISG_EUNSUPPORTED;
+}
+
+extern "C" size_t isg_gat_edge_bwd_workspace_bytes(int64_t N, int64_t E, int H, int C) {
+  const int blocks = bwd_grid_blocks(N > 0 ? N : 1, H > 0 ? H : 1);
+  return align256((size_t)blocks * EDGE_WARPS * (size_t)C * sizeof(float)) +
+         align256((size_t)E * (size_t)H * sizeof(float));
+}
+
+extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r,
+                                int64_t ld_x, const void* e_proj, const float* att, const float* bias,
+                                const float* edge_mask, const float* alpha, const void* out, int64_t ld_out,
+                                const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
+                                const int32_t* src_ptr, const int32_t* src_nbr, const int32_t* src_eid,
+                                void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att,
+                                float* g_edge_mask, int64_t N, int64_t E, int H, int C, float slope, int dtype,
+                                void* workspace, size_t ws_bytes, void* stream_) {
+  if (N < 0 || E < 0 || H <= 0 || C <= 0) return ISG_EINVAL;
+  if (C % 4 != 0 || C > 512 || ld_x % 4 != 0 || ld_out % 4 != 0 || ld_g % 4 != 0 || ld_gx % 4 != 0)
+    return ISG_EUNSUPPORTED;
+  if (!g_att) return ISG_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (N == 0) {
+    cudaError_t err = cudaMemsetAsync(g_att, 0, (size_t)H * C * sizeof(float), stream);
+    return err == cudaSuccess ? ISG_OK : (int)err;
+  }
+  if (!g_out || !x_l || !x_r || !att || !out || !dst_ptr || !src_ptr || !g_xl || !g_xr ||
+      (E > 0 && (!e_proj || !alpha || !g_eproj || !dst_nbr || !dst_eid || !src_nbr || !src_eid)))
+    return ISG_EINVAL;
+  if ((edge_mask != nullptr) != (g_edge_mask != nullptr)) return ISG_EINVAL;
+  if (ws_bytes < isg_gat_edge_bwd_workspace_bytes(N, E, H, C) || !workspace) return ISG_EWORKSPACE;
+  const int blocks = bwd_grid_blocks(N, H);
+  float* gatt_part = (float*)workspace;
+  float* gm_h = (float*)((char*)workspace + align256((size_t)blocks * EDGE_WARPS * (size_t)C * sizeof(float)));
+#define ISG_BWD_CASE(T, V)                                                                                   \
+  return edge_mask                                                                                           \
+             ? launch_bwd<T, V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, bias, edge_mask, alpha, out, \
+                                      ld_out, dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,    \
+                                      g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope, gatt_part, \
+                                      gm_h, stream)                                                          \
+             : launch_bwd<T, V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, bias, edge_mask, alpha, out, \
+                                       ld_out, dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,   \
+                                       g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,          \
+                                       gatt_part, gm_h, stream)
+  const int vpl = vpl_for(C);
+  if (dtype == ISG_F32) {
+    switch (vpl) {
+      case 1: ISG_BWD_CASE(float, 1);
+      case 2: ISG_BWD_CASE(float, 2);
+      case 3: ISG_BWD_CASE(float, 3);
+      case 4: ISG_BWD_CASE(float, 4);
+    }
+  } else if (dtype == ISG_BF16) {
+    switch (vpl) {
+      case 1: ISG_BWD_CASE(__nv_bfloat16, 1);
+      case 2: ISG_BWD_CASE(__nv_bfloat16, 2);
+      case 3: ISG_BWD_CASE(__nv_bfloat16, 3);
+      case 4: ISG_BWD_CASE(__nv_bfloat16, 4);
+    }
+  }
+#undef ISG_BWD_CASE
+  return ISG_EUNSUPPORTED;
+}
+
+extern "C" int isg_node_edge_mask_fwd(const float* node_mask, const int64_t* edge_index, int64_t E,
+                                      float* edge_mask, void* stream_) {
+  if (E < 0) return ISG_EINVAL;
+  if (E == 0) return ISG_OK;
+  if (!node_mask || !edge_index || !edge_mask) return ISG_EINVAL;
+  node_edge_mask_fwd_kernel<<<isg::ceil_div(E, 256), 256, 0, (cudaStream_t)stream_>>>(node_mask, edge_index, E,
+                                                                                      edge_mask);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_node_edge_mask_bwd(const float* g_edge_mask, const int32_t* dst_ptr, const int32_t* dst_eid,
+                                      int64_t N, float* g_node_mask, void* stream_) {
+  if (N < 0) return ISG_EINVAL;
+  if (N == 0) return ISG_OK;
+  if (!g_edge_mask || !dst_ptr || !dst_eid || !g_node_mask) return ISG_EINVAL;
+  node_edge_mask_bwd_kernel<<<isg::ceil_div(N, 128), 128, 0, (cudaStream_t)stream_>>>(g_edge_mask, dst_ptr,
+                                                                                      dst_eid, N, g_node_mask);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}

@@ -1,0 +1,427 @@
+// segment.cu — node-side fused segment ops of the hot path (all fp32, HBM/latency-bound):
+//   * instruction gating           y = gelu(x * ins[batch])            (mgat_v2_conv.py:156-157)
+//   * gate logits theta            gelu(<xn, q[batch[batch]]>/sqrt(D)) (masking.py:151-155)
+//   * scatter-SDPA + GraphNorm + residual, one CTA per graph           (mgat.py:168-172)
+//   * gelu backward, deterministic column sums
+// Every per-graph reduction is done by one CTA over the graph's contiguous node range
+// (batch is sorted), so there are no floating-point atomics and results are run-to-run stable.
+#include "common.cuh"
+
+namespace {
+
+using namespace isg;
+
+// ---------------------------------------------------------------- instruction gating
+__global__ void instr_gate_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ins,
+                                      const int* __restrict__ batch, int64_t N, int D4,
+                                      float* __restrict__ y) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // over N * D4 float4s
+  if (idx >= N * D4) return;
+  const int64_t n = idx / D4;
+  const int c = (int)(idx - n * D4);
+  const float4 xv = Vec4<float>::ld(x + idx * 4);
+  const float4 iv = Vec4<float>::ld(ins + ((int64_t)batch[n] * D4 + c) * 4);
+  float4 o;
+  o.x = gelu_f(xv.x * iv.x);
+  o.y = gelu_f(xv.y * iv.y);
+  o.z = gelu_f(xv.z * iv.z);
+  o.w = gelu_f(xv.w * iv.w);
+  Vec4<float>::st(y + idx * 4, o);
+}
+
+// one CTA per graph; thread c loops over the graph's nodes (coalesced across c)
+__global__ void instr_gate_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                      const float* __restrict__ ins, const int* __restrict__ gptr, int D,
+                                      float* __restrict__ gx, float* __restrict__ gins) {
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], n1 = gptr[b + 1];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float iv = ins[(int64_t)b * D + c];
+    float acc = 0.f;
+    for (int n = n0; n < n1; ++n) {
+      const int64_t o = (int64_t)n * D + c;
+      const float xv = x[o];
+      const float gp = gy[o] * gelu_grad_f(xv * iv);
+      gx[o] = gp * iv;
+      acc = fmaf(gp, xv, acc);
+    }
+    gins[(int64_t)b * D + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------- gate logits theta
+// warp per node
+__global__ void gate_theta_fwd_kernel(const float* __restrict__ xn, const float* __restrict__ q,
+                                      const int* __restrict__ batch, int64_t N, int D, int dbl,
+                                      float* __restrict__ theta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const int qi = dbl ? batch[batch[n]] : batch[n];  // quirk Q1: double gather
+  const float* xr = xn + n * D;
+  const float* qr = q + (int64_t)qi * D;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s = fmaf(xr[c], qr[c], s);
+  s = warp_sum(s);
+  if (lane == 0) theta[n] = gelu_f(s / sqrtf((float)D));
+}
+
+// g_xn: warp per node (recomputes the pre-activation)
+__global__ void gate_theta_bwd_xn_kernel(const float* __restrict__ gth, const float* __restrict__ xn,
+                                         const float* __restrict__ q, const int* __restrict__ batch,
+                                         int64_t N, int D, int dbl, float* __restrict__ gxn,
+                                         float* __restrict__ gpre) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const int qi = dbl ? batch[batch[n]] : batch[n];
+  const float* xr = xn + n * D;
+  const float* qr = q + (int64_t)qi * D;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s = fmaf(xr[c], qr[c], s);
+  s = warp_sum(s);
+  const float rs = 1.0f / sqrtf((float)D);
+  const float gp = gth[n] * gelu_grad_f(s * rs) * rs;  // d loss / d <xn,q>
+  for (int c = lane; c < D; c += 32) gxn[n * D + c] = gp * qr[c];
+  if (lane == 0) gpre[n] = gp;
+}
+
+// g_q[r] = sum over nodes n with batch[batch[n]] == r of gpre[n]*xn[n].  Nodes of graph g all use
+// row batch[g]; the graphs g with batch[g] == r are g in [gptr[r], gptr[r+1]) ∩ [0,B) — a
+// contiguous range of graphs, hence a contiguous range of nodes.  One CTA per row r.
+__global__ void gate_theta_bwd_q_kernel(const float* __restrict__ gpre, const float* __restrict__ xn,
+                                        const int* __restrict__ gptr, int B, int D, int dbl,
+                                        float* __restrict__ gq) {
+  const int r = blockIdx.x;  // row of q: < B when dbl (q is [B,D]); < N otherwise (q is [N,D])
+  int n0 = 0, n1 = 0;
+  if (dbl) {
+    const int g0 = min(gptr[r], B), g1 = min(gptr[r + 1], B);
+    n0 = gptr[g0];
+    n1 = gptr[g1];
+  } else if (r < B) {  // single gather q[batch[n]]: only rows < B are referenced
+    n0 = gptr[r];
+    n1 = gptr[r + 1];
+  }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int n = n0; n < n1; ++n) acc = fmaf(gpre[n], xn[(int64_t)n * D + c], acc);
+    gq[(int64_t)r * D + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------- scatter-SDPA + GraphNorm + residual
+constexpr int SG_THREADS = 320;  // 10 warps; thread c owns channel c (D = 300) in the per-channel phases
+
+__global__ void __launch_bounds__(SG_THREADS)
+sdpa_graphnorm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ ins,
+                          const float* __restrict__ h_in, const float* __restrict__ weight,
+                          const float* __restrict__ bias, const float* __restrict__ mean_scale,
+                          const int* __restrict__ gptr, int D, float eps, float* __restrict__ h_out,
+                          float* __restrict__ a_out, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out) {
+  extern __shared__ float sm[];  // [nmax] attention weights
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], n1 = gptr[b + 1], cnt = n1 - n0;
+  if (cnt <= 0) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      mean_out[(int64_t)b * D + c] = 0.f;
+      rstd_out[(int64_t)b * D + c] = 0.f;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* ib = ins + (int64_t)b * D;
+  const float rs = 1.0f / sqrtf((float)D);
+  // logits: warp per node
+  for (int i = warp; i < cnt; i += nw) {
+    const float* vr = v + (int64_t)(n0 + i) * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s = fmaf(ib[c], vr[c], s);
+    s = warp_sum(s);
+    if (lane == 0) sm[i] = s * rs;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) mx = fmaxf(mx, sm[i]);
+  mx = block_max(mx, red);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float e = expf(sm[i] - mx);
+    sm[i] = e;
+    se += e;
+  }
+  se = block_sum(se, red);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float a = sm[i] / se;  // torch_scatter.scatter_softmax: no epsilon
+    sm[i] = a;
+    a_out[n0 + i] = a;
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / (float)cnt;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s1 = 0.f;
+    for (int i = 0; i < cnt; ++i) s1 = fmaf(sm[i], v[(int64_t)(n0 + i) * D + c], s1);
+    const float mean = s1 * inv_cnt;
+    const float shift = mean * mean_scale[c];
+    float s2 = 0.f;
+    for (int i = 0; i < cnt; ++i) {
+      const float o = sm[i] * v[(int64_t)(n0 + i) * D + c] - shift;
+      s2 = fmaf(o, o, s2);
+    }
+    const float rstd = 1.0f / sqrtf(s2 * inv_cnt + eps);
+    mean_out[(int64_t)b * D + c] = mean;
+    rstd_out[(int64_t)b * D + c] = rstd;
+    const float w = weight[c] * rstd, bb = bias[c];
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t o_ = (int64_t)(n0 + i) * D + c;
+      const float o = sm[i] * v[o_] - shift;
+      h_out[o_] = fmaf(w, o, bb) + h_in[o_];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SG_THREADS)
+sdpa_graphnorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
+                          const float* __restrict__ ins, const float* __restrict__ weight,
+                          const float* __restrict__ mean_scale, const float* __restrict__ a,
+                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const int* __restrict__ gptr, int D, float* __restrict__ g_v,
+                          float* __restrict__ g_ins, float* __restrict__ gw_part,
+                          float* __restrict__ gb_part, float* __restrict__ gms_part) {
+  // dynamic smem: coefA[D], coefB[D], coefC[D], shift[D], sa[nmax], sga[nmax]
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  float* cA = sm;
+  float* cB = cA + D;
+  float* cC = cB + D;
+  float* sh = cC + D;
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], n1 = gptr[b + 1], cnt = n1 - n0;
+  float* sa = sh + D;
+  float* sga = sa + max(cnt, 0);
+  if (cnt <= 0) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      const int64_t o = (int64_t)b * D + c;
+      g_ins[o] = 0.f;
+      gw_part[o] = 0.f;
+      gb_part[o] = 0.f;
+      gms_part[o] = 0.f;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float inv_cnt = 1.0f / (float)cnt;
+  const float rs = 1.0f / sqrtf((float)D);
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) sa[i] = a[n0 + i];
+  __syncthreads();
+  // P1: per-channel sums -> coefficients of g_y = A*G + B*o + C
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const int64_t bc = (int64_t)b * D + c;
+    const float mu = mean[bc], r = rstd[bc], ms = mean_scale[c], w = weight[c];
+    const float shift = mu * ms;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t o_ = (int64_t)(n0 + i) * D + c;
+      const float G = g[o_];
+      const float o = sa[i] * v[o_] - shift;
+      s1 += G;
+      s2 = fmaf(G, o, s2);
+    }
+    gb_part[bc] = s1;
+    gw_part[bc] = s2 * r;
+    const float g_var = -0.5f * (w * s2) * r * r * r;
+    // sum_n g_o = w r S1 + g_var*(2/cnt)*sum_n o ;  sum_n o = cnt*mean*(1-ms)
+    const float sum_go = w * r * s1 + g_var * 2.0f * mu * (1.0f - ms);
+    gms_part[bc] = -mu * sum_go;
+    cA[c] = w * r;
+    cB[c] = g_var * 2.0f * inv_cnt;
+    cC[c] = -ms * sum_go * inv_cnt;
+    sh[c] = shift;
+  }
+  __syncthreads();
+  // P2: g_a[n] = sum_c g_y[n,c] * v[n,c]   (warp per node)
+  for (int i = warp; i < cnt; i += nw) {
+    const int64_t ro = (int64_t)(n0 + i) * D;
+    const float ai = sa[i];
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float vv = v[ro + c];
+      const float gy = fmaf(cA[c], g[ro + c], fmaf(cB[c], ai * vv - sh[c], cC[c]));
+      s = fmaf(gy, vv, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) sga[i] = s;
+  }
+  __syncthreads();
+  // P3: softmax backward  g_logit = a * (g_a - sum a*g_a)
+  float dp = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) dp = fmaf(sa[i], sga[i], dp);
+  dp = block_sum(dp, red);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) sga[i] = sa[i] * (sga[i] - dp) * rs;  // includes 1/sqrt(D)
+  __syncthreads();
+  // P4: g_v and g_ins
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float ic = ins[(int64_t)b * D + c];
+    float gi = 0.f;
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t o_ = (int64_t)(n0 + i) * D + c;
+      const float vv = v[o_];
+      const float gy = fmaf(cA[c], g[o_], fmaf(cB[c], sa[i] * vv - sh[c], cC[c]));
+      g_v[o_] = fmaf(gy, sa[i], sga[i] * ic);
+      gi = fmaf(sga[i], vv, gi);
+    }
+    g_ins[(int64_t)b * D + c] = gi;
+  }
+}
+
+// ---------------------------------------------------------------- misc
+__global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ z,
+                                float* __restrict__ gz, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) gz[i] = gy[i] * gelu_grad_f(z[i]);
+}
+
+constexpr int CS_ROWS = 256;  // rows per partial
+__global__ void colsum_partial_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
+                                      float* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
+  const int64_t r1 = min(rows, r0 + CS_ROWS);
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += in[r * ld + c];
+  part[(int64_t)blockIdx.y * cols + c] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int cols,
+                                    float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * cols + c];
+  out[c] = s;
+}
+
+}  // namespace
+
+extern "C" int isg_instr_gate_fwd(const float* x, const float* ins, const int32_t* batch32, int64_t N, int D,
+                                  float* y, void* stream_) {
+  if (N < 0 || D <= 0) return ISG_EINVAL;
+  if (D % 4 != 0) return ISG_EUNSUPPORTED;
+  if (N == 0) return ISG_OK;
+  if (!x || !ins || !batch32 || !y) return ISG_EINVAL;
+  const int64_t total = N * (D / 4);
+  instr_gate_fwd_kernel<<<isg::ceil_div(total, 256), 256, 0, (cudaStream_t)stream_>>>(x, ins, batch32, N, D / 4, y);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_instr_gate_bwd(const float* g_y, const float* x, const float* ins, const int32_t* gptr,
+                                  int64_t B, int D, float* g_x, float* g_ins, void* stream_) {
+  if (B < 0 || D <= 0) return ISG_EINVAL;
+  if (B == 0) return ISG_OK;
+  if (!g_y || !x || !ins || !gptr || !g_x || !g_ins) return ISG_EINVAL;
+  instr_gate_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, x, ins, gptr, D, g_x, g_ins);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_gate_theta_fwd(const float* xn, const float* q, const int32_t* batch32, int64_t N, int D,
+                                  int double_gather, float* theta, void* stream_) {
+  if (N < 0 || D <= 0) return ISG_EINVAL;
+  if (N == 0) return ISG_OK;
+  if (!xn || !q || !batch32 || !theta) return ISG_EINVAL;
+  gate_theta_fwd_kernel<<<isg::ceil_div(N * 32, 128), 128, 0, (cudaStream_t)stream_>>>(xn, q, batch32, N, D, double_gather, theta);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_gate_theta_bwd(const float* g_theta, const float* xn, const float* q, const int32_t* batch32,
+                                  const int32_t* gptr, int64_t N, int64_t B, int D, int double_gather,
+                                  float* g_xn, float* g_q, float* scratch, void* stream_) {
+  if (N < 0 || B < 0 || D <= 0) return ISG_EINVAL;
+  if (N == 0 || B == 0) return ISG_OK;
+  if (!g_theta || !xn || !q || !batch32 || !gptr || !g_xn || !g_q || !scratch) return ISG_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  gate_theta_bwd_xn_kernel<<<isg::ceil_div(N * 32, 128), 128, 0, stream>>>(g_theta, xn, q, batch32, N, D, double_gather, g_xn, scratch);
+  ISG_CHECK_LAUNCH();
+  gate_theta_bwd_q_kernel<<<(unsigned)(double_gather ? B : N), 320, 0, stream>>>(scratch, xn, gptr, (int)B, D, double_gather, g_q);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_sdpa_graphnorm_fwd(const float* v, const float* ins, const float* h_in, const float* weight,
+                                      const float* bias, const float* mean_scale, const int32_t* gptr, int64_t B,
+                                      int D, int nmax, float eps, float* h_out, float* a, float* mean,
+                                      float* rstd, void* stream_) {
+  if (B < 0 || D <= 0 || nmax < 0) return ISG_EINVAL;
+  if (B == 0) return ISG_OK;
+  if (!v || !ins || !h_in || !weight || !bias || !mean_scale || !gptr || !h_out || !a || !mean || !rstd)
+    return ISG_EINVAL;
+  const size_t smem = (size_t)(nmax > 0 ? nmax : 1) * sizeof(float);
+  if (smem > 200 * 1024) return ISG_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  sdpa_graphnorm_fwd_kernel<<<(unsigned)B, SG_THREADS, smem, (cudaStream_t)stream_>>>(
+      v, ins, h_in, weight, bias, mean_scale, gptr, D, eps, h_out, a, mean, rstd);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const float* ins, const float* weight,
+                                      const float* mean_scale, const float* a, const float* mean,
+                                      const float* rstd, const int32_t* gptr, int64_t B, int D, int nmax,
+                                      float* g_v, float* g_ins, float* gw_part, float* gb_part, float* gms_part,
+                                      void* stream_) {
+  if (B < 0 || D <= 0 || nmax < 0) return ISG_EINVAL;
+  if (B == 0) return ISG_OK;
+  if (!g_out || !v || !ins || !weight || !mean_scale || !a || !mean || !rstd || !gptr || !g_v || !g_ins ||
+      !gw_part || !gb_part || !gms_part)
+    return ISG_EINVAL;
+  const size_t smem = ((size_t)4 * D + 2 * (size_t)(nmax > 0 ? nmax : 1)) * sizeof(float);
+  if (smem > 200 * 1024) return ISG_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  sdpa_graphnorm_bwd_kernel<<<(unsigned)B, SG_THREADS, smem, (cudaStream_t)stream_>>>(
+      g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_t n, void* stream_) {
+  if (n < 0) return ISG_EINVAL;
+  if (n == 0) return ISG_OK;
+  if (!g_y || !z || !g_z) return ISG_EINVAL;
+  gelu_bwd_kernel<<<isg::ceil_div(n, 256), 256, 0, (cudaStream_t)stream_>>>(g_y, z, g_z, n);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" size_t isg_colsum_workspace_bytes(int64_t rows, int cols) {
+  const int64_t parts = (rows + CS_ROWS - 1) / CS_ROWS;
+  return (size_t)(parts > 0 ? parts : 1) * (size_t)cols * sizeof(float);
+}
+
+extern "C" int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, float* out, void* workspace,
+                          size_t ws_bytes, void* stream_) {
+  if (rows < 0 || cols <= 0 || !out) return ISG_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows == 0) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), stream);
+    return e == cudaSuccess ? ISG_OK : (int)e;
+  }
+  if (!in) return ISG_EINVAL;
+  if (ws_bytes < isg_colsum_workspace_bytes(rows, cols) || !workspace) return ISG_EWORKSPACE;
+  const int parts = (int)((rows + CS_ROWS - 1) / CS_ROWS);
+  colsum_partial_kernel<<<dim3(isg::ceil_div(cols, 128), parts), 128, 0, stream>>>(in, ld, rows, cols, (float*)workspace);
+  ISG_CHECK_LAUNCH();
+  colsum_final_kernel<<<isg::ceil_div(cols, 128), 128, 0, stream>>>((const float*)workspace, parts, cols, out);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}

@@ -1,0 +1,84 @@
+"""GraphIndex — device-side index structures shared by every layer of one forward/backward:
+dst- and src-sorted CSR of the COO `edge_index` (kernel (a), csrc/csr.cu), `graph_ptr` from the
+sorted `batch` vector, and Nmax.  Built once per batch (the reference rebuilds gathers / scatter
+indices inside PyG on every one of the 4 layers: models/mgat_v2_conv.py:215)."""
+import torch
+
+from . import lib as L
+
+
+class GraphIndex:
+    __slots__ = ("edge_index", "batch", "N", "E", "B", "dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr",
+                 "src_eid", "status", "graph_ptr", "batch32", "_nmax_dev", "_nmax", "_key")
+
+    def __init__(self, edge_index, batch, num_graphs, num_nodes=None):
+        L.require_cuda(edge_index, batch)
+        if edge_index.dtype != torch.int64 or batch.dtype != torch.int64:
+            raise TypeError("edge_index and batch must be int64 (PyG layout)")
+        lib = L.load()
+        dev = edge_index.device
+        self.edge_index = edge_index.contiguous()
+        self.batch = batch.contiguous()
+        self.N = int(batch.numel()) if num_nodes is None else int(num_nodes)
+        self.E = int(edge_index.size(1))
+        self.B = int(num_graphs)
+        N, E, B = self.N, self.E, self.B
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.dst_ptr = torch.empty(N + 1, **i32)
+        self.src_ptr = torch.empty(N + 1, **i32)
+        self.dst_nbr = torch.empty(E, **i32)
+        self.dst_eid = torch.empty(E, **i32)
+        self.src_nbr = torch.empty(E, **i32)
+        self.src_eid = torch.empty(E, **i32)
+        self.status = torch.empty(1, **i32)
+        ws_bytes = lib.isg_csr_workspace_bytes(N, E)
+        ws = L.workspace(ws_bytes, dev)
+        st = L.stream()
+        L.check(lib.isg_csr_build(L.ptr(self.edge_index), E, N, L.ptr(self.dst_ptr), L.ptr(self.dst_nbr),
+                                  L.ptr(self.dst_eid), L.ptr(self.src_ptr), L.ptr(self.src_nbr),
+                                  L.ptr(self.src_eid), L.ptr(self.status), L.ptr(ws), ws_bytes, st))
+        self.graph_ptr = torch.empty(B + 1, **i32)
+        self.batch32 = torch.empty(max(N, 1), **i32)
+        self._nmax_dev = torch.empty(1, **i32)
+        L.check(lib.isg_graph_ptr(L.ptr(self.batch), N, B, L.ptr(self.graph_ptr), L.ptr(self.batch32),
+                                  L.ptr(self._nmax_dev), st))
+        self._nmax = None
+        self._key = None
+
+    @property
+    def nmax(self):
+        """Max nodes per graph as a Python int.  One device->host read per batch (the reference
+        syncs here too: to_dense_batch's int(num_nodes.max()), models/masking.py:162)."""
+        if self._nmax is None:
+            self._nmax = int(self._nmax_dev.item())
+        return self._nmax
+
+    def set_nmax(self, nmax):
+        """Lets a data loader that already knows the graph sizes skip the device->host read."""
+        self._nmax = int(nmax)
+
+    def check_indices(self):
+        bad = int(self.status.item())
+        if bad:
+            raise IndexError(f"edge_index has {bad} endpoints outside [0, {self.N})")
+
+
+_cache = []  # tiny MRU cache so the 4 conv layers of one forward share one index
+_CACHE_SIZE = 4
+
+
+def get_graph_index(edge_index, batch, num_graphs):
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), batch.data_ptr(),
+           batch._version, int(batch.numel()), int(num_graphs), edge_index.device)
+    for gi in _cache:
+        if gi._key == key:
+            return gi
+    gi = GraphIndex(edge_index, batch, num_graphs)
+    gi._key = key
+    _cache.insert(0, gi)
+    del _cache[_CACHE_SIZE:]
+    return gi
+
+
+def clear_cache():
+    del _cache[:]

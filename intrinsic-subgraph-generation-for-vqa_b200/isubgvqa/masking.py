@@ -1,0 +1,136 @@
+"""Mirror of ISubGVQA/models/masking.py (MaskingModel, get_imle_samplers, get_aimle_samplers)."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .. import lib as L
+from .. import ops
+from ..graph import get_graph_index
+from .samplers import (AdaptiveTargetDistribution, EdgeSIMPLEBatched, GumbelDistribution, GumbelSampler,
+                       IMLEScheme, TargetDistribution, aimle, imle)
+
+
+class _TopKSelect(torch.nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.empty(1, in_channels))
+        bound = 1.0 / math.sqrt(in_channels)
+        torch.nn.init.uniform_(self.weight, -bound, bound)
+
+
+class _TopKPoolingParams(torch.nn.Module):
+    """Parameter container with the state_dict layout of torch_geometric 2.6.1 TopKPooling
+    (`gate_top.select.weight` [1, D]); the reference builds it and never calls it (masking.py:89-90)."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.select = _TopKSelect(in_channels)
+
+
+def get_imle_samplers(sample_k, beta=10, alpha=1.0, tau=1.0, noise_scale=0.3, nb_samples=1, device=None,
+                      noise_source="host"):
+    """masking.py:214-245."""
+    sched = IMLEScheme("edge_candid", sample_k, 1, 1)
+    train = imle(sched.torch_sample_scheme, target_distribution=TargetDistribution(alpha=alpha, beta=beta),
+                 noise_distribution=GumbelDistribution(0.0, noise_scale, device, noise_source),
+                 nb_samples=nb_samples, input_noise_temperature=tau, target_noise_temperature=tau)
+    val = imle(sched.torch_sample_scheme, target_distribution=None,
+               noise_distribution=GumbelDistribution(0.0, noise_scale, device, noise_source),
+               nb_samples=nb_samples, input_noise_temperature=tau if nb_samples > 1 else 0.0,
+               target_noise_temperature=tau)
+    return train, val
+
+
+def get_aimle_samplers(sample_k, alpha=1.0, tau=1.0, noise_scale=0.3, nb_samples=1, device=None,
+                       noise_source="host"):
+    """masking.py:248-283."""
+    sched = IMLEScheme("edge_candid", sample_k, 1, 1)
+    train = aimle(sched.torch_sample_scheme,
+                  target_distribution=AdaptiveTargetDistribution(initial_alpha=alpha, initial_beta=0.0),
+                  noise_distribution=GumbelDistribution(0.0, noise_scale, device, noise_source),
+                  nb_samples=nb_samples, theta_noise_temperature=tau, target_noise_temperature=tau,
+                  symmetric_perturbation=True)
+    val = aimle(sched.torch_sample_scheme, target_distribution=None,
+                noise_distribution=GumbelDistribution(0.0, noise_scale, device, noise_source),
+                nb_samples=nb_samples, theta_noise_temperature=1.0 if nb_samples > 1 else tau,
+                target_noise_temperature=tau, symmetric_perturbation=True)
+    return train, val
+
+
+class MaskingModel(torch.nn.Module):
+    """masking.py:53-199.  Same constructor, attributes (`masking_threshold` is read by the conv)
+    and state_dict keys; forward(x, u, batch, edge_index, size=None, use_all_instrs=True) -> [N,1].
+
+    `injected_noise` / `injected_dropout_mask` (attributes, default None) replace the random draws
+    of the next forward — used by the parity tests to feed both sides the same randomness."""
+
+    def __init__(self, dim_nodes, dim_questions, masking_threshold=0.3, use_topk=False, sample_k=None,
+                 sampler_type=None, nb_samples=1, alpha=1.0, beta=10.0, tau=1.0, noise_source="host"):
+        super().__init__()
+        self.use_topk = use_topk
+        self.sample_k = sample_k
+        self.sampler_type = sampler_type
+        self.masking_threshold = int(masking_threshold) if masking_threshold > 1 else masking_threshold
+        self.dim_nodes, self.dim_questions = dim_nodes, dim_questions
+        self.gate_nn = torch.nn.Sequential(torch.nn.Linear(dim_questions, dim_questions), torch.nn.GELU(),
+                                           torch.nn.Linear(dim_questions, 1))
+        self.node_nn = torch.nn.Sequential(torch.nn.Linear(dim_nodes, dim_questions), torch.nn.GELU())
+        self.ques_nn = torch.nn.Sequential(torch.nn.Linear(dim_questions, dim_questions), torch.nn.GELU())
+        if use_topk:
+            self.gate_top = _TopKPoolingParams(dim_questions)
+        if sampler_type == "imle":
+            self.sampler_train, self.sampler_val = get_imle_samplers(
+                sample_k=sample_k, device=None, nb_samples=nb_samples, alpha=alpha, beta=beta, tau=tau,
+                noise_source=noise_source)
+        elif sampler_type == "aimle":
+            self.sampler_train, self.sampler_val = get_aimle_samplers(
+                sample_k=sample_k, device=None, nb_samples=nb_samples, alpha=alpha, tau=tau,
+                noise_source=noise_source)
+        elif sampler_type == "simple":
+            self.sampler = EdgeSIMPLEBatched(k=sample_k, device="cuda", policy="edge_candid")
+        elif sampler_type == "gumbel":
+            self.sampler = GumbelSampler(k=sample_k, policy="edge_candid", train_ensemble=1, val_ensemble=1)
+        self.injected_noise = None
+        self.injected_dropout_mask = None
+        self.last_theta = None
+
+    def reset_parameters(self):
+        for seq in (self.gate_nn, self.node_nn, self.ques_nn):
+            for m in seq:
+                if hasattr(m, "reset_parameters"):
+                    m.reset_parameters()
+
+    # -- fused path used by MaskingGATv2Conv: u_graph is [B,D] (imle_att BEFORE the [batch] gather)
+    def forward_fused(self, x, u_graph, gi):
+        xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU)
+        q = ops.linear(u_graph, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU)
+        theta = ops.GateTheta.apply(xn, q, gi, True)
+        return self._sample(theta, gi)
+
+    def forward(self, x, u, batch, edge_index, size=None, use_all_instrs=True):
+        if use_all_instrs:
+            raise NotImplementedError("use_all_instrs yields a 2-D dense tensor the reference's own IMLE wrapper "
+                                      "rejects (wrapper.py:115-120); it is dead code on the path")
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        num_graphs = size if size is not None else int(batch[-1].item()) + 1  # masking.py:135
+        gi = get_graph_index(edge_index, batch, num_graphs)
+        xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU)
+        q = ops.linear(u, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU)  # u is [N,D] here
+        theta = ops.GateTheta.apply(xn, q, gi, False)  # q[batch] (masking.py:152)
+        return self._sample(theta, gi)
+
+    def _sample(self, theta, gi):
+        noise, self.injected_noise = self.injected_noise, None
+        drop, self.injected_dropout_mask = self.injected_dropout_mask, None
+        if self.training:  # masking.py:159 / :196 — dropout p=0.2 on theta
+            theta = theta * drop if drop is not None else F.dropout(theta, p=0.2, training=True)
+        self.last_theta = theta
+        if not self.use_topk:  # masking.py:195-198
+            return (torch.sigmoid(theta) > 0.5).to(dtype=theta.dtype)
+        if self.sampler_type in ("imle", "aimle"):
+            sampler = self.sampler_train if self.training else self.sampler_val
+            return sampler.ragged(theta, gi, noise)
+        if self.sampler_type in ("gumbel", "simple"):
+            return self.sampler.ragged(theta, gi, noise)
+        raise ValueError(f"unknown sampler_type {self.sampler_type!r}")

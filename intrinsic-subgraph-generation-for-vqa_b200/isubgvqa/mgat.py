@@ -1,0 +1,90 @@
+"""Mirror of ISubGVQA/models/mgat.py (MGAT)."""
+import torch
+
+from .. import lib as L
+from .. import ops
+from ..graph import get_graph_index
+from .mgat_v2_conv import MaskingGATv2Conv
+
+
+class GraphNormParams(torch.nn.Module):
+    """Parameter container with torch_geometric.nn.norm.GraphNorm's layout (weight, bias, mean_scale)."""
+
+    def __init__(self, in_channels, eps=1e-5):
+        super().__init__()
+        self.in_channels, self.eps = in_channels, eps
+        self.weight = torch.nn.Parameter(torch.ones(in_channels))
+        self.bias = torch.nn.Parameter(torch.zeros(in_channels))
+        self.mean_scale = torch.nn.Parameter(torch.ones(in_channels))
+
+    def reset_parameters(self):
+        torch.nn.init.ones_(self.weight)
+        torch.nn.init.zeros_(self.bias)
+        torch.nn.init.ones_(self.mean_scale)
+
+
+class MGAT(torch.nn.Module):
+    """mgat.py:8-184: num_ins x [MaskingGATv2Conv -> x_proj (Linear GELU Linear GELU) -> scatter-SDPA ->
+    GraphNorm -> residual].  Same constructor / forward signature / 4-tuple return / state_dict."""
+
+    def __init__(self, channels, num_ins, dropout=0.0, heads=4, use_instr=False, masking_thresholds=None,
+                 use_topk=False, interpretable_mode=True, concat_instr=False, use_all_instrs=False,
+                 use_global_mask=False, node_classification=False, sampler_type=None, sample_k=None, nb_samples=1,
+                 alpha=1.0, beta=10.0, tau=1.0):
+        super().__init__()
+        if not use_instr:
+            raise NotImplementedError("the reference MGAT itself only works with use_instr=True (mgat.py:46-53)")
+        self.masking_thresholds = masking_thresholds
+        self.use_global_mask, self.node_classification = use_global_mask, node_classification
+        self.heads, self.use_instr, self.use_topk = heads, use_instr, use_topk
+        self.interpretable_mode, self.use_all_instrs = interpretable_mode, use_all_instrs
+        self.in_channels = channels * 2 if concat_instr else channels
+        self.convs = torch.nn.ModuleList([
+            MaskingGATv2Conv(in_channels=self.in_channels, out_channels=channels, heads=heads, edge_dim=channels,
+                             masking_threshold=self.masking_thresholds[i], add_self_loops=False, use_instr=True,
+                             use_topk=use_topk, concat_instr=concat_instr, use_all_instrs=use_all_instrs,
+                             sampler_type=sampler_type, sample_k=sample_k, nb_samples=nb_samples, alpha=alpha,
+                             beta=beta, tau=tau) for i in range(num_ins)])
+        self.x_proj = torch.nn.ModuleList([
+            torch.nn.Sequential(torch.nn.Linear(heads * channels, channels * int(heads / 2)), torch.nn.GELU(),
+                                torch.nn.Linear(channels * int(heads / 2), channels), torch.nn.GELU())
+            for _ in range(num_ins)])
+        self.bns = torch.nn.ModuleList([GraphNormParams(channels) for _ in range(num_ins)])
+        self.dropout = dropout
+        self.node_logits = torch.nn.Sequential(torch.nn.Linear(channels, 512), torch.nn.GELU(),
+                                               torch.nn.Linear(512, 2577))
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        for bn in self.bns:
+            bn.reset_parameters()
+
+    def forward(self, x, edge_index, instr_vectors, global_language_feats, edge_attr, batch, return_masks=False,
+                explainer=False, explainer_stage=False, expl_bypass_x=False):
+        L.require_cuda(x, edge_index, batch, edge_attr)
+        gi = get_graph_index(edge_index, batch, instr_vectors.shape[1])
+        h = x
+        mask = None
+        if self.use_global_mask:
+            global_mask = torch.ones((h.size(0), 1), device=h.device, dtype=h.dtype)
+        for i, conv in enumerate(self.convs):
+            ins = instr_vectors[i]
+            if explainer:
+                h = expl_bypass_x if (explainer_stage - 1) == i else h
+            conv_res, mask, _edge_att = conv(x=h, edge_index=edge_index, edge_attr=edge_attr, instruction=ins,
+                                             batch=batch, return_masks=return_masks, return_attention_weights=True,
+                                             imle_att=global_language_feats, all_instrs=instr_vectors, gi=gi)
+            p = self.x_proj[i]
+            conv_res = ops.linear(conv_res, p[0].weight, p[0].bias, L.ACT_GELU)
+            conv_res = ops.linear(conv_res, p[2].weight, p[2].bias, L.ACT_GELU)
+            if self.use_global_mask:
+                global_mask = mask * global_mask
+            bn = self.bns[i]
+            h = ops.SdpaGraphNormResidual.apply(conv_res, ins, h, bn.weight, bn.bias, bn.mean_scale, gi,
+                                                float(bn.eps))
+            if self.use_global_mask:
+                h = global_mask * h
+            elif self.interpretable_mode and mask is not None:
+                h = mask * h
+        return h, mask, [], []

@@ -1,0 +1,104 @@
+"""ctypes binding of libisg.so (C ABI declared in include/isg.h).
+
+No CPU fallback and no alternate backend: `load()` raises if the shared library is missing, and
+every wrapper raises RuntimeError on a non-zero return code.  Tensors are passed as raw device
+pointers (`tensor.data_ptr()`), the stream as `torch.cuda.current_stream().cuda_stream`."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisg.so")
+_lib = None
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+
+_P, _I64, _I32, _F, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/isg.h declares (tests check this)
+SIGNATURES = {
+    "isg_version": (_I32, []),
+    "isg_error_string": (ctypes.c_char_p, [_I32]),
+    "isg_csr_workspace_bytes": (_SZ, [_I64, _I64]),
+    "isg_csr_build": (_I32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "isg_graph_ptr": (_I32, [_P, _I64, _I64, _P, _P, _P, _P]),
+    "isg_gat_edge_fwd": (_I32, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32,
+                                _F, _I32, _P]),
+    "isg_gat_edge_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
+    "isg_gat_edge_bwd": (_I32, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P,
+                                _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _I32, _P, _SZ, _P]),
+    "isg_node_edge_mask_fwd": (_I32, [_P, _P, _I64, _P, _P]),
+    "isg_node_edge_mask_bwd": (_I32, [_P, _P, _P, _I64, _P, _P]),
+    "isg_topk_mask_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "isg_imle_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _P, _P]),
+    "isg_aimle_workspace_bytes": (_SZ, []),
+    "isg_aimle_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _I32, _P, _P, _P, _SZ, _P]),
+    "isg_gumbel_topk_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "isg_gumbel_topk_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P]),
+    "isg_instr_gate_fwd": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
+    "isg_instr_gate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "isg_gate_theta_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "isg_gate_theta_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "isg_sdpa_graphnorm_fwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
+    "isg_sdpa_graphnorm_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P,
+                                      _P]),
+    "isg_linear_fwd": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
+    "isg_linear_dgrad": (_I32, [_P, _I64, _P, _P, _I64, _P, _I64, _I32, _I64, _I32, _I32, _I32, _I32, _P]),
+    "isg_linear_wgrad_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "isg_linear_wgrad": (_I32, [_P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
+    "isg_gelu_bwd": (_I32, [_P, _P, _P, _I64, _P]),
+    "isg_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
+    "isg_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
+}
+
+
+def load():
+    """Returns the ctypes handle of libisg.so; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "isg_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().isg_error_string(int(rc)).decode()
+        raise RuntimeError(f"libisg call failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"isg_b200 supports float32 and bfloat16 feature tensors, got {t.dtype}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("isg_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")

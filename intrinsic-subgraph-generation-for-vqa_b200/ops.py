@@ -1,0 +1,384 @@
+"""torch.autograd.Function wrappers over the libisg.so C ABI (include/isg.h).  PyTorch is plumbing
+here — it owns device memory, streams and the autograd tape; all arithmetic happens in the CUDA
+kernels.  Each Function cites the reference code it replaces (paths relative to the reference)."""
+import torch
+
+from . import lib as L
+
+_GEMM_MODE = 0  # 0 = fp32 FFMA (parity). tcgen05 modes are selected via set_gemm_mode().
+
+
+def set_gemm_mode(mode):
+    global _GEMM_MODE
+    _GEMM_MODE = int(mode)
+
+
+def gemm_mode():
+    return _GEMM_MODE
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# dense projections (kernel d)
+# ------------------------------------------------------------------------------------------
+def linear_fwd_raw(x, w, b, act, want_pre):
+    lib = L.load()
+    M, K = x.shape
+    Nout = w.shape[0]
+    y = torch.empty(M, Nout, dtype=x.dtype, device=x.device)
+    z = torch.empty(M, Nout, dtype=x.dtype, device=x.device) if want_pre else None
+    L.check(lib.isg_linear_fwd(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(y), Nout, L.ptr(z), Nout, M, Nout, K,
+                               act, _GEMM_MODE, L.dtype_code(x), L.stream()))
+    return y, z
+
+
+def linear_dgrad_raw(gy, w, z_prev=None, out=None, accumulate=False):
+    lib = L.load()
+    M, Nout = gy.shape
+    K = w.shape[1]
+    gx = out if out is not None else torch.empty(M, K, dtype=gy.dtype, device=gy.device)
+    L.check(lib.isg_linear_dgrad(L.ptr(gy), gy.stride(0), L.ptr(w), L.ptr(z_prev), K, L.ptr(gx), gx.stride(0),
+                                 1 if accumulate else 0, M, Nout, K, _GEMM_MODE, L.dtype_code(gy), L.stream()))
+    return gx
+
+
+def linear_wgrad_raw(gy, x):
+    lib = L.load()
+    M, Nout = gy.shape
+    K = x.shape[1]
+    gw = torch.empty(Nout, K, dtype=torch.float32, device=gy.device)
+    nbytes = lib.isg_linear_wgrad_workspace_bytes(M, Nout, K)
+    ws = L.workspace(nbytes, gy.device)
+    L.check(lib.isg_linear_wgrad(L.ptr(gy), gy.stride(0), L.ptr(x), x.stride(0), L.ptr(gw), None, M, Nout, K,
+                                 _GEMM_MODE, L.dtype_code(gy), L.ptr(ws), nbytes, L.stream()))
+    return gw
+
+
+def colsum(t):
+    lib = L.load()
+    rows, cols = t.shape
+    out = torch.empty(cols, dtype=torch.float32, device=t.device)
+    nbytes = lib.isg_colsum_workspace_bytes(rows, cols)
+    ws = L.workspace(nbytes, t.device)
+    L.check(lib.isg_colsum(L.ptr(t), t.stride(0), rows, cols, L.ptr(out), L.ptr(ws), nbytes, L.stream()))
+    return out
+
+
+def gelu_bwd(gy, z):
+    lib = L.load()
+    gz = torch.empty_like(gy)
+    L.check(lib.isg_gelu_bwd(L.ptr(gy), L.ptr(z), L.ptr(gz), gy.numel(), L.stream()))
+    return gz
+
+
+class LinearAct(torch.autograd.Function):
+    """y = act(x W^T + b) — replaces PyG `Linear` / torch.nn.Linear (+ torch.nn.GELU) call sites:
+    lin_l/lin_r/lin_edge (models/mgat_v2_conv.py:177,181,259), x_proj (models/mgat.py:156),
+    node_nn / ques_nn (models/masking.py:137,152)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        L.require_cuda(x, w, b)
+        x, w = _c(x), _c(w)
+        b = _c(b) if b is not None else None
+        y, z = linear_fwd_raw(x, w, b, act, want_pre=(act != L.ACT_NONE))
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w, z)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, z = ctx.saved_tensors
+        if ctx.act == L.ACT_GELU:
+            gy = gelu_bwd(_c(gy), z)
+        elif gy.stride(1) != 1 or gy.stride(0) % 4 != 0:
+            gy = gy.contiguous()  # column views of a wider buffer are consumed through their pitch
+        gx = linear_dgrad_raw(gy, w) if ctx.needs_input_grad[0] else None
+        gw = linear_wgrad_raw(gy, x) if ctx.needs_input_grad[1] else None
+        gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None
+
+
+def linear(x, w, b=None, act=L.ACT_NONE):
+    return LinearAct.apply(x, w, b, act)
+
+
+# ------------------------------------------------------------------------------------------
+# node-side fused ops
+# ------------------------------------------------------------------------------------------
+class InstrGate(torch.autograd.Function):
+    """x = gelu(x * instruction[batch])  (models/mgat_v2_conv.py:156-157)."""
+
+    @staticmethod
+    def forward(ctx, x, ins, gi):
+        L.require_cuda(x, ins)
+        x, ins = _c(x), _c(ins)
+        y = torch.empty_like(x)
+        L.check(L.load().isg_instr_gate_fwd(L.ptr(x), L.ptr(ins), L.ptr(gi.batch32), x.shape[0], x.shape[1],
+                                            L.ptr(y), L.stream()))
+        ctx.gi = gi
+        ctx.save_for_backward(x, ins)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, ins = ctx.saved_tensors
+        gi = ctx.gi
+        gy = _c(gy)
+        gx = torch.empty_like(x)
+        gins = torch.empty_like(ins)
+        L.check(L.load().isg_instr_gate_bwd(L.ptr(gy), L.ptr(x), L.ptr(ins), L.ptr(gi.graph_ptr), gi.B, x.shape[1],
+                                            L.ptr(gx), L.ptr(gins), L.stream()))
+        return gx, gins, None
+
+
+class GateTheta(torch.autograd.Function):
+    """theta = gelu(<xn, q[batch[batch]]> / sqrt(D))  (models/masking.py:151-155, double gather via
+    models/mgat_v2_conv.py:166-168).  q is [B, D] (one row per graph)."""
+
+    @staticmethod
+    def forward(ctx, xn, q, gi, double_gather):
+        xn, q = _c(xn), _c(q)
+        dbl = 1 if double_gather else 0
+        if q.shape[0] != (gi.B if dbl else xn.shape[0]):
+            raise ValueError("GateTheta: q must be [B,D] with double_gather, [N,D] without")
+        theta = torch.empty(xn.shape[0], 1, dtype=torch.float32, device=xn.device)
+        L.check(L.load().isg_gate_theta_fwd(L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), xn.shape[0], xn.shape[1], dbl,
+                                            L.ptr(theta), L.stream()))
+        ctx.gi, ctx.dbl = gi, dbl
+        ctx.save_for_backward(xn, q)
+        return theta
+
+    @staticmethod
+    def backward(ctx, gth):
+        xn, q = ctx.saved_tensors
+        gi = ctx.gi
+        gth = _c(gth)
+        gxn = torch.empty_like(xn)
+        gq = torch.empty_like(q)
+        scratch = torch.empty(xn.shape[0], dtype=torch.float32, device=xn.device)
+        L.check(L.load().isg_gate_theta_bwd(L.ptr(gth), L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), L.ptr(gi.graph_ptr),
+                                            xn.shape[0], gi.B, xn.shape[1], ctx.dbl, L.ptr(gxn), L.ptr(gq),
+                                            L.ptr(scratch), L.stream()))
+        return gxn, gq, None, None
+
+
+class SdpaGraphNormResidual(torch.autograd.Function):
+    """h_out = GraphNorm(scatter_sdpa(ins, v, v, batch), batch) + h_in  (models/mgat.py:168-172;
+    utils/scatter_scaled_dot_product.py:6-15; torch_geometric GraphNorm, eps 1e-5)."""
+
+    @staticmethod
+    def forward(ctx, v, ins, h_in, weight, bias, mean_scale, gi, eps):
+        v, ins, h_in = _c(v), _c(ins), _c(h_in)
+        N, D = v.shape
+        h_out = torch.empty_like(v)
+        a = torch.empty(N, dtype=torch.float32, device=v.device)
+        mean = torch.empty(gi.B, D, dtype=torch.float32, device=v.device)
+        rstd = torch.empty(gi.B, D, dtype=torch.float32, device=v.device)
+        L.check(L.load().isg_sdpa_graphnorm_fwd(L.ptr(v), L.ptr(ins), L.ptr(h_in), L.ptr(weight), L.ptr(bias),
+                                                L.ptr(mean_scale), L.ptr(gi.graph_ptr), gi.B, D, gi.nmax, eps,
+                                                L.ptr(h_out), L.ptr(a), L.ptr(mean), L.ptr(rstd), L.stream()))
+        ctx.gi = gi
+        ctx.save_for_backward(v, ins, weight, mean_scale, a, mean, rstd)
+        return h_out
+
+    @staticmethod
+    def backward(ctx, g):
+        v, ins, weight, mean_scale, a, mean, rstd = ctx.saved_tensors
+        gi = ctx.gi
+        g = _c(g)
+        N, D = v.shape
+        gv = torch.empty_like(v)
+        gins = torch.empty_like(ins)
+        parts = torch.empty(3, gi.B, D, dtype=torch.float32, device=v.device)
+        L.check(L.load().isg_sdpa_graphnorm_bwd(L.ptr(g), L.ptr(v), L.ptr(ins), L.ptr(weight), L.ptr(mean_scale),
+                                                L.ptr(a), L.ptr(mean), L.ptr(rstd), L.ptr(gi.graph_ptr), gi.B, D,
+                                                gi.nmax, L.ptr(gv), L.ptr(gins), L.ptr(parts[0]), L.ptr(parts[1]),
+                                                L.ptr(parts[2]), L.stream()))
+        gw, gb, gms = colsum(parts[0]), colsum(parts[1]), colsum(parts[2])
+        return gv, gins, g, gw, gb, gms, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# edge kernel (b)
+# ------------------------------------------------------------------------------------------
+class GatEdge(torch.autograd.Function):
+    """MaskingGATv2Conv.message + propagate + softmax + aggregate + bias
+    (models/mgat_v2_conv.py:215,226-232,243-279).  x_l/x_r [N,H*C] (may be column views of one
+    fused projection), e_proj [E,H*C], att [1,H,C], bias [H*C], edge_mask [E,1] or None.
+    Returns (out [N,H*C], alpha [E,H])."""
+
+    @staticmethod
+    def forward(ctx, x_l, x_r, e_proj, att, bias, edge_mask, gi, heads, slope):
+        L.require_cuda(x_l, x_r, e_proj, att)
+        if x_l.stride(1) != 1 or x_r.stride(1) != 1 or x_l.stride(0) != x_r.stride(0):
+            x_l, x_r = x_l.contiguous(), x_r.contiguous()
+        e_proj, att = _c(e_proj), _c(att)
+        em = _c(edge_mask) if edge_mask is not None else None
+        N, HC = x_l.shape
+        C = HC // heads
+        out = torch.empty(N, HC, dtype=x_l.dtype, device=x_l.device)
+        alpha = torch.empty(gi.E, heads, dtype=torch.float32, device=x_l.device)
+        L.check(L.load().isg_gat_edge_fwd(L.ptr(x_l), L.ptr(x_r), x_l.stride(0), L.ptr(e_proj), L.ptr(att),
+                                          L.ptr(bias), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr),
+                                          L.ptr(gi.dst_eid), L.ptr(out), HC, L.ptr(alpha), N, gi.E, heads, C,
+                                          slope, L.dtype_code(x_l), L.stream()))
+        ctx.gi, ctx.heads, ctx.slope = gi, heads, slope
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x_l, x_r, e_proj, att, bias, em, alpha, out)
+        ctx.mark_non_differentiable(alpha)
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, g_out, _g_alpha):
+        x_l, x_r, e_proj, att, bias, em, alpha, out = ctx.saved_tensors
+        gi, H = ctx.gi, ctx.heads
+        lib = L.load()
+        g_out = _c(g_out)
+        N, HC = out.shape
+        C = HC // H
+        dev = out.device
+        g_xlr = torch.empty(N, 2 * HC, dtype=x_l.dtype, device=dev)  # [g_xl | g_xr], one pitch
+        g_xl, g_xr = g_xlr[:, :HC], g_xlr[:, HC:]
+        g_ep = torch.empty(gi.E, HC, dtype=e_proj.dtype, device=dev)
+        g_att = torch.empty(att.shape, dtype=torch.float32, device=dev)
+        g_em = torch.empty(gi.E, 1, dtype=torch.float32, device=dev) if em is not None else None
+        nbytes = lib.isg_gat_edge_bwd_workspace_bytes(N, gi.E, H, C)
+        ws = L.workspace(nbytes, dev)
+        L.check(lib.isg_gat_edge_bwd(L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), x_l.stride(0),
+                                     L.ptr(e_proj), L.ptr(att), L.ptr(bias), L.ptr(em), L.ptr(alpha), L.ptr(out), HC,
+                                     L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr),
+                                     L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(g_xl), L.ptr(g_xr), 2 * HC,
+                                     L.ptr(g_ep), L.ptr(g_att), L.ptr(g_em), N, gi.E, H, C, ctx.slope,
+                                     L.dtype_code(x_l), L.ptr(ws), nbytes, L.stream()))
+        g_bias = colsum(g_out) if ctx.has_bias else None
+        return g_xl, g_xr, g_ep, g_att, g_bias, g_em, None, None, None
+
+
+class NodeMaskToEdgeMaskFn(torch.autograd.Function):
+    """sampling/node_edge_masks.py:5-19 — including its custom (dst-only) backward."""
+
+    @staticmethod
+    def forward(ctx, mask, gi):
+        mask = _c(mask.to(torch.float32))
+        em = torch.empty(gi.E, 1, dtype=torch.float32, device=mask.device)
+        L.check(L.load().isg_node_edge_mask_fwd(L.ptr(mask), L.ptr(gi.edge_index), gi.E, L.ptr(em), L.stream()))
+        ctx.gi = gi
+        ctx.shape = mask.shape
+        return em
+
+    @staticmethod
+    def backward(ctx, g_em):
+        gi = ctx.gi
+        g_em = _c(g_em)
+        g_m = torch.empty(ctx.shape, dtype=torch.float32, device=g_em.device)
+        L.check(L.load().isg_node_edge_mask_bwd(L.ptr(g_em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_eid), gi.N, L.ptr(g_m),
+                                                L.stream()))
+        return g_m, None
+
+
+# ------------------------------------------------------------------------------------------
+# samplers (kernel c).  theta is ragged [N,1]; noise is dense [B,Nmax] (or [B,1,Nmax,1]).
+# ------------------------------------------------------------------------------------------
+def _noise2d(noise, gi):
+    if noise is None:
+        return None
+    n = noise.reshape(gi.B, -1)
+    if n.shape[1] != gi.nmax:
+        raise ValueError(f"noise has {n.shape[1]} slots per graph, expected Nmax = {gi.nmax}")
+    return _c(n.to(torch.float32))
+
+
+class TopkImle(torch.autograd.Function):
+    """IMLE perturb-and-MAP top-k mask (sampling/methods/wrapper.py:75-172, target.py:44-48,
+    imle_scheme.py:16-29, deterministic_scheme.py:36-43), nb_samples = 1.  Returns the ragged
+    mask [N,1] (== `output[0].squeeze(0)[valid]`, models/masking.py:169-173)."""
+
+    @staticmethod
+    def forward(ctx, theta, noise, gi, k, alpha, beta, tau_in, tau_tgt):
+        theta = _c(theta)
+        noise = _noise2d(noise, gi)
+        N = theta.shape[0]
+        mask = torch.empty(N, 1, dtype=torch.float32, device=theta.device)
+        zd = torch.empty(gi.B, gi.nmax, dtype=torch.float32, device=theta.device)
+        L.check(L.load().isg_topk_mask_fwd(L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
+                                           tau_in, L.ptr(mask), L.ptr(zd), L.stream()))
+        ctx.gi, ctx.cfg = gi, (k, alpha, beta, tau_tgt)
+        ctx.save_for_backward(theta, noise, zd)
+        return mask
+
+    @staticmethod
+    def backward(ctx, dy):
+        theta, noise, zd = ctx.saved_tensors
+        gi = ctx.gi
+        k, alpha, beta, tau_tgt = ctx.cfg
+        dy = _c(dy)
+        g = torch.empty_like(theta)
+        L.check(L.load().isg_imle_bwd(L.ptr(dy), L.ptr(theta), L.ptr(noise), L.ptr(zd), L.ptr(gi.graph_ptr), gi.B,
+                                      gi.nmax, k, alpha, beta, tau_tgt, L.ptr(g), L.stream()))
+        return g, None, None, None, None, None, None, None
+
+
+class TopkAimle(torch.autograd.Function):
+    """AIMLE (sampling/methods/aimle.py:83-243 + target_aimle.py:87-162), symmetric perturbation,
+    adaptive beta kept in a device-resident state vector (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, theta, noise, gi, k, state, adaptive, tau_in, tau_tgt):
+        theta = _c(theta)
+        noise = _noise2d(noise, gi)
+        N = theta.shape[0]
+        mask = torch.empty(N, 1, dtype=torch.float32, device=theta.device)
+        zd = torch.empty(gi.B, gi.nmax, dtype=torch.float32, device=theta.device)
+        L.check(L.load().isg_topk_mask_fwd(L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
+                                           tau_in, L.ptr(mask), L.ptr(zd), L.stream()))
+        ctx.gi, ctx.cfg, ctx.state = gi, (k, adaptive, tau_tgt), state
+        ctx.save_for_backward(theta, noise)
+        return mask
+
+    @staticmethod
+    def backward(ctx, dy):
+        theta, noise = ctx.saved_tensors
+        gi, state = ctx.gi, ctx.state
+        k, adaptive, tau_tgt = ctx.cfg
+        lib = L.load()
+        dy = _c(dy)
+        g = torch.empty_like(theta)
+        nbytes = lib.isg_aimle_workspace_bytes()
+        ws = L.workspace(nbytes, theta.device)
+        L.check(lib.isg_aimle_bwd(L.ptr(dy), L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), theta.shape[0], gi.B,
+                                  gi.nmax, k, tau_tgt, 1 if adaptive else 0, L.ptr(state), L.ptr(g), L.ptr(ws),
+                                  nbytes, L.stream()))
+        return g, None, None, None, None, None, None, None
+
+
+class GumbelTopk(torch.autograd.Function):
+    """Relaxed Gumbel top-k with straight-through (sampling/methods/gumbel_scheme.py:26-107)."""
+
+    @staticmethod
+    def forward(ctx, theta, gumbel, gi, k, tau):
+        theta = _c(theta)
+        gumbel = _noise2d(gumbel, gi)
+        N = theta.shape[0]
+        mask = torch.empty(N, 1, dtype=torch.float32, device=theta.device)
+        saved = torch.empty(gi.B, k, gi.nmax, dtype=torch.float32, device=theta.device)
+        L.check(L.load().isg_gumbel_topk_fwd(L.ptr(theta), L.ptr(gumbel), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
+                                             L.ptr(mask), L.ptr(saved), L.stream()))
+        ctx.gi, ctx.cfg = gi, (k, tau)
+        ctx.save_for_backward(saved)
+        return mask
+
+    @staticmethod
+    def backward(ctx, dy):
+        (saved,) = ctx.saved_tensors
+        gi = ctx.gi
+        k, tau = ctx.cfg
+        dy = _c(dy)
+        g = torch.empty(dy.shape, dtype=torch.float32, device=dy.device)
+        L.check(L.load().isg_gumbel_topk_bwd(L.ptr(dy), L.ptr(saved), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
+                                             L.ptr(g), L.stream()))
+        return g, None, None, None, None

@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt by running the UNMODIFIED reference
+(/root/reference, imported through oracle/reference_loader.py on the pure-torch shim) on seeded
+synthetic inputs with injected randomness.  Run in the authoring container only:
+
+    python oracle/make_golden.py
+
+Each fixture stores the seed/config needed to regenerate inputs and weights
+(isg_b200.synth.make_batch / make_state_dict / gumbel_noise) plus the reference's outputs:
+h, mask, alpha of every layer's checksum, gradients w.r.t. the inputs and a set of parameter
+gradients (full tensors when small, (sum, abs-sum, first 64 values) digests when large)."""
+import math
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import reference_loader as rl  # noqa: E402
+from isg_b200 import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+CASES = [
+    # name, sampler, train, channels, B, mean_nodes, mean_edges, k, seed
+    ("imle_train_c300", "imle", True, 300, 5, 8, 40, 2, 101),
+    ("imle_eval_c300", "imle", False, 300, 5, 8, 40, 2, 102),
+    ("aimle_train_c300", "aimle", True, 300, 5, 8, 40, 2, 103),
+    ("gumbel_train_c300", "gumbel", True, 300, 5, 8, 40, 2, 104),
+    ("gumbel_eval_c300", "gumbel", False, 300, 5, 8, 40, 3, 105),
+    ("imle_train_c16_k3", "imle", True, 16, 7, 6, 24, 3, 106),
+    ("aimle_train_c64", "aimle", True, 64, 6, 12, 70, 2, 107),
+]
+
+
+def digest(t):
+    t = t.detach().flatten().to(torch.float64)
+    return dict(sum=float(t.sum()), abssum=float(t.abs().sum()), head=t[:64].to(torch.float32).clone(),
+                numel=t.numel())
+
+
+def case_noise(sampler, B, nmax, seed):
+    if sampler in ("imle", "aimle"):
+        return synth.gumbel_noise(B, nmax, 0.3, seed=seed)
+    if sampler == "gumbel":
+        return synth.gumbel_noise(B, nmax, 1.0, seed=seed)[:, 0, :, 0].contiguous()
+    npad = 2 ** math.ceil(math.log2(nmax))
+    return synth.gumbel_noise(B, npad, 1.0, seed=seed)[:, 0, :, 0].contiguous()
+
+
+def case_dropout(N, train, seed):
+    if not train:
+        return None
+    g = torch.Generator().manual_seed(seed + 17)
+    return (torch.rand(N, 1, generator=g) > 0.2).float() / 0.8
+
+
+def run_reference(sampler, train, C, B, mn, me, k, seed, aimle_steps=1):
+    from ISubGVQA.models.mgat import MGAT
+
+    b = synth.make_batch(B, channels=C, mean_nodes=mn, mean_edges=me, seed=seed)
+    with rl.scratch_cwd():
+        ref = MGAT(channels=C, num_ins=4, heads=4, use_instr=True, masking_thresholds=[1.0, 1.0, 1.0, 0.1],
+                   use_topk=True, interpretable_mode=False, sampler_type=sampler, sample_k=k, nb_samples=1,
+                   alpha=1.0, beta=10.0, tau=1.0)
+    ref.load_state_dict(synth.make_state_dict(C, 4, 4, seed))
+    ref.train(train)
+    if sampler == "simple":
+        for c in ref.convs:
+            c.mask.sampler.device = "cpu"
+    N = b["x"].shape[0]
+    outs = []
+    for step in range(aimle_steps):
+        noise = case_noise(sampler, B, b["nmax"], seed + step)
+        drop = case_dropout(N, train, seed + step)
+        x = b["x"].clone().requires_grad_(True)
+        ea = b["edge_attr"].clone().requires_grad_(True)
+        iv = b["instr_vectors"].clone().requires_grad_(True)
+        gl = b["global_language_feats"].clone().requires_grad_(True)
+        ref.zero_grad()
+        with rl.scratch_cwd(), rl.inject_theta_dropout(drop):
+            ctx = rl.inject_noise(noise) if sampler in ("imle", "aimle") else rl.inject_device_gumbel(noise)
+            with ctx:
+                h, mask, _, _ = ref(x, b["edge_index"], iv, gl, ea, b["batch"], return_masks=True)
+                w = torch.sin(torch.arange(h.numel(), dtype=torch.float32)).view_as(h)
+                loss = (h * w).sum() / h.shape[0] + (h * h).mean()
+                loss.backward()
+        pg = {}
+        for name, p in ref.named_parameters():
+            if p.grad is None:
+                pg[name] = None
+            elif p.numel() <= 4096:
+                pg[name] = p.grad.clone()
+            else:
+                pg[name] = digest(p.grad)
+        outs.append(dict(h=h.detach().clone(), mask=mask.detach().clone(), loss=float(loss), gx=x.grad.clone(),
+                         g_edge_attr=ea.grad.clone(), g_instr=iv.grad.clone(), g_glf=gl.grad.clone(),
+                         param_grads=pg))
+    return outs
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    with rl.scratch_cwd():
+        rl.load()
+    for name, sampler, train, C, B, mn, me, k, seed in CASES:
+        steps = 3 if sampler == "aimle" else 1  # AIMLE: 3 consecutive steps pin the adaptive beta state
+        torch.manual_seed(seed)
+        outs = run_reference(sampler, train, C, B, mn, me, k, seed, steps)
+        fix = dict(config=dict(sampler=sampler, train=train, channels=C, num_graphs=B, mean_nodes=mn,
+                               mean_edges=me, k=k, seed=seed, steps=steps),
+                   steps=outs, generator="oracle/make_golden.py", torch=torch.__version__)
+        path = os.path.join(GOLDEN_DIR, name + ".pt")
+        torch.save(fix, path)
+        print(name, "h", tuple(outs[0]["h"].shape), "mask_sum", float(outs[0]["mask"].sum()), "loss",
+              outs[0]["loss"], os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

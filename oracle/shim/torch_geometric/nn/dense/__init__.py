@@ -1,0 +1,1 @@
+from .linear import Linear  # noqa: F401

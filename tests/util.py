@@ -1,0 +1,149 @@
+"""Shared helpers for the parity tests: rebuild a golden case's inputs from its config, run the
+oracle / the CUDA drop-in on it, compare."""
+import glob
+import math
+import os
+
+import torch
+
+from isg_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-4  # BASELINE.json north_star: logits, answers and gradients within 1e-4 relative in fp32
+
+
+def golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+
+
+def load_golden(path):
+    return torch.load(path, weights_only=False)
+
+
+def case_noise(sampler, B, nmax, seed):
+    if sampler in ("imle", "aimle"):
+        return synth.gumbel_noise(B, nmax, 0.3, seed=seed)
+    if sampler == "gumbel":
+        return synth.gumbel_noise(B, nmax, 1.0, seed=seed)[:, 0, :, 0].contiguous()
+    npad = 2 ** math.ceil(math.log2(nmax))
+    return synth.gumbel_noise(B, npad, 1.0, seed=seed)[:, 0, :, 0].contiguous()
+
+
+def case_dropout(N, train, seed):
+    if not train:
+        return None
+    g = torch.Generator().manual_seed(seed + 17)
+    return (torch.rand(N, 1, generator=g) > 0.2).float() / 0.8
+
+
+def loss_fn(h):
+    w = torch.sin(torch.arange(h.numel(), dtype=torch.float32, device=h.device)).view_as(h)
+    return (h * w).sum() / h.shape[0] + (h * h).mean()
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  (relative to the tensor's scale, the metric the 1e-4 bound is read in)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    denom = float(b.abs().max())
+    if denom == 0.0:
+        return float((a - b).abs().max())
+    return float((a - b).abs().max()) / denom
+
+
+def digest(t):
+    t = t.detach().flatten().to(torch.float64).cpu()
+    return dict(sum=float(t.sum()), abssum=float(t.abs().sum()), head=t[:64].to(torch.float32).clone(),
+                numel=t.numel())
+
+
+def check_param_grad(name, got, want, rtol=RTOL):
+    if want is None:
+        assert got is None or float(got.abs().max()) == 0.0, f"{name}: reference has no grad"
+        return
+    assert got is not None, f"{name}: missing grad"
+    if isinstance(want, dict):
+        d = digest(got)
+        assert d["numel"] == want["numel"], name
+        scale = max(want["abssum"], 1e-30)
+        assert abs(d["abssum"] - want["abssum"]) <= rtol * scale, (name, d["abssum"], want["abssum"])
+        assert abs(d["sum"] - want["sum"]) <= rtol * scale, (name, d["sum"], want["sum"])
+        hscale = max(float(want["head"].abs().max()), want["abssum"] / want["numel"])
+        assert float((d["head"] - want["head"]).abs().max()) <= rtol * hscale * 4, name
+    else:
+        assert rel_err(got, want) <= rtol, (name, rel_err(got, want))
+
+
+def run_oracle_case(cfg, step_count=None):
+    """Runs oracle/isg_oracle.py::OracleMGAT on a golden config; returns per-step result dicts."""
+    import isg_oracle as O
+
+    C, B, seed, sampler, train = cfg["channels"], cfg["num_graphs"], cfg["seed"], cfg["sampler"], cfg["train"]
+    b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
+    model = O.OracleMGAT(channels=C, sampler_type=sampler, sample_k=cfg["k"])
+    model.load_state_dict(synth.make_state_dict(C, 4, 4, seed))
+    model.train(train)
+    N = b["x"].shape[0]
+    outs = []
+    for step in range(step_count or cfg["steps"]):
+        noise = case_noise(sampler, B, b["nmax"], seed + step)
+        drop = case_dropout(N, train, seed + step)
+        x = b["x"].clone().requires_grad_(True)
+        ea = b["edge_attr"].clone().requires_grad_(True)
+        iv = b["instr_vectors"].clone().requires_grad_(True)
+        gl = b["global_language_feats"].clone().requires_grad_(True)
+        model.zero_grad()
+        h, mask, _, _ = model(x, b["edge_index"], iv, gl, ea, b["batch"], noise=noise, theta_dropout_mask=drop)
+        loss = loss_fn(h)
+        loss.backward()
+        pg = {k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_ref_parameters()}
+        outs.append(dict(h=h.detach(), mask=mask.detach(), loss=float(loss.detach()), gx=x.grad, g_edge_attr=ea.grad,
+                         g_instr=iv.grad, g_glf=gl.grad, param_grads=pg))
+    return outs
+
+
+def run_cuda_case(cfg, step_count=None, device="cuda"):
+    """Runs the CUDA drop-in (isg_b200.isubgvqa.MGAT) on a golden config."""
+    from isg_b200.isubgvqa import MGAT
+
+    C, B, seed, sampler, train = cfg["channels"], cfg["num_graphs"], cfg["seed"], cfg["sampler"], cfg["train"]
+    b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
+    model = MGAT(channels=C, num_ins=4, heads=4, use_instr=True, masking_thresholds=[1.0, 1.0, 1.0, 0.1],
+                 use_topk=True, interpretable_mode=False, sampler_type=sampler, sample_k=cfg["k"], nb_samples=1,
+                 alpha=1.0, beta=10.0, tau=1.0)
+    model.load_state_dict(synth.make_state_dict(C, 4, 4, seed))
+    model.to(device)
+    model.train(train)
+    N = b["x"].shape[0]
+    ei, batch = b["edge_index"].to(device), b["batch"].to(device)
+    outs = []
+    for step in range(step_count or cfg["steps"]):
+        noise = case_noise(sampler, B, b["nmax"], seed + step).to(device)
+        drop = case_dropout(N, train, seed + step)
+        x = b["x"].to(device).requires_grad_(True)
+        ea = b["edge_attr"].to(device).requires_grad_(True)
+        iv = b["instr_vectors"].to(device).requires_grad_(True)
+        gl = b["global_language_feats"].to(device).requires_grad_(True)
+        model.zero_grad()
+        for conv in model.convs:
+            if conv.mask.masking_threshold != 1.0:
+                conv.mask.injected_noise = noise
+                conv.mask.injected_dropout_mask = drop.to(device) if drop is not None else None
+        h, mask, _, _ = model(x, ei, iv, gl, ea, batch, return_masks=True)
+        loss = loss_fn(h)
+        loss.backward()
+        pg = {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in model.named_parameters()}
+        outs.append(dict(h=h.detach().cpu(), mask=mask.detach().cpu(), loss=float(loss.detach()), gx=x.grad.cpu(),
+                         g_edge_attr=ea.grad.cpu(), g_instr=iv.grad.cpu(), g_glf=gl.grad.cpu(), param_grads=pg))
+    return outs
+
+
+def compare_step(got, want, sampler, rtol=RTOL):
+    if sampler in ("imle", "aimle"):
+        assert torch.equal(got["mask"], want["mask"]), "top-k node mask must be bit-exact given the same noise"
+    else:
+        assert rel_err(got["mask"], want["mask"]) <= rtol
+    for key in ("h", "gx", "g_edge_attr", "g_instr", "g_glf"):
+        e = rel_err(got[key], want[key])
+        assert e <= rtol, (key, e)
+    for name, w in want["param_grads"].items():
+        check_param_grad(name, got["param_grads"].get(name), w, rtol)
