@@ -135,6 +135,11 @@ __device__ __forceinline__ float4 f4_scale(float4 a, float s) {
 __device__ __forceinline__ float4 f4_fma(float4 a, float s, float4 c) {  // a*s + c
   return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
 }
+// explicit fma chain: two call sites with the same inputs produce bit-identical results (the edge
+// backward relies on that; `a.x*b.x + ...` may be contracted differently per site)
+__device__ __forceinline__ float f4_dot_acc(float4 a, float4 b, float acc) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc))));
+}
 __device__ __forceinline__ float f4_dot(float4 a, float4 b) {
   return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
 }

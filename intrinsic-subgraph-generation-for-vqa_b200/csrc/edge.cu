@@ -171,8 +171,8 @@ gat_edge_fwd_kernel(const T* __restrict__ xl, const T* __restrict__ xr, int64_t 
 
 // ------------------------------------------------------------------------------------------
 // backward, pass 1 (dst-major): g_eproj, g_xr, g_att partials, per-head g_edge_mask terms.
-// Uses the identity  sum_e a_e * (m_e t_e) = <G[i,h,:], out[i,h,:] - bias[h,:]>  so every edge
-// is independent given one per-(node,head) dot product — a single sweep over the in-edges.
+// Two sweeps over the in-edges of a (node, head): the first accumulates the softmax-backward dot
+// product sum_e a_e m_e t_e, the second produces the per-edge gradients.
 // Persistent over (node, head) pairs with the head fixed per warp so the g_att partial lives
 // in registers; partials are reduced by gat_att_reduce_kernel in a fixed order (deterministic).
 // ------------------------------------------------------------------------------------------
@@ -195,14 +195,9 @@ gat_edge_bwd_dst_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __res
   const int64_t HC = (int64_t)H * C;
   const int hoff = head * C;
 
-  float4 att_v[VPL], gatt[VPL], bias_v[VPL];
+  float4 att_v[VPL], gatt[VPL];
   load_row_f32<VPL>(att + hoff, lane, c4, att_v);
-  if (bias != nullptr) {
-    load_row_f32<VPL>(bias + hoff, lane, c4, bias_v);
-  } else {
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) bias_v[k] = f4_zero();
-  }
+  (void)bias; (void)out; (void)ld_out;  // kept in the ABI; the direct softmax backward does not need them
 #pragma unroll
   for (int k = 0; k < VPL; ++k) gatt[k] = f4_zero();
 
@@ -210,20 +205,51 @@ gat_edge_bwd_dst_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __res
     float4 G[VPL], xr_v[VPL], gxr[VPL];
     load_row<T, VPL>(gout + node * ld_g + hoff, lane, c4, G);
     load_row<T, VPL>(xr + node * ld_x + hoff, lane, c4, xr_v);
-    float dpart = 0.f;
-    {
-      float4 o[VPL];
-      load_row<T, VPL>(out + node * ld_out + hoff, lane, c4, o);
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) {
-        dpart += G[k].x * (o[k].x - bias_v[k].x) + G[k].y * (o[k].y - bias_v[k].y) +
-                 G[k].z * (o[k].z - bias_v[k].z) + G[k].w * (o[k].w - bias_v[k].w);
-        gxr[k] = f4_zero();
+    for (int k = 0; k < VPL; ++k) gxr[k] = f4_zero();
+    const int beg = rowptr[node], end = rowptr[node + 1];
+
+    // sweep 1: dot = sum_e a_e * m_e * t_e with t_e = <G, x_l[src_e]>.  (The flash-attention
+    // shortcut dot = <G, out - bias> is NOT used: once the segment softmax saturates, t_e - dot
+    // cancels catastrophically unless both come from the very same t_e roundings; measured 6e-2
+    // relative error on lin_r.weight gradients with the shortcut.)  Sweep 2 recomputes the
+    // bit-identical t_e, so nothing is stored; the gathered rows are re-read from L1/L2.
+    float dot = 0.f;
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_src = 0;
+      float my_am = 0.f;
+      if (lane < cnt) {
+        my_src = nbr[base + lane];
+        const int e = eid[base + lane];
+        my_am = alpha[(int64_t)e * H + head];
+        if (MASKED) my_am *= emask[e];
+      }
+      for (int t = 0; t < cnt; t += 2) {
+        const bool has2 = (t + 1) < cnt;
+        const int j0 = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        const int j1 = __shfl_sync(ISG_FULL_MASK, my_src, has2 ? t + 1 : t);
+        const float am0 = __shfl_sync(ISG_FULL_MASK, my_am, t);
+        const float am1 = has2 ? __shfl_sync(ISG_FULL_MASK, my_am, t + 1) : 0.f;
+        float4 x0[VPL], x1[VPL];
+        load_row<T, VPL>(xl + (int64_t)j0 * ld_x + hoff, lane, c4, x0);
+        load_row<T, VPL>(xl + (int64_t)j1 * ld_x + hoff, lane, c4, x1);
+        float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          p0 = f4_dot_acc(G[k], x0[k], p0);
+          p1 = f4_dot_acc(G[k], x1[k], p1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          p0 += __shfl_xor_sync(ISG_FULL_MASK, p0, o);
+          p1 += __shfl_xor_sync(ISG_FULL_MASK, p1, o);
+        }
+        dot = fmaf(am0, p0, dot);
+        dot = fmaf(am1, p1, dot);
       }
     }
-    const float dot = warp_sum(dpart);
 
-    const int beg = rowptr[node], end = rowptr[node + 1];
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
       int my_src = 0, my_eid = 0;
@@ -244,7 +270,7 @@ gat_edge_bwd_dst_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __res
         load_row_stream<T, VPL>(ep + (int64_t)e * HC + hoff, lane, c4, pv);
         float tpart = 0.f;
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) tpart += f4_dot(G[k], xv[k]);
+        for (int k = 0; k < VPL; ++k) tpart = f4_dot_acc(G[k], xv[k], tpart);
         const float tt = warp_sum(tpart);
         const float gl = a * (m * tt - dot);  // d loss / d logit[e,h]
         float gmpart = 0.f;

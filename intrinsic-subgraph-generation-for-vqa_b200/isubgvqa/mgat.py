@@ -75,14 +75,24 @@ class MGAT(torch.nn.Module):
             conv_res, mask, _edge_att = conv(x=h, edge_index=edge_index, edge_attr=edge_attr, instruction=ins,
                                              batch=batch, return_masks=return_masks, return_attention_weights=True,
                                              imle_att=global_language_feats, all_instrs=instr_vectors, gi=gi)
+            dbg = getattr(self, "debug_tensors", None)
+            if dbg is not None:
+                conv_res.retain_grad()
+                dbg[f"conv_out.{i}"] = conv_res
             p = self.x_proj[i]
             conv_res = ops.linear(conv_res, p[0].weight, p[0].bias, L.ACT_GELU)
             conv_res = ops.linear(conv_res, p[2].weight, p[2].bias, L.ACT_GELU)
+            if dbg is not None:
+                conv_res.retain_grad()
+                dbg[f"proj.{i}"] = conv_res
             if self.use_global_mask:
                 global_mask = mask * global_mask
             bn = self.bns[i]
             h = ops.SdpaGraphNormResidual.apply(conv_res, ins, h, bn.weight, bn.bias, bn.mean_scale, gi,
                                                 float(bn.eps))
+            if dbg is not None:
+                h.retain_grad()
+                dbg[f"h.{i}"] = h
             if self.use_global_mask:
                 h = global_mask * h
             elif self.interpretable_mode and mask is not None:

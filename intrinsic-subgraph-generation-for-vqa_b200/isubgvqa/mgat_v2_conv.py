@@ -94,6 +94,12 @@ class MaskingGATv2Conv(torch.nn.Module):
         x_r = x_l if self.share_weights else ops.linear(x, self.lin_r.weight, self.lin_r.bias)  # :181
         if e_proj is None:
             e_proj = ops.linear(edge_attr, self.lin_edge.weight, None)  # :259 (inside message() in the reference)
+        dbg = getattr(self, "debug_tensors", None)
+        if dbg is not None:
+            for name, t in (("xg", x), ("x_l", x_l), ("x_r", x_r), ("e_proj", e_proj)):
+                if t.requires_grad:
+                    t.retain_grad()
+                dbg[name] = t
         out, alpha = ops.GatEdge.apply(x_l, x_r, e_proj, self.att, self.bias, edge_mask, gi, H,
                                        float(self.negative_slope))
         if isinstance(return_attention_weights, bool):

@@ -5,6 +5,7 @@ import torch
 
 from . import lib as L
 
+_DEBUG_EDGE_BWD = None  # diagnostics: set to a list to capture GatEdge.backward inputs/outputs
 _GEMM_MODE = 0  # 0 = fp32 FFMA (parity). tcgen05 modes are selected via set_gemm_mode().
 
 
@@ -256,6 +257,12 @@ class GatEdge(torch.autograd.Function):
                                      L.ptr(g_ep), L.ptr(g_att), L.ptr(g_em), N, gi.E, H, C, ctx.slope,
                                      L.dtype_code(x_l), L.ptr(ws), nbytes, L.stream()))
         g_bias = colsum(g_out) if ctx.has_bias else None
+        if _DEBUG_EDGE_BWD is not None:
+            _DEBUG_EDGE_BWD.append(dict(g_out=g_out.clone(), x_l=x_l.clone(), x_r=x_r.clone(), e_proj=e_proj.clone(),
+                                        att=att.clone(), bias=bias.clone() if bias is not None else None,
+                                        em=em.clone() if em is not None else None, alpha=alpha.clone(),
+                                        out=out.clone(), g_xl=g_xl.clone(), g_xr=g_xr.clone(), g_ep=g_ep.clone(),
+                                        g_att=g_att.clone()))
         return g_xl, g_xr, g_ep, g_att, g_bias, g_em, None, None, None
 
 

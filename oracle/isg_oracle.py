@@ -399,6 +399,22 @@ def simple_sample(theta_dense, gumbel, k):
 # --------------------------------------------------------------------------------------
 
 
+class _ForcedMask(torch.autograd.Function):
+    """Replays a recorded discrete sampler decision (mask) and its perturbation-based gradient.
+    Lets the fp64 arbiter evaluate everything AROUND the sampler at high precision while the
+    discrete part — compared bit-exactly elsewhere — is held fixed."""
+
+    @staticmethod
+    def forward(ctx, theta, mask, g_theta):
+        ctx.save_for_backward(g_theta)
+        return mask.clone()
+
+    @staticmethod
+    def backward(ctx, dy):
+        (g_theta,) = ctx.saved_tensors
+        return g_theta.clone(), None, None
+
+
 class OracleMGAT(torch.nn.Module):
     """models/mgat.py:9-184 + mgat_v2_conv.py:21-241 + masking.py:53-199 restated functionally.
     Parameters are held in a flat dict whose keys equal the reference `state_dict()` keys, so
@@ -418,6 +434,10 @@ class OracleMGAT(torch.nn.Module):
         self.alpha, self.beta, self.tau = alpha, beta, tau
         self.interpretable_mode, self.use_global_mask = interpretable_mode, use_global_mask
         self.noise_scale = 0.3  # masking.py:215
+        self.teacher = None  # dict of forced forward values {"x_l.i", "x_r.i", "e_proj.i"} (see conv())
+        self.kink_margin = None  # set to [] to collect min |pre-activation| per layer
+        self.record = None  # set to {} to capture the sampler's mask and theta-gradient of a run
+        self.replay = None  # set to a recorded dict to force those discrete decisions (fp64 arbiter)
         self.aimle_state = [AimleState(alpha, 0.0) for _ in range(num_ins)]
         D, H = channels, heads
         shapes = {}
@@ -472,6 +492,11 @@ class OracleMGAT(torch.nn.Module):
                 theta = theta * drop_mask
             else:
                 theta = F.dropout(theta, p=0.2, training=True)
+        if self.replay is not None:  # fp64 arbiter runs: discrete decisions replayed from an fp32 run
+            mask = _ForcedMask.apply(theta, self.replay["mask"].to(theta.dtype), self.replay["g_theta"].to(theta.dtype))
+            return mask, theta
+        if self.record is not None and theta.requires_grad:
+            theta.register_hook(lambda g: self.record.__setitem__("g_theta", g.detach().clone()))
         dense, valid = to_dense_batch(theta, batch, num_graphs)
         st = self.sampler_type
         if st == "imle":  # masking.py:214-245 ; eval: tau_in = 0 when S == 1 (:238)
@@ -505,6 +530,26 @@ class OracleMGAT(torch.nn.Module):
         x_l = F.linear(x, self.p(pre + "lin_l.weight"), self.p(pre + "lin_l.bias")).view(-1, H, C)
         x_r = F.linear(x, self.p(pre + "lin_r.weight"), self.p(pre + "lin_r.bias")).view(-1, H, C)
         e_proj = F.linear(edge_attr, self.p(pre + "lin_edge.weight")).view(-1, H, C)
+        if self.teacher is not None:
+            # Teacher forcing of the edge kernel's forward inputs (values only; gradients still flow
+            # through the oracle's own projections).  leaky_relu has a discontinuous derivative, so two
+            # fp32 implementations whose pre-activations differ by 1e-6 can disagree by O(1) on single
+            # gradient elements wherever |s| ~ 1e-6.  Forcing identical forward values removes that
+            # artefact of the reference's own non-smoothness from end-to-end gradient comparisons.
+            x_l = x_l + (self.teacher[f"x_l.{i}"].to(x_l.dtype).view_as(x_l) - x_l).detach()
+            x_r = x_r + (self.teacher[f"x_r.{i}"].to(x_r.dtype).view_as(x_r) - x_r).detach()
+            e_proj = e_proj + (self.teacher[f"e_proj.{i}"].to(e_proj.dtype).view_as(e_proj) - e_proj).detach()
+        if self.kink_margin is not None:
+            with torch.no_grad():
+                s_ = x_r.index_select(0, edge_index[1]) + x_l.index_select(0, edge_index[0]) + e_proj
+                if em is not None:
+                    s_ = s_[em.view(-1) != 0]
+                if s_.numel():
+                    self.kink_margin.append(float(s_.abs().min()))
+        if getattr(self, "debug_tensors", None) is not None:
+            for name, t in (("xg", x), ("x_l", x_l), ("x_r", x_r), ("e_proj", e_proj)):
+                t.retain_grad()
+                self.debug_tensors[f"{name}.{i}"] = t
         out, alpha = gat_edge(x_l, x_r, e_proj, self.p(pre + "att"), edge_index, em)
         out = out.view(-1, H * C) + self.p(pre + "bias")
         return out, mask, alpha, theta
@@ -522,6 +567,8 @@ class OracleMGAT(torch.nn.Module):
             ins = instr_vectors[i]
             conv_res, mask, alpha, theta = self.conv(i, h, edge_index, batch, edge_attr, ins,
                                                      global_language_feats, noise, theta_dropout_mask, B)
+            if mask is not None and self.record is not None:
+                self.record["mask"] = mask.detach().clone()
             aux["alpha"].append(alpha)
             aux["conv_out"].append(conv_res)
             if theta is not None:
@@ -529,12 +576,14 @@ class OracleMGAT(torch.nn.Module):
             pre = f"x_proj.{i}."
             conv_res = F.gelu(F.linear(conv_res, self.p(pre + "0.weight"), self.p(pre + "0.bias")))
             conv_res = F.gelu(F.linear(conv_res, self.p(pre + "2.weight"), self.p(pre + "2.bias")))
+            aux.setdefault("proj", []).append(conv_res)
             if self.use_global_mask:
                 global_mask = mask * global_mask
             conv_res = scatter_sdpa(ins, conv_res, conv_res, batch)
             conv_res = graph_norm(conv_res, batch, self.p(f"bns.{i}.weight"), self.p(f"bns.{i}.bias"),
                                   self.p(f"bns.{i}.mean_scale"), B)
             h = conv_res + h
+            aux.setdefault("h", []).append(h)
             if self.use_global_mask:
                 h = global_mask * h
             elif self.interpretable_mode and mask is not None:

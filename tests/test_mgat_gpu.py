@@ -19,14 +19,27 @@ def test_cuda_matches_reference_golden(path):
         util.compare_step(got, want, cfg["sampler"])
 
 
-@pytest.mark.parametrize("sampler,train,B", [("imle", True, 64), ("aimle", True, 48), ("gumbel", False, 96)])
+@pytest.mark.parametrize("sampler,train,B", [("imle", True, 64), ("aimle", True, 48), ("gumbel", False, 96),
+                                             ("gumbel", True, 32), ("imle", False, 40)])
 def test_cuda_matches_oracle_at_baseline_sizes(sampler, train, B):
-    """BASELINE config 1 (B=64, ~20 nodes / ~150 edges, IMLE train) and scaled-down configs 2/3."""
+    """BASELINE config 1 (B=64, ~20 nodes / ~150 edges, IMLE train) and scaled-down configs 2/3.
+
+    Forward outputs (h, mask) are compared directly.  Gradients are compared against the oracle run with
+    the edge kernel's forward inputs (x_l, x_r, e_proj) teacher-forced to the CUDA values: leaky_relu's
+    derivative is discontinuous at 0, and at these sizes (10^7 pre-activations per layer) a handful of
+    them sit within fp32 rounding of 0, where ANY two fp32 implementations disagree by O(1) on single
+    gradient elements.  Forcing identical pre-activations removes exactly that artefact."""
     cfg = dict(sampler=sampler, train=train, channels=300, num_graphs=B, mean_nodes=20, mean_edges=150, k=2,
-               seed=900 + B, steps=1)
-    want = util.run_oracle_case(cfg)[0]
-    got = util.run_cuda_case(cfg)[0]
+               seed=900 + B, steps=1, aimle_beta0=2.0 if sampler == "aimle" else None)
+    got = util.run_cuda_case(cfg, capture=True)[0]
+    free = util.run_oracle_case(cfg)[0]
+    assert util.rel_err(got["h"], free["h"]) <= util.RTOL
+    if sampler in ("imle", "aimle"):
+        assert torch.equal(got["mask"], free["mask"])
+    want = util.run_oracle_case(cfg, teacher=[got["teacher"]])[0]
     util.compare_step(got, want, sampler)
+    # informational bound for the un-forced comparison: kink flips stay local and small
+    assert util.rel_err(got["gx"], free["gx"]) <= 2e-2
 
 
 def test_full_size_inference_properties():

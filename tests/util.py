@@ -37,7 +37,7 @@ def case_dropout(N, train, seed):
 
 
 def loss_fn(h):
-    w = torch.sin(torch.arange(h.numel(), dtype=torch.float32, device=h.device)).view_as(h)
+    w = torch.sin(torch.arange(h.numel(), dtype=torch.float32, device=h.device)).to(h.dtype).view_as(h)
     return (h * w).sum() / h.shape[0] + (h * h).mean()
 
 
@@ -73,36 +73,56 @@ def check_param_grad(name, got, want, rtol=RTOL):
         assert rel_err(got, want) <= rtol, (name, rel_err(got, want))
 
 
-def run_oracle_case(cfg, step_count=None):
-    """Runs oracle/isg_oracle.py::OracleMGAT on a golden config; returns per-step result dicts."""
+def run_oracle_case(cfg, step_count=None, dtype=torch.float32, replay=None, record=False, teacher=None,
+                    kink_margin=False):
+    """Runs oracle/isg_oracle.py::OracleMGAT on a golden config; returns per-step result dicts.
+    dtype=float64 + replay=<records of an fp32 run> gives the high-precision arbiter: the discrete
+    sampler decisions (mask, perturbation gradient) are replayed, everything else is fp64."""
     import isg_oracle as O
 
     C, B, seed, sampler, train = cfg["channels"], cfg["num_graphs"], cfg["seed"], cfg["sampler"], cfg["train"]
     b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
-    model = O.OracleMGAT(channels=C, sampler_type=sampler, sample_k=cfg["k"])
-    model.load_state_dict(synth.make_state_dict(C, 4, 4, seed))
+    model = O.OracleMGAT(channels=C, sampler_type=sampler, sample_k=cfg["k"]).to(dtype)
+    model.load_state_dict({k: v.to(dtype) for k, v in synth.make_state_dict(C, 4, 4, seed).items()})
     model.train(train)
+    if cfg.get("aimle_beta0") is not None:
+        for st in model.aimle_state:
+            st.beta = cfg["aimle_beta0"]
     N = b["x"].shape[0]
     outs = []
     for step in range(step_count or cfg["steps"]):
-        noise = case_noise(sampler, B, b["nmax"], seed + step)
+        noise = case_noise(sampler, B, b["nmax"], seed + step).to(dtype)
         drop = case_dropout(N, train, seed + step)
-        x = b["x"].clone().requires_grad_(True)
-        ea = b["edge_attr"].clone().requires_grad_(True)
-        iv = b["instr_vectors"].clone().requires_grad_(True)
-        gl = b["global_language_feats"].clone().requires_grad_(True)
+        drop = drop.to(dtype) if drop is not None else None
+        x = b["x"].to(dtype).clone().requires_grad_(True)
+        ea = b["edge_attr"].to(dtype).clone().requires_grad_(True)
+        iv = b["instr_vectors"].to(dtype).clone().requires_grad_(True)
+        gl = b["global_language_feats"].to(dtype).clone().requires_grad_(True)
         model.zero_grad()
+        model.record = {} if record else None
+        model.replay = replay[step] if replay is not None else None
+        model.teacher = teacher[step] if teacher is not None else None
+        model.kink_margin = [] if kink_margin else None
         h, mask, _, _ = model(x, b["edge_index"], iv, gl, ea, b["batch"], noise=noise, theta_dropout_mask=drop)
         loss = loss_fn(h)
         loss.backward()
         pg = {k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_ref_parameters()}
         outs.append(dict(h=h.detach(), mask=mask.detach(), loss=float(loss.detach()), gx=x.grad, g_edge_attr=ea.grad,
-                         g_instr=iv.grad, g_glf=gl.grad, param_grads=pg))
+                         g_instr=iv.grad, g_glf=gl.grad, param_grads=pg, record=model.record,
+                         kink_margin=model.kink_margin))
     return outs
 
 
-def run_cuda_case(cfg, step_count=None, device="cuda"):
-    """Runs the CUDA drop-in (isg_b200.isubgvqa.MGAT) on a golden config."""
+def run_oracle_fp64_arbiter(cfg):
+    """fp32 oracle run (records the discrete sampler decisions) followed by an fp64 replay."""
+    o32 = run_oracle_case(cfg, record=True)
+    o64 = run_oracle_case(cfg, dtype=torch.float64, replay=[o["record"] for o in o32])
+    return o32, o64
+
+
+def run_cuda_case(cfg, step_count=None, device="cuda", capture=False):
+    """Runs the CUDA drop-in (isg_b200.isubgvqa.MGAT) on a golden config.  capture=True also returns the
+    edge kernel's forward inputs of every layer (`teacher` dict for run_oracle_case)."""
     from isg_b200.isubgvqa import MGAT
 
     C, B, seed, sampler, train = cfg["channels"], cfg["num_graphs"], cfg["seed"], cfg["sampler"], cfg["train"]
@@ -113,6 +133,8 @@ def run_cuda_case(cfg, step_count=None, device="cuda"):
     model.load_state_dict(synth.make_state_dict(C, 4, 4, seed))
     model.to(device)
     model.train(train)
+    if cfg.get("aimle_beta0") is not None:
+        model.convs[3].mask.sampler_train.target._init[0] = float(cfg["aimle_beta0"])
     N = b["x"].shape[0]
     ei, batch = b["edge_index"].to(device), b["batch"].to(device)
     outs = []
@@ -125,6 +147,7 @@ def run_cuda_case(cfg, step_count=None, device="cuda"):
         gl = b["global_language_feats"].to(device).requires_grad_(True)
         model.zero_grad()
         for conv in model.convs:
+            conv.debug_tensors = {} if capture else None
             if conv.mask.masking_threshold != 1.0:
                 conv.mask.injected_noise = noise
                 conv.mask.injected_dropout_mask = drop.to(device) if drop is not None else None
@@ -132,8 +155,13 @@ def run_cuda_case(cfg, step_count=None, device="cuda"):
         loss = loss_fn(h)
         loss.backward()
         pg = {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in model.named_parameters()}
+        teacher = None
+        if capture:
+            teacher = {f"{n}.{i}": conv.debug_tensors[n].detach().cpu() for i, conv in enumerate(model.convs)
+                       for n in ("x_l", "x_r", "e_proj")}
         outs.append(dict(h=h.detach().cpu(), mask=mask.detach().cpu(), loss=float(loss.detach()), gx=x.grad.cpu(),
-                         g_edge_attr=ea.grad.cpu(), g_instr=iv.grad.cpu(), g_glf=gl.grad.cpu(), param_grads=pg))
+                         g_edge_attr=ea.grad.cpu(), g_instr=iv.grad.cpu(), g_glf=gl.grad.cpu(), param_grads=pg,
+                         teacher=teacher))
     return outs
 
 
