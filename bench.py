@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — scene graphs/s of the ISubGVQA hot path (MGAT fwd+bwd + sampler) on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c3|c1|c2] [--impl isg|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic GQA-shaped scene graphs:
+4-layer MGAT forward + backward (+ the gradient all-reduce when N > 1).  Default workload = BASELINE.json
+config 3/4 (training step, AIMLE sampler, 256 graphs per GPU, fp32): the metric is quoted as
+"scene graphs/sec fwd+bwd at 1/2/4/8 B200", i.e. on the training configuration, which is also the one
+that weak-scales over GPUs (config 4).  `value` times the step with inputs resident in HBM; `e2e` times
+the same step through the public nn.Module API with pinned HOST buffers (H2D of the batch and D2H of
+loss + mask inside the timed region).  `roofline` is for the dominant HBM kernel of the path (the fused
+edge-attention backward), measured live with CUDA events inside the timed steps.  `cpu_baseline` /
+`--impl reference` time the CPU restatement of the reference (oracle/, kind "port": the reference's PyG
+dependencies are not installable offline and /root/reference does not exist on the GPU box).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, sampler, train, graphs per GPU)
+    "c3": ("BASELINE config 3/4: training step, AIMLE top-k sampler, 256 graphs/GPU, fp32", "aimle", True, 256),
+    "c1": ("BASELINE config 1: fwd+bwd, 64 graphs, GAT + IMLE top-k", "imle", True, 64),
+    "c2": ("BASELINE config 2: inference only, 1024 graphs, Gumbel top-k", "gumbel", False, 1024),
+}
+CHANNELS, HEADS, LAYERS, K_SAMPLE = 300, 4, 4, 2
+METRIC, UNIT = "scene_graphs_per_sec_fwd_bwd", "graphs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons during the timed region (recipe in B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def edge_bytes(N, E, masked, s=4):
+    """Algorithmic HBM bytes of the fused edge kernel per layer (unfused lin_edge)."""
+    HC, H = HEADS * CHANNELS, HEADS
+    fwd = s * HC * (E + 3 * N) + 4 * E * H + (4 * E if masked else 0) + 4 * (2 * E + N + 1) + 2 * s * HC
+    bwd = s * HC * (2 * E + 5 * N) + 4 * E * H + (8 * E if masked else 0) + 4 * (4 * E + 2 * N + 2) + 2 * s * HC
+    return fwd, bwd
+
+
+def make_inputs(B, seed):
+    from isg_b200 import synth
+
+    b = synth.make_batch(B, channels=CHANNELS, num_ins=LAYERS, seed=seed)
+    return b
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def run_cpu_port(sampler, train, B, steps, warmup, seed=3407):
+    """oracle/isg_oracle.py::OracleMGAT (CPU restatement of the reference) on all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import isg_oracle as O
+    from isg_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = make_inputs(B, seed)
+    model = O.OracleMGAT(channels=CHANNELS, sampler_type=sampler, sample_k=K_SAMPLE)
+    model.load_state_dict(synth.make_state_dict(CHANNELS, HEADS, LAYERS, seed))
+    model.train(train)
+    for st in model.aimle_state:
+        st.beta = 1.0
+    if sampler in ("imle", "aimle"):
+        noise = synth.gumbel_noise(B, b["nmax"], 0.3, seed)
+    else:
+        noise = synth.gumbel_noise(B, b["nmax"], 1.0, seed)[:, 0, :, 0].contiguous()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        if train:
+            x = b["x"].clone().requires_grad_(True)
+            ea = b["edge_attr"].clone().requires_grad_(True)
+            model.zero_grad()
+            h, _, _, _ = model(x, b["edge_index"], b["instr_vectors"], b["global_language_feats"], ea, b["batch"],
+                               noise=noise)
+            (h * h).mean().backward()
+        else:
+            with torch.no_grad():
+                model(b["x"], b["edge_index"], b["instr_vectors"], b["global_language_feats"], b["edge_attr"],
+                      b["batch"], noise=noise)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "N": int(b["x"].shape[0]), "E": int(b["edge_index"].shape[1])}
+
+
+def main_reference(args, rank, world):
+    desc, sampler, train, _ = WORKLOADS[args.workload]
+    if rank != 0:
+        return
+    sample_B = 64
+    r = run_cpu_port(sampler, train, sample_B, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "sample": f"{sample_B} graphs per step "
+                   f"(N={r['N']}, E={r['E']}), CPU only"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": f"oracle/isg_oracle.py OracleMGAT, {sample_B}-graph batches of the same "
+                                   f"workload, {args.steps} steps after {args.warmup} warm-up"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def main_isg(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import isg_b200  # noqa: F401
+    from isg_b200 import lib as L
+    from isg_b200 import synth
+    from isg_b200.dp import GradAllReduce
+    from isg_b200.graph import clear_cache
+    from isg_b200.isubgvqa import MGAT
+
+    L.load()  # fails loudly if libisg.so is missing — there is no fallback path
+    desc, sampler, train, B = WORKLOADS[args.workload]
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    seed = 3407 + rank
+    b = make_inputs(B, seed)
+    N, E, nmax = int(b["x"].shape[0]), int(b["edge_index"].shape[1]), b["nmax"]
+    model = MGAT(channels=CHANNELS, num_ins=LAYERS, heads=HEADS, use_instr=True,
+                 masking_thresholds=[1.0, 1.0, 1.0, 0.1], use_topk=True, interpretable_mode=False,
+                 sampler_type=sampler, sample_k=K_SAMPLE, nb_samples=1, alpha=1.0, beta=10.0, tau=1.0)
+    model.load_state_dict(synth.make_state_dict(CHANNELS, HEADS, LAYERS, 3407))  # same weights on every rank
+    model.to(dev).train(train)
+    if sampler == "aimle":
+        model.convs[3].mask.sampler_train.target._init[0] = 1.0  # warmed-up beta (beta0 = 0 gives zero grads)
+    reducer = GradAllReduce(model) if (train and world > 1) else None
+
+    keys = ("x", "edge_index", "instr_vectors", "global_language_feats", "edge_attr", "batch")
+    host = {k: b[k].pin_memory() for k in keys}
+    if sampler in ("imle", "aimle"):
+        noise_h = synth.gumbel_noise(B, nmax, 0.3, seed).pin_memory()
+    else:
+        noise_h = synth.gumbel_noise(B, nmax, 1.0, seed)[:, 0, :, 0].contiguous().pin_memory()
+    resident = {k: host[k].to(dev) for k in keys}
+    noise_d = noise_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(t, noise):
+        model.convs[3].mask.injected_noise = noise
+        if train:
+            x = t["x"].detach().requires_grad_(True)
+            ea = t["edge_attr"].detach().requires_grad_(True)
+            for p in model.parameters():
+                p.grad = None
+            h, mask, _, _ = model(x, t["edge_index"], t["instr_vectors"], t["global_language_feats"], ea, t["batch"],
+                                  return_masks=True)
+            loss = (h * h).mean()
+            loss.backward()
+            if reducer is not None:
+                reducer.all_reduce_mean()
+            return loss, mask
+        with torch.no_grad():
+            h, mask, _, _ = model(t["x"], t["edge_index"], t["instr_vectors"], t["global_language_feats"],
+                                  t["edge_attr"], t["batch"], return_masks=True)
+            return (h * h).mean(), mask
+
+    def step_e2e():
+        clear_cache()  # a new batch arrives: CSR / graph_ptr are rebuilt inside the timed region
+        t = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        nz = noise_h.to(dev, non_blocking=True)
+        loss, mask = step(t, nz)
+        return float(loss.item()), mask.to("cpu")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, timing_names=None):
+        evs = []
+        barrier()
+        if timing_names:
+            L.enable_timing(timing_names)
+        launches0 = L.launch_count
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations (untimed)
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            e.record()
+            evs.append((a, e))
+        barrier()
+        t = L.disable_timing() if timing_names else None
+        ms = sum(a.elapsed_time(e) for a, e in evs)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, L.launch_count - launches0, L.timing_summary(t) if t else {}
+
+    # warm-up (also builds the CSR once for the resident batch, as a data loader would at collate time)
+    for _ in range(max(args.warmup, 3)):
+        step(resident, noise_d)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    edge_names = ["isg_gat_edge_fwd", "isg_gat_edge_bwd"]
+    ms, launches, tsum = timed(lambda: step(resident, noise_d), args.steps, edge_names)
+    clk = clocks.stop() if rank == 0 else None
+    # kernel-family breakdown of one extra (untimed) step, for DESIGN.md / the JSON line
+    ms_b, _, tall = timed(lambda: step(resident, noise_d), 2, None if not args.breakdown else list(L.KERNELS_PER_CALL))
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    graphs = B * world * args.steps
+    value = graphs / (ms / 1e3)
+    e2e_value = graphs / (ms_e2e / 1e3)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in keys) + noise_h.numel() * 4
+    d2h = 4 + N * 4
+    peak, peak_src = peaks()
+    fwd_b_un, bwd_b_un = edge_bytes(N, E, False)
+    fwd_b_m, bwd_b_m = edge_bytes(N, E, True)
+    roof = None
+    if train and "isg_gat_edge_bwd" in tsum:
+        calls, tot = tsum["isg_gat_edge_bwd"]
+        per_launch_ms = tot / calls
+        alg = (3 * bwd_b_un + bwd_b_m) / 4.0  # 3 unmasked layers + 1 masked layer per step
+        ach = alg / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst + att_reduce + gat_edge_bwd_src)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
+                "launches_timed": calls}
+    elif "isg_gat_edge_fwd" in tsum:
+        calls, tot = tsum["isg_gat_edge_fwd"]
+        per_launch_ms = tot / calls
+        alg = (3 * fwd_b_un + fwd_b_m) / 4.0
+        ach = alg / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "isg_gat_edge_fwd (gat_edge_fwd_kernel)", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms, "launches_timed": calls}
+    edge_fwd = None
+    if "isg_gat_edge_fwd" in tsum:
+        calls, tot = tsum["isg_gat_edge_fwd"]
+        alg = (3 * fwd_b_un + fwd_b_m) / 4.0
+        edge_fwd = {"ms_per_launch": tot / calls, "achieved_GBps": alg / (tot / calls * 1e-3) / 1e9,
+                    "frac": alg / (tot / calls * 1e-3) / 1e9 / peak}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_B = 64
+        r = run_cpu_port(sampler, train, sample_B, 3, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"oracle/isg_oracle.py OracleMGAT on {sample_B}-graph batches (N={r['N']}, E={r['E']}) of "
+                         f"the same workload, 3 steps after 1 warm-up, {r['ms_per_step']:.0f} ms/step"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "graphs_per_gpu": B, "nodes": N, "edges": E, "nmax": nmax,
+                   "channels": CHANNELS, "heads": HEADS, "layers": LAYERS, "sample_k": K_SAMPLE,
+                   "step": "MGAT forward+backward" + (" + NCCL gradient all-reduce (42 MB flat bucket)" if world > 1
+                                                      else "") if train else "MGAT forward (no_grad)",
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
+                         f"~{(4 * 4 * HEADS * CHANNELS * (3 * E + 8 * N)) / 1e9:.2f} GB also exceeds the 126 MB L2",
+                   "gemm_mode": "fp32 FFMA (mode 0)", "optimizer": "out of scope (SURVEY.md §8 f4)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps,
+                "what": "pinned host batch -> .to(cuda) -> CSR build -> MGAT fwd+bwd -> loss.item() + mask.cpu()"},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roof,
+        "edge_fwd": edge_fwd,
+        "cpu_baseline": cpu,
+    }
+    if args.breakdown:
+        line["breakdown_ms_per_step"] = {k: round(v[1] / 2, 4) for k, v in sorted(tall.items(), key=lambda kv: -kv[1][1])}
+        line["breakdown_step_ms"] = ms_b / 2
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="isg", choices=["isg", "reference"])
+    ap.add_argument("--breakdown", action="store_true", help="add per-entry-point CUDA-event times to the JSON line")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl isg needs a CUDA device (no CPU fallback)")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    main_isg(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

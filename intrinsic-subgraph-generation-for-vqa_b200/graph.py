@@ -34,14 +34,14 @@ class GraphIndex:
         ws_bytes = lib.isg_csr_workspace_bytes(N, E)
         ws = L.workspace(ws_bytes, dev)
         st = L.stream()
-        L.check(lib.isg_csr_build(L.ptr(self.edge_index), E, N, L.ptr(self.dst_ptr), L.ptr(self.dst_nbr),
+        L.call("isg_csr_build", L.ptr(self.edge_index), E, N, L.ptr(self.dst_ptr), L.ptr(self.dst_nbr),
                                   L.ptr(self.dst_eid), L.ptr(self.src_ptr), L.ptr(self.src_nbr),
-                                  L.ptr(self.src_eid), L.ptr(self.status), L.ptr(ws), ws_bytes, st))
+                                  L.ptr(self.src_eid), L.ptr(self.status), L.ptr(ws), ws_bytes, st)
         self.graph_ptr = torch.empty(B + 1, **i32)
         self.batch32 = torch.empty(max(N, 1), **i32)
         self._nmax_dev = torch.empty(1, **i32)
-        L.check(lib.isg_graph_ptr(L.ptr(self.batch), N, B, L.ptr(self.graph_ptr), L.ptr(self.batch32),
-                                  L.ptr(self._nmax_dev), st))
+        L.call("isg_graph_ptr", L.ptr(self.batch), N, B, L.ptr(self.graph_ptr), L.ptr(self.batch32),
+                                  L.ptr(self._nmax_dev), st)
         self._nmax = None
         self._key = None
 

@@ -114,8 +114,8 @@ def select_from_edge_candidates(scores, k):
     flat = scores.detach().to(torch.float32).reshape(B * nmax, 1).contiguous()
     mask = torch.empty_like(flat)
     zd = torch.empty(B, nmax, dtype=torch.float32, device=scores.device)
-    L.check(L.load().isg_topk_mask_fwd(L.ptr(flat), None, L.ptr(di.graph_ptr), B, nmax, int(k), 0.0, L.ptr(mask),
-                                       L.ptr(zd), L.stream()))
+    L.call("isg_topk_mask_fwd", L.ptr(flat), None, L.ptr(di.graph_ptr), B, nmax, int(k), 0.0, L.ptr(mask),
+                                       L.ptr(zd), L.stream())
     return zd.view(B, nmax, 1)
 
 

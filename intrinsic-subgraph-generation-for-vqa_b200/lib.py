@@ -72,6 +72,59 @@ def load():
     return lib
 
 
+# kernels launched per C-ABI call (memsets excluded); used for the bench's `gpu_launches` claim
+KERNELS_PER_CALL = {
+    "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 3,
+    "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_imle_bwd": 1,
+    "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_instr_gate_fwd": 1,
+    "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
+    "isg_sdpa_graphnorm_bwd": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
+    "isg_gelu_bwd": 1, "isg_colsum": 2,
+}
+launch_count = 0
+_timing = None  # name -> list of (start_event, end_event) when enabled
+
+
+def enable_timing(names=None):
+    """Record CUDA events (on the launching stream) around the named C-ABI calls; names=None -> all."""
+    global _timing
+    _timing = {"__names__": set(names) if names is not None else None}
+
+
+def disable_timing():
+    global _timing
+    t, _timing = _timing, None
+    return t
+
+
+def timing_summary(t):
+    """-> {name: (calls, total_ms)}; call after torch.cuda.synchronize()."""
+    out = {}
+    for name, evs in (t or {}).items():
+        if name == "__names__":
+            continue
+        out[name] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+    return out
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point, check its return code, count its kernel launches."""
+    global launch_count
+    fn = getattr(load(), name)
+    t = _timing
+    if t is not None and (t["__names__"] is None or name in t["__names__"]):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        t.setdefault(name, []).append((a, b))
+    else:
+        rc = fn(*args)
+    if rc != 0:
+        check(rc)
+    launch_count += KERNELS_PER_CALL.get(name, 0)
+
+
 def check(rc):
     if rc != 0:
         msg = load().isg_error_string(int(rc)).decode()

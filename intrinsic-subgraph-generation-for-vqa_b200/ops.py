@@ -31,8 +31,8 @@ def linear_fwd_raw(x, w, b, act, want_pre):
     Nout = w.shape[0]
     y = torch.empty(M, Nout, dtype=x.dtype, device=x.device)
     z = torch.empty(M, Nout, dtype=x.dtype, device=x.device) if want_pre else None
-    L.check(lib.isg_linear_fwd(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(y), Nout, L.ptr(z), Nout, M, Nout, K,
-                               act, _GEMM_MODE, L.dtype_code(x), L.stream()))
+    L.call("isg_linear_fwd", L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(y), Nout, L.ptr(z), Nout, M, Nout, K,
+                               act, _GEMM_MODE, L.dtype_code(x), L.stream())
     return y, z
 
 
@@ -41,8 +41,8 @@ def linear_dgrad_raw(gy, w, z_prev=None, out=None, accumulate=False):
     M, Nout = gy.shape
     K = w.shape[1]
     gx = out if out is not None else torch.empty(M, K, dtype=gy.dtype, device=gy.device)
-    L.check(lib.isg_linear_dgrad(L.ptr(gy), gy.stride(0), L.ptr(w), L.ptr(z_prev), K, L.ptr(gx), gx.stride(0),
-                                 1 if accumulate else 0, M, Nout, K, _GEMM_MODE, L.dtype_code(gy), L.stream()))
+    L.call("isg_linear_dgrad", L.ptr(gy), gy.stride(0), L.ptr(w), L.ptr(z_prev), K, L.ptr(gx), gx.stride(0),
+                                 1 if accumulate else 0, M, Nout, K, _GEMM_MODE, L.dtype_code(gy), L.stream())
     return gx
 
 
@@ -53,8 +53,8 @@ def linear_wgrad_raw(gy, x):
     gw = torch.empty(Nout, K, dtype=torch.float32, device=gy.device)
     nbytes = lib.isg_linear_wgrad_workspace_bytes(M, Nout, K)
     ws = L.workspace(nbytes, gy.device)
-    L.check(lib.isg_linear_wgrad(L.ptr(gy), gy.stride(0), L.ptr(x), x.stride(0), L.ptr(gw), None, M, Nout, K,
-                                 _GEMM_MODE, L.dtype_code(gy), L.ptr(ws), nbytes, L.stream()))
+    L.call("isg_linear_wgrad", L.ptr(gy), gy.stride(0), L.ptr(x), x.stride(0), L.ptr(gw), None, M, Nout, K,
+                                 _GEMM_MODE, L.dtype_code(gy), L.ptr(ws), nbytes, L.stream())
     return gw
 
 
@@ -64,14 +64,14 @@ def colsum(t):
     out = torch.empty(cols, dtype=torch.float32, device=t.device)
     nbytes = lib.isg_colsum_workspace_bytes(rows, cols)
     ws = L.workspace(nbytes, t.device)
-    L.check(lib.isg_colsum(L.ptr(t), t.stride(0), rows, cols, L.ptr(out), L.ptr(ws), nbytes, L.stream()))
+    L.call("isg_colsum", L.ptr(t), t.stride(0), rows, cols, L.ptr(out), L.ptr(ws), nbytes, L.stream())
     return out
 
 
 def gelu_bwd(gy, z):
     lib = L.load()
     gz = torch.empty_like(gy)
-    L.check(lib.isg_gelu_bwd(L.ptr(gy), L.ptr(z), L.ptr(gz), gy.numel(), L.stream()))
+    L.call("isg_gelu_bwd", L.ptr(gy), L.ptr(z), L.ptr(gz), gy.numel(), L.stream())
     return gz
 
 
@@ -119,8 +119,8 @@ class InstrGate(torch.autograd.Function):
         L.require_cuda(x, ins)
         x, ins = _c(x), _c(ins)
         y = torch.empty_like(x)
-        L.check(L.load().isg_instr_gate_fwd(L.ptr(x), L.ptr(ins), L.ptr(gi.batch32), x.shape[0], x.shape[1],
-                                            L.ptr(y), L.stream()))
+        L.call("isg_instr_gate_fwd", L.ptr(x), L.ptr(ins), L.ptr(gi.batch32), x.shape[0], x.shape[1],
+                                            L.ptr(y), L.stream())
         ctx.gi = gi
         ctx.save_for_backward(x, ins)
         return y
@@ -132,8 +132,8 @@ class InstrGate(torch.autograd.Function):
         gy = _c(gy)
         gx = torch.empty_like(x)
         gins = torch.empty_like(ins)
-        L.check(L.load().isg_instr_gate_bwd(L.ptr(gy), L.ptr(x), L.ptr(ins), L.ptr(gi.graph_ptr), gi.B, x.shape[1],
-                                            L.ptr(gx), L.ptr(gins), L.stream()))
+        L.call("isg_instr_gate_bwd", L.ptr(gy), L.ptr(x), L.ptr(ins), L.ptr(gi.graph_ptr), gi.B, x.shape[1],
+                                            L.ptr(gx), L.ptr(gins), L.stream())
         return gx, gins, None
 
 
@@ -148,8 +148,8 @@ class GateTheta(torch.autograd.Function):
         if q.shape[0] != (gi.B if dbl else xn.shape[0]):
             raise ValueError("GateTheta: q must be [B,D] with double_gather, [N,D] without")
         theta = torch.empty(xn.shape[0], 1, dtype=torch.float32, device=xn.device)
-        L.check(L.load().isg_gate_theta_fwd(L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), xn.shape[0], xn.shape[1], dbl,
-                                            L.ptr(theta), L.stream()))
+        L.call("isg_gate_theta_fwd", L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), xn.shape[0], xn.shape[1], dbl,
+                                            L.ptr(theta), L.stream())
         ctx.gi, ctx.dbl = gi, dbl
         ctx.save_for_backward(xn, q)
         return theta
@@ -162,9 +162,9 @@ class GateTheta(torch.autograd.Function):
         gxn = torch.empty_like(xn)
         gq = torch.empty_like(q)
         scratch = torch.empty(xn.shape[0], dtype=torch.float32, device=xn.device)
-        L.check(L.load().isg_gate_theta_bwd(L.ptr(gth), L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), L.ptr(gi.graph_ptr),
+        L.call("isg_gate_theta_bwd", L.ptr(gth), L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), L.ptr(gi.graph_ptr),
                                             xn.shape[0], gi.B, xn.shape[1], ctx.dbl, L.ptr(gxn), L.ptr(gq),
-                                            L.ptr(scratch), L.stream()))
+                                            L.ptr(scratch), L.stream())
         return gxn, gq, None, None
 
 
@@ -180,9 +180,9 @@ class SdpaGraphNormResidual(torch.autograd.Function):
         a = torch.empty(N, dtype=torch.float32, device=v.device)
         mean = torch.empty(gi.B, D, dtype=torch.float32, device=v.device)
         rstd = torch.empty(gi.B, D, dtype=torch.float32, device=v.device)
-        L.check(L.load().isg_sdpa_graphnorm_fwd(L.ptr(v), L.ptr(ins), L.ptr(h_in), L.ptr(weight), L.ptr(bias),
+        L.call("isg_sdpa_graphnorm_fwd", L.ptr(v), L.ptr(ins), L.ptr(h_in), L.ptr(weight), L.ptr(bias),
                                                 L.ptr(mean_scale), L.ptr(gi.graph_ptr), gi.B, D, gi.nmax, eps,
-                                                L.ptr(h_out), L.ptr(a), L.ptr(mean), L.ptr(rstd), L.stream()))
+                                                L.ptr(h_out), L.ptr(a), L.ptr(mean), L.ptr(rstd), L.stream())
         ctx.gi = gi
         ctx.save_for_backward(v, ins, weight, mean_scale, a, mean, rstd)
         return h_out
@@ -196,10 +196,10 @@ class SdpaGraphNormResidual(torch.autograd.Function):
         gv = torch.empty_like(v)
         gins = torch.empty_like(ins)
         parts = torch.empty(3, gi.B, D, dtype=torch.float32, device=v.device)
-        L.check(L.load().isg_sdpa_graphnorm_bwd(L.ptr(g), L.ptr(v), L.ptr(ins), L.ptr(weight), L.ptr(mean_scale),
+        L.call("isg_sdpa_graphnorm_bwd", L.ptr(g), L.ptr(v), L.ptr(ins), L.ptr(weight), L.ptr(mean_scale),
                                                 L.ptr(a), L.ptr(mean), L.ptr(rstd), L.ptr(gi.graph_ptr), gi.B, D,
                                                 gi.nmax, L.ptr(gv), L.ptr(gins), L.ptr(parts[0]), L.ptr(parts[1]),
-                                                L.ptr(parts[2]), L.stream()))
+                                                L.ptr(parts[2]), L.stream())
         gw, gb, gms = colsum(parts[0]), colsum(parts[1]), colsum(parts[2])
         return gv, gins, g, gw, gb, gms, None, None
 
@@ -224,10 +224,10 @@ class GatEdge(torch.autograd.Function):
         C = HC // heads
         out = torch.empty(N, HC, dtype=x_l.dtype, device=x_l.device)
         alpha = torch.empty(gi.E, heads, dtype=torch.float32, device=x_l.device)
-        L.check(L.load().isg_gat_edge_fwd(L.ptr(x_l), L.ptr(x_r), x_l.stride(0), L.ptr(e_proj), L.ptr(att),
+        L.call("isg_gat_edge_fwd", L.ptr(x_l), L.ptr(x_r), x_l.stride(0), L.ptr(e_proj), L.ptr(att),
                                           L.ptr(bias), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr),
                                           L.ptr(gi.dst_eid), L.ptr(out), HC, L.ptr(alpha), N, gi.E, heads, C,
-                                          slope, L.dtype_code(x_l), L.stream()))
+                                          slope, L.dtype_code(x_l), L.stream())
         ctx.gi, ctx.heads, ctx.slope = gi, heads, slope
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x_l, x_r, e_proj, att, bias, em, alpha, out)
@@ -250,12 +250,12 @@ class GatEdge(torch.autograd.Function):
         g_em = torch.empty(gi.E, 1, dtype=torch.float32, device=dev) if em is not None else None
         nbytes = lib.isg_gat_edge_bwd_workspace_bytes(N, gi.E, H, C)
         ws = L.workspace(nbytes, dev)
-        L.check(lib.isg_gat_edge_bwd(L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), x_l.stride(0),
+        L.call("isg_gat_edge_bwd", L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), x_l.stride(0),
                                      L.ptr(e_proj), L.ptr(att), L.ptr(bias), L.ptr(em), L.ptr(alpha), L.ptr(out), HC,
                                      L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr),
                                      L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(g_xl), L.ptr(g_xr), 2 * HC,
                                      L.ptr(g_ep), L.ptr(g_att), L.ptr(g_em), N, gi.E, H, C, ctx.slope,
-                                     L.dtype_code(x_l), L.ptr(ws), nbytes, L.stream()))
+                                     L.dtype_code(x_l), L.ptr(ws), nbytes, L.stream())
         g_bias = colsum(g_out) if ctx.has_bias else None
         if _DEBUG_EDGE_BWD is not None:
             _DEBUG_EDGE_BWD.append(dict(g_out=g_out.clone(), x_l=x_l.clone(), x_r=x_r.clone(), e_proj=e_proj.clone(),
@@ -273,7 +273,7 @@ class NodeMaskToEdgeMaskFn(torch.autograd.Function):
     def forward(ctx, mask, gi):
         mask = _c(mask.to(torch.float32))
         em = torch.empty(gi.E, 1, dtype=torch.float32, device=mask.device)
-        L.check(L.load().isg_node_edge_mask_fwd(L.ptr(mask), L.ptr(gi.edge_index), gi.E, L.ptr(em), L.stream()))
+        L.call("isg_node_edge_mask_fwd", L.ptr(mask), L.ptr(gi.edge_index), gi.E, L.ptr(em), L.stream())
         ctx.gi = gi
         ctx.shape = mask.shape
         return em
@@ -283,8 +283,8 @@ class NodeMaskToEdgeMaskFn(torch.autograd.Function):
         gi = ctx.gi
         g_em = _c(g_em)
         g_m = torch.empty(ctx.shape, dtype=torch.float32, device=g_em.device)
-        L.check(L.load().isg_node_edge_mask_bwd(L.ptr(g_em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_eid), gi.N, L.ptr(g_m),
-                                                L.stream()))
+        L.call("isg_node_edge_mask_bwd", L.ptr(g_em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_eid), gi.N, L.ptr(g_m),
+                                                L.stream())
         return g_m, None
 
 
@@ -312,8 +312,8 @@ class TopkImle(torch.autograd.Function):
         N = theta.shape[0]
         mask = torch.empty(N, 1, dtype=torch.float32, device=theta.device)
         zd = torch.empty(gi.B, gi.nmax, dtype=torch.float32, device=theta.device)
-        L.check(L.load().isg_topk_mask_fwd(L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
-                                           tau_in, L.ptr(mask), L.ptr(zd), L.stream()))
+        L.call("isg_topk_mask_fwd", L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
+                                           tau_in, L.ptr(mask), L.ptr(zd), L.stream())
         ctx.gi, ctx.cfg = gi, (k, alpha, beta, tau_tgt)
         ctx.save_for_backward(theta, noise, zd)
         return mask
@@ -325,8 +325,8 @@ class TopkImle(torch.autograd.Function):
         k, alpha, beta, tau_tgt = ctx.cfg
         dy = _c(dy)
         g = torch.empty_like(theta)
-        L.check(L.load().isg_imle_bwd(L.ptr(dy), L.ptr(theta), L.ptr(noise), L.ptr(zd), L.ptr(gi.graph_ptr), gi.B,
-                                      gi.nmax, k, alpha, beta, tau_tgt, L.ptr(g), L.stream()))
+        L.call("isg_imle_bwd", L.ptr(dy), L.ptr(theta), L.ptr(noise), L.ptr(zd), L.ptr(gi.graph_ptr), gi.B,
+                                      gi.nmax, k, alpha, beta, tau_tgt, L.ptr(g), L.stream())
         return g, None, None, None, None, None, None, None
 
 
@@ -341,8 +341,8 @@ class TopkAimle(torch.autograd.Function):
         N = theta.shape[0]
         mask = torch.empty(N, 1, dtype=torch.float32, device=theta.device)
         zd = torch.empty(gi.B, gi.nmax, dtype=torch.float32, device=theta.device)
-        L.check(L.load().isg_topk_mask_fwd(L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
-                                           tau_in, L.ptr(mask), L.ptr(zd), L.stream()))
+        L.call("isg_topk_mask_fwd", L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
+                                           tau_in, L.ptr(mask), L.ptr(zd), L.stream())
         ctx.gi, ctx.cfg, ctx.state = gi, (k, adaptive, tau_tgt), state
         ctx.save_for_backward(theta, noise)
         return mask
@@ -357,9 +357,9 @@ class TopkAimle(torch.autograd.Function):
         g = torch.empty_like(theta)
         nbytes = lib.isg_aimle_workspace_bytes()
         ws = L.workspace(nbytes, theta.device)
-        L.check(lib.isg_aimle_bwd(L.ptr(dy), L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), theta.shape[0], gi.B,
+        L.call("isg_aimle_bwd", L.ptr(dy), L.ptr(theta), L.ptr(noise), L.ptr(gi.graph_ptr), theta.shape[0], gi.B,
                                   gi.nmax, k, tau_tgt, 1 if adaptive else 0, L.ptr(state), L.ptr(g), L.ptr(ws),
-                                  nbytes, L.stream()))
+                                  nbytes, L.stream())
         return g, None, None, None, None, None, None, None
 
 
@@ -373,8 +373,8 @@ class GumbelTopk(torch.autograd.Function):
         N = theta.shape[0]
         mask = torch.empty(N, 1, dtype=torch.float32, device=theta.device)
         saved = torch.empty(gi.B, k, gi.nmax, dtype=torch.float32, device=theta.device)
-        L.check(L.load().isg_gumbel_topk_fwd(L.ptr(theta), L.ptr(gumbel), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
-                                             L.ptr(mask), L.ptr(saved), L.stream()))
+        L.call("isg_gumbel_topk_fwd", L.ptr(theta), L.ptr(gumbel), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
+                                             L.ptr(mask), L.ptr(saved), L.stream())
         ctx.gi, ctx.cfg = gi, (k, tau)
         ctx.save_for_backward(saved)
         return mask
@@ -386,6 +386,6 @@ class GumbelTopk(torch.autograd.Function):
         k, tau = ctx.cfg
         dy = _c(dy)
         g = torch.empty(dy.shape, dtype=torch.float32, device=dy.device)
-        L.check(L.load().isg_gumbel_topk_bwd(L.ptr(dy), L.ptr(saved), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
-                                             L.ptr(g), L.stream()))
+        L.call("isg_gumbel_topk_bwd", L.ptr(dy), L.ptr(saved), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
+                                             L.ptr(g), L.stream())
         return g, None, None, None, None
