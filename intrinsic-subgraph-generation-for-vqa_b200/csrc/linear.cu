@@ -8,6 +8,7 @@
 //   dgrad gx[m,k] = sum_n gy[m,n] W[n,k]     A: [rows,R] R-contiguous   B: [R,cols] cols-contiguous
 //   wgrad gW[n,k] = sum_m gy[m,n] x[m,k]     A: [R,rows] rows-contiguous B: [R,cols] cols-contiguous
 #include "common.cuh"
+#include "linear_tc.h"
 
 namespace {
 
@@ -185,8 +186,16 @@ extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const f
   if (M < 0 || Nout <= 0 || K <= 0) return ISG_EINVAL;
   if (M == 0) return ISG_OK;
   if (!x || !w || !y) return ISG_EINVAL;
-  if (mode != 0 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
+  if (mode < 0 || mode > 3 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
   if (K % 4 || Nout % 4 || ldx % 4 || ldy % 4 || (z_pre && ldz % 4)) return ISG_EUNSUPPORTED;
+  if (mode != 0) {
+    isg::TcGemm t{};
+    t.A = (const float*)x; t.lda = ldx; t.B = (const float*)w; t.ldb = K; t.C = (float*)y; t.ldc = ldy;
+    t.rows = M; t.cols = Nout; t.R = K; t.a_mn = 0; t.b_mn = 0; t.epi = 0; t.splits = 1;
+    t.r_chunk = ((int64_t)K + 31) / 32 * 32;
+    t.bias = bias; t.Z = (float*)z_pre; t.ldz = ldz; t.act = act; t.split3 = (mode == 1) ? 1 : (mode == 3 ? 3 : 0);
+    return isg::tc_gemm(t, stream_);
+  }
   GemmArgs g{};
   g.A = (const float*)x; g.lda = ldx; g.B = (const float*)w; g.ldb = K; g.C = (float*)y; g.ldc = ldy;
   g.rows = M; g.cols = Nout; g.R = K; g.r_chunk = K; g.c_split_stride = 0;
@@ -203,8 +212,16 @@ extern "C" int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, con
   if (M < 0 || Nout <= 0 || K <= 0) return ISG_EINVAL;
   if (M == 0) return ISG_OK;
   if (!g_y || !w || !g_x) return ISG_EINVAL;
-  if (mode != 0 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
+  if (mode < 0 || mode > 3 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
   if (K % 4 || Nout % 4 || ldg % 4 || ldgx % 4 || (z_prev && ldz % 4)) return ISG_EUNSUPPORTED;
+  if (mode != 0) {
+    isg::TcGemm t{};
+    t.A = (const float*)g_y; t.lda = ldg; t.B = (const float*)w; t.ldb = K; t.C = (float*)g_x; t.ldc = ldgx;
+    t.rows = M; t.cols = K; t.R = Nout; t.a_mn = 0; t.b_mn = 1; t.epi = 1; t.splits = 1;
+    t.r_chunk = ((int64_t)Nout + 31) / 32 * 32;
+    t.Zprev = (const float*)z_prev; t.ldz = ldz; t.accumulate = accumulate; t.split3 = (mode == 1) ? 1 : (mode == 3 ? 3 : 0);
+    return isg::tc_gemm(t, stream_);
+  }
   GemmArgs g{};
   g.A = (const float*)g_y; g.lda = ldg; g.B = (const float*)w; g.ldb = K; g.C = (float*)g_x; g.ldc = ldgx;
   g.rows = M; g.cols = K; g.R = Nout; g.r_chunk = Nout; g.c_split_stride = 0;
@@ -216,7 +233,11 @@ extern "C" int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, con
 }
 
 extern "C" size_t isg_linear_wgrad_workspace_bytes(int64_t M, int Nout, int K) {
-  const int s = wgrad_splits(M, Nout, K);
+  // mode-agnostic: large enough for the FFMA split and for the tensor-core split
+  int64_t chunk = 0;
+  const int s0 = wgrad_splits(M, Nout, K);
+  const int s1 = isg::tc_wgrad_splits(M > 0 ? M : 1, Nout, K, &chunk);
+  const int s = s0 > s1 ? s0 : s1;
   return s > 1 ? (size_t)s * (size_t)Nout * (size_t)K * sizeof(float) : 0;
 }
 
@@ -224,7 +245,7 @@ extern "C" int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int
                                 int64_t M, int Nout, int K, int mode, int dtype, void* workspace, size_t ws_bytes,
                                 void* stream_) {
   if (M < 0 || Nout <= 0 || K <= 0 || !g_w) return ISG_EINVAL;
-  if (mode != 0 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
+  if (mode < 0 || mode > 3 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
   if (K % 4 || Nout % 4 || ldg % 4 || ldx % 4) return ISG_EUNSUPPORTED;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (M == 0) {
@@ -233,9 +254,27 @@ extern "C" int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int
     return e == cudaSuccess ? ISG_OK : (int)e;
   }
   if (!g_y || !x) return ISG_EINVAL;
-  const int splits = wgrad_splits(M, Nout, K);
   const size_t need = isg_linear_wgrad_workspace_bytes(M, Nout, K);
   if (need > 0 && (ws_bytes < need || !workspace)) return ISG_EWORKSPACE;
+  if (mode != 0) {
+    isg::TcGemm t{};
+    int64_t chunk = 0;
+    const int ts = isg::tc_wgrad_splits(M, Nout, K, &chunk);
+    t.A = (const float*)g_y; t.lda = ldg; t.B = (const float*)x; t.ldb = ldx;
+    t.rows = Nout; t.cols = K; t.R = M; t.a_mn = 1; t.b_mn = 1; t.epi = 2; t.splits = ts; t.r_chunk = chunk;
+    t.split3 = (mode == 1) ? 1 : (mode == 3 ? 3 : 0);
+    if (ts > 1) { t.C = (float*)workspace; t.ldc = K; t.c_split_stride = (int64_t)Nout * K; }
+    else { t.C = g_w; t.ldc = K; t.c_split_stride = 0; }
+    const int rc = isg::tc_gemm(t, stream_);
+    if (rc != ISG_OK) return rc;
+    if (ts > 1) {
+      const int64_t n = (int64_t)Nout * K;
+      split_reduce_kernel<<<isg::ceil_div(n / 4, 256), 256, 0, stream>>>((const float*)workspace, ts, n, n, g_w);
+      ISG_CHECK_LAUNCH();
+    }
+    return ISG_OK;
+  }
+  const int splits = wgrad_splits(M, Nout, K);
   GemmArgs g{};
   g.A = (const float*)g_y; g.lda = ldg; g.B = (const float*)x; g.ldb = ldx;
   g.rows = Nout; g.cols = K; g.R = M;

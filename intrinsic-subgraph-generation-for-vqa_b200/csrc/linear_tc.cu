@@ -1,0 +1,522 @@
+// linear_tc.cu — kernel (d), modes 1 and 2: the dense projections on the 5th-gen tensor cores.
+//
+//   mode 1  3xTF32 split (fp32-grade):  D = A_hi*B_hi  (+)  [A_hi*B_lo + A_lo*B_hi]
+//           the big product and the two correction products accumulate in SEPARATE TMEM
+//           accumulators (the tensor core truncates on accumulate, so error grows with the number of
+//           accumulation steps: keeping the corrections off the main chain cuts that 3x) and are
+//           added once, in fp32 round-to-nearest, by the epilogue
+//   mode 2  single-pass TF32 (~2^-11 per product; reported separately, not the parity config)
+//
+// One persistent, warp-specialised kernel (one CTA per SM, 384 threads) covers the three products
+// of a Linear layer (reference call sites: models/mgat_v2_conv.py:177,181,259, models/mgat.py:156,
+// models/masking.py:137,152 and their autograd backward):
+//   fwd    y[m,n]  = sum_k x[m,k]  W[n,k]    A K-major,  B K-major
+//   dgrad  gx[m,k] = sum_n gy[m,n] W[n,k]    A K-major,  B MN-major (W read in place, no transpose)
+//   wgrad  gW[n,k] = sum_m gy[m,n] x[m,k]    A MN-major, B MN-major, deterministic split over m
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of raw fp32 operand tiles
+//   warps 4-7   splitters (mode 1): lo = x - (x & ~0x1fff) (exact) into a twin buffer at the same
+//               (swizzled) offsets, fence.proxy.async, mbarrier arrive.  The raw tile serves as `hi`:
+//               kind::tf32 ignores the low 13 mantissa bits (verified: bit-identical results with an
+//               explicit hi write-back)
+//   warp 1      one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN<=256, K=8) into TMEM and
+//               tcgen05.commit's the stage back to the producer / the accumulator to the epilogue
+//   warps 8-11  epilogue: tcgen05.ld 32x32b -> padded smem transpose -> coalesced float4 rows with
+//               the fused bias / GELU / pre-activation side output / GELU-derivative / accumulate
+//   warp 2      TMEM allocation (512 columns = two accumulator stages x {main, correction} x BN<=128
+//               in mode 1, two stages x BN<=256 in mode 2; the epilogue of tile i overlaps the MMAs
+//               of tile i+1)
+#include <cuda.h>
+
+#include "common.cuh"
+#include "linear_tc.h"
+
+namespace {
+
+using namespace isg;
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;     // kind::tf32
+constexpr int NTHREADS = 384;
+constexpr int MAX_BN = 256;
+constexpr int A_TILE_BYTES = BM * BK * 4;         // 16 KiB
+constexpr int EPI_ROW_BYTES = 144;                // 32 floats + 16 B pad (conflict-free float4 transpose)
+constexpr int EPI_BYTES = 4 * 32 * EPI_ROW_BYTES;  // 4 epilogue warps
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int MAX_STAGES = 4;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t CORR_COL = 128;  // mode 1: correction accumulator sits 128 columns after the main one
+
+enum Epi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_PLAIN = 2 };
+
+struct TcArgs {
+  float* C;
+  int64_t ldc;
+  int64_t rows;  // output rows
+  int cols;      // output cols
+  int64_t R;     // reduction length
+  int BN;
+  int stages;
+  int stage_bytes;
+  int m_tiles, n_tiles, splits;
+  int64_t r_chunk;  // reduction elements per split (multiple of BK)
+  int64_t c_split_stride;
+  const float* bias;
+  float* Z;
+  int64_t ldz;
+  const float* Zprev;
+  int act;
+  int accumulate;
+  int split3;    // 1: 3xTF32 (hi/lo split in smem, two accumulators), 0: single-pass TF32
+  int write_hi;  // mode 1: write the truncated hi part back in place (0 relies on the MMA ignoring the low 13 bits)
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (the launch fails loudly) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0xff) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();  // ~2 s
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptors (sm_100 format: version 1)
+//   K-major : SWIZZLE_128B (2): rows of 128 B (32 fp32 along K), 8-row groups 1024 B apart (SBO);
+//             LBO unused.
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (1) — 32-byte swizzle chunks, the
+//             pattern TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  A tile is a row of
+//             32-wide MN chunks, each [BK k-rows][128 B]: chunk stride = LBO = BK*128 B, groups of
+//             4 k-rows 512 B apart (SBO).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (uint64_t)((BK * 128) >> 4) : 1ull;
+  const uint64_t sbo = mn_major ? (512 >> 4) : (1024 >> 4);
+  const uint64_t layout = mn_major ? 1ull : 2ull;
+  return (uint64_t)((saddr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// ------------------------------------------------------------------------------ the kernel
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int S = g.stages;
+  const int BN = g.BN;
+  const uint32_t b_tile_bytes = (uint32_t)BN * 128u;
+  // stage layout: mode 1 [A_hi 16K][A_lo 16K][B_hi BN*128][B_lo BN*128]; mode 2 [A 16K][B BN*128]
+  const uint32_t off_a_lo = A_TILE_BYTES;
+  const uint32_t off_b_hi = g.split3 ? 2 * A_TILE_BYTES : A_TILE_BYTES;
+  const uint32_t off_b_lo = off_b_hi + b_tile_bytes;
+  const uint32_t epi_base = smem_base + (uint32_t)S * g.stage_bytes;
+  const uint32_t bar_base = epi_base + EPI_BYTES;
+  // barriers: full[S], conv[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
+  const int tiles_mn = g.m_tiles * g.n_tiles;
+
+  if (threadIdx.x == 0) {
+    // ===================================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn, rem = t - split * tiles_mn;
+      const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      const int64_t r_beg = (int64_t)split * g.r_chunk;
+      const int64_t r_end = min(g.R, r_beg + g.r_chunk);
+      const int num_kb = (int)((r_end - r_beg + BK - 1) / BK);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
+        const uint32_t fb = full_bar(stage);
+        mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + b_tile_bytes);
+        const int r0 = (int)(r_beg + (int64_t)kb * BK);
+        if (!A_MN) {
+          tma_load_2d(sa, &map_a, fb, r0, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &map_a, fb, m0 + 32 * c, r0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0);
+        } else {
+          for (int c = 0; c < BN / 32; ++c)
+            tma_load_2d(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + 32 * c, r0);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    // ===================================================================== MMA issuer (one thread)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                           ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t a_kstep = A_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);  // descriptor units of 16 B
+    const uint32_t b_kstep = B_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int split = t / tiles_mn;
+      const int64_t r_beg = (int64_t)split * g.r_chunk;
+      const int64_t r_end = min(g.R, r_beg + g.r_chunk);
+      const int num_kb = (int)((r_end - r_beg + BK - 1) / BK);
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * MAX_BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(g.split3 ? conv_bar(stage) : full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
+        const uint64_t a_hi = make_desc(sa, A_MN), a_lo = make_desc(sa + off_a_lo, A_MN);
+        const uint64_t b_hi = make_desc(sa + off_b_hi, B_MN), b_lo = make_desc(sa + off_b_lo, B_MN);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t ak = (uint64_t)(a_kstep * k), bk = (uint64_t)(b_kstep * k);
+          const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+          if (g.split3) {
+            umma_tf32(d_tmem, a_hi + ak, b_hi + bk, idesc, first);
+            umma_tf32(d_tmem + CORR_COL, a_hi + ak, b_lo + bk, idesc, first);
+            umma_tf32(d_tmem + CORR_COL, a_lo + ak, b_hi + bk, idesc, 1u);
+          } else {
+            umma_tf32(d_tmem, a_hi + ak, b_hi + bk, idesc, first);
+          }
+        }
+        umma_commit(empty_bar(stage));  // frees the smem stage once the MMAs above have read it
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================================== hi/lo splitters (mode 1)
+    if (g.split3) {
+      const int tid = threadIdx.x - 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int64_t r_beg = (int64_t)split * g.r_chunk;
+        const int64_t r_end = min(g.R, r_beg + g.r_chunk);
+        const int num_kb = (int)((r_end - r_beg + BK - 1) / BK);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          uint8_t* st = smem_gen + (size_t)stage * g.stage_bytes;
+          // A: 1024 float4, B: BN*8 float4; lo lives at the same swizzled offset of the twin buffer
+          const int na = A_TILE_BYTES / 16, nb = (int)(b_tile_bytes / 16);
+          for (int i = tid; i < na + nb; i += 128) {
+            const bool is_a = i < na;
+            uint8_t* hi_p = is_a ? st + (size_t)i * 16 : st + off_b_hi + (size_t)(i - na) * 16;
+            uint8_t* lo_p = hi_p + (is_a ? (size_t)off_a_lo : (size_t)b_tile_bytes);
+            const float4 v = *reinterpret_cast<const float4*>(hi_p);
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            if (g.write_hi) *reinterpret_cast<float4*>(hi_p) = h;
+            *reinterpret_cast<float4*>(lo_p) = l;
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          mbar_arrive(conv_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================================================================== epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* stg = smem_gen + (size_t)S * g.stage_bytes + (size_t)q * 32 * EPI_ROW_BYTES;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int split = t / tiles_mn, rem = t - split * tiles_mn;
+      const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+      const int64_t m0 = (int64_t)m_blk * BM + q * 32;
+      const int n0 = n_blk * BN;
+      const int n_lim = min(g.cols, n0 + BN);
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      float* Cb = g.C + (int64_t)split * g.c_split_stride;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * MAX_BN;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        if (g.split3) {
+          uint32_t rc[32];
+          tmem_ld32(taddr + CORR_COL + (uint32_t)c0, rc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * EPI_ROW_BYTES + j * 16) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        const int col = n0 + c0 + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + (lane >> 3);
+          const int64_t row = m0 + rl;
+          float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_ROW_BYTES + (lane & 7) * 16);
+          if (row < g.rows && col < n_lim) {
+            if (EPI == EPI_FWD) {
+              if (g.bias) v = f4_add(v, Vec4<float>::ld(g.bias + col));
+              if (g.Z) Vec4<float>::st(g.Z + row * g.ldz + col, v);
+              if (g.act == ISG_ACT_GELU) v = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
+            } else if (EPI == EPI_DGRAD) {
+              if (g.Zprev) {
+                const float4 z = Vec4<float>::ld(g.Zprev + row * g.ldz + col);
+                v = make_float4(v.x * gelu_grad_f(z.x), v.y * gelu_grad_f(z.y), v.z * gelu_grad_f(z.z),
+                                v.w * gelu_grad_f(z.w));
+              }
+              if (g.accumulate) v = f4_add(v, *reinterpret_cast<const float4*>(Cb + row * g.ldc + col));
+            }
+            Vec4<float>::st(Cb + row * g.ldc + col, v);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));  // 128 epilogue threads -> accumulator stage reusable
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;  // resolved once; a function pointer, not device state
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 (contiguous) x dim1 with row pitch `ld` elements; 128-byte swizzle,
+// out-of-range elements read as zero (this is what pads K = 300 to the 32-wide k-blocks).
+int make_map(CUtensorMap* m, const float* base, int64_t dim0, int64_t dim1, int64_t ld, int box0, int box1,
+             bool mn_major) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return ISG_EUNSUPPORTED;
+  if (((uintptr_t)base & 15) || (ld % 4)) return ISG_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ISG_OK : ISG_EINVAL;
+}
+
+int pick_bn(int cols, bool mn_major, int max_bn) {
+  const int q = mn_major ? 32 : 16;
+  const int parts = (cols + max_bn - 1) / max_bn;
+  int bn = (cols + parts - 1) / parts;
+  bn = ((bn + q - 1) / q) * q;
+  return bn > max_bn ? max_bn : bn;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+int launch(const isg::TcGemm& p, cudaStream_t stream) {
+  TcArgs g{};
+  g.C = p.C; g.ldc = p.ldc; g.rows = p.rows; g.cols = p.cols; g.R = p.R;
+  g.BN = pick_bn(p.cols, B_MN, p.split3 ? 128 : MAX_BN);
+  g.stage_bytes = (p.split3 ? 2 : 1) * (A_TILE_BYTES + g.BN * 128);
+  g.stages = (SMEM_LIMIT - 1024 - EPI_BYTES - BAR_BYTES) / g.stage_bytes;
+  if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
+  if (g.stages < 2) return ISG_EUNSUPPORTED;
+  g.m_tiles = ceil_div(p.rows, BM);
+  g.n_tiles = ceil_div(p.cols, g.BN);
+  g.splits = p.splits;
+  g.r_chunk = p.r_chunk;
+  g.c_split_stride = p.c_split_stride;
+  g.bias = p.bias; g.Z = p.Z; g.ldz = p.ldz; g.Zprev = p.Zprev; g.act = p.act; g.accumulate = p.accumulate;
+  g.split3 = p.split3 ? 1 : 0;
+  g.write_hi = p.split3 == 3 ? 1 : 0;  // measured on B200: kind::tf32 ignores the low 13 mantissa bits, so the
+                                        // raw fp32 tile already acts as `hi` (identical results with the write-back)
+  if (p.rows >= (1ll << 31) || p.R >= (1ll << 31)) return ISG_EUNSUPPORTED;  // TMA coordinates are int32
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!A_MN) rc = make_map(&ma, p.A, p.R, p.rows, p.lda, BK, BM, false);
+  else rc = make_map(&ma, p.A, p.rows, p.R, p.lda, 32, BK, true);
+  if (rc != ISG_OK) return rc;
+  if (!B_MN) rc = make_map(&mb, p.B, p.R, p.cols, p.ldb, BK, g.BN, false);
+  else rc = make_map(&mb, p.B, p.cols, p.R, p.ldb, 32, BK, true);
+  if (rc != ISG_OK) return rc;
+
+  const int smem = 1024 + g.stages * g.stage_bytes + EPI_BYTES + BAR_BYTES;
+  auto kern = tc_gemm_kernel<A_MN, B_MN, EPI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  const int total = g.m_tiles * g.n_tiles * g.splits;
+  const int grid = total < ISG_NUM_SMS ? total : ISG_NUM_SMS;
+  kern<<<grid, NTHREADS, smem, stream>>>(ma, mb, g);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+}  // namespace
+
+namespace isg {
+
+int tc_gemm(const TcGemm& p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!p.a_mn && !p.b_mn && p.epi == 0) return launch<false, false, EPI_FWD>(p, stream);
+  if (!p.a_mn && p.b_mn && p.epi == 1) return launch<false, true, EPI_DGRAD>(p, stream);
+  if (p.a_mn && p.b_mn && p.epi == 2) return launch<true, true, EPI_PLAIN>(p, stream);
+  return ISG_EUNSUPPORTED;
+}
+
+int tc_wgrad_splits(int64_t M, int Nout, int K, int64_t* r_chunk) {
+  // Splits bound the length of one tensor-core accumulation chain (truncating accumulate): target
+  // <= 1024 reduction rows per split; the partials are then summed in fp32 round-to-nearest, in a
+  // fixed order.  At least one wave of tiles, at most 64 splits.
+  const int tiles = ceil_div(Nout, BM) * ceil_div(K, pick_bn(K, true, 128));
+  int64_t s = (M + 1023) / 1024;
+  const int64_t one_wave = ISG_NUM_SMS / tiles;
+  if (s < one_wave) s = one_wave;
+  const int64_t max_by_len = (M + 8 * BK - 1) / (8 * BK);  // >= 8 k-blocks per split
+  if (s > max_by_len) s = max_by_len;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  int64_t chunk = (M + s - 1) / s;
+  chunk = ((chunk + BK - 1) / BK) * BK;
+  if (chunk < BK) chunk = BK;
+  s = (M + chunk - 1) / chunk;  // every split non-empty
+  if (s < 1) s = 1;
+  *r_chunk = chunk;
+  return (int)s;
+}
+
+}  // namespace isg

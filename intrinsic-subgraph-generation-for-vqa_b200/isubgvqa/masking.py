@@ -65,6 +65,11 @@ class MaskingModel(torch.nn.Module):
     `injected_noise` / `injected_dropout_mask` (attributes, default None) replace the random draws
     of the next forward — used by the parity tests to feed both sides the same randomness."""
 
+    # The two 300x300 gate projections feed a DISCRETE decision (top-k) and, for Gumbel, a tau = 0.1 softmax
+    # that amplifies logit perturbations 10x per round: they always run in strict fp32 (FFMA), whatever
+    # the global projection mode is.  Cost: 2 x N x 300 x 300 FMAs per step.
+    GATE_GEMM_MODE = 0
+
     def __init__(self, dim_nodes, dim_questions, masking_threshold=0.3, use_topk=False, sample_k=None,
                  sampler_type=None, nb_samples=1, alpha=1.0, beta=10.0, tau=1.0, noise_source="host"):
         super().__init__()
@@ -103,8 +108,8 @@ class MaskingModel(torch.nn.Module):
 
     # -- fused path used by MaskingGATv2Conv: u_graph is [B,D] (imle_att BEFORE the [batch] gather)
     def forward_fused(self, x, u_graph, gi):
-        xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU)
-        q = ops.linear(u_graph, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU)
+        xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)
+        q = ops.linear(u_graph, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)
         theta = ops.GateTheta.apply(xn, q, gi, True)
         return self._sample(theta, gi)
 
@@ -115,8 +120,8 @@ class MaskingModel(torch.nn.Module):
         x = x.unsqueeze(-1) if x.dim() == 1 else x
         num_graphs = size if size is not None else int(batch[-1].item()) + 1  # masking.py:135
         gi = get_graph_index(edge_index, batch, num_graphs)
-        xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU)
-        q = ops.linear(u, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU)  # u is [N,D] here
+        xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)
+        q = ops.linear(u, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)  # u [N,D]
         theta = ops.GateTheta.apply(xn, q, gi, False)  # q[batch] (masking.py:152)
         return self._sample(theta, gi)
 

@@ -1,12 +1,15 @@
 """torch.autograd.Function wrappers over the libisg.so C ABI (include/isg.h).  PyTorch is plumbing
 here — it owns device memory, streams and the autograd tape; all arithmetic happens in the CUDA
 kernels.  Each Function cites the reference code it replaces (paths relative to the reference)."""
+import os
+
 import torch
 
 from . import lib as L
 
 _DEBUG_EDGE_BWD = None  # diagnostics: set to a list to capture GatEdge.backward inputs/outputs
-_GEMM_MODE = 0  # 0 = fp32 FFMA (parity). tcgen05 modes are selected via set_gemm_mode().
+# projection arithmetic: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-grade), 2 = tcgen05 single-pass TF32
+_GEMM_MODE = int(os.environ.get("ISG_GEMM_MODE", "0"))
 
 
 def set_gemm_mode(mode):
@@ -25,36 +28,39 @@ def _c(t):
 # ------------------------------------------------------------------------------------------
 # dense projections (kernel d)
 # ------------------------------------------------------------------------------------------
-def linear_fwd_raw(x, w, b, act, want_pre):
+def linear_fwd_raw(x, w, b, act, want_pre, mode=None):
     lib = L.load()
+    mode = _GEMM_MODE if mode is None else mode
     M, K = x.shape
     Nout = w.shape[0]
     y = torch.empty(M, Nout, dtype=x.dtype, device=x.device)
     z = torch.empty(M, Nout, dtype=x.dtype, device=x.device) if want_pre else None
     L.call("isg_linear_fwd", L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(y), Nout, L.ptr(z), Nout, M, Nout, K,
-                               act, _GEMM_MODE, L.dtype_code(x), L.stream())
+                               act, mode, L.dtype_code(x), L.stream())
     return y, z
 
 
-def linear_dgrad_raw(gy, w, z_prev=None, out=None, accumulate=False):
+def linear_dgrad_raw(gy, w, z_prev=None, out=None, accumulate=False, mode=None):
     lib = L.load()
+    mode = _GEMM_MODE if mode is None else mode
     M, Nout = gy.shape
     K = w.shape[1]
     gx = out if out is not None else torch.empty(M, K, dtype=gy.dtype, device=gy.device)
     L.call("isg_linear_dgrad", L.ptr(gy), gy.stride(0), L.ptr(w), L.ptr(z_prev), K, L.ptr(gx), gx.stride(0),
-                                 1 if accumulate else 0, M, Nout, K, _GEMM_MODE, L.dtype_code(gy), L.stream())
+                                 1 if accumulate else 0, M, Nout, K, mode, L.dtype_code(gy), L.stream())
     return gx
 
 
-def linear_wgrad_raw(gy, x):
+def linear_wgrad_raw(gy, x, mode=None):
     lib = L.load()
+    mode = _GEMM_MODE if mode is None else mode
     M, Nout = gy.shape
     K = x.shape[1]
     gw = torch.empty(Nout, K, dtype=torch.float32, device=gy.device)
     nbytes = lib.isg_linear_wgrad_workspace_bytes(M, Nout, K)
     ws = L.workspace(nbytes, gy.device)
     L.call("isg_linear_wgrad", L.ptr(gy), gy.stride(0), L.ptr(x), x.stride(0), L.ptr(gw), None, M, Nout, K,
-                                 _GEMM_MODE, L.dtype_code(gy), L.ptr(ws), nbytes, L.stream())
+                                 mode, L.dtype_code(gy), L.ptr(ws), nbytes, L.stream())
     return gw
 
 
@@ -81,12 +87,14 @@ class LinearAct(torch.autograd.Function):
     node_nn / ques_nn (models/masking.py:137,152)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act):
+    def forward(ctx, x, w, b, act, mode=None):
         L.require_cuda(x, w, b)
         x, w = _c(x), _c(w)
         b = _c(b) if b is not None else None
-        y, z = linear_fwd_raw(x, w, b, act, want_pre=(act != L.ACT_NONE))
+        mode = _GEMM_MODE if mode is None else mode
+        y, z = linear_fwd_raw(x, w, b, act, want_pre=(act != L.ACT_NONE), mode=mode)
         ctx.act = act
+        ctx.mode = mode
         ctx.has_bias = b is not None
         ctx.save_for_backward(x, w, z)
         return y
@@ -98,14 +106,15 @@ class LinearAct(torch.autograd.Function):
             gy = gelu_bwd(_c(gy), z)
         elif gy.stride(1) != 1 or gy.stride(0) % 4 != 0:
             gy = gy.contiguous()  # column views of a wider buffer are consumed through their pitch
-        gx = linear_dgrad_raw(gy, w) if ctx.needs_input_grad[0] else None
-        gw = linear_wgrad_raw(gy, x) if ctx.needs_input_grad[1] else None
+        gx = linear_dgrad_raw(gy, w, mode=ctx.mode) if ctx.needs_input_grad[0] else None
+        gw = linear_wgrad_raw(gy, x, mode=ctx.mode) if ctx.needs_input_grad[1] else None
         gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def linear(x, w, b=None, act=L.ACT_NONE):
-    return LinearAct.apply(x, w, b, act)
+def linear(x, w, b=None, act=L.ACT_NONE, mode=None):
+    """mode=None -> the global projection mode (set_gemm_mode / ISG_GEMM_MODE)."""
+    return LinearAct.apply(x, w, b, act, mode)
 
 
 # ------------------------------------------------------------------------------------------
