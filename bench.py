@@ -176,6 +176,11 @@ def main_isg(args, rank, world, local_rank):
     from isg_b200.isubgvqa import MGAT
 
     L.load()  # fails loudly if libisg.so is missing — there is no fallback path
+    from isg_b200 import ops
+
+    ops.set_gemm_mode(args.gemm_mode)
+    gemm_desc = {0: "fp32 FFMA (mode 0)", 1: "tcgen05 3xTF32 split, fp32-grade (mode 1)",
+                 2: "tcgen05 single-pass TF32 (mode 2, NOT the parity configuration)"}[args.gemm_mode]
     desc, sampler, train, B = WORKLOADS[args.workload]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -324,7 +329,7 @@ def main_isg(args, rank, world, local_rank):
                                                       else "") if train else "MGAT forward (no_grad)",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
                          f"~{(4 * 4 * HEADS * CHANNELS * (3 * E + 8 * N)) / 1e9:.2f} GB also exceeds the 126 MB L2",
-                   "gemm_mode": "fp32 FFMA (mode 0)", "optimizer": "out of scope (SURVEY.md §8 f4)"},
+                   "gemm_mode": gemm_desc, "optimizer": "out of scope (SURVEY.md §8 f4)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "what": "pinned host batch -> .to(cuda) -> CSR build -> MGAT fwd+bwd -> loss.item() + mask.cpu()"},
@@ -351,6 +356,8 @@ def main():
     ap.add_argument("--impl", default="isg", choices=["isg", "reference"])
     ap.add_argument("--breakdown", action="store_true", help="add per-entry-point CUDA-event times to the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2],
+                    help="projection arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32 (default), 2 tcgen05 1xTF32")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -151,6 +151,24 @@ int isg_gumbel_topk_bwd(const float* dy, const float* saved, const int32_t* grap
                         int64_t num_graphs, int nmax, int k, float tau,
                         float* g_theta, void* stream);
 
+/* SIMPLE: exact k-subset marginals + Gumbel top-k sample + straight-through
+ * (sampling/methods/simple_scheme.py:44-162 'edge_candid'; sampling/methods/simple.py:113-252 evaluated over
+ * the SDD of create_simple_constraint.py:34-73, including simple.py's -1000 dummy pads, which decide the
+ * result whenever a logit is exactly 0 — to_dense_batch pads and dropped-out logits are).
+ * n_pad = isg_simple_npad(nmax) = nmax rounded up to a power of two (simple_scheme.py:87, slots >= nmax are
+ * -1e10).  gumbel [B, n_pad] = Gumbel(0,1) noise (-log(-log U), simple.py:91-96).
+ * fwd: mask [N] ragged = (hot - marginals) + marginals, hot = one-hot of topk(theta_pad + gumbel, min(k,nmax));
+ *      marginals [B, nmax] or NULL.
+ * bwd: g_theta [N] from dy [N] (gradient of mask) and optionally d_marginals [B, nmax] (or NULL); flows
+ *      through the positive literals only (simple.py:215-217 detaches the negative weight).
+ * Supported: 2 <= n_pad <= 1024, k <= 7, circuit must fit 200 KB of shared memory per graph. */
+int isg_simple_npad(int nmax);
+int isg_simple_marginals_fwd(const float* theta, const float* gumbel, const int32_t* graph_ptr,
+                             int64_t num_graphs, int nmax, int k, float* mask, float* marginals, void* stream);
+int isg_simple_marginals_bwd(const float* dy, const float* d_marginals, const float* theta,
+                             const int32_t* graph_ptr, int64_t num_graphs, int nmax, int k, float* g_theta,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * node-side fused segment ops
  * ------------------------------------------------------------------------------------- */
@@ -199,7 +217,8 @@ int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const float* ins,
  *   dgrad: g_x = (g_y W) [* gelu'(z_prev) if z_prev != NULL]
  *   wgrad: g_W = g_y^T x (deterministic split over M; bias gradient = isg_colsum(g_y))
  * x [M,K] pitch ldx; W [Nout,K] dense; y [M,Nout] pitch ldy.
- * `mode`: 0 = fp32 FFMA (parity), 1 = tcgen05 3xTF32 split (fp32-grade), 2 = tcgen05 bf16.
+ * `mode`: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 split (fp32-grade), 2 = tcgen05 single-pass TF32
+ *         (3 = mode 1 with an explicit hi write-back, verification only).
  * ------------------------------------------------------------------------------------- */
 int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
                    void* y, int64_t ldy, void* z_pre /* or NULL */, int64_t ldz,

@@ -320,14 +320,23 @@ gat_edge_bwd_dst_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __res
 }
 
 // g_att[h*C + c] = sum over warps w with (w % H == h) of part[w, c], fixed order.
+// grid (ceil(C/32), H), block (32, 8): 8 row lanes stride through the partials, then a fixed-order
+// shared-memory fold -> deterministic.
 __global__ void gat_att_reduce_kernel(const float* __restrict__ part, int64_t nwarps, int H, int C,
                                       float* __restrict__ g_att) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= H * C) return;
-  const int h = idx / C, c = idx - h * C;
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, h = blockIdx.y;
   float s = 0.f;
-  for (int64_t w = h; w < nwarps; w += H) s += part[w * C + c];
-  g_att[idx] = s;
+  if (c < C)
+    for (int64_t w = h + (int64_t)H * threadIdx.y; w < nwarps; w += (int64_t)H * 8) s += part[w * C + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    g_att[h * C + c] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -449,8 +458,8 @@ int launch_bwd(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r
       (const T*)out, ld_out, dst_ptr, dst_nbr, dst_eid, (T*)g_xr, ld_gx, (T*)g_eproj, gatt_part, gm_h, N, H,
       C, slope);
   ISG_CHECK_LAUNCH();
-  gat_att_reduce_kernel<<<ceil_div(H * C, 128), 128, 0, stream>>>(gatt_part, (int64_t)blocks * EDGE_WARPS, H,
-                                                                  C, g_att);
+  gat_att_reduce_kernel<<<dim3(ceil_div(C, 32), H), dim3(32, 8), 0, stream>>>(
+      gatt_part, (int64_t)blocks * EDGE_WARPS, H, C, g_att);
   ISG_CHECK_LAUNCH();
   const int64_t NH = N * H;
   gat_edge_bwd_src_kernel<T, VPL, MASKED><<<ceil_div(NH, EDGE_WARPS), EDGE_WARPS * 32, 0, stream>>>(

@@ -506,6 +506,13 @@ int tc_wgrad_splits(int64_t M, int Nout, int K, int64_t* r_chunk) {
   int64_t s = (M + 1023) / 1024;
   const int64_t one_wave = ISG_NUM_SMS / tiles;
   if (s < one_wave) s = one_wave;
+  // wave quantisation: a few tiles past a whole number of waves cost a full extra wave
+  const int64_t waves = (s * tiles) / ISG_NUM_SMS;
+  if (waves >= 1 && waves <= 3 && (s * tiles) % ISG_NUM_SMS != 0 &&
+      (s * tiles) % ISG_NUM_SMS < ISG_NUM_SMS / 3) {
+    const int64_t s_fit = (waves * ISG_NUM_SMS) / tiles;
+    if (s_fit >= 1 && (M + s_fit - 1) / s_fit <= 1536) s = s_fit;
+  }
   const int64_t max_by_len = (M + 8 * BK - 1) / (8 * BK);  // >= 8 k-blocks per split
   if (s > max_by_len) s = max_by_len;
   if (s < 1) s = 1;

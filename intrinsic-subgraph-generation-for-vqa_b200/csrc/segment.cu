@@ -284,24 +284,34 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __res
   if (i < n) gz[i] = gy[i] * gelu_grad_f(z[i]);
 }
 
-constexpr int CS_ROWS = 256;  // rows per partial
+constexpr int CS_ROWS = 64;  // rows per partial
+// Each thread owns 4 adjacent columns (one float4) of a CS_ROWS-row slab: 16-byte coalesced loads,
+// CS_ROWS independent loads per thread, grid = (cols/4/128) x (rows/CS_ROWS) CTAs.
 __global__ void colsum_partial_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
                                       float* __restrict__ part) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= cols) return;
   const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
   const int64_t r1 = min(rows, r0 + CS_ROWS);
-  float s = 0.f;
-  for (int64_t r = r0; r < r1; ++r) s += in[r * ld + c];
-  part[(int64_t)blockIdx.y * cols + c] = s;
+  float4 s = f4_zero();
+  int64_t r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = Vec4<float>::ld(in + (r + u) * ld + c);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
+  }
+  for (; r < r1; ++r) s = f4_add(s, Vec4<float>::ld(in + r * ld + c));
+  Vec4<float>::st(part + (int64_t)blockIdx.y * cols + c, s);
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int cols,
                                     float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= cols) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * cols + c];
-  out[c] = s;
+  float4 s = f4_zero();
+  for (int p = 0; p < nparts; ++p) s = f4_add(s, Vec4<float>::ld(part + (int64_t)p * cols + c));
+  Vec4<float>::st(out + c, s);
 }
 
 }  // namespace
@@ -417,11 +427,12 @@ extern "C" int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, f
     return e == cudaSuccess ? ISG_OK : (int)e;
   }
   if (!in) return ISG_EINVAL;
+  if (cols % 4 != 0 || ld % 4 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return ISG_EUNSUPPORTED;
   if (ws_bytes < isg_colsum_workspace_bytes(rows, cols) || !workspace) return ISG_EWORKSPACE;
   const int parts = (int)((rows + CS_ROWS - 1) / CS_ROWS);
-  colsum_partial_kernel<<<dim3(isg::ceil_div(cols, 128), parts), 128, 0, stream>>>(in, ld, rows, cols, (float*)workspace);
+  colsum_partial_kernel<<<dim3(isg::ceil_div(cols / 4, 64), parts), 64, 0, stream>>>(in, ld, rows, cols, (float*)workspace);
   ISG_CHECK_LAUNCH();
-  colsum_final_kernel<<<isg::ceil_div(cols, 128), 128, 0, stream>>>((const float*)workspace, parts, cols, out);
+  colsum_final_kernel<<<isg::ceil_div(cols / 4, 64), 64, 0, stream>>>((const float*)workspace, parts, cols, out);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

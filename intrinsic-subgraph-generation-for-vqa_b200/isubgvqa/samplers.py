@@ -263,20 +263,44 @@ class GumbelSampler(torch.nn.Module):
 
 
 class EdgeSIMPLEBatched(torch.nn.Module):
-    """simple_scheme.py:24-162 — SIMPLE exact k-subset marginals.  The CUDA circuit kernel is not
-    built yet in this round; constructing the sampler works (state_dict / module tree parity),
-    calling it raises."""
+    """simple_scheme.py:24-162 — SIMPLE exact k-subset marginals ('edge_candid', ensembles 1, no logits
+    activation).  forward(scores [B,Nmax,1], train) -> (mask [1,B,Nmax,1], marginals [B,Nmax,1]).
+    The SDD circuit is evaluated by csrc/simple.cu straight from its closed form (a balanced tree of
+    count nodes), so no ./simple_configs/*.pkl is written or read (simple.py:114-122 does both)."""
 
     def __init__(self, k, device, policy, val_ensemble=1, train_ensemble=1, logits_activation=None):
         super().__init__()
+        if policy != "edge_candid" or val_ensemble != 1 or train_ensemble != 1 or \
+                logits_activation not in (None, "None"):
+            raise NotImplementedError("ISubGVQA builds EdgeSIMPLEBatched(policy='edge_candid'), ensembles 1, no "
+                                      "logits activation (models/masking.py:109-113)")
         self.k, self.device, self.policy = k, device, policy
         self.layer_configs = dict()
         self.adj = None
         self.val_ensemble, self.train_ensemble = val_ensemble, train_ensemble
         self.logits_activation = logits_activation
 
-    def ragged(self, theta, gi, gumbel=None):
-        raise NotImplementedError("SIMPLE sampler kernel (isg_simple_marginals_*) lands in a later round")
+    @staticmethod
+    def _gumbel(B, npad, device):
+        u = torch.rand(B, npad, dtype=torch.float32, device=device)  # simple.py:94-96 (device generator)
+        return -torch.log(-torch.log(u))
 
-    def forward(self, scores, train=True):
-        raise NotImplementedError("SIMPLE sampler kernel (isg_simple_marginals_*) lands in a later round")
+    def ragged(self, theta, gi, gumbel=None):
+        if gumbel is None:
+            gumbel = self._gumbel(gi.B, L.load().isg_simple_npad(gi.nmax), theta.device)
+        mask, _marg = ops.SimpleTopk.apply(theta, gumbel, gi, int(self.k))
+        return mask
+
+    def forward(self, scores, train=True, gumbel=None):
+        B, nmax, ens = scores.shape
+        if ens != 1:
+            raise NotImplementedError("ensemble > 1 is not used on the ISubGVQA path")
+        di = _DenseIndex(B, nmax, scores.device)
+        if gumbel is None:
+            gumbel = self._gumbel(B, L.load().isg_simple_npad(nmax), scores.device)
+        mask, marg = ops.SimpleTopk.apply(scores.reshape(B * nmax, 1), gumbel, di, int(self.k))
+        return mask.view(1, B, nmax, 1), marg.view(B, nmax, 1)
+
+    @torch.no_grad()
+    def validation(self, scores):
+        return select_from_edge_candidates(scores, self.k)[None], None

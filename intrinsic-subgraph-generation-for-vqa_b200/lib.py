@@ -37,6 +37,9 @@ SIGNATURES = {
     "isg_aimle_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _I32, _P, _P, _P, _SZ, _P]),
     "isg_gumbel_topk_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
     "isg_gumbel_topk_bwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P]),
+    "isg_simple_npad": (_I32, [_I32]),
+    "isg_simple_marginals_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "isg_simple_marginals_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "isg_instr_gate_fwd": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
     "isg_instr_gate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
     "isg_gate_theta_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
@@ -76,7 +79,7 @@ def load():
 KERNELS_PER_CALL = {
     "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 3,
     "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_imle_bwd": 1,
-    "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_instr_gate_fwd": 1,
+    "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
     "isg_sdpa_graphnorm_bwd": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
     "isg_gelu_bwd": 1, "isg_colsum": 2,

@@ -398,3 +398,37 @@ class GumbelTopk(torch.autograd.Function):
         L.call("isg_gumbel_topk_bwd", L.ptr(dy), L.ptr(saved), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
                                              L.ptr(g), L.stream())
         return g, None, None, None, None
+
+
+class SimpleTopk(torch.autograd.Function):
+    """SIMPLE exact k-subset marginals + Gumbel top-k sample + straight-through
+    (sampling/methods/simple_scheme.py:44-162, simple.py:113-252).  theta [N,1] ragged, gumbel
+    [B, n_pad] Gumbel(0,1).  Returns (mask [N,1], marginals [B,Nmax])."""
+
+    @staticmethod
+    def forward(ctx, theta, gumbel, gi, k):
+        theta = _c(theta)
+        lib = L.load()
+        npad = lib.isg_simple_npad(gi.nmax)
+        g = gumbel.reshape(gi.B, -1)
+        if g.shape[1] != npad:
+            raise ValueError(f"SIMPLE noise has {g.shape[1]} slots per graph, expected n_pad = {npad}")
+        g = _c(g.to(torch.float32))
+        mask = torch.empty(theta.shape[0], 1, dtype=torch.float32, device=theta.device)
+        marg = torch.empty(gi.B, gi.nmax, dtype=torch.float32, device=theta.device)
+        L.call("isg_simple_marginals_fwd", L.ptr(theta), L.ptr(g), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
+               L.ptr(mask), L.ptr(marg), L.stream())
+        ctx.gi, ctx.k = gi, k
+        ctx.save_for_backward(theta)
+        return mask, marg
+
+    @staticmethod
+    def backward(ctx, dy, dmarg):
+        (theta,) = ctx.saved_tensors
+        gi = ctx.gi
+        dy = _c(dy)
+        dmarg = _c(dmarg) if dmarg is not None else None
+        g = torch.empty_like(theta)
+        L.call("isg_simple_marginals_bwd", L.ptr(dy), L.ptr(dmarg), L.ptr(theta), L.ptr(gi.graph_ptr), gi.B,
+               gi.nmax, ctx.k, L.ptr(g), L.stream())
+        return g, None, None, None

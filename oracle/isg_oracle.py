@@ -345,34 +345,94 @@ def _log1mexp(x):
     return torch.where(x > -0.6931471805599453094, torch.log(-torch.expm1(x)), torch.log1p(-torch.exp(x)))
 
 
+def simple_circuit_plan(n, k):
+    """Structure of the SDD that sampling/methods/create_simple_constraint.py:34-73 builds for
+    "exactly k of n" (n = 2^p): a balanced binary tree; the node (level L, position i, count j) is a
+    decomposition whose elements are the pairs (left child count jj, right child count j - jj) for
+    which both children exist (:52-60).  A child exists iff its count fits its subtree
+    (jj <= min(k, 2^(L-1)); leaves: jj <= 1, :44-47).  Only nodes reachable from the root
+    (level p, count k) are evaluated (simple.py:124-139 iterate `beta.positive_iter()`).
+    simple.py pads every node's element list to `max_elements` with a dummy node of log-value -1000
+    (:192-203, :222) and every node's parent list to `max_parents` with (dummy, 0) (:153-161); those
+    pads are NOT neutral once a literal weight is -inf (theta == 0 gives log(1 - e^0) = -inf), so the
+    pad counts are part of the function and are reproduced here.
+    Returns dict(p, cap[L], reach[L], elems[L][j] = [jj...], max_elements, max_parents)."""
+    p = int(round(math.log2(n)))
+    assert 2 ** p == n and p >= 1, "SIMPLE needs n = 2^p >= 2 (the reference fails for n = 1 too)"
+    cap = [1] + [min(k, 2 ** L) for L in range(1, p + 1)]
+    elems = [None] + [{j: [jj for jj in range(j + 1) if jj <= cap[L - 1] and j - jj <= cap[L - 1]]
+                       for j in range(cap[L] + 1)} for L in range(1, p + 1)]
+    reach = [set() for _ in range(p + 1)]
+    reach[p] = {k} if k <= cap[p] else set()
+    for L in range(p, 0, -1):
+        for j in reach[L]:
+            for jj in elems[L][j]:
+                reach[L - 1].add(jj)
+                reach[L - 1].add(j - jj)
+    max_elements = max(len(elems[L][j]) for L in range(1, p + 1) for j in reach[L])
+    max_parents = 0
+    for L in range(0, p):
+        for c in reach[L]:
+            # parent entries of a child with count c: one per reachable parent count j that has c as one side
+            cnt = sum(1 for j in reach[L + 1] if 0 <= j - c <= cap[L] and (j - c) in reach[L])
+            max_parents = max(max_parents, cnt)
+    return dict(p=p, cap=cap, reach=[sorted(r) for r in reach], elems=elems, max_elements=max_elements,
+                max_parents=max_parents)
+
+
+_SIMPLE_DUMMY = -1000.0  # simple.py:222  data[self.id] = -float(1000)
+
+
 def simple_marginals(theta, k):
-    """Exact k-subset marginals of sampling/methods/simple.py:113-244 (SDD circuit built by
-    create_simple_constraint.py:34-73) restated as a balanced-tree DP over elementary symmetric
-    polynomials in log space: p(S) ∝ prod_{i in S} e^{theta_i} * prod_{i notin S} (1 - e^{-|theta_i|}),
-    |S| = k.  theta [R, n] (n = Nmax padded to 2^p with -1e10 by simple_scheme.py:87-106 — the
-    caller pads).  The negative-literal weight uses theta.detach() (simple.py:215-217), so
-    autograd through this function flows only through the positive literals, like the reference.
-    Returns marginals [R, n]."""
+    """Layer.log_pr(theta).exp() of sampling/methods/simple.py:214-244 restated as a balanced-tree DP
+    (no pickle, no node objects): bottom-up pass = levelwiseSL (:16-27), top-down pass = levelwiseMars
+    (:30-41), including the -1000 dummy pads.  theta [R, n] (n = Nmax padded to 2^p with -1e10 by
+    simple_scheme.py:87-106 — the caller pads).  The negative-literal weight uses theta.detach()
+    (simple.py:215-217), so autograd flows only through the positive literals, like the reference.
+    Returns marginals [R, n]; differentiable (the reference differentiates through both passes)."""
     R, n = theta.shape
-    pos = theta
-    neg = _log1mexp(-theta.detach())
-    ninf = torch.full_like(pos, -float("inf"))
-    # level 0: poly_i(j) for j = 0..k : [neg_i, pos_i, -inf, ...]
-    polys = torch.stack([neg, pos] + [ninf] * (k - 1), dim=-1) if k >= 1 else neg.unsqueeze(-1)
-    polys = polys[..., : k + 1]
-    levels = [polys]
-    while polys.shape[1] > 1:
-        a, b = polys[:, 0::2], polys[:, 1::2]
-        outs = []
-        for j in range(k + 1):
-            terms = [a[..., jj] + b[..., j - jj] for jj in range(j + 1)]
-            outs.append(torch.logsumexp(torch.stack(terms, dim=-1), dim=-1))
-        polys = torch.stack(outs, dim=-1)
-        levels.append(polys)
-    log_z = polys[:, 0, k]
-    # marginal_i = d logZ / d pos_i
-    (grad,) = torch.autograd.grad(log_z.sum(), pos, create_graph=True)
-    return grad
+    plan = simple_circuit_plan(n, k)
+    p, reach, elems = plan["p"], plan["reach"], plan["elems"]
+    me, mp = plan["max_elements"], plan["max_parents"]
+    # ---- bottom-up (levelwiseSL): D[L][j] [R, n/2^L] log-values, C[L][j][e] log-conditionals
+    D = [{0: _log1mexp(-theta.detach()), 1: theta}]
+    C = [None]
+    for L in range(1, p + 1):
+        prev = D[L - 1]
+        dl, cl = {}, {}
+        for j in reach[L]:
+            terms = [prev[jj][:, 0::2] + prev[j - jj][:, 1::2] for jj in elems[L][j]]
+            pads = me - len(terms)
+            stack = torch.stack(terms + [torch.full_like(terms[0], 2 * _SIMPLE_DUMMY)] * pads, dim=-1)
+            val = torch.logsumexp(stack, dim=-1)
+            dl[j] = val
+            cl[j] = [t - val for t in terms]
+        D.append(dl)
+        C.append(cl)
+    # ---- top-down (levelwiseMars): M[L][j] log-marginal of node (L, ., j); root: data - data (:229)
+    root = D[p][k]
+    M = [None] * (p + 1)
+    M[p] = {k: root - root}
+    for L in range(p - 1, -1, -1):
+        ml = {}
+        width = n >> L
+        for c in reach[L]:
+            left, right = [], []  # contributions to even (left-child) and odd (right-child) positions
+            for j in reach[L + 1]:
+                js = elems[L + 1][j]
+                if c in js:  # this node is the LEFT child (prime) of element jj = c
+                    left.append(C[L + 1][j][js.index(c)] + M[L + 1][j])
+                if (j - c) in js:  # this node is the RIGHT child (sub) of element jj = j - c
+                    right.append(C[L + 1][j][js.index(j - c)] + M[L + 1][j])
+            out = theta.new_empty(R, width)
+            for side, lst in ((0, left), (1, right)):
+                pads = mp - len(lst)
+                ref_shape = M[L + 1][reach[L + 1][0]]
+                stack = torch.stack(lst + [torch.full_like(ref_shape, _SIMPLE_DUMMY)] * pads, dim=-1)
+                out[:, side::2] = torch.logsumexp(stack, dim=-1)
+            ml[c] = out
+        M[L] = ml
+    return M[0][1].exp()
 
 
 def simple_sample(theta_dense, gumbel, k):

@@ -37,6 +37,10 @@ CASES = [
     ("gumbel_eval_c300", "gumbel", False, 300, 4, 7, 28, 3, 1160),
     ("imle_train_c16_k3", "imle", True, 16, 7, 6, 24, 3, 1000),
     ("aimle_train_c64", "aimle", True, 64, 6, 12, 70, 2, 1166),
+    # SIMPLE: ragged graphs (zero pads in the dense layout) + theta dropout in training => exact-zero logits,
+    # i.e. the regime where simple.py's -1000 dummy pads decide the marginals (oracle/isg_oracle.py).
+    ("simple_train_c64", "simple", True, 64, 6, 12, 70, 2, 1166),
+    ("simple_eval_c300_k3", "simple", False, 300, 4, 7, 28, 3, 1368),
 ]
 
 
@@ -119,7 +123,10 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     with rl.scratch_cwd():
         rl.load()
+    only = set(sys.argv[1:])
     for name, sampler, train, C, B, mn, me, k, seed in CASES:
+        if only and name not in only:
+            continue
         steps = 3 if sampler == "aimle" else 1  # AIMLE: 3 consecutive steps pin the adaptive beta state
         torch.manual_seed(seed)
         outs = run_reference(sampler, train, C, B, mn, me, k, seed, steps)

@@ -431,11 +431,47 @@ def test_sdpa_graphnorm_residual(D, with_empty):
         assert util.rel_err(lc.grad, lo.grad) <= RTOL, name
 
 
+@pytest.mark.parametrize("B,mn,k,zeros", [(9, 6, 2, True), (16, 20, 2, True), (5, 40, 3, True), (7, 12, 5, True),
+                                           (33, 20, 2, False), (3, 100, 4, True)])
+def test_simple_marginals_fwd_bwd(B, mn, k, zeros):
+    """SIMPLE sampler kernel vs the oracle's restatement of simple.py's circuit (pinned to the live reference,
+    incl. the -1000 dummy-pad regime that exact-zero logits — dense pads, dropout — put it in)."""
+    import isg_oracle as O
+    from isg_b200 import lib as L
+    from isg_b200 import ops
+
+    batch, theta, nmax = _ragged(B, mn, seed=300 + B + k)
+    g = torch.Generator().manual_seed(B * 7 + k)
+    if zeros:
+        theta[torch.rand(theta.shape, generator=g) < 0.2] = 0.0  # dropout-style exact zeros
+    npad = L.load().isg_simple_npad(nmax)
+    gum = synth.gumbel_noise(B, npad, 1.0, seed=77 + B)[:, 0, :, 0].contiguous()
+    w = torch.randn(theta.shape[0], 1, generator=g)
+    wm = torch.randn(B, nmax, generator=g)
+    # oracle on the dense layout (to_dense_batch pads are exact zeros, too)
+    to = theta.clone().requires_grad_(True)
+    dense, valid = O.to_dense_batch(to, batch, B)
+    mo, margo = O.simple_sample(dense, gum, k)
+    mo_r = mo.squeeze(0)[valid]
+    ((mo_r * w).sum() + (margo[..., 0] * wm).sum()).backward()
+    # CUDA, ragged layout
+    tc = theta.clone().to(DEV).requires_grad_(True)
+    gi = _gi(torch.zeros(2, 0, dtype=torch.int64), batch, B)
+    mc, margc = ops.SimpleTopk.apply(tc, gum.to(DEV), gi, k)
+    ((mc * w.to(DEV)).sum() + (margc * wm.to(DEV)).sum()).backward()
+    assert util.rel_err(margc, margo[..., 0]) <= 1e-5
+    assert util.rel_err(mc, mo_r) <= 1e-5
+    assert torch.equal(mc.detach().cpu().round(), mo_r.detach().round())  # same hard sample given the same noise
+    assert util.rel_err(tc.grad, to.grad) <= 1e-4
+
+
 # ------------------------------------------------------------------------------------------ (d) projections
 @pytest.mark.parametrize("M,K,Nout,act", [(1, 300, 1200, 0), (37, 300, 1200, 0), (515, 1200, 600, 1),
                                           (130, 600, 300, 1), (9600, 300, 1200, 0), (64, 8, 32, 1),
                                           (257, 300, 300, 1)])
-def test_linear_fwd_dgrad_wgrad(M, K, Nout, act):
+@pytest.mark.parametrize("mode,tol", [(0, 1e-5), (1, 1e-5), (2, 3e-3)], ids=["ffma", "tc3xtf32", "tc1xtf32"])
+def test_linear_fwd_dgrad_wgrad(M, K, Nout, act, mode, tol):
+    """mode 0: fp32 FFMA; mode 1: tcgen05 3xTF32 split (fp32-grade, same bound); mode 2: single-pass TF32."""
     from isg_b200 import ops
 
     g = torch.Generator().manual_seed(M + K)
@@ -449,12 +485,33 @@ def test_linear_fwd_dgrad_wgrad(M, K, Nout, act):
         yo = torch.nn.functional.gelu(yo)
     yo.backward(gy.double())
     xc, wc, bc = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
-    yc = ops.linear(xc, wc, bc, act)
+    yc = ops.linear(xc, wc, bc, act, mode)
     yc.backward(gy.to(DEV))
-    assert util.rel_err(yc, yo) <= 1e-5
-    assert util.rel_err(xc.grad, xo.grad) <= 1e-5
-    assert util.rel_err(wc.grad, wo.grad) <= 1e-5
-    assert util.rel_err(bc.grad, bo.grad) <= 1e-5
+    assert util.rel_err(yc, yo) <= tol
+    assert util.rel_err(xc.grad, xo.grad) <= tol
+    assert util.rel_err(wc.grad, wo.grad) <= tol
+    assert util.rel_err(bc.grad, bo.grad) <= max(tol, 1e-5)
+
+
+def test_linear_tc_pitched_views_and_long_reduction():
+    """tcgen05 path on column views of a wider buffer (x_l | x_r share one pitch) and on a reduction long
+    enough to need many wgrad splits (E = 40k rows, BASELINE config 3 size)."""
+    from isg_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    M, K, Nout = 40000, 300, 1200
+    xw = torch.randn(M, 2 * K, generator=g).to(DEV)
+    x = xw[:, K:]  # pitched view, 16-byte aligned offset
+    w = (torch.randn(Nout, K, generator=g) / math.sqrt(K)).to(DEV)
+    gy = torch.randn(M, Nout, generator=g).to(DEV)
+    y, _ = ops.linear_fwd_raw(x, w, None, 0, False, mode=1)
+    assert util.rel_err(y, x.double() @ w.double().t()) <= 1e-5
+    gw = ops.linear_wgrad_raw(gy, x, mode=1)
+    assert util.rel_err(gw, gy.double().t() @ x.double()) <= 1e-5
+    gx = ops.linear_dgrad_raw(gy, w, mode=1)
+    assert util.rel_err(gx, gy.double() @ w.double()) <= 1e-5
+    # deterministic: the split reduction has a fixed order
+    assert torch.equal(gw, ops.linear_wgrad_raw(gy, x, mode=1))
 
 
 def test_ops_reject_cpu_tensors():
