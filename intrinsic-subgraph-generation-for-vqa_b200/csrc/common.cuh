@@ -144,6 +144,104 @@ __device__ __forceinline__ float f4_dot(float4 a, float4 b) {
   return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
 }
 
+// ---- packed fp32 (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE-rn fp32 lanes per instruction).  The edge
+// kernels need ~10 fp32 ops per streamed element; at the HBM roofline that is ~0.9 issued
+// instructions per cycle per scheduler with scalar ops, so halving the FP instruction count is what
+// lets them approach the memory bound.
+__device__ __forceinline__ float4 p4_add(float4 a, float4 b) {
+  const float2 l = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 h = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(l.x, l.y, h.x, h.y);
+}
+__device__ __forceinline__ float4 p4_mul(float4 a, float4 b) {
+  const float2 l = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 h = __fmul2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(l.x, l.y, h.x, h.y);
+}
+__device__ __forceinline__ float4 p4_scale(float4 a, float s) {
+  const float2 ss = make_float2(s, s);
+  const float2 l = __fmul2_rn(make_float2(a.x, a.y), ss);
+  const float2 h = __fmul2_rn(make_float2(a.z, a.w), ss);
+  return make_float4(l.x, l.y, h.x, h.y);
+}
+__device__ __forceinline__ float4 p4_fma(float4 a, float4 b, float4 c) {  // a*b + c
+  const float2 l = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  const float2 h = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w));
+  return make_float4(l.x, l.y, h.x, h.y);
+}
+__device__ __forceinline__ float4 p4_fma_s(float4 a, float s, float4 c) {  // a*s + c
+  const float2 ss = make_float2(s, s);
+  const float2 l = __ffma2_rn(make_float2(a.x, a.y), ss, make_float2(c.x, c.y));
+  const float2 h = __ffma2_rn(make_float2(a.z, a.w), ss, make_float2(c.z, c.w));
+  return make_float4(l.x, l.y, h.x, h.y);
+}
+// leaky_relu for 0 < slope < 1: max(u, slope*u) has the same value as (u > 0 ? u : slope*u)
+__device__ __forceinline__ float4 p4_leaky(float4 u, float slope) {
+  const float4 l = p4_scale(u, slope);
+  return make_float4(fmaxf(u.x, l.x), fmaxf(u.y, l.y), fmaxf(u.z, l.z), fmaxf(u.w, l.w));
+}
+// two-lane dot-product accumulator: acc2 += a * b (pairwise); reduce with p2_sum
+__device__ __forceinline__ float2 p4_dot_acc(float4 a, float4 b, float2 acc) {
+  acc = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), acc);
+  return __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), acc);
+}
+__device__ __forceinline__ float p2_sum(float2 a) { return a.x + a.y; }
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// Row ring: per-warp shared-memory staging of gathered / streamed feature rows with bulk async
+// copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers.  One elected lane issues the copies
+// of the next edges while the warp computes on the current one, so the bytes in flight per SM are
+// set by the ring depth and not by the register file (a row slice of C fp32 = 3 float4 per lane).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ring_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ring_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void ring_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                          uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void ring_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 24)) __trap();  // a lost copy must fail loudly, not hang the GPU
+  }
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
 
 }  // namespace isg

@@ -390,6 +390,396 @@ gat_edge_bwd_src_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __res
   }
 }
 
+
+// ==========================================================================================
+// fp32 kernels with shared-memory row staging (the ones the fp32 path runs).
+// Every gathered (x_l[src], G[dst]) or streamed (e_proj[e], g_eproj[e]) head-row slice — C floats =
+// 1200 B at C = 300 — is brought in by one cp.async.bulk (UBLKCP) issued by lane 0 into a per-warp
+// ring of RING slots; the copies of edges t+1 .. t+RING are in flight while the warp reduces edge t.
+// The register-load kernels above keep ~2 rows per warp in flight at 128 registers / 25 % occupancy
+// (ncu: 31 % DRAM utilisation, profiles/r1b_ncu_edge_kernels.txt); the ring decouples bytes in flight
+// from registers.  Streamed rows carry an L2 evict_first policy, gathered rows evict_last, so the
+// node-feature rows of the batch stay L2-resident.
+// ==========================================================================================
+constexpr int RING = 4;  // slots per warp (power of two)
+
+struct WarpRing {
+  uint32_t data, bars, slot_bytes, seq;
+  __device__ __forceinline__ void init(uint32_t data_, uint32_t bars_, uint32_t slot_bytes_, int lane) {
+    data = data_; bars = bars_; slot_bytes = slot_bytes_; seq = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < RING; ++r) ring_bar_init(bars + 8u * r, 1);
+      ring_fence_init();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ uint32_t slot(uint32_t s) const { return data + (s & (RING - 1)) * slot_bytes; }
+  __device__ __forceinline__ uint32_t bar(uint32_t s) const { return bars + 8u * (s & (RING - 1)); }
+  // lane 0 only
+  __device__ __forceinline__ void issue2(uint32_t s, const void* a, uint64_t pol_a, const void* b, uint64_t pol_b,
+                                         uint32_t bytes_each) const {
+    ring_expect(bar(s), 2 * bytes_each);
+    ring_copy(slot(s), a, bytes_each, bar(s), pol_a);
+    ring_copy(slot(s) + bytes_each, b, bytes_each, bar(s), pol_b);
+  }
+  __device__ __forceinline__ void issue1(uint32_t s, const void* a, uint64_t pol_a, uint32_t bytes) const {
+    ring_expect(bar(s), bytes);
+    ring_copy(slot(s), a, bytes, bar(s), pol_a);
+  }
+  __device__ __forceinline__ void wait(uint32_t s) const { ring_wait(bar(s), (s / RING) & 1u); }
+};
+
+template <int VPL>
+__device__ __forceinline__ void lds_row(uint32_t addr, int lane, int c4, float4 (&r)[VPL]) {
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    r[k] = (v < c4) ? lds_f4(addr + 16u * v) : f4_zero();
+  }
+}
+
+template <int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 4)
+gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__ xr, int64_t ld_x,
+                         const float* __restrict__ ep, const float* __restrict__ att,
+                         const float* __restrict__ bias, const float* __restrict__ emask,
+                         const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                         const int* __restrict__ eid, float* __restrict__ out, int64_t ld_out,
+                         float* __restrict__ alpha, int64_t NH, int H, int C, float slope) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = C >> 2;
+  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const int64_t HC = (int64_t)H * C;
+  WarpRing ring;
+  ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+
+  for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
+    const int64_t node = wid / H;
+    const int head = (int)(wid - node * H);
+    const int hoff = head * C;
+    float4 xr_v[VPL], att_v[VPL], acc[VPL];
+    load_row<float, VPL>(xr + node * ld_x + hoff, lane, c4, xr_v);
+    load_row_f32<VPL>(att + hoff, lane, c4, att_v);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
+    const int beg = rowptr[node], end = rowptr[node + 1];
+    float m_run = -INFINITY, s_run = 0.f;
+
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_src = 0, my_eid = 0;
+      float my_m = 1.f, my_logit = 0.f;
+      if (lane < cnt) {
+        my_src = nbr[base + lane];
+        my_eid = eid[base + lane];
+        if (MASKED) my_m = emask[my_eid];
+      }
+      const int npre = min(RING, cnt);
+      for (int t = 0; t < npre; ++t) {
+        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (lane == 0)
+          ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff, pol_stream,
+                      row_bytes);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t s = ring.seq + t;
+        const float m0 = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+        const int tn = t + RING < cnt ? t + RING : t;
+        const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
+        const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+        ring.wait(s);
+        float4 x0[VPL], p0[VPL];
+        lds_row<VPL>(ring.slot(s), lane, c4, x0);
+        lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, p0);
+        __syncwarp();  // every lane has read the slot -> it may be refilled
+        if (lane == 0 && t + RING < cnt)
+          ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
+                      row_bytes);
+        float2 part2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          float4 sv = p4_add(p4_add(xr_v[k], x0[k]), p0[k]);
+          if (MASKED) sv = p4_scale(sv, m0);
+          float4 w = p4_leaky(sv, slope);
+          if (MASKED) w = p4_scale(w, m0);
+          part2 = p4_dot_acc(w, att_v[k], part2);
+        }
+        const float part0 = warp_sum(p2_sum(part2));
+        if (part0 > m_run) {  // new running max: rescale (exp(0) = 1 otherwise, so skipping is exact)
+          const float sc = expf(m_run - part0);
+          s_run *= sc;
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) acc[k] = p4_scale(acc[k], sc);
+          m_run = part0;
+        }
+        const float pe = expf(part0 - m_run);
+        s_run += pe;
+        const float pm = MASKED ? pe * m0 : pe;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = p4_fma_s(x0[k], pm, acc[k]);
+        if (lane == t) my_logit = part0;
+      }
+      ring.seq += cnt;
+      if (lane < cnt) alpha[(int64_t)my_eid * H + head] = my_logit;  // raw logit, normalised below
+    }
+
+    const float inv = 1.f / (s_run + 1e-16f);  // PyG softmax epsilon (mgat_v2_conv.py:272)
+    float* orow = out + node * ld_out + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = lane + 32 * k;
+      if (v < c4) {
+        float4 o = f4_scale(acc[k], inv);
+        if (bias != nullptr) o = f4_add(o, Vec4<float>::ld(bias + hoff + 4 * v));
+        Vec4<float>::st(orow + 4 * v, o);
+      }
+    }
+    for (int base = beg; base < end; base += 32) {
+      if (base + lane < end) {
+        const int64_t idx = (int64_t)eid[base + lane] * H + head;
+        alpha[idx] = expf(alpha[idx] - m_run) * inv;
+      }
+    }
+  }
+}
+
+template <int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 4)
+gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const float* __restrict__ xl,
+                             const float* __restrict__ xr, int64_t ld_x, const float* __restrict__ ep,
+                             const float* __restrict__ att, const float* __restrict__ emask,
+                             const float* __restrict__ alpha, const int* __restrict__ rowptr,
+                             const int* __restrict__ nbr, const int* __restrict__ eid, float* __restrict__ g_xr,
+                             int64_t ld_gx, float* __restrict__ g_ep, float* __restrict__ gatt_part,
+                             float* __restrict__ gm_h, int64_t N, int H, int C, float slope) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wid0 = (int64_t)blockIdx.x * EDGE_WARPS + warp;
+  const int64_t nwarps = (int64_t)gridDim.x * EDGE_WARPS;  // multiple of H by construction
+  const int head = (int)(wid0 % H);
+  const int c4 = C >> 2;
+  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const int64_t HC = (int64_t)H * C;
+  const int hoff = head * C;
+  WarpRing ring;
+  ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+
+  float4 att_v[VPL], gatt[VPL];
+  load_row_f32<VPL>(att + hoff, lane, c4, att_v);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) gatt[k] = f4_zero();
+
+  for (int64_t node = wid0 / H; node < N; node += nwarps / H) {
+    float4 G[VPL], xr_v[VPL], gxr[VPL];
+    load_row<float, VPL>(gout + node * ld_g + hoff, lane, c4, G);
+    load_row<float, VPL>(xr + node * ld_x + hoff, lane, c4, xr_v);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) gxr[k] = f4_zero();
+    const int beg = rowptr[node], end = rowptr[node + 1];
+
+    // sweep 1: dot = sum_e a_e m_e <G, x_l[src_e]>  (see the note in gat_edge_bwd_dst_kernel)
+    float dot = 0.f;
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_src = 0;
+      float my_am = 0.f;
+      if (lane < cnt) {
+        my_src = nbr[base + lane];
+        const int e = eid[base + lane];
+        my_am = alpha[(int64_t)e * H + head];
+        if (MASKED) my_am *= emask[e];
+      }
+      const int npre = min(RING, cnt);
+      for (int t = 0; t < npre; ++t) {
+        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        if (lane == 0) ring.issue1(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t s = ring.seq + t;
+        const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+        const int jn = __shfl_sync(ISG_FULL_MASK, my_src, t + RING < cnt ? t + RING : t);
+        ring.wait(s);
+        float4 xv[VPL];
+        lds_row<VPL>(ring.slot(s), lane, c4, xv);
+        __syncwarp();
+        if (lane == 0 && t + RING < cnt) ring.issue1(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, row_bytes);
+        float2 pp2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) pp2 = p4_dot_acc(G[k], xv[k], pp2);
+        const float pp = warp_sum(p2_sum(pp2));  // sweep 2 repeats exactly this sequence
+        dot = fmaf(am, pp, dot);
+      }
+      ring.seq += cnt;
+    }
+
+    // sweep 2: per-edge gradients (recomputes the bit-identical t_e)
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_src = 0, my_eid = 0;
+      float my_m = 1.f, my_a = 0.f, my_gm = 0.f;
+      if (lane < cnt) {
+        my_src = nbr[base + lane];
+        my_eid = eid[base + lane];
+        if (MASKED) my_m = emask[my_eid];
+        my_a = alpha[(int64_t)my_eid * H + head];
+      }
+      const int npre = min(RING, cnt);
+      for (int t = 0; t < npre; ++t) {
+        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (lane == 0)
+          ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff, pol_stream,
+                      row_bytes);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t s = ring.seq + t;
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+        const float a = __shfl_sync(ISG_FULL_MASK, my_a, t);
+        const int tn = t + RING < cnt ? t + RING : t;
+        const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
+        const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+        ring.wait(s);
+        float4 xv[VPL], pv[VPL];
+        lds_row<VPL>(ring.slot(s), lane, c4, xv);
+        lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, pv);
+        __syncwarp();
+        if (lane == 0 && t + RING < cnt)
+          ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
+                      row_bytes);
+        float2 tp2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) tp2 = p4_dot_acc(G[k], xv[k], tp2);
+        const float tt = warp_sum(p2_sum(tp2));
+        const float gl = a * (m * tt - dot);  // d loss / d logit[e,h]
+        const float glmm = MASKED ? gl * m * m : gl;
+        float2 av2 = make_float2(0.f, 0.f);  // sum_c att*v (edge-mask gradient, see below)
+        float* gerow = g_ep + (int64_t)e * HC + hoff;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const float4 sx = p4_add(p4_add(xr_v[k], xv[k]), pv[k]);
+          const float4 u = MASKED ? p4_scale(sx, m) : sx;
+          const float4 v = p4_leaky(u, slope);
+          // g_att += gl * (v*m);  g_s = gl*m*m * att * leaky'(u)
+          gatt[k] = p4_fma_s(MASKED ? p4_scale(v, m) : v, gl, gatt[k]);
+          const float4 lk = make_float4(u.x > 0.f ? 1.f : slope, u.y > 0.f ? 1.f : slope, u.z > 0.f ? 1.f : slope,
+                                        u.w > 0.f ? 1.f : slope);
+          const float4 gs = p4_scale(p4_mul(att_v[k], lk), glmm);
+          gxr[k] = p4_add(gxr[k], gs);
+          if (MASKED) av2 = p4_dot_acc(att_v[k], v, av2);
+          const int v4 = lane + 32 * k;
+          if (v4 < c4) Vec4<float>::st_stream(gerow + 4 * v4, gs);
+        }
+        // d/dm of logit = sum_c att*(dw/dm): w = leaky(s*m)*m  =>  gw*v + gu*s = 2*gl*att*v per channel
+        // (gu*s = gw*m*leaky'(u)*s = gw*v), so the per-head edge-mask gradient is 2*gl*sum_c att*v + t*a.
+        const float gmpart = MASKED ? 2.f * gl * p2_sum(av2) : 0.f;
+        if (MASKED) {
+          const float gm = warp_sum(gmpart) + tt * a;
+          if (lane == t) my_gm = gm;
+        }
+      }
+      ring.seq += cnt;
+      if (MASKED && lane < cnt) gm_h[(int64_t)my_eid * H + head] = my_gm;
+    }
+    float* grow = g_xr + node * ld_gx + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v4 = lane + 32 * k;
+      if (v4 < c4) Vec4<float>::st(grow + 4 * v4, gxr[k]);
+    }
+  }
+  float* prow = gatt_part + wid0 * C;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v4 = lane + 32 * k;
+    if (v4 < c4) Vec4<float>::st(prow + 4 * v4, gatt[k]);
+  }
+}
+
+template <int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32)
+gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const float* __restrict__ g_ep,
+                             const float* __restrict__ emask, const float* __restrict__ alpha,
+                             const int* __restrict__ colptr, const int* __restrict__ nbr,
+                             const int* __restrict__ eid, float* __restrict__ g_xl, int64_t ld_gx, int64_t NH,
+                             int H, int C) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = C >> 2;
+  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const int64_t HC = (int64_t)H * C;
+  WarpRing ring;
+  ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+
+  for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
+    const int64_t node = wid / H;
+    const int head = (int)(wid - node * H);
+    const int hoff = head * C;
+    float4 acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
+    const int beg = colptr[node], end = colptr[node + 1];
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_dst = 0, my_eid = 0;
+      float my_am = 0.f;
+      if (lane < cnt) {
+        my_dst = nbr[base + lane];
+        my_eid = eid[base + lane];
+        my_am = alpha[(int64_t)my_eid * H + head];
+        if (MASKED) my_am *= emask[my_eid];
+      }
+      const int npre = min(RING, cnt);
+      for (int t = 0; t < npre; ++t) {
+        const int i = __shfl_sync(ISG_FULL_MASK, my_dst, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (lane == 0)
+          ring.issue2(ring.seq + t, g_ep + (int64_t)e * HC + hoff, pol_stream, gout + (int64_t)i * ld_g + hoff,
+                      pol_keep, row_bytes);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t s = ring.seq + t;
+        const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+        const int tn = t + RING < cnt ? t + RING : t;
+        const int in_ = __shfl_sync(ISG_FULL_MASK, my_dst, tn);
+        const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+        ring.wait(s);
+        float4 gv[VPL], Gv[VPL];
+        lds_row<VPL>(ring.slot(s), lane, c4, gv);
+        lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, Gv);
+        __syncwarp();
+        if (lane == 0 && t + RING < cnt)
+          ring.issue2(s + RING, g_ep + (int64_t)en * HC + hoff, pol_stream, gout + (int64_t)in_ * ld_g + hoff,
+                      pol_keep, row_bytes);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = p4_add(acc[k], p4_fma_s(Gv[k], am, gv[k]));
+      }
+      ring.seq += cnt;
+    }
+    float* grow = g_xl + node * ld_gx + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v4 = lane + 32 * k;
+      if (v4 < c4) Vec4<float>::st(grow + 4 * v4, acc[k]);
+    }
+  }
+}
+
+inline size_t ring_smem_bytes(int C) { return (size_t)EDGE_WARPS * RING * (2 * (size_t)C * 4 + 8); }
+inline int ring_ctas_per_sm(int C) {
+  int n = (int)((200 * 1024) / ring_smem_bytes(C));
+  return n < 1 ? 1 : (n > 6 ? 6 : n);
+}
+
 // ------------------------------------------------------------------------------------------
 // NodeMaskToEdgeMask (reference sampling/node_edge_masks.py:5-19)
 // ------------------------------------------------------------------------------------------
@@ -429,6 +819,61 @@ inline int bwd_grid_blocks(int64_t N, int H) {
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <int VPL, bool MASKED>
+int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj, const float* att,
+                    const float* bias, const float* emask, const int* dst_ptr, const int* dst_nbr,
+                    const int* dst_eid, void* out, int64_t ld_out, float* alpha, int64_t N, int H, int C,
+                    float slope, cudaStream_t stream) {
+  const int64_t NH = N * H;
+  const size_t smem = ring_smem_bytes(C);
+  auto kern = gat_edge_fwd_ring_kernel<VPL, MASKED>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int64_t blocks = ceil_div(NH, EDGE_WARPS);
+  const int64_t cap = (int64_t)ISG_NUM_SMS * ring_ctas_per_sm(C);
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, EDGE_WARPS * 32, smem, stream>>>(
+      (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, bias, emask, dst_ptr, dst_nbr,
+      dst_eid, (float*)out, ld_out, alpha, NH, H, C, slope);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+template <int VPL, bool MASKED>
+int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r, int64_t ld_x,
+                    const void* e_proj, const float* att, const float* emask, const float* alpha,
+                    const int* dst_ptr, const int* dst_nbr, const int* dst_eid, const int* src_ptr,
+                    const int* src_nbr, const int* src_eid, void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj,
+                    float* g_att, float* g_emask, int64_t N, int64_t E, int H, int C, float slope,
+                    float* gatt_part, float* gm_h, int blocks, cudaStream_t stream) {
+  const size_t smem = ring_smem_bytes(C);
+  auto kd = gat_edge_bwd_dst_ring_kernel<VPL, MASKED>;
+  auto ks = gat_edge_bwd_src_ring_kernel<VPL, MASKED>;
+  cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kd<<<blocks, EDGE_WARPS * 32, smem, stream>>>((const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r,
+                                                ld_x, (const float*)e_proj, att, emask, alpha, dst_ptr, dst_nbr,
+                                                dst_eid, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H,
+                                                C, slope);
+  ISG_CHECK_LAUNCH();
+  gat_att_reduce_kernel<<<dim3(ceil_div(C, 32), H), dim3(32, 8), 0, stream>>>(
+      gatt_part, (int64_t)blocks * EDGE_WARPS, H, C, g_att);
+  ISG_CHECK_LAUNCH();
+  const int64_t NH = N * H;
+  int64_t sb = ceil_div(NH, EDGE_WARPS);
+  const int64_t cap = (int64_t)ISG_NUM_SMS * ring_ctas_per_sm(C);
+  if (sb > cap) sb = cap;
+  ks<<<(unsigned)sb, EDGE_WARPS * 32, smem, stream>>>((const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha,
+                                                      src_ptr, src_nbr, src_eid, (float*)g_xl, ld_gx, NH, H, C);
+  ISG_CHECK_LAUNCH();
+  if (MASKED && E > 0) {
+    gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
+    ISG_CHECK_LAUNCH();
+  }
+  return ISG_OK;
+}
 
 template <typename T, int VPL>
 int launch_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj, const float* att,
@@ -484,6 +929,7 @@ extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, 
                                 float slope, int dtype, void* stream_) {
   if (N < 0 || E < 0 || H <= 0 || C <= 0) return ISG_EINVAL;
   if (C % 4 != 0 || C > 512 || ld_x % 4 != 0 || ld_out % 4 != 0) return ISG_EUNSUPPORTED;
+  if (!(slope >= 0.f && slope <= 1.f)) return ISG_EUNSUPPORTED;  // leaky_relu evaluated as max(u, slope*u)
   if (N == 0) return ISG_OK;
   if (!x_l || !x_r || !att || !dst_ptr || !out || (E > 0 && (!e_proj || !dst_nbr || !dst_eid || !alpha)))
     return ISG_EINVAL;
@@ -493,12 +939,19 @@ extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, 
                           ld_out, alpha, N, H, C, slope, stream)
   const int vpl = vpl_for(C);
   if (dtype == ISG_F32) {
+#define ISG_FWD_RING(V)                                                                                  \
+  return edge_mask ? launch_fwd_ring<V, true>(x_l, x_r, ld_x, e_proj, att, bias, edge_mask, dst_ptr, dst_nbr, \
+                                              dst_eid, out, ld_out, alpha, N, H, C, slope, stream)       \
+                   : launch_fwd_ring<V, false>(x_l, x_r, ld_x, e_proj, att, bias, edge_mask, dst_ptr, dst_nbr, \
+                                               dst_eid, out, ld_out, alpha, N, H, C, slope, stream)
+    if (((uintptr_t)x_l & 15) || ((uintptr_t)x_r & 15) || ((uintptr_t)e_proj & 15)) return ISG_EUNSUPPORTED;
     switch (vpl) {
-      case 1: ISG_FWD_CASE(float, 1);
-      case 2: ISG_FWD_CASE(float, 2);
-      case 3: ISG_FWD_CASE(float, 3);
-      case 4: ISG_FWD_CASE(float, 4);
+      case 1: ISG_FWD_RING(1);
+      case 2: ISG_FWD_RING(2);
+      case 3: ISG_FWD_RING(3);
+      case 4: ISG_FWD_RING(4);
     }
+#undef ISG_FWD_RING
   } else if (dtype == ISG_BF16) {
     switch (vpl) {
       case 1: ISG_FWD_CASE(__nv_bfloat16, 1);
@@ -528,6 +981,7 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
   if (N < 0 || E < 0 || H <= 0 || C <= 0) return ISG_EINVAL;
   if (C % 4 != 0 || C > 512 || ld_x % 4 != 0 || ld_out % 4 != 0 || ld_g % 4 != 0 || ld_gx % 4 != 0)
     return ISG_EUNSUPPORTED;
+  if (!(slope >= 0.f && slope <= 1.f)) return ISG_EUNSUPPORTED;
   if (!g_att) return ISG_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (N == 0) {
@@ -554,12 +1008,24 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
                                        gatt_part, gm_h, stream)
   const int vpl = vpl_for(C);
   if (dtype == ISG_F32) {
+#define ISG_BWD_RING(V)                                                                                        \
+  return edge_mask ? launch_bwd_ring<V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,     \
+                                              dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,     \
+                                              g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,    \
+                                              gatt_part, gm_h, blocks, stream)                               \
+                   : launch_bwd_ring<V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,    \
+                                               dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,    \
+                                               g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,   \
+                                               gatt_part, gm_h, blocks, stream)
+    if (((uintptr_t)x_l & 15) || ((uintptr_t)g_out & 15) || ((uintptr_t)e_proj & 15) || ((uintptr_t)g_eproj & 15))
+      return ISG_EUNSUPPORTED;
     switch (vpl) {
-      case 1: ISG_BWD_CASE(float, 1);
-      case 2: ISG_BWD_CASE(float, 2);
-      case 3: ISG_BWD_CASE(float, 3);
-      case 4: ISG_BWD_CASE(float, 4);
+      case 1: ISG_BWD_RING(1);
+      case 2: ISG_BWD_RING(2);
+      case 3: ISG_BWD_RING(3);
+      case 4: ISG_BWD_RING(4);
     }
+#undef ISG_BWD_RING
   } else if (dtype == ISG_BF16) {
     switch (vpl) {
       case 1: ISG_BWD_CASE(__nv_bfloat16, 1);

@@ -1,0 +1,131 @@
+"""Edge-kernel roofline study (BASELINE.json config 5 and a quick single-size check): times isg_gat_edge_fwd /
+isg_gat_edge_bwd alone on synthetic GQA-shaped graphs, CUDA events on the launching stream, L2 flushed between
+repetitions, and reports achieved algorithmic GB/s (SURVEY.md §8d byte counts) against the measured HBM peak.
+
+    python scripts/bench_edge.py                     # B=256, 20 nodes / 150 edges (the c3 training size)
+    python scripts/bench_edge.py --sweep             # B=4096, (10,50) (20,150) (50,600) (100,1500) (200,4000)
+
+Large points are processed in chunks of whole graphs (the [E,1200] fp32 edge projections of the largest point are
+78 GB); bytes and times are summed over the chunks."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import isg_b200  # noqa: E402,F401
+from isg_b200 import lib as L  # noqa: E402
+from isg_b200 import synth  # noqa: E402
+from isg_b200.graph import GraphIndex  # noqa: E402
+
+H, C = 4, 300
+HC = H * C
+
+
+def edge_bytes(N, E, masked, s=4):
+    fwd = s * HC * (E + 3 * N) + 4 * E * H + (4 * E if masked else 0) + 4 * (2 * E + N + 1) + 2 * s * HC
+    bwd = s * HC * (2 * E + 5 * N) + 4 * E * H + (8 * E if masked else 0) + 4 * (4 * E + 2 * N + 2) + 2 * s * HC
+    return fwd, bwd
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7):
+    dev = torch.device("cuda")
+    lib = L.load()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tot = dict(fwd_ms=0.0, bwd_ms=0.0, fwd_b=0, bwd_b=0, N=0, E=0)
+    done = 0
+    while done < B:
+        nb = min(chunk_graphs, B - done)
+        g = synth.make_topology(nb, mean_nodes=mn, mean_edges=me, seed=seed + done, max_nodes=None)
+        ei, batch = g["edge_index"].to(dev), g["batch"].to(dev)
+        N, E = int(batch.numel()), int(ei.shape[1])
+        gi = GraphIndex(ei, batch, nb)
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        xlr = torch.randn(N, 2 * HC, device=dev, generator=gen)
+        ep = torch.randn(E, HC, device=dev, generator=gen)
+        att = torch.randn(HC, device=dev, generator=gen) * 0.1
+        bias = torch.zeros(HC, device=dev)
+        em = (torch.rand(E, device=dev, generator=gen) > 0.3).float() if masked else None
+        out = torch.empty(N, HC, device=dev)
+        alpha = torch.empty(E, H, device=dev)
+        gout = torch.randn(N, HC, device=dev, generator=gen)
+        gxlr = torch.empty(N, 2 * HC, device=dev)
+        gep = torch.empty(E, HC, device=dev)
+        gatt = torch.empty(HC, device=dev)
+        gem = torch.empty(E, device=dev) if masked else None
+        wsb = lib.isg_gat_edge_bwd_workspace_bytes(N, E, H, C)
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        st = L.stream()
+
+        def fwd():
+            L.call("isg_gat_edge_fwd", xlr.data_ptr(), xlr.data_ptr() + HC * 4, 2 * HC, ep.data_ptr(), att.data_ptr(),
+                   bias.data_ptr(), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), out.data_ptr(),
+                   HC, alpha.data_ptr(), N, E, H, C, 0.2, 0, st)
+
+        def bwd():
+            L.call("isg_gat_edge_bwd", gout.data_ptr(), HC, xlr.data_ptr(), xlr.data_ptr() + HC * 4, 2 * HC,
+                   ep.data_ptr(), att.data_ptr(), bias.data_ptr(), L.ptr(em), alpha.data_ptr(), out.data_ptr(), HC,
+                   L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr), L.ptr(gi.src_nbr),
+                   L.ptr(gi.src_eid), gxlr.data_ptr(), gxlr.data_ptr() + HC * 4, 2 * HC, gep.data_ptr(),
+                   gatt.data_ptr(), L.ptr(gem), N, E, H, C, 0.2, 0, ws.data_ptr(), wsb, st)
+
+        for fn, key in ((fwd, "fwd_ms"), (bwd, "bwd_ms")):
+            for _ in range(3):
+                fn()
+            times = []
+            for _ in range(reps):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                times.append(a.elapsed_time(b))
+            times.sort()
+            tot[key] += times[len(times) // 2]
+        fb, bb = edge_bytes(N, E, masked)
+        tot["fwd_b"] += fb
+        tot["bwd_b"] += bb
+        tot["N"] += N
+        tot["E"] += E
+        done += nb
+        del xlr, ep, out, alpha, gout, gxlr, gep, ws, gi
+        torch.cuda.empty_cache()
+    return tot
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--masked", action="store_true")
+    args = ap.parse_args()
+    pk, src = peak()
+    points = [(4096, 10, 50), (4096, 20, 150), (4096, 50, 600), (4096, 100, 1500), (4096, 200, 4000)] \
+        if args.sweep else [(256, 20, 150), (1024, 20, 150)]
+    for B, mn, me in points:
+        # keep e_proj + g_eproj of one chunk under ~40 GB
+        chunk = max(1, min(B, int(40e9 / (2 * 4 * HC * me))))
+        t = run_point(B, mn, me, args.masked, args.reps if B * me < 2e6 else max(3, args.reps // 4), chunk)
+        f = t["fwd_b"] / (t["fwd_ms"] * 1e-3) / 1e9
+        b = t["bwd_b"] / (t["bwd_ms"] * 1e-3) / 1e9
+        print(json.dumps({"graphs": B, "mean_nodes": mn, "mean_edges": me, "N": t["N"], "E": t["E"],
+                          "masked": args.masked, "fwd_ms": round(t["fwd_ms"], 4), "bwd_ms": round(t["bwd_ms"], 4),
+                          "fwd_GBps": round(f, 1), "bwd_GBps": round(b, 1), "fwd_frac": round(f / pk, 4),
+                          "bwd_frac": round(b / pk, 4), "peak_GBps": pk, "peak_source": src,
+                          "chunk_graphs": chunk}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
