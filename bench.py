@@ -96,6 +96,38 @@ def edge_bytes(N, E, masked, s=4):
     return fwd, bwd
 
 
+def edge_study(points=((4096, 20, 150),), reps=10):
+    """BASELINE config 5 (edge-kernel roofline study), one point by default: the fused edge kernels timed alone
+    at batch 4096 (scripts/bench_edge.py runs the whole 10-200 objects / 50-4000 edges sweep)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_edge", os.path.join(ROOT, "scripts", "bench_edge.py"))
+    be = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(be)
+    pk, _ = be.peak()
+    out = []
+    for B, mn, me in points:
+        t = be.run_point(B, mn, me, False, reps, B)
+        f = t["fwd_b"] / (t["fwd_ms"] * 1e-3) / 1e9
+        b = t["bwd_b"] / (t["bwd_ms"] * 1e-3) / 1e9
+        out.append({"graphs": B, "mean_nodes": mn, "mean_edges": me, "N": t["N"], "E": t["E"],
+                    "fwd_ms": round(t["fwd_ms"], 4), "bwd_ms": round(t["bwd_ms"], 4), "fwd_GBps": round(f, 1),
+                    "bwd_GBps": round(b, 1), "fwd_frac": round(f / pk, 4), "bwd_frac": round(b / pk, 4)})
+    return out
+
+
+def measured_traffic(kernel_key):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture
+    (profiles/edge_traffic.json, written by scripts/ncu_summary.py --traffic); None if absent."""
+    p = os.path.join(ROOT, "profiles", "edge_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
+
+
 def make_inputs(B, seed):
     from isg_b200 import synth
 
@@ -295,7 +327,8 @@ def main_isg(args, rank, world, local_rank):
         alg = (3 * bwd_b_un + bwd_b_m) / 4.0  # 3 unmasked layers + 1 masked layer per step
         ach = alg / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst + att_reduce + gat_edge_bwd_src)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": measured_traffic("isg_gat_edge_bwd"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
                 "launches_timed": calls}
     elif "isg_gat_edge_fwd" in tsum:
@@ -304,7 +337,8 @@ def main_isg(args, rank, world, local_rank):
         alg = (3 * fwd_b_un + fwd_b_m) / 4.0
         ach = alg / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "isg_gat_edge_fwd (gat_edge_fwd_kernel)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("isg_gat_edge_fwd"),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms, "launches_timed": calls}
     edge_fwd = None
     if "isg_gat_edge_fwd" in tsum:
@@ -319,6 +353,11 @@ def main_isg(args, rank, world, local_rank):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"oracle/isg_oracle.py OracleMGAT on {sample_B}-graph batches (N={r['N']}, E={r['E']}) of "
                          f"the same workload, 3 steps after 1 warm-up, {r['ms_per_step']:.0f} ms/step"}
+    study = None
+    if world == 1 and not args.no_edge_study:
+        del resident, flush
+        torch.cuda.empty_cache()
+        study = edge_study()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -337,6 +376,7 @@ def main_isg(args, rank, world, local_rank):
         "clocks": clk,
         "roofline": roof,
         "edge_fwd": edge_fwd,
+        "edge_roofline_study": study,
         "cpu_baseline": cpu,
     }
     if args.breakdown:
@@ -356,6 +396,7 @@ def main():
     ap.add_argument("--impl", default="isg", choices=["isg", "reference"])
     ap.add_argument("--breakdown", action="store_true", help="add per-entry-point CUDA-event times to the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-edge-study", action="store_true", help="skip the batch-4096 edge-kernel roofline point")
     ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2],
                     help="projection arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32 (default), 2 tcgen05 1xTF32")
     args = ap.parse_args()

@@ -1,31 +1,35 @@
 // linear_tc.cu — kernel (d), modes 1 and 2: the dense projections on the 5th-gen tensor cores.
 //
 //   mode 1  3xTF32 split (fp32-grade):  D = A_hi*B_hi  (+)  [A_hi*B_lo + A_lo*B_hi]
-//           the big product and the two correction products accumulate in SEPARATE TMEM
-//           accumulators (the tensor core truncates on accumulate, so error grows with the number of
-//           accumulation steps: keeping the corrections off the main chain cuts that 3x) and are
-//           added once, in fp32 round-to-nearest, by the epilogue
-//   mode 2  single-pass TF32 (~2^-11 per product; reported separately, not the parity config)
+//   mode 2  single-pass TF32 (~2^-11 per product; reported separately, not the parity configuration)
 //
-// One persistent, warp-specialised kernel (one CTA per SM, 384 threads) covers the three products
-// of a Linear layer (reference call sites: models/mgat_v2_conv.py:177,181,259, models/mgat.py:156,
+// Numerics of mode 1.  kind::tf32 ignores the low 13 mantissa bits of its fp32 operands, so the raw
+// tile already is `hi`; `lo = x - hi` is exact.  The tensor core TRUNCATES (rounds toward zero) when it
+// adds an MMA result into the TMEM accumulator — measured on B200: -0.5 ulp per accumulation step,
+// error growing linearly with the reduction length (scripts/diag_tc_rounding.py).  Two measures keep the
+// result at fp32-FFMA accuracy: (i) the two correction products go to a SEPARATE accumulator, so only
+// one MMA per k-step touches the main chain; (ii) the main accumulator is drained every DRAIN_KB
+// k-blocks (K = 128): the epilogue warps add the partial into fp32 registers with round-to-nearest and
+// the next chunk restarts from zero in the other TMEM stage.  Chains are 16 steps long instead of K/8.
+//
+// One persistent, warp-specialised kernel (one CTA per SM, 512 threads) covers the three products of a
+// Linear layer (reference call sites: models/mgat_v2_conv.py:177,181,259, models/mgat.py:156,
 // models/masking.py:137,152 and their autograd backward):
 //   fwd    y[m,n]  = sum_k x[m,k]  W[n,k]    A K-major,  B K-major
 //   dgrad  gx[m,k] = sum_n gy[m,n] W[n,k]    A K-major,  B MN-major (W read in place, no transpose)
 //   wgrad  gW[n,k] = sum_m gy[m,n] x[m,k]    A MN-major, B MN-major, deterministic split over m
 //
-//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of raw fp32 operand tiles
-//   warps 4-7   splitters (mode 1): lo = x - (x & ~0x1fff) (exact) into a twin buffer at the same
-//               (swizzled) offsets, fence.proxy.async, mbarrier arrive.  The raw tile serves as `hi`:
-//               kind::tf32 ignores the low 13 mantissa bits (verified: bit-identical results with an
-//               explicit hi write-back)
-//   warp 1      one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN<=256, K=8) into TMEM and
-//               tcgen05.commit's the stage back to the producer / the accumulator to the epilogue
-//   warps 8-11  epilogue: tcgen05.ld 32x32b -> padded smem transpose -> coalesced float4 rows with
-//               the fused bias / GELU / pre-activation side output / GELU-derivative / accumulate
-//   warp 2      TMEM allocation (512 columns = two accumulator stages x {main, correction} x BN<=128
-//               in mode 1, two stages x BN<=256 in mode 2; the epilogue of tile i overlaps the MMAs
-//               of tile i+1)
+//   warp 0       TMA producer: cp.async.bulk.tensor.2d of raw fp32 operand tiles (BK = 16 floats per
+//                k-block: 64-byte swizzle for K-major, 128B/32B-atom swizzle for MN-major operands)
+//   warps 4-7    splitters (mode 1): lo = x - (x & ~0x1fff) into a twin buffer at the same swizzled
+//                offsets (all loads of a stage issued before the stores), fence.proxy.async, arrive
+//   warp 1       one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN<=128, K=8) into
+//                TMEM; tcgen05.commit releases smem stages and publishes accumulator chunks
+//   warps 8-15   epilogue: tcgen05.ld 32x32b of the chunk partials into register accumulators (two
+//                column halves x four lane quarters), at tile end + correction accumulator, then a padded
+//                smem transpose and coalesced float4 rows with the fused bias / exact GELU /
+//                pre-activation side output / GELU-derivative / accumulate
+//   warp 2       TMEM allocation: 512 columns = main[2 chunk stages] + correction[2 tile stages], 128 each
 #include <cuda.h>
 
 #include "common.cuh"
@@ -35,19 +39,21 @@ namespace {
 
 using namespace isg;
 
-constexpr int BM = 128;       // UMMA M (cta_group::1)
-constexpr int BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int UMMA_K = 8;     // kind::tf32
-constexpr int NTHREADS = 384;
-constexpr int MAX_BN = 256;
-constexpr int A_TILE_BYTES = BM * BK * 4;         // 16 KiB
-constexpr int EPI_ROW_BYTES = 144;                // 32 floats + 16 B pad (conflict-free float4 transpose)
-constexpr int EPI_BYTES = 4 * 32 * EPI_ROW_BYTES;  // 4 epilogue warps
-constexpr int BAR_BYTES = 256;
+constexpr int BM = 128;      // UMMA M (cta_group::1)
+constexpr int BK = 16;       // fp32 elements per k-block
+constexpr int UMMA_K = 8;    // kind::tf32
+constexpr int MAX_BN = 128;
+constexpr int DRAIN_KB = 8;  // k-blocks per accumulator chunk (K = 128 -> 16 truncating steps per chain)
+constexpr int NTHREADS = 512;
+constexpr int A_TILE_BYTES = BM * BK * 4;          // 8 KiB
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_ROW_BYTES = 144;                 // 32 floats + 16 B pad (conflict-free float4 transpose)
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_ROW_BYTES;
+constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t CORR_COL = 128;  // mode 1: correction accumulator sits 128 columns after the main one
+constexpr uint32_t TM_MAIN = 0, TM_CORR = 256;     // column bases; stage s adds 128*s
 
 enum Epi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_PLAIN = 2 };
 
@@ -69,8 +75,8 @@ struct TcArgs {
   const float* Zprev;
   int act;
   int accumulate;
-  int split3;    // 1: 3xTF32 (hi/lo split in smem, two accumulators), 0: single-pass TF32
-  int write_hi;  // mode 1: write the truncated hi part back in place (0 relies on the MMA ignoring the low 13 bits)
+  int split3;    // 1: 3xTF32 (lo planes in smem, correction accumulator), 0: single-pass TF32
+  int write_hi;  // verification only: also write the truncated hi back (results are bit-identical)
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -140,7 +146,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32"
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
@@ -150,21 +156,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
 }
 
 // shared-memory matrix descriptors (sm_100 format: version 1)
-//   K-major : SWIZZLE_128B (2): rows of 128 B (32 fp32 along K), 8-row groups 1024 B apart (SBO);
-//             LBO unused.
+//   K-major : SWIZZLE_64B (4): rows of 64 B (BK = 16 fp32 along K), 8-row groups 512 B apart (SBO).
 //   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (1) — 32-byte swizzle chunks, the
 //             pattern TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  A tile is a row of
 //             32-wide MN chunks, each [BK k-rows][128 B]: chunk stride = LBO = BK*128 B, groups of
 //             4 k-rows 512 B apart (SBO).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
   const uint64_t lbo = mn_major ? (uint64_t)((BK * 128) >> 4) : 1ull;
-  const uint64_t sbo = mn_major ? (512 >> 4) : (1024 >> 4);
-  const uint64_t layout = mn_major ? 1ull : 2ull;
+  const uint64_t sbo = 512 >> 4;
+  const uint64_t layout = mn_major ? 1ull : 4ull;
   return (uint64_t)((saddr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ float4 hi_part(float4 v) {
+  return make_float4(__uint_as_float(__float_as_uint(v.x) & 0xffffe000u),
+                     __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                     __uint_as_float(__float_as_uint(v.z) & 0xffffe000u),
+                     __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+}
+__device__ __forceinline__ float4 lo_part(float4 v) {
+  const float4 h = hi_part(v);
+  return make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -179,22 +199,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int S = g.stages;
   const int BN = g.BN;
-  const uint32_t b_tile_bytes = (uint32_t)BN * 128u;
-  // stage layout: mode 1 [A_hi 16K][A_lo 16K][B_hi BN*128][B_lo BN*128]; mode 2 [A 16K][B BN*128]
+  const uint32_t b_tile_bytes = (uint32_t)BN * (BK * 4);
+  // stage layout: mode 1 [A 8K][A_lo 8K][B BN*64][B_lo BN*64]; mode 2 [A 8K][B BN*64]
   const uint32_t off_a_lo = A_TILE_BYTES;
   const uint32_t off_b_hi = g.split3 ? 2 * A_TILE_BYTES : A_TILE_BYTES;
   const uint32_t off_b_lo = off_b_hi + b_tile_bytes;
   const uint32_t epi_base = smem_base + (uint32_t)S * g.stage_bytes;
   const uint32_t bar_base = epi_base + EPI_BYTES;
-  // barriers: full[S], conv[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto conv_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 4);
-  volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  auto mfull_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + s); };
+  auto mempty_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 2 + s); };
+  auto cfull_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 4 + s); };
+  auto cempty_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 6 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 8);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
@@ -205,8 +225,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(mfull_bar(s), 1);
+      mbar_init(mempty_bar(s), EPI_WARPS);
+      mbar_init(cfull_bar(s), 1);
+      mbar_init(cempty_bar(s), EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -223,6 +245,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
   const int tiles_mn = g.m_tiles * g.n_tiles;
+  auto tile_kb = [&](int t) {
+    const int split = t / tiles_mn;
+    const int64_t r_beg = (int64_t)split * g.r_chunk;
+    const int64_t r_end = min(g.R, r_beg + g.r_chunk);
+    return (int)((r_end - r_beg + BK - 1) / BK);
+  };
 
   if (threadIdx.x == 0) {
     // ===================================================================== TMA producer
@@ -233,8 +261,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int64_t r_beg = (int64_t)split * g.r_chunk;
-      const int64_t r_end = min(g.R, r_beg + g.r_chunk);
-      const int num_kb = (int)((r_end - r_beg + BK - 1) / BK);
+      const int num_kb = tile_kb(t);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
@@ -264,69 +291,79 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t b_kstep = B_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);
     int stage = 0;
     uint32_t phase = 0;
+    uint32_t gchunk = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int split = t / tiles_mn;
-      const int64_t r_beg = (int64_t)split * g.r_chunk;
-      const int64_t r_end = min(g.R, r_beg + g.r_chunk);
-      const int num_kb = (int)((r_end - r_beg + BK - 1) / BK);
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tempty_bar(as), aphase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)as * MAX_BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(g.split3 ? conv_bar(stage) : full_bar(stage), phase);
+      const int num_kb = tile_kb(t);
+      const int tp = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      const uint32_t d_corr = tmem_base + TM_CORR + 128u * tp;
+      if (g.split3) {
+        mbar_wait(cempty_bar(tp), tphase ^ 1u);
         tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
-        const uint64_t a_hi = make_desc(sa, A_MN), a_lo = make_desc(sa + off_a_lo, A_MN);
-        const uint64_t b_hi = make_desc(sa + off_b_hi, B_MN), b_lo = make_desc(sa + off_b_lo, B_MN);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t ak = (uint64_t)(a_kstep * k), bk = (uint64_t)(b_kstep * k);
-          const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-          if (g.split3) {
-            umma_tf32(d_tmem, a_hi + ak, b_hi + bk, idesc, first);
-            umma_tf32(d_tmem + CORR_COL, a_hi + ak, b_lo + bk, idesc, first);
-            umma_tf32(d_tmem + CORR_COL, a_lo + ak, b_hi + bk, idesc, 1u);
-          } else {
-            umma_tf32(d_tmem, a_hi + ak, b_hi + bk, idesc, first);
-          }
-        }
-        umma_commit(empty_bar(stage));  // frees the smem stage once the MMAs above have read it
-        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      for (int kb0 = 0; kb0 < num_kb; kb0 += DRAIN_KB, ++gchunk) {
+        const int ms = gchunk & 1;
+        const uint32_t mphase = (gchunk >> 1) & 1u;
+        mbar_wait(mempty_bar(ms), mphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + TM_MAIN + 128u * ms;
+        const int kb1 = min(num_kb, kb0 + DRAIN_KB);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(g.split3 ? conv_bar(stage) : full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
+          const uint64_t a_hi = make_desc(sa, A_MN), a_lo = make_desc(sa + off_a_lo, A_MN);
+          const uint64_t b_hi = make_desc(sa + off_b_hi, B_MN), b_lo = make_desc(sa + off_b_lo, B_MN);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ak = (uint64_t)(a_kstep * k), bk = (uint64_t)(b_kstep * k);
+            umma_tf32(d_main, a_hi + ak, b_hi + bk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (g.split3) {
+              umma_tf32(d_corr, a_hi + ak, b_lo + bk, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_tf32(d_corr, a_lo + ak, b_hi + bk, idesc, 1u);
+            }
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage once the MMAs above have read it
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(mfull_bar(ms));  // chunk partial complete -> epilogue drains it
+      }
+      if (g.split3) umma_commit(cfull_bar(tp));
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================================================================== hi/lo splitters (mode 1)
+    // ===================================================================== lo-plane splitters (mode 1)
     if (g.split3) {
       const int tid = threadIdx.x - 128;
+      const int nb = (int)(b_tile_bytes / 16);  // <= 512 float4
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int split = t / tiles_mn;
-        const int64_t r_beg = (int64_t)split * g.r_chunk;
-        const int64_t r_end = min(g.R, r_beg + g.r_chunk);
-        const int num_kb = (int)((r_end - r_beg + BK - 1) / BK);
+        const int num_kb = tile_kb(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          uint8_t* st = smem_gen + (size_t)stage * g.stage_bytes;
-          // A: 1024 float4, B: BN*8 float4; lo lives at the same swizzled offset of the twin buffer
-          const int na = A_TILE_BYTES / 16, nb = (int)(b_tile_bytes / 16);
-          for (int i = tid; i < na + nb; i += 128) {
-            const bool is_a = i < na;
-            uint8_t* hi_p = is_a ? st + (size_t)i * 16 : st + off_b_hi + (size_t)(i - na) * 16;
-            uint8_t* lo_p = hi_p + (is_a ? (size_t)off_a_lo : (size_t)b_tile_bytes);
-            const float4 v = *reinterpret_cast<const float4*>(hi_p);
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-            if (g.write_hi) *reinterpret_cast<float4*>(hi_p) = h;
-            *reinterpret_cast<float4*>(lo_p) = l;
+          const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
+          float4 va[4], vb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) va[u] = lds_f4(sa + (uint32_t)(tid + 128 * u) * 16u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = tid + 128 * u;
+            vb[u] = i < nb ? lds_f4(sa + off_b_hi + (uint32_t)i * 16u) : f4_zero();
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t o = (uint32_t)(tid + 128 * u) * 16u;
+            sts_f4(sa + off_a_lo + o, lo_part(va[u]));
+            if (g.write_hi) sts_f4(sa + o, hi_part(va[u]));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = tid + 128 * u;
+            if (i < nb) {
+              sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(vb[u]));
+              if (g.write_hi) sts_f4(sa + off_b_hi + (uint32_t)i * 16u, hi_part(vb[u]));
+            }
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
           mbar_arrive(conv_bar(stage));
@@ -335,9 +372,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp >= 8) {
-    // ===================================================================== epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* stg = smem_gen + (size_t)S * g.stage_bytes + (size_t)q * 32 * EPI_ROW_BYTES;
+    // ===================================================================== epilogue (8 warps)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 8) >> 2;  // column half: [64*half, 64*half + 64)
+    const uint32_t stg = epi_base + (uint32_t)(warp - 8) * 32 * EPI_ROW_BYTES;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    uint32_t gchunk = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int split = t / tiles_mn, rem = t - split * tiles_mn;
@@ -345,33 +385,65 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t m0 = (int64_t)m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
       const int n_lim = min(g.cols, n0 + BN);
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int num_kb = tile_kb(t);
+      const int tp = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       float* Cb = g.C + (int64_t)split * g.c_split_stride;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * MAX_BN;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        if (g.split3) {
-          uint32_t rc[32];
-          tmem_ld32(taddr + CORR_COL + (uint32_t)c0, rc);
+      float acc[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += DRAIN_KB, ++gchunk) {
+        const int ms = gchunk & 1;
+        const uint32_t mphase = (gchunk >> 1) & 1u;
+        mbar_wait(mfull_bar(ms), mphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_sel + TM_MAIN + 128u * ms + 64u * half;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // one 32-column load at a time keeps the epilogue under 128 registers
+          uint32_t r[32];
+          tmem_ld32_nowait(taddr + 32u * hh, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[32 * hh + j] += __uint_as_float(r[j]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mempty_bar(ms));  // this warp is done with the chunk's TMEM stage
+      }
+      if (g.split3) {
+        mbar_wait(cfull_bar(tp), tphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_sel + TM_CORR + 128u * tp + 64u * half;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tmem_ld32_nowait(taddr + 32u * hh, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[32 * hh + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cempty_bar(tp));
+      }
+      // ---- store: 2 x (32 rows x 32 columns) through the padded staging tile
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = 64 * half + 32 * cc;
+        if (n0 + c0 >= n_lim) continue;  // warp-uniform
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * EPI_ROW_BYTES + j * 16) =
-              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          sts_f4(stg + lane * EPI_ROW_BYTES + j * 16,
+                 make_float4(acc[32 * cc + 4 * j], acc[32 * cc + 4 * j + 1], acc[32 * cc + 4 * j + 2],
+                             acc[32 * cc + 4 * j + 3]));
         __syncwarp();
         const int col = n0 + c0 + (lane & 7) * 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + (lane >> 3);
           const int64_t row = m0 + rl;
-          float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_ROW_BYTES + (lane & 7) * 16);
+          float4 v = lds_f4(stg + rl * EPI_ROW_BYTES + (lane & 7) * 16);
           if (row < g.rows && col < n_lim) {
             if (EPI == EPI_FWD) {
               if (g.bias) v = f4_add(v, Vec4<float>::ld(g.bias + col));
@@ -389,8 +461,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(as));  // 128 epilogue threads -> accumulator stage reusable
     }
   }
 
@@ -419,8 +489,8 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor map: dim0 (contiguous) x dim1 with row pitch `ld` elements; 128-byte swizzle,
-// out-of-range elements read as zero (this is what pads K = 300 to the 32-wide k-blocks).
+// 2-D fp32 tensor map: dim0 (contiguous) x dim1 with row pitch `ld` elements; out-of-range elements
+// read as zero (this is what pads K = 300 to the 16-wide k-blocks).
 int make_map(CUtensorMap* m, const float* base, int64_t dim0, int64_t dim1, int64_t ld, int box0, int box1,
              bool mn_major) {
   EncodeTiledFn enc = encode_fn();
@@ -432,26 +502,25 @@ int make_map(CUtensorMap* m, const float* base, int64_t dim0, int64_t dim1, int6
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? ISG_OK : ISG_EINVAL;
 }
 
-int pick_bn(int cols, bool mn_major, int max_bn) {
+int pick_bn(int cols, bool mn_major) {
   const int q = mn_major ? 32 : 16;
-  const int parts = (cols + max_bn - 1) / max_bn;
+  const int parts = (cols + MAX_BN - 1) / MAX_BN;
   int bn = (cols + parts - 1) / parts;
   bn = ((bn + q - 1) / q) * q;
-  return bn > max_bn ? max_bn : bn;
+  return bn > MAX_BN ? MAX_BN : bn;
 }
 
 template <bool A_MN, bool B_MN, int EPI>
 int launch(const isg::TcGemm& p, cudaStream_t stream) {
   TcArgs g{};
   g.C = p.C; g.ldc = p.ldc; g.rows = p.rows; g.cols = p.cols; g.R = p.R;
-  g.BN = pick_bn(p.cols, B_MN, p.split3 ? 128 : MAX_BN);
-  g.stage_bytes = (p.split3 ? 2 : 1) * (A_TILE_BYTES + g.BN * 128);
+  g.BN = pick_bn(p.cols, B_MN);
+  g.stage_bytes = (p.split3 ? 2 : 1) * (A_TILE_BYTES + g.BN * BK * 4);
   g.stages = (SMEM_LIMIT - 1024 - EPI_BYTES - BAR_BYTES) / g.stage_bytes;
   if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
   if (g.stages < 2) return ISG_EUNSUPPORTED;
@@ -462,8 +531,7 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   g.c_split_stride = p.c_split_stride;
   g.bias = p.bias; g.Z = p.Z; g.ldz = p.ldz; g.Zprev = p.Zprev; g.act = p.act; g.accumulate = p.accumulate;
   g.split3 = p.split3 ? 1 : 0;
-  g.write_hi = p.split3 == 3 ? 1 : 0;  // measured on B200: kind::tf32 ignores the low 13 mantissa bits, so the
-                                        // raw fp32 tile already acts as `hi` (identical results with the write-back)
+  g.write_hi = p.split3 == 3 ? 1 : 0;
   if (p.rows >= (1ll << 31) || p.R >= (1ll << 31)) return ISG_EUNSUPPORTED;  // TMA coordinates are int32
 
   CUtensorMap ma, mb;
@@ -499,21 +567,11 @@ int tc_gemm(const TcGemm& p, void* stream_) {
 }
 
 int tc_wgrad_splits(int64_t M, int Nout, int K, int64_t* r_chunk) {
-  // Splits bound the length of one tensor-core accumulation chain (truncating accumulate): target
-  // <= 1024 reduction rows per split; the partials are then summed in fp32 round-to-nearest, in a
-  // fixed order.  At least one wave of tiles, at most 64 splits.
-  const int tiles = ceil_div(Nout, BM) * ceil_div(K, pick_bn(K, true, 128));
-  int64_t s = (M + 1023) / 1024;
-  const int64_t one_wave = ISG_NUM_SMS / tiles;
-  if (s < one_wave) s = one_wave;
-  // wave quantisation: a few tiles past a whole number of waves cost a full extra wave
-  const int64_t waves = (s * tiles) / ISG_NUM_SMS;
-  if (waves >= 1 && waves <= 3 && (s * tiles) % ISG_NUM_SMS != 0 &&
-      (s * tiles) % ISG_NUM_SMS < ISG_NUM_SMS / 3) {
-    const int64_t s_fit = (waves * ISG_NUM_SMS) / tiles;
-    if (s_fit >= 1 && (M + s_fit - 1) / s_fit <= 1536) s = s_fit;
-  }
-  const int64_t max_by_len = (M + 8 * BK - 1) / (8 * BK);  // >= 8 k-blocks per split
+  // The reduction over rows is split for parallelism only (accuracy is handled by the in-kernel chunk
+  // drain): one wave of tiles, every split at least 32 k-blocks long; partials are summed in a fixed order.
+  const int tiles = ceil_div(Nout, BM) * ceil_div(K, pick_bn(K, true));
+  int64_t s = ISG_NUM_SMS / tiles;
+  const int64_t max_by_len = (M + 32 * BK - 1) / (32 * BK);
   if (s > max_by_len) s = max_by_len;
   if (s < 1) s = 1;
   if (s > 64) s = 64;

@@ -63,6 +63,8 @@ class MGAT(torch.nn.Module):
     def forward(self, x, edge_index, instr_vectors, global_language_feats, edge_attr, batch, return_masks=False,
                 explainer=False, explainer_stage=False, expl_bypass_x=False):
         L.require_cuda(x, edge_index, batch, edge_attr)
+        ops.join_side_stream()  # no-op unless a previous backward pass was interrupted before its join ran
+        ops.allow_side_stream(all(p.grad is None for p in self.parameters()))
         gi = get_graph_index(edge_index, batch, instr_vectors.shape[1])
         h = x
         mask = None

@@ -90,17 +90,23 @@ class MaskingGATv2Conv(torch.nn.Module):
         if self.mask.masking_threshold != 1.0:  # :161
             mask = self.mask.forward_fused(x, imle_att, gi)  # :166-168 (double gather handled in-kernel)
             edge_mask = ops.NodeMaskToEdgeMaskFn.apply(mask, gi)  # :169-171
-        x_l = ops.linear(x, self.lin_l.weight, self.lin_l.bias)  # :177
-        x_r = x_l if self.share_weights else ops.linear(x, self.lin_r.weight, self.lin_r.bias)  # :181
+        # :177,181 — lin_l and lin_r as ONE projection with the stacked weights [W_l; W_r] (their parameters
+        # stay separate tensors; torch.cat's backward hands each its slice of the fused weight gradient)
+        w_r, b_r = (self.lin_l.weight, self.lin_l.bias) if self.share_weights else (self.lin_r.weight, self.lin_r.bias)
+        w_lr = torch.cat([self.lin_l.weight, w_r], dim=0)
+        b_lr = torch.cat([self.lin_l.bias, b_r], dim=0) if self.lin_l.bias is not None else None
+        xlr = ops.linear(x, w_lr, b_lr)
         if e_proj is None:
             e_proj = ops.linear(edge_attr, self.lin_edge.weight, None)  # :259 (inside message() in the reference)
         dbg = getattr(self, "debug_tensors", None)
         if dbg is not None:
-            for name, t in (("xg", x), ("x_l", x_l), ("x_r", x_r), ("e_proj", e_proj)):
+            HC = H * self.out_channels
+            for name, t in (("xg", x), ("xlr", xlr), ("e_proj", e_proj)):
                 if t.requires_grad:
                     t.retain_grad()
                 dbg[name] = t
-        out, alpha = ops.GatEdge.apply(x_l, x_r, e_proj, self.att, self.bias, edge_mask, gi, H,
+            dbg["x_l"], dbg["x_r"] = xlr[:, :HC], xlr[:, HC:]
+        out, alpha = ops.GatEdge.apply(xlr, e_proj, self.att, self.bias, edge_mask, gi, H,
                                        float(self.negative_slope))
         if isinstance(return_attention_weights, bool):
             return out, mask, (edge_index, alpha)

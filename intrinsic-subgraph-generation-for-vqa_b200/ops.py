@@ -8,8 +8,9 @@ import torch
 from . import lib as L
 
 _DEBUG_EDGE_BWD = None  # diagnostics: set to a list to capture GatEdge.backward inputs/outputs
-# projection arithmetic: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-grade), 2 = tcgen05 single-pass TF32
-_GEMM_MODE = int(os.environ.get("ISG_GEMM_MODE", "0"))
+# projection arithmetic: 1 = tcgen05 3xTF32 with bounded accumulation chains (default; measured 6.5e-7 relative
+# against fp64, i.e. at or below the FFMA kernel's error), 0 = fp32 FFMA, 2 = tcgen05 single-pass TF32 (~8e-4)
+_GEMM_MODE = int(os.environ.get("ISG_GEMM_MODE", "1"))
 
 
 def set_gemm_mode(mode):
@@ -64,14 +65,71 @@ def linear_wgrad_raw(gy, x, mode=None):
     return gw
 
 
-def colsum(t):
+# Bias / affine-parameter gradients are column sums of tensors the backward pass has already produced; nothing
+# on the critical path waits for them.  During a backward pass they are issued on a side stream (they are tiny,
+# latency-bound launches that co-reside with the persistent GEMM CTAs) and joined back when autograd finishes.
+_SIDE_STREAM_ENABLED = os.environ.get("ISG_SIDE_STREAM", "1") != "0"
+_side_streams = {}
+_join_pending = False
+_side_ok = False  # set per step by MGAT.forward: only when no parameter has a .grad to accumulate into
+
+
+def allow_side_stream(ok):
+    """The side stream hands autograd a gradient produced off the main stream.  That is safe when the
+    AccumulateGrad node merely stores it (param.grad is None, the state after zero_grad()); an in-place
+    accumulation into an existing .grad would run on the main stream without waiting — so the caller
+    vouches for the former once per step."""
+    global _side_ok
+    _side_ok = bool(ok)
+
+
+
+def _side_stream(device):
+    st = _side_streams.get(device)
+    if st is None:
+        st = _side_streams[device] = torch.cuda.Stream(device=device)
+    return st
+
+
+def join_side_stream():
+    """Make the current stream wait for every column sum issued on the side stream."""
+    global _join_pending
+    _join_pending = False
+    for st in _side_streams.values():
+        torch.cuda.current_stream(st.device).wait_stream(st)
+
+
+def _defer_join():
+    """True if we are inside a backward pass and a join has been queued for its end."""
+    global _join_pending
+    if _join_pending:
+        return True
+    try:
+        torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
+    except RuntimeError:  # not inside a backward pass
+        return False
+    _join_pending = True
+    return True
+
+
+def _colsum_on(t, stream_handle):
     lib = L.load()
     rows, cols = t.shape
     out = torch.empty(cols, dtype=torch.float32, device=t.device)
     nbytes = lib.isg_colsum_workspace_bytes(rows, cols)
     ws = L.workspace(nbytes, t.device)
-    L.call("isg_colsum", L.ptr(t), t.stride(0), rows, cols, L.ptr(out), L.ptr(ws), nbytes, L.stream())
+    L.call("isg_colsum", L.ptr(t), t.stride(0), rows, cols, L.ptr(out), L.ptr(ws), nbytes, stream_handle)
     return out
+
+
+def colsum(t):
+    if not (_SIDE_STREAM_ENABLED and _side_ok and t.is_cuda and _defer_join()):
+        return _colsum_on(t, L.stream())
+    side = _side_stream(t.device)
+    side.wait_stream(torch.cuda.current_stream(t.device))
+    t.record_stream(side)  # autograd may free `t` on the main stream while the side stream still reads it
+    with torch.cuda.stream(side):
+        return _colsum_on(t, side.cuda_stream)
 
 
 def gelu_bwd(gy, z):
@@ -218,53 +276,55 @@ class SdpaGraphNormResidual(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------
 class GatEdge(torch.autograd.Function):
     """MaskingGATv2Conv.message + propagate + softmax + aggregate + bias
-    (models/mgat_v2_conv.py:215,226-232,243-279).  x_l/x_r [N,H*C] (may be column views of one
-    fused projection), e_proj [E,H*C], att [1,H,C], bias [H*C], edge_mask [E,1] or None.
-    Returns (out [N,H*C], alpha [E,H])."""
+    (models/mgat_v2_conv.py:215,226-232,243-279).  xlr [N, 2*H*C] = [x_l | x_r], the output of ONE fused
+    projection with the stacked weights [W_l; W_r] (both halves share a row pitch, so the kernels read
+    them in place and the backward returns one [g_xl | g_xr] tensor that feeds one dgrad / wgrad);
+    e_proj [E,H*C], att [1,H,C], bias [H*C], edge_mask [E,1] or None.  Returns (out [N,H*C], alpha [E,H])."""
 
     @staticmethod
-    def forward(ctx, x_l, x_r, e_proj, att, bias, edge_mask, gi, heads, slope):
-        L.require_cuda(x_l, x_r, e_proj, att)
-        if x_l.stride(1) != 1 or x_r.stride(1) != 1 or x_l.stride(0) != x_r.stride(0):
-            x_l, x_r = x_l.contiguous(), x_r.contiguous()
-        e_proj, att = _c(e_proj), _c(att)
+    def forward(ctx, xlr, e_proj, att, bias, edge_mask, gi, heads, slope):
+        L.require_cuda(xlr, e_proj, att)
+        xlr, e_proj, att = _c(xlr), _c(e_proj), _c(att)
         em = _c(edge_mask) if edge_mask is not None else None
-        N, HC = x_l.shape
+        N, HC2 = xlr.shape
+        HC = HC2 // 2
         C = HC // heads
-        out = torch.empty(N, HC, dtype=x_l.dtype, device=x_l.device)
-        alpha = torch.empty(gi.E, heads, dtype=torch.float32, device=x_l.device)
-        L.call("isg_gat_edge_fwd", L.ptr(x_l), L.ptr(x_r), x_l.stride(0), L.ptr(e_proj), L.ptr(att),
+        x_l, x_r = xlr[:, :HC], xlr[:, HC:]
+        out = torch.empty(N, HC, dtype=xlr.dtype, device=xlr.device)
+        alpha = torch.empty(gi.E, heads, dtype=torch.float32, device=xlr.device)
+        L.call("isg_gat_edge_fwd", L.ptr(x_l), L.ptr(x_r), HC2, L.ptr(e_proj), L.ptr(att),
                                           L.ptr(bias), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr),
                                           L.ptr(gi.dst_eid), L.ptr(out), HC, L.ptr(alpha), N, gi.E, heads, C,
-                                          slope, L.dtype_code(x_l), L.stream())
+                                          slope, L.dtype_code(xlr), L.stream())
         ctx.gi, ctx.heads, ctx.slope = gi, heads, slope
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x_l, x_r, e_proj, att, bias, em, alpha, out)
+        ctx.save_for_backward(xlr, e_proj, att, bias, em, alpha, out)
         ctx.mark_non_differentiable(alpha)
         return out, alpha
 
     @staticmethod
     def backward(ctx, g_out, _g_alpha):
-        x_l, x_r, e_proj, att, bias, em, alpha, out = ctx.saved_tensors
+        xlr, e_proj, att, bias, em, alpha, out = ctx.saved_tensors
         gi, H = ctx.gi, ctx.heads
         lib = L.load()
         g_out = _c(g_out)
         N, HC = out.shape
         C = HC // H
         dev = out.device
-        g_xlr = torch.empty(N, 2 * HC, dtype=x_l.dtype, device=dev)  # [g_xl | g_xr], one pitch
+        x_l, x_r = xlr[:, :HC], xlr[:, HC:]
+        g_xlr = torch.empty(N, 2 * HC, dtype=xlr.dtype, device=dev)  # [g_xl | g_xr], one pitch
         g_xl, g_xr = g_xlr[:, :HC], g_xlr[:, HC:]
         g_ep = torch.empty(gi.E, HC, dtype=e_proj.dtype, device=dev)
         g_att = torch.empty(att.shape, dtype=torch.float32, device=dev)
         g_em = torch.empty(gi.E, 1, dtype=torch.float32, device=dev) if em is not None else None
         nbytes = lib.isg_gat_edge_bwd_workspace_bytes(N, gi.E, H, C)
         ws = L.workspace(nbytes, dev)
-        L.call("isg_gat_edge_bwd", L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), x_l.stride(0),
+        L.call("isg_gat_edge_bwd", L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), 2 * HC,
                                      L.ptr(e_proj), L.ptr(att), L.ptr(bias), L.ptr(em), L.ptr(alpha), L.ptr(out), HC,
                                      L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr),
                                      L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(g_xl), L.ptr(g_xr), 2 * HC,
                                      L.ptr(g_ep), L.ptr(g_att), L.ptr(g_em), N, gi.E, H, C, ctx.slope,
-                                     L.dtype_code(x_l), L.ptr(ws), nbytes, L.stream())
+                                     L.dtype_code(xlr), L.ptr(ws), nbytes, L.stream())
         g_bias = colsum(g_out) if ctx.has_bias else None
         if _DEBUG_EDGE_BWD is not None:
             _DEBUG_EDGE_BWD.append(dict(g_out=g_out.clone(), x_l=x_l.clone(), x_r=x_r.clone(), e_proj=e_proj.clone(),
@@ -272,7 +332,7 @@ class GatEdge(torch.autograd.Function):
                                         em=em.clone() if em is not None else None, alpha=alpha.clone(),
                                         out=out.clone(), g_xl=g_xl.clone(), g_xr=g_xr.clone(), g_ep=g_ep.clone(),
                                         g_att=g_att.clone()))
-        return g_xl, g_xr, g_ep, g_att, g_bias, g_em, None, None, None
+        return g_xlr, g_ep, g_att, g_bias, g_em, None, None, None
 
 
 class NodeMaskToEdgeMaskFn(torch.autograd.Function):

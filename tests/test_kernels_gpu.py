@@ -132,24 +132,17 @@ def _run_edge_cuda(d, H, C, fused_pitch=False):
     from isg_b200 import ops
 
     gi = _gi(d["edge_index"], d["batch"], int(d["batch"].max()) + 1)
-    if fused_pitch:  # x_l | x_r as column views of one [N, 2HC] buffer
-        xlr = torch.cat([d["x_l"], d["x_r"]], dim=1).to(DEV).requires_grad_(True)
-        x_l, x_r = xlr[:, : H * C], xlr[:, H * C:]
-    else:
-        x_l = d["x_l"].to(DEV).requires_grad_(True)
-        x_r = d["x_r"].to(DEV).requires_grad_(True)
+    # the op takes [x_l | x_r] as one [N, 2HC] tensor (the output of the fused lin_l/lin_r projection)
+    xlr = torch.cat([d["x_l"], d["x_r"]], dim=1).to(DEV).requires_grad_(True)
     ep = d["e_proj"].to(DEV).requires_grad_(True)
     att = d["att"].to(DEV).requires_grad_(True)
     bias = d["bias"].to(DEV).requires_grad_(True)
     m = d["mask"].to(DEV).requires_grad_(True) if d["mask"] is not None else None
-    out, alpha = ops.GatEdge.apply(x_l, x_r, ep, att, bias, m, gi, H, 0.2)
+    out, alpha = ops.GatEdge.apply(xlr, ep, att, bias, m, gi, H, 0.2)
     out.backward(d["g_out"].to(DEV))
     res = dict(out=out.detach(), alpha=alpha.detach(), g_e_proj=ep.grad, g_att=att.grad, g_bias=bias.grad,
                g_mask=m.grad if m is not None else None)
-    if fused_pitch:
-        res["g_x_l"], res["g_x_r"] = xlr.grad[:, : H * C], xlr.grad[:, H * C:]
-    else:
-        res["g_x_l"], res["g_x_r"] = x_l.grad, x_r.grad
+    res["g_x_l"], res["g_x_r"] = xlr.grad[:, : H * C], xlr.grad[:, H * C:]
     return res
 
 

@@ -165,13 +165,24 @@ def run_cuda_case(cfg, step_count=None, device="cuda", capture=False):
     return outs
 
 
-def compare_step(got, want, sampler, rtol=RTOL):
+def compare_step(got, want, sampler, rtol=RTOL, exact=None):
+    """got vs want (the fp32 reference / oracle).  `exact`, when given, is the fp64 arbiter replay of the same
+    step (run_oracle_case(dtype=float64, replay=...)): a float tensor that misses rtol against the fp32
+    reference still passes if it is within rtol of the exact value — two fp32 evaluations of an
+    ill-conditioned quantity can legitimately differ by more than either differs from the truth."""
     if sampler in ("imle", "aimle"):
         assert torch.equal(got["mask"], want["mask"]), "top-k node mask must be bit-exact given the same noise"
     else:
         assert rel_err(got["mask"], want["mask"]) <= rtol
     for key in ("h", "gx", "g_edge_attr", "g_instr", "g_glf"):
         e = rel_err(got[key], want[key])
+        if e > rtol and exact is not None:
+            e = min(e, rel_err(got[key], exact[key]))
         assert e <= rtol, (key, e)
     for name, w in want["param_grads"].items():
-        check_param_grad(name, got["param_grads"].get(name), w, rtol)
+        try:
+            check_param_grad(name, got["param_grads"].get(name), w, rtol)
+        except AssertionError:
+            if exact is None or exact["param_grads"].get(name) is None:
+                raise
+            check_param_grad(name, got["param_grads"].get(name), exact["param_grads"][name], rtol)
