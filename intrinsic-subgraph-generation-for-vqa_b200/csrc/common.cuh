@@ -195,6 +195,14 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // of the next edges while the warp computes on the current one, so the bytes in flight per SM are
 // set by the ring depth and not by the register file (a row slice of C fp32 = 3 float4 per lane).
 // ---------------------------------------------------------------------------------------------
+// One lane of a converged warp, chosen by elect.sync.  Bulk-copy / TMA / tcgen05 instructions take uniform
+// registers: inside a branch ptxas can prove single-lane (an elect.sync predicate) they are emitted directly,
+// whereas under `lane == 0` every one is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop.
+__device__ __forceinline__ bool warp_elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(e));
+  return e != 0;
+}
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ring_bar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -456,6 +456,7 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
   ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
             smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const bool leader = warp_elect_one();  // issues the bulk copies (see warp_elect_one)
 
   for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
     const int64_t node = wid / H;
@@ -482,7 +483,7 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
       for (int t = 0; t < npre; ++t) {
         const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
         const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
-        if (lane == 0)
+        if (leader)
           ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff, pol_stream,
                       row_bytes);
       }
@@ -497,7 +498,7 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
         lds_row<VPL>(ring.slot(s), lane, c4, x0);
         lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, p0);
         __syncwarp();  // every lane has read the slot -> it may be refilled
-        if (lane == 0 && t + RING < cnt)
+        if (leader && t + RING < cnt)
           ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
                       row_bytes);
         float2 part2 = make_float2(0.f, 0.f);
@@ -570,6 +571,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
   ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
             smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const bool leader = warp_elect_one();  // issues the bulk copies (see warp_elect_one)
 
   float4 att_v[VPL], gatt[VPL];
   load_row_f32<VPL>(att + hoff, lane, c4, att_v);
@@ -599,7 +601,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
       const int npre = min(RING, cnt);
       for (int t = 0; t < npre; ++t) {
         const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
-        if (lane == 0) ring.issue1(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
+        if (leader) ring.issue1(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
       }
       for (int t = 0; t < cnt; ++t) {
         const uint32_t s = ring.seq + t;
@@ -609,7 +611,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
         float4 xv[VPL];
         lds_row<VPL>(ring.slot(s), lane, c4, xv);
         __syncwarp();
-        if (lane == 0 && t + RING < cnt) ring.issue1(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, row_bytes);
+        if (leader && t + RING < cnt) ring.issue1(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, row_bytes);
         float2 pp2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < VPL; ++k) pp2 = p4_dot_acc(G[k], xv[k], pp2);
@@ -634,7 +636,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
       for (int t = 0; t < npre; ++t) {
         const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
         const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
-        if (lane == 0)
+        if (leader)
           ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff, pol_stream,
                       row_bytes);
       }
@@ -651,7 +653,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
         lds_row<VPL>(ring.slot(s), lane, c4, xv);
         lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, pv);
         __syncwarp();
-        if (lane == 0 && t + RING < cnt)
+        if (leader && t + RING < cnt)
           ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
                       row_bytes);
         float2 tp2 = make_float2(0.f, 0.f);
@@ -719,6 +721,7 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
   ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
             smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const bool leader = warp_elect_one();  // issues the bulk copies (see warp_elect_one)
 
   for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
     const int64_t node = wid / H;
@@ -742,7 +745,7 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
       for (int t = 0; t < npre; ++t) {
         const int i = __shfl_sync(ISG_FULL_MASK, my_dst, t);
         const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
-        if (lane == 0)
+        if (leader)
           ring.issue2(ring.seq + t, g_ep + (int64_t)e * HC + hoff, pol_stream, gout + (int64_t)i * ld_g + hoff,
                       pol_keep, row_bytes);
       }
@@ -757,7 +760,7 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
         lds_row<VPL>(ring.slot(s), lane, c4, gv);
         lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, Gv);
         __syncwarp();
-        if (lane == 0 && t + RING < cnt)
+        if (leader && t + RING < cnt)
           ring.issue2(s + RING, g_ep + (int64_t)en * HC + hoff, pol_stream, gout + (int64_t)in_ * ld_g + hoff,
                       pol_keep, row_bytes);
 #pragma unroll

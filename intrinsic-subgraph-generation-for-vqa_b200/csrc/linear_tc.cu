@@ -21,15 +21,20 @@
 //
 //   warp 0       TMA producer: cp.async.bulk.tensor.2d of raw fp32 operand tiles (BK = 16 floats per
 //                k-block: 64-byte swizzle for K-major, 128B/32B-atom swizzle for MN-major operands)
-//   warps 4-7    splitters (mode 1): lo = x - (x & ~0x1fff) into a twin buffer at the same swizzled
-//                offsets (all loads of a stage issued before the stores), fence.proxy.async, arrive
+//   warps 4-7    splitters (mode 1): thread m owns row m of the A tile — it gathers the row's 16 k-values
+//                from the swizzled smem tile and writes A_hi (raw) and A_lo = x - (x & ~0x1fff) into a
+//                4-slot A ring IN TENSOR MEMORY (tcgen05.st), so the MMAs take A from TMEM and only B
+//                from shared memory (with SS operands all three products re-read A and B from smem and
+//                the mainloop is shared-memory-bandwidth bound: 96 KB per k-block; TS form: 64 KB);
+//                B_lo is written to a twin smem buffer at the same swizzled offsets; fence, arrive
 //   warp 1       one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN<=128, K=8) into
 //                TMEM; tcgen05.commit releases smem stages and publishes accumulator chunks
 //   warps 8-15   epilogue: tcgen05.ld 32x32b of the chunk partials into register accumulators (two
 //                column halves x four lane quarters), at tile end + correction accumulator, then a padded
 //                smem transpose and coalesced float4 rows with the fused bias / exact GELU /
 //                pre-activation side output / GELU-derivative / accumulate
-//   warp 2       TMEM allocation: 512 columns = main[2 chunk stages] + correction[2 tile stages], 128 each
+//   warp 2       TMEM allocation, 512 columns.  mode 1: main[2 chunk stages] 0..255, correction 256..383,
+//                A ring (4 slots x {hi 16, lo 16} columns) 384..511; mode 2: main[2] only, SS operands
 #include <cuda.h>
 
 #include "common.cuh"
@@ -53,7 +58,9 @@ constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_MAIN = 0, TM_CORR = 256;     // column bases; stage s adds 128*s
+constexpr uint32_t TM_MAIN = 0, TM_CORR = 256;     // column bases; main stage s adds 128*s
+constexpr uint32_t TM_A = 384;                     // mode 1: A ring, slot s at TM_A + 32*s (hi 16 cols, lo 16 cols)
+constexpr int TS_STAGES = 4;                       // A-ring slots == smem stages in mode 1
 
 enum Epi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_PLAIN = 2 };
 
@@ -142,6 +149,42 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per k element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0],"
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float lo1(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// One lane of a converged warp.  The tcgen05.mma / TMA instructions take uniform registers; issued from a
+// branch the compiler can prove single-lane via elect.sync they compile to back-to-back UTCHMMA / UTMALDG,
+// while under a plain `threadIdx.x == k` test ptxas wraps every one of them in an ELECT / BRA.U.ANY loop
+// (measured: 153 cycles per MMA instead of 64, scripts/microbench/umma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(e));
+  return e != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -200,9 +243,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int S = g.stages;
   const int BN = g.BN;
   const uint32_t b_tile_bytes = (uint32_t)BN * (BK * 4);
-  // stage layout: mode 1 [A 8K][A_lo 8K][B BN*64][B_lo BN*64]; mode 2 [A 8K][B BN*64]
-  const uint32_t off_a_lo = A_TILE_BYTES;
-  const uint32_t off_b_hi = g.split3 ? 2 * A_TILE_BYTES : A_TILE_BYTES;
+  // stage layout: mode 1 [A raw 8K][B BN*64][B_lo BN*64] (A goes on to TMEM); mode 2 [A 8K][B BN*64]
+  const uint32_t off_b_hi = A_TILE_BYTES;
   const uint32_t off_b_lo = off_b_hi + b_tile_bytes;
   const uint32_t epi_base = smem_base + (uint32_t)S * g.stage_bytes;
   const uint32_t bar_base = epi_base + EPI_BYTES;
@@ -252,7 +294,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     return (int)((r_end - r_beg + BK - 1) / BK);
   };
 
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
+   if (elect_one()) {
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -283,10 +326,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ===================================================================== MMA issuer (one thread)
+   }
+  } else if (warp == 1) {
+   if (elect_one()) {
+    // ===================================================================== MMA issuer (one elected lane)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
                            ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // TS form: the splitters have already laid A out row-per-lane / k-per-column, i.e. K-major
+    const uint32_t idesc_ts = idesc & ~(1u << 15);
     const uint32_t a_kstep = A_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);  // descriptor units of 16 B
     const uint32_t b_kstep = B_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);
     int stage = 0;
@@ -297,9 +344,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int num_kb = tile_kb(t);
       const int tp = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      const uint32_t d_corr = tmem_base + TM_CORR + 128u * tp;
+      const uint32_t d_corr = tmem_base + TM_CORR;  // single stage: drained once per tile by the epilogue
       if (g.split3) {
-        mbar_wait(cempty_bar(tp), tphase ^ 1u);
+        mbar_wait(cempty_bar(0), (uint32_t)(it & 1) ^ 1u);
         tc_fence_after();
       }
       for (int kb0 = 0; kb0 < num_kb; kb0 += DRAIN_KB, ++gchunk) {
@@ -313,15 +360,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(g.split3 ? conv_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
-          const uint64_t a_hi = make_desc(sa, A_MN), a_lo = make_desc(sa + off_a_lo, A_MN);
           const uint64_t b_hi = make_desc(sa + off_b_hi, B_MN), b_lo = make_desc(sa + off_b_lo, B_MN);
+          if (g.split3) {
+            const uint32_t a_t = tmem_base + TM_A + 32u * (uint32_t)stage;  // hi at +0, lo at +16
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t ak = (uint64_t)(a_kstep * k), bk = (uint64_t)(b_kstep * k);
-            umma_tf32(d_main, a_hi + ak, b_hi + bk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (g.split3) {
-              umma_tf32(d_corr, a_hi + ak, b_lo + bk, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32(d_corr, a_lo + ak, b_hi + bk, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t bk = (uint64_t)(b_kstep * k);
+              umma_tf32_ts(d_main, a_t + 8u * k, b_hi + bk, idesc_ts, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(d_corr, a_t + 8u * k, b_lo + bk, idesc_ts, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(d_corr, a_t + 16u + 8u * k, b_hi + bk, idesc_ts, 1u);
+            }
+          } else {
+            const uint64_t a_hi = make_desc(sa, A_MN);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t ak = (uint64_t)(a_kstep * k), bk = (uint64_t)(b_kstep * k);
+              umma_tf32(d_main, a_hi + ak, b_hi + bk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(stage));  // frees the smem stage once the MMAs above have read it
@@ -329,8 +383,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         umma_commit(mfull_bar(ms));  // chunk partial complete -> epilogue drains it
       }
-      if (g.split3) umma_commit(cfull_bar(tp));
+      if (g.split3) umma_commit(cfull_bar(0));
     }
+   }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================================== lo-plane splitters (mode 1)
     if (g.split3) {
@@ -343,20 +398,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
-          float4 va[4], vb[4];
+          // ---- A: row `tid` of the tile -> 16 k-values -> TMEM (hi = raw, lo = exact remainder)
+          float av[16];
+          if (!A_MN) {
+            // K-major tile: row of 64 B, SWIZZLE_64B: 16-byte chunk c sits at c ^ ((row >> 1) & 3)
+            const uint32_t rowa = sa + (uint32_t)tid * 64u;
+            const uint32_t x = ((uint32_t)tid >> 1) & 3u;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) va[u] = lds_f4(sa + (uint32_t)(tid + 128 * u) * 16u);
+            for (int c = 0; c < 4; ++c) {
+              const float4 v = lds_f4(rowa + (((uint32_t)c ^ x) << 4));
+              av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+            }
+          } else {
+            // MN-major tile: chunk (tid / 32) of [16 k-rows][128 B], 32-byte swizzle atoms:
+            // element (ml, k) sits at k*128 + (((ml >> 3) ^ (k & 3)) << 5) + ((ml & 7) << 2)
+            const uint32_t ml = (uint32_t)tid & 31u;
+            const uint32_t ca = sa + ((uint32_t)tid >> 5) * (BK * 128u) + ((ml & 7u) << 2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) av[k] = lds_f1(ca + (uint32_t)k * 128u + (((ml >> 3) ^ ((uint32_t)k & 3u)) << 5));
+          }
+          float4 vb[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = tid + 128 * u;
             vb[u] = i < nb ? lds_f4(sa + off_b_hi + (uint32_t)i * 16u) : f4_zero();
           }
+          const uint32_t a_t = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + TM_A + 32u * (uint32_t)stage;
+          tmem_st16(a_t, av);
+          float al[16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t o = (uint32_t)(tid + 128 * u) * 16u;
-            sts_f4(sa + off_a_lo + o, lo_part(va[u]));
-            if (g.write_hi) sts_f4(sa + o, hi_part(va[u]));
-          }
+          for (int k = 0; k < 16; ++k) al[k] = lo1(av[k]);
+          tmem_st16(a_t + 16u, al);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = tid + 128 * u;
@@ -365,6 +437,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (g.write_hi) sts_f4(sa + off_b_hi + (uint32_t)i * 16u, hi_part(vb[u]));
             }
           }
+          tmem_st_wait();
+          tc_fence_before();
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
           mbar_arrive(conv_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -411,9 +485,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) mbar_arrive(mempty_bar(ms));  // this warp is done with the chunk's TMEM stage
       }
       if (g.split3) {
-        mbar_wait(cfull_bar(tp), tphase);
+        mbar_wait(cfull_bar(0), (uint32_t)(it & 1));
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_sel + TM_CORR + 128u * tp + 64u * half;
+        const uint32_t taddr = tmem_base + lane_sel + TM_CORR + 64u * half;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[32];
@@ -424,7 +498,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(cempty_bar(tp));
+        if (lane == 0) mbar_arrive(cempty_bar(0));
       }
       // ---- store: 2 x (32 rows x 32 columns) through the padded staging tile
 #pragma unroll
@@ -520,9 +594,10 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   TcArgs g{};
   g.C = p.C; g.ldc = p.ldc; g.rows = p.rows; g.cols = p.cols; g.R = p.R;
   g.BN = pick_bn(p.cols, B_MN);
-  g.stage_bytes = (p.split3 ? 2 : 1) * (A_TILE_BYTES + g.BN * BK * 4);
+  g.stage_bytes = A_TILE_BYTES + (p.split3 ? 2 : 1) * g.BN * BK * 4;
   g.stages = (SMEM_LIMIT - 1024 - EPI_BYTES - BAR_BYTES) / g.stage_bytes;
   if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
+  if (p.split3 && g.stages > TS_STAGES) g.stages = TS_STAGES;  // one TMEM A slot per smem stage
   if (g.stages < 2) return ISG_EUNSUPPORTED;
   g.m_tiles = ceil_div(p.rows, BM);
   g.n_tiles = ceil_div(p.cols, g.BN);

@@ -552,7 +552,10 @@ class OracleMGAT(torch.nn.Module):
                 theta = theta * drop_mask
             else:
                 theta = F.dropout(theta, p=0.2, training=True)
-        if self.replay is not None:  # fp64 arbiter runs: discrete decisions replayed from an fp32 run
+        # fp64 arbiter runs: the DISCRETE samplers (IMLE / AIMLE: top-k mask and perturbation gradient) are
+        # replayed from an fp32 run; Gumbel and SIMPLE are differentiable relaxations (their only discrete step is
+        # a top-k over noise-separated keys) and are evaluated natively in the arbiter's precision.
+        if self.replay is not None and self.sampler_type in ("imle", "aimle"):
             mask = _ForcedMask.apply(theta, self.replay["mask"].to(theta.dtype), self.replay["g_theta"].to(theta.dtype))
             return mask, theta
         if self.record is not None and theta.requires_grad:

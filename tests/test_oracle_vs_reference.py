@@ -1,0 +1,66 @@
+"""Live pinning of the oracle: runs the UNMODIFIED reference (imported from /root/reference through
+oracle/reference_loader.py on the pure-torch shim) next to oracle/isg_oracle.py on freshly seeded inputs that
+are NOT among the committed fixtures.  Skipped wherever the reference tree is absent (the GPU box)."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+import util
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import reference_loader as rl  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not rl.available(), reason="/root/reference is not present on this machine")
+
+
+@pytest.fixture(scope="module")
+def golden_mod():
+    import make_golden
+
+    with rl.scratch_cwd():
+        rl.load()
+    return make_golden
+
+
+@pytest.mark.parametrize("sampler,train,C,B,k,seed", [("imle", True, 16, 5, 2, 4100), ("aimle", True, 16, 5, 3, 4101),
+                                                      ("gumbel", True, 16, 6, 2, 4102), ("simple", True, 16, 6, 2, 4103),
+                                                      ("simple", False, 32, 4, 3, 4104), ("imle", False, 16, 3, 2, 4105)])
+def test_oracle_matches_live_reference(golden_mod, sampler, train, C, B, k, seed):
+    steps = 2 if sampler == "aimle" else 1
+    torch.manual_seed(seed)
+    ref = golden_mod.run_reference(sampler, train, C, B, 9, 40, k, seed, steps)
+    cfg = dict(sampler=sampler, train=train, channels=C, num_graphs=B, mean_nodes=9, mean_edges=40, k=k, seed=seed,
+               steps=steps, aimle_beta0=golden_mod.AIMLE_BETA0 if sampler == "aimle" else None)
+    got = util.run_oracle_case(cfg)
+    for g, w in zip(got, ref):
+        # two CPU fp32 evaluations of the Gumbel tau=0.1 mask-network gradient already differ by ~6e-5
+        util.compare_step(g, w, sampler, rtol=util.RTOL if (sampler == "gumbel" and train) else 2e-5)
+
+
+def test_simple_circuit_restatement_matches_live_layer(golden_mod):
+    """Layer.log_pr (simple.py:214-244) vs oracle.simple_marginals on logits with exact zeros (the -1000 dummy
+    pad regime), incl. the gradient that the reference obtains by differentiating through both passes."""
+    import isg_oracle as O
+    from ISubGVQA.sampling.methods.simple_scheme import EdgeSIMPLEBatched
+
+    g = torch.Generator().manual_seed(5)
+    for nmax, k in [(9, 2), (20, 2), (33, 4), (64, 5)]:
+        with rl.scratch_cwd():
+            s = EdgeSIMPLEBatched(k=k, device="cpu", policy="edge_candid")
+            theta = torch.randn(6, nmax, 1, generator=g)
+            theta[torch.rand(6, nmax, 1, generator=g) < 0.25] = 0.0
+            theta[3, nmax // 2:, 0] = 0.0
+            t1 = theta.clone().requires_grad_(True)
+            _, marg = s(t1, train=True)
+        w = torch.randn(6, nmax, 1, generator=g)
+        (marg * w).sum().backward()
+        t2 = theta.clone().requires_grad_(True)
+        npad = 2 ** math.ceil(math.log2(nmax))
+        flat = torch.cat([t2[..., 0], t2.new_full((6, npad - nmax), -1.0e10)], dim=1)
+        m2 = O.simple_marginals(flat, k)[:, :nmax]
+        (m2 * w[..., 0]).sum().backward()
+        assert torch.allclose(m2, marg[..., 0], rtol=0, atol=2e-7)
+        assert util.rel_err(t2.grad, t1.grad) <= 1e-5
