@@ -15,6 +15,7 @@ edge-attention backward), measured live with CUDA events inside the timed steps.
 dependencies are not installable offline and /root/reference does not exist on the GPU box).
 """
 import argparse
+import contextlib
 import json
 import math
 import os
@@ -216,8 +217,13 @@ def main_isg(args, rank, world, local_rank):
     desc, sampler, train, B = WORKLOADS[args.workload]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    out_stream = sys.stdout
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to fd 1; the contract is ONE JSON line on stdout, so the process's
+        # fd 1 is pointed at stderr for the run and the JSON line goes to a private copy of the real stdout
+        sys.stdout.flush()
+        out_stream = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
     seed = 3407 + rank
     b = make_inputs(B, seed)
     N, E, nmax = int(b["x"].shape[0]), int(b["edge_index"].shape[1]), b["nmax"]
@@ -228,7 +234,7 @@ def main_isg(args, rank, world, local_rank):
     model.to(dev).train(train)
     if sampler == "aimle":
         model.convs[3].mask.sampler_train.target._init[0] = 1.0  # warmed-up beta (beta0 = 0 gives zero grads)
-    reducer = GradAllReduce(model) if (train and world > 1) else None
+    reducer = None  # created after the CUDA-graph capture (the NCCL all-reduce stays outside the graph)
 
     keys = ("x", "edge_index", "instr_vectors", "global_language_feats", "edge_attr", "batch")
     host = {k: b[k].pin_memory() for k in keys}
@@ -240,7 +246,8 @@ def main_isg(args, rank, world, local_rank):
     noise_d = noise_h.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step(t, noise):
+    def step_core(t, noise):
+        """MGAT forward (+ backward): the part that is captured into the CUDA graph."""
         model.convs[3].mask.injected_noise = noise
         if train:
             x = t["x"].detach().requires_grad_(True)
@@ -251,13 +258,17 @@ def main_isg(args, rank, world, local_rank):
                                   return_masks=True)
             loss = (h * h).mean()
             loss.backward()
-            if reducer is not None:
-                reducer.all_reduce_mean()
             return loss, mask
         with torch.no_grad():
             h, mask, _, _ = model(t["x"], t["edge_index"], t["instr_vectors"], t["global_language_feats"],
                                   t["edge_attr"], t["batch"], return_masks=True)
             return (h * h).mean(), mask
+
+    def step(t, noise):
+        out = step_core(t, noise)
+        if reducer is not None:
+            reducer.all_reduce_mean()
+        return out
 
     def step_e2e():
         clear_cache()  # a new batch arrives: CSR / graph_ptr are rebuilt inside the timed region
@@ -293,14 +304,61 @@ def main_isg(args, rank, world, local_rank):
             ms = float(tt.item())
         return ms, L.launch_count - launches0, L.timing_summary(t) if t else {}
 
-    # warm-up (also builds the CSR once for the resident batch, as a data loader would at collate time)
-    for _ in range(max(args.warmup, 3)):
-        step(resident, noise_d)
+    # warm-up (also builds the CSR once for the resident batch, as a data loader would at collate time).  With
+    # CUDA-graph capture every pre-capture step runs on the capture stream: autograd binds each parameter's
+    # AccumulateGrad node to the stream it was first used on, and a mismatch with the capture stream makes the
+    # engine synchronise with an uncaptured stream, which invalidates the capture.
+    cap_stream = torch.cuda.Stream(device=dev) if not args.no_graph else None
+    if cap_stream is not None:
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(cap_stream) if cap_stream is not None else contextlib.nullcontext():
+        for _ in range(max(args.warmup, 3)):
+            step_core(resident, noise_d)
+    torch.cuda.synchronize()
+    edge_names = ["isg_gat_edge_fwd", "isg_gat_edge_bwd"]
+
+    # The resident-input step is launch-bound on the host (~180 kernel launches + autograd bookkeeping take
+    # about as long as the GPU needs for them), so forward+backward is captured ONCE into a CUDA graph and the
+    # timed region replays it (the NCCL all-reduce, if any, is issued eagerly after each replay): identical
+    # kernels, no per-launch host cost.  The per-kernel CUDA-event timings for the roofline come from an eager
+    # pass of the same K steps (events cannot be recorded inside a replay).  A failed capture leaves the CUDA
+    # RNG in capture mode, so the process re-executes itself with --no-graph (before any process group exists).
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap_stream):
+                step_core(resident, noise_d)
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {str(exc)[:200]}); "
+                             "re-running with --no-graph\n")
+            sys.stderr.flush()
+            if world > 1:
+                os.dup2(out_stream.fileno(), 1)
+            os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        if train:
+            reducer = GradAllReduce(model)
+
+    def graphed_step():
+        graph.replay()
+        if reducer is not None:
+            reducer.all_reduce_mean()
+
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    edge_names = ["isg_gat_edge_fwd", "isg_gat_edge_bwd"]
-    ms, launches, tsum = timed(lambda: step(resident, noise_d), args.steps, edge_names)
+    launches_per_step = None
+    ms_eager, launches, tsum = timed(lambda: step(resident, noise_d), args.steps, edge_names)
+    if graph is not None:
+        ms, _, _ = timed(graphed_step, args.steps)
+    else:
+        ms = ms_eager
     clk = clocks.stop() if rank == 0 else None
     # kernel-family breakdown of one extra (untimed) step, for DESIGN.md / the JSON line
     ms_b, _, tall = timed(lambda: step(resident, noise_d), 2, None if not args.breakdown else list(L.KERNELS_PER_CALL))
@@ -368,7 +426,9 @@ def main_isg(args, rank, world, local_rank):
                                                       else "") if train else "MGAT forward (no_grad)",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
                          f"~{(4 * 4 * HEADS * CHANNELS * (3 * E + 8 * N)) / 1e9:.2f} GB also exceeds the 126 MB L2",
-                   "gemm_mode": gemm_desc, "optimizer": "out of scope (SURVEY.md §8 f4)"},
+                   "gemm_mode": gemm_desc,
+                   "cuda_graph": ("value: K replays of one captured step (eager: %.3f ms/step); roofline kernel times "
+                                  "and e2e are eager" % (ms_eager / args.steps)) if graph is not None else "off", "optimizer": "out of scope (SURVEY.md §8 f4)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "what": "pinned host batch -> .to(cuda) -> CSR build -> MGAT fwd+bwd -> loss.item() + mask.cpu()"},
@@ -382,7 +442,8 @@ def main_isg(args, rank, world, local_rank):
     if args.breakdown:
         line["breakdown_ms_per_step"] = {k: round(v[1] / 2, 4) for k, v in sorted(tall.items(), key=lambda kv: -kv[1][1])}
         line["breakdown_step_ms"] = ms_b / 2
-    print(json.dumps(line))
+    out_stream.write(json.dumps(line) + "\n")
+    out_stream.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -396,6 +457,7 @@ def main():
     ap.add_argument("--impl", default="isg", choices=["isg", "reference"])
     ap.add_argument("--breakdown", action="store_true", help="add per-entry-point CUDA-event times to the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the resident-input step eagerly (no CUDA graph)")
     ap.add_argument("--no-edge-study", action="store_true", help="skip the batch-4096 edge-kernel roofline point")
     ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2],
                     help="projection arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32 (default), 2 tcgen05 1xTF32")

@@ -92,8 +92,12 @@ def _side_stream(device):
 
 
 def join_side_stream():
-    """Make the current stream wait for every column sum issued on the side stream."""
+    """Make the current stream wait for every column sum issued on the side stream.  A no-op unless a backward
+    pass has issued side-stream work that was not joined yet (and never during CUDA-graph capture, where the
+    side stream is not used and waiting on an uncaptured stream would invalidate the capture)."""
     global _join_pending
+    if not _join_pending or torch.cuda.is_current_stream_capturing():
+        return
     _join_pending = False
     for st in _side_streams.values():
         torch.cuda.current_stream(st.device).wait_stream(st)
@@ -123,7 +127,8 @@ def _colsum_on(t, stream_handle):
 
 
 def colsum(t):
-    if not (_SIDE_STREAM_ENABLED and _side_ok and t.is_cuda and _defer_join()):
+    if not (_SIDE_STREAM_ENABLED and _side_ok and t.is_cuda and not torch.cuda.is_current_stream_capturing()
+            and _defer_join()):
         return _colsum_on(t, L.stream())
     side = _side_stream(t.device)
     side.wait_stream(torch.cuda.current_stream(t.device))

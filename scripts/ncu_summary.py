@@ -1,7 +1,11 @@
 """Summarise an `ncu --set full` report (.ncu-rep) into a small text table: per captured launch the duration,
 DRAM bytes (read + write = `traffic`), DRAM / tensor-pipe utilisation, occupancy and registers.
-Usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.txt"""
+Usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.txt
+       python scripts/ncu_summary.py gpurun_out/prof.ncu-rep --traffic profiles/edge_traffic.json
+           (also writes the per-launch DRAM traffic of the edge forward / backward entry points, which
+            bench.py reports as roofline.traffic)"""
 import csv
+import json
 import subprocess
 import sys
 
@@ -39,3 +43,30 @@ for r in rd:
                 pass
         cells.append(f"{short}={v}")
     print("  ".join(cells))
+
+
+if "--traffic" in sys.argv:
+    out_path = sys.argv[sys.argv.index("--traffic") + 1]
+    rd = csv.reader(out.splitlines())
+    hdr = next(rd)
+    next(rd)
+    ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    per = {}
+    for r in rd:
+        name = r[ik]
+        mb = float(r[ir].replace(",", "")) + float(r[iw].replace(",", ""))
+        key = None
+        for frag in ("gat_edge_fwd", "gat_edge_bwd_dst", "gat_edge_bwd_src", "gat_att_reduce", "gm_head_sum"):
+            if frag in name:
+                key = frag
+        if key:
+            per.setdefault(key, []).append(mb * 1e6)
+    avg = {k: sum(v) / len(v) for k, v in per.items()}
+    res = {"source": sys.argv[1], "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+           "kernels": avg}
+    if "gat_edge_fwd" in avg:
+        res["isg_gat_edge_fwd"] = avg["gat_edge_fwd"]
+    if "gat_edge_bwd_dst" in avg and "gat_edge_bwd_src" in avg:
+        res["isg_gat_edge_bwd"] = sum(avg.get(k, 0.0) for k in ("gat_edge_bwd_dst", "gat_edge_bwd_src",
+                                                                 "gat_att_reduce", "gm_head_sum"))
+    json.dump(res, open(out_path, "w"), indent=1)
