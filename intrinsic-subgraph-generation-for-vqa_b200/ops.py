@@ -117,6 +117,8 @@ def _defer_join():
 
 
 def _colsum_on(t, stream_handle):
+    if t.dtype != torch.float32:
+        raise TypeError("isg_colsum is fp32-only")
     lib = L.load()
     rows, cols = t.shape
     out = torch.empty(cols, dtype=torch.float32, device=t.device)
@@ -330,7 +332,8 @@ class GatEdge(torch.autograd.Function):
                                      L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(g_xl), L.ptr(g_xr), 2 * HC,
                                      L.ptr(g_ep), L.ptr(g_att), L.ptr(g_em), N, gi.E, H, C, ctx.slope,
                                      L.dtype_code(xlr), L.ptr(ws), nbytes, L.stream())
-        g_bias = colsum(g_out) if ctx.has_bias else None
+        # the column-sum kernel is fp32-only: bf16 storage converts g_out once (N x HC, small next to the edge pass)
+        g_bias = colsum(g_out if g_out.dtype == torch.float32 else g_out.float()) if ctx.has_bias else None
         if _DEBUG_EDGE_BWD is not None:
             _DEBUG_EDGE_BWD.append(dict(g_out=g_out.clone(), x_l=x_l.clone(), x_r=x_r.clone(), e_proj=e_proj.clone(),
                                         att=att.clone(), bias=bias.clone() if bias is not None else None,

@@ -39,7 +39,7 @@ def peak():
     return 6650.0, "fallback"
 
 
-def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7):
+def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7, bf16=False):
     dev = torch.device("cuda")
     lib = L.load()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -52,16 +52,19 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7):
         N, E = int(batch.numel()), int(ei.shape[1])
         gi = GraphIndex(ei, batch, nb)
         gen = torch.Generator(device=dev).manual_seed(seed)
-        xlr = torch.randn(N, 2 * HC, device=dev, generator=gen)
-        ep = torch.randn(E, HC, device=dev, generator=gen)
+        fdt = torch.bfloat16 if bf16 else torch.float32
+        es = 2 if bf16 else 4
+        code = 1 if bf16 else 0
+        xlr = torch.randn(N, 2 * HC, device=dev, generator=gen).to(fdt)
+        ep = torch.randn(E, HC, device=dev, generator=gen).to(fdt)
         att = torch.randn(HC, device=dev, generator=gen) * 0.1
         bias = torch.zeros(HC, device=dev)
         em = (torch.rand(E, device=dev, generator=gen) > 0.3).float() if masked else None
-        out = torch.empty(N, HC, device=dev)
+        out = torch.empty(N, HC, device=dev, dtype=fdt)
         alpha = torch.empty(E, H, device=dev)
-        gout = torch.randn(N, HC, device=dev, generator=gen)
-        gxlr = torch.empty(N, 2 * HC, device=dev)
-        gep = torch.empty(E, HC, device=dev)
+        gout = torch.randn(N, HC, device=dev, generator=gen).to(fdt)
+        gxlr = torch.empty(N, 2 * HC, device=dev, dtype=fdt)
+        gep = torch.empty(E, HC, device=dev, dtype=fdt)
         gatt = torch.empty(HC, device=dev)
         gem = torch.empty(E, device=dev) if masked else None
         wsb = lib.isg_gat_edge_bwd_workspace_bytes(N, E, H, C)
@@ -69,16 +72,16 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7):
         st = L.stream()
 
         def fwd():
-            L.call("isg_gat_edge_fwd", xlr.data_ptr(), xlr.data_ptr() + HC * 4, 2 * HC, ep.data_ptr(), att.data_ptr(),
+            L.call("isg_gat_edge_fwd", xlr.data_ptr(), xlr.data_ptr() + HC * es, 2 * HC, ep.data_ptr(), att.data_ptr(),
                    bias.data_ptr(), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), out.data_ptr(),
-                   HC, alpha.data_ptr(), N, E, H, C, 0.2, 0, st)
+                   HC, alpha.data_ptr(), N, E, H, C, 0.2, code, st)
 
         def bwd():
-            L.call("isg_gat_edge_bwd", gout.data_ptr(), HC, xlr.data_ptr(), xlr.data_ptr() + HC * 4, 2 * HC,
+            L.call("isg_gat_edge_bwd", gout.data_ptr(), HC, xlr.data_ptr(), xlr.data_ptr() + HC * es, 2 * HC,
                    ep.data_ptr(), att.data_ptr(), bias.data_ptr(), L.ptr(em), alpha.data_ptr(), out.data_ptr(), HC,
                    L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr), L.ptr(gi.src_nbr),
-                   L.ptr(gi.src_eid), gxlr.data_ptr(), gxlr.data_ptr() + HC * 4, 2 * HC, gep.data_ptr(),
-                   gatt.data_ptr(), L.ptr(gem), N, E, H, C, 0.2, 0, ws.data_ptr(), wsb, st)
+                   L.ptr(gi.src_eid), gxlr.data_ptr(), gxlr.data_ptr() + HC * es, 2 * HC, gep.data_ptr(),
+                   gatt.data_ptr(), L.ptr(gem), N, E, H, C, 0.2, code, ws.data_ptr(), wsb, st)
 
         for fn, key in ((fwd, "fwd_ms"), (bwd, "bwd_ms")):
             for _ in range(3):
@@ -94,7 +97,7 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7):
                 times.append(a.elapsed_time(b))
             times.sort()
             tot[key] += times[len(times) // 2]
-        fb, bb = edge_bytes(N, E, masked)
+        fb, bb = edge_bytes(N, E, masked, es)
         tot["fwd_b"] += fb
         tot["bwd_b"] += bb
         tot["N"] += N
@@ -110,6 +113,7 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--masked", action="store_true")
+    ap.add_argument("--bf16", action="store_true", help="bf16 storage of the feature tensors (fp32 accumulation)")
     args = ap.parse_args()
     pk, src = peak()
     points = [(4096, 10, 50), (4096, 20, 150), (4096, 50, 600), (4096, 100, 1500), (4096, 200, 4000)] \
@@ -117,11 +121,12 @@ def main():
     for B, mn, me in points:
         # keep e_proj + g_eproj of one chunk under ~40 GB
         chunk = max(1, min(B, int(40e9 / (2 * 4 * HC * me))))
-        t = run_point(B, mn, me, args.masked, args.reps if B * me < 2e6 else max(3, args.reps // 4), chunk)
+        t = run_point(B, mn, me, args.masked, args.reps if B * me < 2e6 else max(3, args.reps // 4), chunk,
+                      bf16=args.bf16)
         f = t["fwd_b"] / (t["fwd_ms"] * 1e-3) / 1e9
         b = t["bwd_b"] / (t["bwd_ms"] * 1e-3) / 1e9
         print(json.dumps({"graphs": B, "mean_nodes": mn, "mean_edges": me, "N": t["N"], "E": t["E"],
-                          "masked": args.masked, "fwd_ms": round(t["fwd_ms"], 4), "bwd_ms": round(t["bwd_ms"], 4),
+                          "masked": args.masked, "storage": "bf16" if args.bf16 else "fp32", "fwd_ms": round(t["fwd_ms"], 4), "bwd_ms": round(t["bwd_ms"], 4),
                           "fwd_GBps": round(f, 1), "bwd_GBps": round(b, 1), "fwd_frac": round(f / pk, 4),
                           "bwd_frac": round(b / pk, 4), "peak_GBps": pk, "peak_source": src,
                           "chunk_graphs": chunk}), flush=True)

@@ -181,6 +181,39 @@ def test_edge_fused_pitch_and_isolated_nodes():
     assert torch.allclose(got["out"][N:].cpu(), d["bias"].expand(2, -1))
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_edge_bf16_storage(masked):
+    """bf16 STORAGE of the edge-kernel tensors (x_l|x_r, e_proj, out and their gradients), fp32 accumulation
+    inside the kernel — the configuration BASELINE states separately.  Reference = the oracle in fp64 on the
+    bf16-rounded inputs; bound = bf16 output rounding (2^-8 relative) with margin."""
+    import isg_oracle as O
+    from isg_b200 import ops
+
+    H, C = 4, 300
+    d = _edge_case(12, 14, 90, C, H, masked, seed=21)
+    for k in ("x_l", "x_r", "e_proj", "g_out"):
+        d[k] = d[k].to(torch.bfloat16).float()  # inputs exactly representable in bf16
+    want = _run_edge_oracle(d, H, C)
+    gi = _gi(d["edge_index"], d["batch"], int(d["batch"].max()) + 1)
+    xlr = torch.cat([d["x_l"], d["x_r"]], dim=1).to(DEV, torch.bfloat16).requires_grad_(True)
+    ep = d["e_proj"].to(DEV, torch.bfloat16).requires_grad_(True)
+    att = d["att"].to(DEV).requires_grad_(True)
+    bias = d["bias"].to(DEV).requires_grad_(True)
+    m = d["mask"].to(DEV).requires_grad_(True) if d["mask"] is not None else None
+    out, alpha = ops.GatEdge.apply(xlr, ep, att, bias, m, gi, H, 0.2)
+    assert out.dtype == torch.bfloat16
+    out.backward(d["g_out"].to(DEV, torch.bfloat16))
+    tol = 1.2e-2
+    assert util.rel_err(out.float(), want["out"]) <= tol
+    assert util.rel_err(alpha, want["alpha"]) <= 1e-4  # alpha is fp32 and the inputs are bf16-exact
+    assert util.rel_err(xlr.grad[:, : H * C].float(), want["g_x_l"]) <= tol
+    assert util.rel_err(xlr.grad[:, H * C:].float(), want["g_x_r"]) <= tol
+    assert util.rel_err(ep.grad.float(), want["g_e_proj"]) <= tol
+    assert util.rel_err(att.grad, want["g_att"]) <= tol
+    if masked:
+        assert util.rel_err(m.grad, want["g_mask"]) <= tol
+
+
 def test_edge_softmax_rows_sum_to_one_at_full_size():
     """BASELINE config 2 size (B=1024): size-independent property of the segment softmax."""
     d = _edge_case(1024, 20, 150, 300, 4, False, seed=1)
