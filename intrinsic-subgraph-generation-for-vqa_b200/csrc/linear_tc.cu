@@ -20,7 +20,11 @@
 //   wgrad  gW[n,k] = sum_m gy[m,n] x[m,k]    A MN-major, B MN-major, deterministic split over m
 //
 //   warp 0       TMA producer: cp.async.bulk.tensor.2d of raw fp32 operand tiles (BK = 16 floats per
-//                k-block: 64-byte swizzle for K-major, 128B/32B-atom swizzle for MN-major operands)
+//                k-block: 64-byte swizzle for K-major, 128B/32B-atom swizzle for MN-major operands).
+//                CTAs run as CLUSTERS OF TWO on adjacent M tiles of the same N block: each CTA fetches
+//                its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory
+//                (the mainloop is bound by L2->SM operand traffic: 16 KB per k-block per CTA alone,
+//                12 KB as a pair); smem stages are released by both CTAs' MMA commits (multicast arrive)
 //   warps 4-7    splitters (mode 1): thread m owns row m of the A tile — it gathers the row's 16 k-values
 //                from the swizzled smem tile and writes A_hi (raw) and A_lo = x - (x & ~0x1fff) into a
 //                4-slot A ring IN TENSOR MEMORY (tcgen05.st), so the MMAs take A from TMEM and only B
@@ -36,6 +40,7 @@
 //   warp 2       TMEM allocation, 512 columns.  mode 1: main[2 chunk stages] 0..255, correction 256..383,
 //                A ring (4 slots x {hi 16, lo 16} columns) 384..511; mode 2: main[2] only, SS operands
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "linear_tc.h"
@@ -119,6 +124,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -136,6 +152,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(map), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -189,6 +227,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
+// arrive on the barrier at the same shared-memory offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32"
@@ -239,6 +284,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t CL = cluster_nctarank();  // 1 (plain launch) or 2 (cluster pair sharing the B tile)
+  const uint32_t cta_rank = cluster_ctarank();
 
   const int S = g.stages;
   const int BN = g.BN;
@@ -264,7 +311,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(conv_bar(s), 128);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);  // released by the MMA commits of every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(mfull_bar(s), 1);
@@ -281,12 +328,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
-  const int tiles_mn = g.m_tiles * g.n_tiles;
+  // Work items are (split, M-tile group of CL adjacent tiles, N block); CTA `cta_rank` of the cluster takes
+  // M tile  group*CL + cta_rank  (possibly past the end: zero operands, nothing stored).
+  const int m_groups = (g.m_tiles + (int)CL - 1) / (int)CL;
+  const int tiles_mn = m_groups * g.n_tiles;
+  const int total_tiles = tiles_mn * g.splits;
+  const int work0 = (int)(blockIdx.x / CL), work_stride = (int)(gridDim.x / CL);
   auto tile_kb = [&](int t) {
     const int split = t / tiles_mn;
     const int64_t r_beg = (int64_t)split * g.r_chunk;
@@ -299,9 +351,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = work0; t < total_tiles; t += work_stride) {
       const int split = t / tiles_mn, rem = t - split * tiles_mn;
-      const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+      const int m_grp = rem / g.n_tiles, n_blk = rem - m_grp * g.n_tiles;
+      const int m_blk = m_grp * (int)CL + (int)cta_rank;
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int64_t r_beg = (int64_t)split * g.r_chunk;
       const int num_kb = tile_kb(t);
@@ -317,11 +370,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &map_a, fb, m0 + 32 * c, r0);
         }
-        if (!B_MN) {
-          tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0);
+        if (CL == 1) {
+          if (!B_MN) {
+            tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0);
+          } else {
+            for (int c = 0; c < BN / 32; ++c)
+              tma_load_2d(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + 32 * c, r0);
+          }
         } else {
-          for (int c = 0; c < BN / 32; ++c)
-            tma_load_2d(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + 32 * c, r0);
+          // this CTA fetches half of the B tile and multicasts it into both CTAs of the pair
+          if (!B_MN) {
+            const int half_rows = BN / 2;  // the tensor map's box is BN/2 rows in cluster mode
+            tma_load_2d_mc(sa + off_b_hi + cta_rank * (uint32_t)half_rows * (BK * 4), &map_b, fb, r0,
+                           n0 + (int)cta_rank * half_rows, (uint16_t)0x3);
+          } else {
+            const int nch = BN / 32, h = nch / 2;
+            for (int c = (int)cta_rank * h; c < ((int)cta_rank + 1) * h; ++c)
+              tma_load_2d_mc(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + 32 * c, r0, (uint16_t)0x3);
+          }
         }
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
@@ -340,7 +406,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t phase = 0;
     uint32_t gchunk = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = work0; t < total_tiles; t += work_stride, ++it) {
       const int num_kb = tile_kb(t);
       const int tp = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
@@ -378,7 +444,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               umma_tf32(d_main, a_hi + ak, b_hi + bk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage once the MMAs above have read it
+          // frees the smem stage (in every CTA of the cluster: the peer's multicast writes land here too)
+          if (CL > 1) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);
+          else umma_commit(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         umma_commit(mfull_bar(ms));  // chunk partial complete -> epilogue drains it
@@ -388,16 +456,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
    }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================================== lo-plane splitters (mode 1)
+    // (A software-pipelined variant that prefetched the next k-block's operands while the TMEM stores drained
+    // measured 5-9 % SLOWER; the straightforward per-k-block sequence below is the faster one.)
     if (g.split3) {
       const int tid = threadIdx.x - 128;
       const int nb = (int)(b_tile_bytes / 16);  // <= 512 float4
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = work0; t < total_tiles; t += work_stride) {
         const int num_kb = tile_kb(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
+          if (g.write_hi == 2) {  // timing experiment only (mode 4): skip the split work, results are garbage
+            tc_fence_before();
+            mbar_arrive(conv_bar(stage));
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           // ---- A: row `tid` of the tile -> 16 k-values -> TMEM (hi = raw, lo = exact remainder)
           float av[16];
           if (!A_MN) {
@@ -453,9 +529,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     uint32_t gchunk = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = work0; t < total_tiles; t += work_stride, ++it) {
       const int split = t / tiles_mn, rem = t - split * tiles_mn;
-      const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+      const int m_grp = rem / g.n_tiles, n_blk = rem - m_grp * g.n_tiles;
+      const int m_blk = m_grp * (int)CL + (int)cta_rank;
       const int64_t m0 = (int64_t)m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
       const int n_lim = min(g.cols, n0 + BN);
@@ -539,7 +616,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on it
+  else __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
@@ -606,15 +684,25 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   g.c_split_stride = p.c_split_stride;
   g.bias = p.bias; g.Z = p.Z; g.ldz = p.ldz; g.Zprev = p.Zprev; g.act = p.act; g.accumulate = p.accumulate;
   g.split3 = p.split3 ? 1 : 0;
-  g.write_hi = p.split3 == 3 ? 1 : 0;
+  g.write_hi = p.split3 == 3 ? 1 : (p.split3 == 4 ? 2 : 0);
   if (p.rows >= (1ll << 31) || p.R >= (1ll << 31)) return ISG_EUNSUPPORTED;  // TMA coordinates are int32
+
+  // cluster pairs whenever there are at least two M tiles to pair and the B tile splits evenly
+  // Measured (B200, c3 step): the single-pass mode is bound by L2->SM operand traffic and gains 1.33x from the
+  // pair (0.160 -> 0.120 ms on [39809,300]x[300,1200]); the 3xTF32 mode is bound by its splitter / MMA chain
+  // and runs 1.7 % SLOWER as pairs (lock-step coupling), so it launches single CTAs unless ISG_TC_CLUSTER is set.
+  static const bool env_no_cluster = getenv("ISG_TC_NO_CLUSTER") != nullptr;
+  static const bool env_cluster = getenv("ISG_TC_CLUSTER") != nullptr;
+  const bool want_pair = (p.split3 == 0 || env_cluster) && !p.no_cluster && !env_no_cluster;
+  const bool pair = want_pair && g.m_tiles >= 2 && (B_MN ? ((g.BN / 32) % 2 == 0) : true);
+  const int CLh = pair ? 2 : 1;
 
   CUtensorMap ma, mb;
   int rc;
   if (!A_MN) rc = make_map(&ma, p.A, p.R, p.rows, p.lda, BK, BM, false);
   else rc = make_map(&ma, p.A, p.rows, p.R, p.lda, 32, BK, true);
   if (rc != ISG_OK) return rc;
-  if (!B_MN) rc = make_map(&mb, p.B, p.R, p.cols, p.ldb, BK, g.BN, false);
+  if (!B_MN) rc = make_map(&mb, p.B, p.R, p.cols, p.ldb, BK, g.BN / CLh, false);
   else rc = make_map(&mb, p.B, p.cols, p.R, p.ldb, 32, BK, true);
   if (rc != ISG_OK) return rc;
 
@@ -622,9 +710,24 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   auto kern = tc_gemm_kernel<A_MN, B_MN, EPI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  const int total = g.m_tiles * g.n_tiles * g.splits;
-  const int grid = total < ISG_NUM_SMS ? total : ISG_NUM_SMS;
-  kern<<<grid, NTHREADS, smem, stream>>>(ma, mb, g);
+  const int m_groups = (g.m_tiles + CLh - 1) / CLh;
+  const int total = m_groups * g.n_tiles * g.splits;
+  int grid = total * CLh < ISG_NUM_SMS ? total * CLh : ISG_NUM_SMS;
+  grid -= grid % CLh;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CLh;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, ma, mb, g);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

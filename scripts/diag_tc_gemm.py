@@ -81,7 +81,7 @@ if __name__ == "__main__":
         child(sys.argv[1], int(sys.argv[2]))
         sys.exit(0)
     rc = 0
-    for mode in (1, 2):
+    for mode in [int(m) for m in os.environ.get("DIAG_MODES", "1,2").split(",")]:
         for which in ("fwd", "dgrad", "wgrad"):
             try:
                 p = subprocess.run([sys.executable, __file__, which, str(mode)], timeout=120)
