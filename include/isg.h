@@ -210,6 +210,17 @@ int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const float* ins,
                            float* g_v, float* g_ins, float* gw_part, float* gb_part, float* gms_part,
                            void* stream);
 
+/* masked attention pooling — SURVEY.md section 8 row f1, GlobalAttention.forward
+ * (models/att_pooling.py:57-77; called from models/isubgvqa.py:280-287) after its node_nn / ques_nn MLPs:
+ *   xm = x * node_mask;  l_n = <xm_n, q[b]> / sqrt(D);  a = torch_geometric softmax over the nodes of graph b
+ *   (exp(l - max) / (sum + 1e-16));  out[b] = sum_n a_n * xm_n;  gate [N] = a.
+ * node_mask [N] or NULL.  bwd: g_gate [N] or NULL (gradient of the returned gate); g_mask NULL iff node_mask NULL. */
+int isg_attn_pool_fwd(const float* x, const float* node_mask, const float* q, const int32_t* graph_ptr,
+                      int64_t num_graphs, int dim, int nmax, float* out, float* gate, void* stream);
+int isg_attn_pool_bwd(const float* g_out, const float* g_gate, const float* x, const float* node_mask,
+                      const float* q, const float* gate, const int32_t* graph_ptr, int64_t num_graphs, int dim,
+                      int nmax, float* g_x, float* g_mask, float* g_q, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * (d) dense projections (lin_l / lin_r / lin_edge models/mgat_v2_conv.py:63-103,177,181,259;
  * x_proj models/mgat.py:79-89,156; node_nn / ques_nn models/masking.py:82-87,137,152).

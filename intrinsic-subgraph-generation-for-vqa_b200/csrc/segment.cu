@@ -278,6 +278,125 @@ sdpa_graphnorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__
 }
 
 // ---------------------------------------------------------------- misc
+
+// ---------------------------------------------------------------- masked attention pooling (§8 f1)
+// GlobalAttention.forward (reference models/att_pooling.py:57-77) after its node_nn / ques_nn projections:
+//   xm = x * node_mask;  l_n = <xm_n, q[b]> / sqrt(D);  a = softmax over the nodes of graph b
+//   (torch_geometric.utils.softmax: exp(l - max) / (sum + 1e-16));  out[b] = sum_n a_n * xm_n.
+// One CTA per graph (batch is sorted, nodes of a graph are contiguous); logits live in shared memory.
+constexpr int AP_THREADS = 256;
+
+__global__ void __launch_bounds__(AP_THREADS)
+attn_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ q,
+                     const int* __restrict__ gptr, int D, float* __restrict__ out, float* __restrict__ gate) {
+  extern __shared__ float ap_smem[];
+  __shared__ float red[32];
+  float* lg = ap_smem;  // [n_b] logits, then attention weights
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], nb = gptr[b + 1] - n0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = AP_THREADS / 32;
+  const int d4 = D >> 2;
+  const float inv_sqrt_d = 1.0f / sqrtf((float)D);
+  const float* qb = q + (size_t)b * D;
+  for (int n = warp; n < nb; n += nwarps) {
+    const float* xr = x + (size_t)(n0 + n) * D;
+    const float m = mask ? mask[n0 + n] : 1.f;
+    float acc = 0.f;
+    for (int v = lane; v < d4; v += 32) {
+      const float4 xv = Vec4<float>::ld(xr + 4 * v), qv = Vec4<float>::ld(qb + 4 * v);
+      acc += (xv.x * m) * qv.x + (xv.y * m) * qv.y + (xv.z * m) * qv.z + (xv.w * m) * qv.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) lg[n] = acc * inv_sqrt_d;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int n = threadIdx.x; n < nb; n += AP_THREADS) mx = fmaxf(mx, lg[n]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int n = threadIdx.x; n < nb; n += AP_THREADS) {
+    const float e = expf(lg[n] - mx);
+    lg[n] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / (sum + 1e-16f);
+  __syncthreads();
+  for (int n = threadIdx.x; n < nb; n += AP_THREADS) {
+    const float a = lg[n] * inv;
+    lg[n] = a;
+    gate[n0 + n] = a;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < d4; v += AP_THREADS) {
+    float4 o = f4_zero();
+    for (int n = 0; n < nb; ++n) {
+      const float w = lg[n] * (mask ? mask[n0 + n] : 1.f);
+      o = f4_fma(Vec4<float>::ld(x + (size_t)(n0 + n) * D + 4 * v), w, o);
+    }
+    Vec4<float>::st(out + (size_t)b * D + 4 * v, o);
+  }
+}
+
+// backward: g_out [B,D], g_gate [N] or NULL -> g_x [N,D], g_mask [N] (or NULL), g_q [B,D]
+__global__ void __launch_bounds__(AP_THREADS)
+attn_pool_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g_gate,
+                     const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ q,
+                     const float* __restrict__ gate, const int* __restrict__ gptr, int D,
+                     float* __restrict__ g_x, float* __restrict__ g_mask, float* __restrict__ g_q) {
+  extern __shared__ float ap_smem[];
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], nb = gptr[b + 1] - n0;
+  float* ga = ap_smem;       // [n_b] dL/da_n, then dL/dl_n
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = AP_THREADS / 32;
+  const int d4 = D >> 2;
+  const float inv_sqrt_d = 1.0f / sqrtf((float)D);
+  const float* qb = q + (size_t)b * D;
+  const float* gob = g_out + (size_t)b * D;
+  for (int n = warp; n < nb; n += nwarps) {
+    const float* xr = x + (size_t)(n0 + n) * D;
+    const float m = mask ? mask[n0 + n] : 1.f;
+    float acc = 0.f;
+    for (int v = lane; v < d4; v += 32) {
+      const float4 xv = Vec4<float>::ld(xr + 4 * v), gv = Vec4<float>::ld(gob + 4 * v);
+      acc += (xv.x * m) * gv.x + (xv.y * m) * gv.y + (xv.z * m) * gv.z + (xv.w * m) * gv.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) ga[n] = acc + (g_gate ? g_gate[n0 + n] : 0.f);
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int n = threadIdx.x; n < nb; n += AP_THREADS) dot += gate[n0 + n] * ga[n];
+  dot = block_sum(dot, red);
+  __syncthreads();
+  for (int n = threadIdx.x; n < nb; n += AP_THREADS) ga[n] = gate[n0 + n] * (ga[n] - dot);  // dL/dl_n
+  __syncthreads();
+  for (int n = warp; n < nb; n += nwarps) {
+    const float* xr = x + (size_t)(n0 + n) * D;
+    const float m = mask ? mask[n0 + n] : 1.f;
+    const float a = gate[n0 + n], gl = ga[n] * inv_sqrt_d;
+    float gm = 0.f;
+    for (int v = lane; v < d4; v += 32) {
+      const float4 xv = Vec4<float>::ld(xr + 4 * v), gv = Vec4<float>::ld(gob + 4 * v), qv = Vec4<float>::ld(qb + 4 * v);
+      const float4 gxm = make_float4(fmaf(gl, qv.x, a * gv.x), fmaf(gl, qv.y, a * gv.y), fmaf(gl, qv.z, a * gv.z),
+                                     fmaf(gl, qv.w, a * gv.w));
+      gm += gxm.x * xv.x + gxm.y * xv.y + gxm.z * xv.z + gxm.w * xv.w;
+      Vec4<float>::st(g_x + (size_t)(n0 + n) * D + 4 * v, f4_scale(gxm, m));
+    }
+    gm = warp_sum(gm);
+    if (g_mask && lane == 0) g_mask[n0 + n] = gm;
+  }
+  for (int v = threadIdx.x; v < d4; v += AP_THREADS) {
+    float4 o = f4_zero();
+    for (int n = 0; n < nb; ++n) {
+      const float w = ga[n] * inv_sqrt_d * (mask ? mask[n0 + n] : 1.f);
+      o = f4_fma(Vec4<float>::ld(x + (size_t)(n0 + n) * D + 4 * v), w, o);
+    }
+    Vec4<float>::st(g_q + (size_t)b * D + 4 * v, o);
+  }
+}
+
 __global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ z,
                                 float* __restrict__ gz, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -400,6 +519,43 @@ extern "C" int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const 
   }
   sdpa_graphnorm_bwd_kernel<<<(unsigned)B, SG_THREADS, smem, (cudaStream_t)stream_>>>(
       g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_attn_pool_fwd(const float* x, const float* node_mask, const float* q, const int32_t* gptr,
+                                 int64_t B, int D, int nmax, float* out, float* gate, void* stream_) {
+  if (B < 0 || D <= 0 || nmax < 0) return ISG_EINVAL;
+  if (D % 4 != 0) return ISG_EUNSUPPORTED;
+  if (B == 0) return ISG_OK;
+  if (!x || !q || !gptr || !out || !gate) return ISG_EINVAL;
+  const size_t smem = (size_t)(nmax > 0 ? nmax : 1) * sizeof(float);
+  if (smem > 200 * 1024) return ISG_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attn_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  attn_pool_fwd_kernel<<<(unsigned)B, AP_THREADS, smem, (cudaStream_t)stream_>>>(x, node_mask, q, gptr, D, out, gate);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_attn_pool_bwd(const float* g_out, const float* g_gate, const float* x, const float* node_mask,
+                                 const float* q, const float* gate, const int32_t* gptr, int64_t B, int D, int nmax,
+                                 float* g_x, float* g_mask, float* g_q, void* stream_) {
+  if (B < 0 || D <= 0 || nmax < 0) return ISG_EINVAL;
+  if (D % 4 != 0) return ISG_EUNSUPPORTED;
+  if (B == 0) return ISG_OK;
+  if (!g_out || !x || !q || !gate || !gptr || !g_x || !g_q) return ISG_EINVAL;
+  if ((node_mask == nullptr) != (g_mask == nullptr)) return ISG_EINVAL;
+  const size_t smem = (size_t)(nmax > 0 ? nmax : 1) * sizeof(float);
+  if (smem > 200 * 1024) return ISG_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attn_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  attn_pool_bwd_kernel<<<(unsigned)B, AP_THREADS, smem, (cudaStream_t)stream_>>>(g_out, g_gate, x, node_mask, q, gate,
+                                                                               gptr, D, g_x, g_mask, g_q);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

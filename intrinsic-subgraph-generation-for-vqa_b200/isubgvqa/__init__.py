@@ -4,7 +4,8 @@ arithmetic done by libisg.so.  `install()` makes the reference's own import stat
 modules, so main.py / training / eval run unchanged."""
 import sys
 
-from . import masking, mgat, mgat_v2_conv, node_edge_masks, samplers  # noqa: F401
+from . import att_pooling, masking, mgat, mgat_v2_conv, node_edge_masks, samplers  # noqa: F401
+from .att_pooling import GlobalAttention  # noqa: F401
 from .masking import MaskingModel, get_aimle_samplers, get_imle_samplers  # noqa: F401
 from .mgat import MGAT  # noqa: F401
 from .mgat_v2_conv import MaskingGATv2Conv  # noqa: F401
@@ -14,6 +15,7 @@ _ALIASES = {
     "ISubGVQA.models.mgat": mgat,
     "ISubGVQA.models.mgat_v2_conv": mgat_v2_conv,
     "ISubGVQA.models.masking": masking,
+    "ISubGVQA.models.att_pooling": att_pooling,
     "ISubGVQA.sampling.node_edge_masks": node_edge_masks,
     "ISubGVQA.sampling.methods.wrapper": samplers,
     "ISubGVQA.sampling.methods.aimle": samplers,

@@ -500,3 +500,37 @@ class SimpleTopk(torch.autograd.Function):
         L.call("isg_simple_marginals_bwd", L.ptr(dy), L.ptr(dmarg), L.ptr(theta), L.ptr(gi.graph_ptr), gi.B,
                gi.nmax, ctx.k, L.ptr(g), L.stream())
         return g, None, None, None
+
+
+class AttnPool(torch.autograd.Function):
+    """Masked per-graph attention pooling — GlobalAttention.forward after its MLPs (models/att_pooling.py:64-77):
+    gate = pyg_softmax(<x*mask, q[batch]>/sqrt(D), batch); out = scatter_add(gate * x*mask).  x [N,D],
+    node_mask [N,1] or None, q [B,D].  Returns (out [B,D], gate [N,1])."""
+
+    @staticmethod
+    def forward(ctx, x, node_mask, q, gi):
+        L.require_cuda(x, q)
+        x, q = _c(x), _c(q)
+        m = _c(node_mask.to(torch.float32)) if node_mask is not None else None
+        N, D = x.shape
+        out = torch.empty(gi.B, D, dtype=torch.float32, device=x.device)
+        gate = torch.empty(N, 1, dtype=torch.float32, device=x.device)
+        L.call("isg_attn_pool_fwd", L.ptr(x), L.ptr(m), L.ptr(q), L.ptr(gi.graph_ptr), gi.B, D, gi.nmax, L.ptr(out),
+               L.ptr(gate), L.stream())
+        ctx.gi = gi
+        ctx.has_mask = m is not None
+        ctx.save_for_backward(x, m, q, gate)
+        return out, gate
+
+    @staticmethod
+    def backward(ctx, g_out, g_gate):
+        x, m, q, gate = ctx.saved_tensors
+        gi = ctx.gi
+        g_out = _c(g_out)
+        g_gate = _c(g_gate) if g_gate is not None else None
+        g_x = torch.empty_like(x)
+        g_m = torch.empty(x.shape[0], 1, dtype=torch.float32, device=x.device) if ctx.has_mask else None
+        g_q = torch.empty_like(q)
+        L.call("isg_attn_pool_bwd", L.ptr(g_out), L.ptr(g_gate), L.ptr(x), L.ptr(m), L.ptr(q), L.ptr(gate),
+               L.ptr(gi.graph_ptr), gi.B, x.shape[1], gi.nmax, L.ptr(g_x), L.ptr(g_m), L.ptr(g_q), L.stream())
+        return g_x, g_m, g_q, None

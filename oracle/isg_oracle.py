@@ -159,6 +159,22 @@ def scatter_sdpa(query, key, value, batch):
     return a.unsqueeze(1) * value
 
 
+def global_attention_pool(x, u, batch, num_graphs, params, node_mask=None):
+    """GlobalAttention.forward (models/att_pooling.py:57-77): node_nn / ques_nn are Linear-GELU-Linear
+    (:36-46); gate = <x_n, q[batch_n]>/sqrt(D) (:67-70); torch_geometric.utils.softmax over the nodes of a graph
+    (:72); out = scatter_add(gate * x) (:74).  params: dict with node_nn.{0,2}.{weight,bias}, ques_nn.{0,2}.*"""
+    x = F.linear(F.gelu(F.linear(x, params["node_nn.0.weight"], params["node_nn.0.bias"])),
+                 params["node_nn.2.weight"], params["node_nn.2.bias"])
+    if node_mask is not None:
+        x = x * node_mask
+    q = F.linear(F.gelu(F.linear(u, params["ques_nn.0.weight"], params["ques_nn.0.bias"])),
+                 params["ques_nn.2.weight"], params["ques_nn.2.bias"])
+    gate = torch.bmm(x.unsqueeze(1), q[batch].unsqueeze(2)).squeeze(-1) / torch.sqrt(torch.tensor(x.size(1)))
+    gate = pyg_softmax(gate, batch, num_graphs)
+    out = _seg_sum(gate * x, batch, num_graphs)
+    return out, gate
+
+
 def graph_norm(x, batch, weight, bias, mean_scale, num_graphs, eps=1e-5):
     """torch_geometric.nn.norm.GraphNorm(eps=1e-5) (call site models/mgat.py:93-95,171)."""
     cnt = torch.bincount(batch, minlength=num_graphs).clamp(min=1).to(x.dtype).unsqueeze(-1)

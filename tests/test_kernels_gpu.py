@@ -491,6 +491,47 @@ def test_simple_marginals_fwd_bwd(B, mn, k, zeros):
     assert util.rel_err(tc.grad, to.grad) <= 1e-4
 
 
+@pytest.mark.parametrize("D,masked,with_empty", [(300, True, False), (300, False, True), (16, True, True)])
+def test_global_attention_pooling(D, masked, with_empty):
+    """the drop-in GlobalAttention module (projections + fused masked softmax-pool kernel)
+    against the oracle restatement of models/att_pooling.py:57-77, forward and all gradients (incl. the gate)."""
+    import isg_oracle as O
+    from isg_b200.isubgvqa import GlobalAttention
+
+    B = 11
+    g = torch.Generator().manual_seed(D + 5)
+    counts = torch.randint(1, 30, (B,), generator=g)
+    if with_empty:
+        counts[3] = 0
+    batch = torch.repeat_interleave(torch.arange(B), counts)
+    N = int(counts.sum())
+    mod = GlobalAttention(num_node_features=D, num_out_features=D)
+    params = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    x = torch.randn(N, D, generator=g)
+    u = torch.randn(B, D, generator=g)
+    mask = (torch.rand(N, 1, generator=g) > 0.3).float() if masked else None
+    wo, wg = torch.randn(B, D, generator=g), torch.randn(N, 1, generator=g)
+    xo, uo = x.clone().requires_grad_(True), u.clone().requires_grad_(True)
+    mo = mask.clone().requires_grad_(True) if masked else None
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    oo, go = O.global_attention_pool(xo, uo, batch, B, po, node_mask=mo)
+    ((oo * wo).sum() + (go * wg).sum()).backward()
+    mod = mod.to(DEV)
+    xc, uc = x.to(DEV).requires_grad_(True), u.to(DEV).requires_grad_(True)
+    mc = mask.to(DEV).requires_grad_(True) if masked else None
+    oc, gc = mod(xc, uc, batch.to(DEV), size=B, return_mask=True, node_mask=mc)
+    ((oc * wo.to(DEV)).sum() + (gc * wg.to(DEV)).sum()).backward()
+    assert util.rel_err(oc, oo) <= RTOL and util.rel_err(gc, go) <= RTOL
+    assert util.rel_err(xc.grad, xo.grad) <= RTOL and util.rel_err(uc.grad, uo.grad) <= RTOL
+    if masked:
+        assert util.rel_err(mc.grad, mo.grad) <= RTOL
+    for name, p in mod.named_parameters():
+        if name.startswith("gate_nn"):
+            assert p.grad is None  # built, never used (as in the reference)
+        else:
+            assert util.rel_err(p.grad, po[name].grad) <= RTOL, name
+
+
 # ------------------------------------------------------------------------------------------ (d) projections
 @pytest.mark.parametrize("M,K,Nout,act", [(1, 300, 1200, 0), (37, 300, 1200, 0), (515, 1200, 600, 1),
                                           (130, 600, 300, 1), (9600, 300, 1200, 0), (64, 8, 32, 1),

@@ -64,3 +64,34 @@ def test_simple_circuit_restatement_matches_live_layer(golden_mod):
         (m2 * w[..., 0]).sum().backward()
         assert torch.allclose(m2, marg[..., 0], rtol=0, atol=2e-7)
         assert util.rel_err(t2.grad, t1.grad) <= 1e-5
+
+
+def test_global_attention_pool_matches_live_reference(golden_mod):
+    """oracle.global_attention_pool vs the reference GlobalAttention
+    (models/att_pooling.py), whose hard-coded `.cuda()` calls are neutralised on this CPU-only machine."""
+    import isg_oracle as O
+    from ISubGVQA.models.att_pooling import GlobalAttention
+
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        g = torch.Generator().manual_seed(77)
+        counts = torch.tensor([5, 1, 9, 3, 7])
+        batch = torch.repeat_interleave(torch.arange(5), counts)
+        N, D = int(counts.sum()), 48
+        ref = GlobalAttention(num_node_features=D, num_out_features=D)
+        x = torch.randn(N, D, generator=g, requires_grad=True)
+        u = torch.randn(5, D, generator=g, requires_grad=True)
+        mask = (torch.rand(N, 1, generator=g) > 0.4).float().requires_grad_(True)
+        wo, wg = torch.randn(5, D, generator=g), torch.randn(N, 1, generator=g)
+        out, gate = ref(x, u, batch, size=None, return_mask=True, node_mask=mask)
+        ((out * wo).sum() + (gate * wg).sum()).backward()
+        want = (out.detach(), gate.detach(), x.grad.clone(), u.grad.clone(), mask.grad.clone())
+        params = {k: v.detach() for k, v in ref.state_dict().items()}
+        x2, u2, m2 = (t.detach().clone().requires_grad_(True) for t in (x, u, mask))
+        o2, g2 = O.global_attention_pool(x2, u2, batch, 5, params, node_mask=m2)
+        ((o2 * wo).sum() + (g2 * wg).sum()).backward()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    for a, b in zip((o2, g2, x2.grad, u2.grad, m2.grad), want):
+        assert util.rel_err(a, b) <= 1e-6
