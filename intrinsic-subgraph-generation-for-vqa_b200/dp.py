@@ -14,6 +14,9 @@ import torch.distributed as dist
 
 class GradAllReduce:
     def __init__(self, module, process_group=None):
+        from . import ops
+
+        ops.set_side_stream_with_dist(True)  # gradients are read after backward() has returned (and joined)
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1

@@ -74,12 +74,25 @@ _join_pending = False
 _side_ok = False  # set per step by MGAT.forward: only when no parameter has a .grad to accumulate into
 
 
+_side_with_dist = False
+
+
+def set_side_stream_with_dist(ok):
+    """torch.distributed wrappers that consume gradients DURING backward (DistributedDataParallel's bucket hooks)
+    would read a side-stream gradient before it is joined, so once a process group exists the side stream is off
+    unless the caller states that gradients are only read after backward() returns (isg_b200.dp.GradAllReduce)."""
+    global _side_with_dist
+    _side_with_dist = bool(ok)
+
+
 def allow_side_stream(ok):
     """The side stream hands autograd a gradient produced off the main stream.  That is safe when the
     AccumulateGrad node merely stores it (param.grad is None, the state after zero_grad()); an in-place
     accumulation into an existing .grad would run on the main stream without waiting — so the caller
     vouches for the former once per step."""
     global _side_ok
+    if ok and not _side_with_dist and torch.distributed.is_available() and torch.distributed.is_initialized():
+        ok = False
     _side_ok = bool(ok)
 
 
