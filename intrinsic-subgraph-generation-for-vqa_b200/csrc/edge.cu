@@ -9,6 +9,8 @@
 //
 // HBM-bound: algorithmic bytes per layer (fp32) = 4*HC*(E + 3N) + 4*E*H (+4E mask) + CSR ints
 // (SURVEY.md §8d).  No tensor-core work here by design.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -394,29 +396,35 @@ gat_edge_bwd_src_kernel(const T* __restrict__ gout, int64_t ld_g, const T* __res
 // ==========================================================================================
 // fp32 kernels with shared-memory row staging (the ones the fp32 path runs).
 // Every gathered (x_l[src], G[dst]) or streamed (e_proj[e], g_eproj[e]) head-row slice — C floats =
-// 1200 B at C = 300 — is brought in by one cp.async.bulk (UBLKCP) issued by lane 0 into a per-warp
-// ring of RING slots; the copies of edges t+1 .. t+RING are in flight while the warp reduces edge t.
-// The register-load kernels above keep ~2 rows per warp in flight at 128 registers / 25 % occupancy
-// (ncu: 31 % DRAM utilisation, profiles/r1b_ncu_edge_kernels.txt); the ring decouples bytes in flight
-// from registers.  Streamed rows carry an L2 evict_first policy, gathered rows evict_last, so the
-// node-feature rows of the batch stay L2-resident.
+// 1200 B at C = 300 — is brought in by one cp.async.bulk (UBLKCP) issued by an elected lane into a
+// per-warp ring of RING slots; the copy of edge t+RING is issued as soon as edge t has been consumed.
+// Streamed rows carry an L2 evict_first policy, gathered rows evict_last, so the node-feature rows of
+// the batch stay L2-resident.
+//
+// Register diet (r1f): the first ring kernels kept x_r[dst], att[h] and the current edge's rows in
+// registers (118-128 regs -> 16 warps/SM) and ran a persistent grid with a static stride over the
+// (node, head) tasks.  ncu showed them latency-bound at 20 % warps active, and the static stride left
+// a long tail at the c3 size (5 tasks of 1..75 edges per warp).  Now the per-task constants (x_r[dst,h,:],
+// att[h,:]) live in per-warp shared memory, the edge rows are read from their ring slot where they are
+// used, the ring is 2 deep, and the grid is one CTA per EDGE_WARPS tasks (hardware block scheduling
+// balances the tail): 72-80 regs -> 24-28 warps/SM.  Forward at B=256: 106 -> 79 us (L2 flushed).
 // ==========================================================================================
-constexpr int RING = 4;  // slots per warp (power of two)
+constexpr int RING = 2;  // slots per warp (power of two)
 
 struct WarpRing {
   uint32_t data, bars, slot_bytes, seq;
-  __device__ __forceinline__ void init(uint32_t data_, uint32_t bars_, uint32_t slot_bytes_, int lane) {
+  __device__ __forceinline__ void init(uint32_t data_, uint32_t bars_, uint32_t slot_bytes_, int lane, int extra_bars) {
     data = data_; bars = bars_; slot_bytes = slot_bytes_; seq = 0;
     if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < RING; ++r) ring_bar_init(bars + 8u * r, 1);
+      for (int r = 0; r < RING + extra_bars; ++r) ring_bar_init(bars + 8u * r, 1);
       ring_fence_init();
     }
     __syncwarp();
   }
   __device__ __forceinline__ uint32_t slot(uint32_t s) const { return data + (s & (RING - 1)) * slot_bytes; }
   __device__ __forceinline__ uint32_t bar(uint32_t s) const { return bars + 8u * (s & (RING - 1)); }
-  // lane 0 only
+  __device__ __forceinline__ uint32_t extra_bar(int i) const { return bars + 8u * (RING + i); }
+  // elected lane only
   __device__ __forceinline__ void issue2(uint32_t s, const void* a, uint64_t pol_a, const void* b, uint64_t pol_b,
                                          uint32_t bytes_each) const {
     ring_expect(bar(s), 2 * bytes_each);
@@ -430,45 +438,78 @@ struct WarpRing {
   __device__ __forceinline__ void wait(uint32_t s) const { ring_wait(bar(s), (s / RING) & 1u); }
 };
 
-template <int VPL>
-__device__ __forceinline__ void lds_row(uint32_t addr, int lane, int c4, float4 (&r)[VPL]) {
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    r[k] = (v < c4) ? lds_f4(addr + 16u * v) : f4_zero();
-  }
+// Per-warp shared-memory layout of the three kernels: RING slots of 2 rows, then `extra_rows` rows of
+// per-task constants; the mbarriers of all warps follow the data of all warps.
+__host__ __device__ inline uint32_t ring_warp_bytes(int C, int extra_rows) {
+  return (uint32_t)(2 * RING + extra_rows) * (uint32_t)C * 4u;
+}
+inline size_t ring_smem_bytes(int C, int extra_rows, int extra_bars) {
+  return (size_t)EDGE_WARPS * (ring_warp_bytes(C, extra_rows) + 8 * (RING + extra_bars));
 }
 
-template <int VPL, bool MASKED>
-__global__ void __launch_bounds__(EDGE_WARPS * 32, 4)
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 a) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: one warp per (node, head); online segment softmax over the in-edges.
+// smem per warp: [slot0: x_l | e_proj][slot1][x_r row][att row]; barriers: RING + 1 (x_r).
+// CT/HT > 0 bake C and H in as compile-time constants (the reference shape C=300, H=4): all row
+// offsets become immediates, which removes ~40 % of the integer instructions of the generic build.
+// ------------------------------------------------------------------------------------------
+template <int VPL, int CT>
+__device__ __forceinline__ bool col_active(int k, int lane, int c4) {
+  if (k < VPL - 1) return true;  // vpl_for(): c4 > 32*(VPL-1), only the last 32-column group is ragged
+  return lane + 32 * k < (CT > 0 ? CT / 4 : c4);
+}
+
+template <int VPL, bool MASKED, int CT, int HT>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 7)
 gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__ xr, int64_t ld_x,
                          const float* __restrict__ ep, const float* __restrict__ att,
                          const float* __restrict__ bias, const float* __restrict__ emask,
                          const int* __restrict__ rowptr, const int* __restrict__ nbr,
                          const int* __restrict__ eid, float* __restrict__ out, int64_t ld_out,
-                         float* __restrict__ alpha, int64_t NH, int H, int C, float slope) {
+                         float* __restrict__ alpha, int64_t NH, int H_, int C_, float slope) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2;
-  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
   const int64_t HC = (int64_t)H * C;
+  const uint32_t wbytes = ring_warp_bytes(C, 2);
   WarpRing ring;
-  ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
-            smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
+  ring.init(smem_addr_u32(ring_smem) + warp * wbytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * (RING + 1), 2 * row_bytes, lane, 1);
+  const uint32_t xr_s = ring.data + 2 * RING * row_bytes, att_s = xr_s + row_bytes;
+  const uint32_t xbar = ring.extra_bar(0);
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   const bool leader = warp_elect_one();  // issues the bulk copies (see warp_elect_one)
+  uint32_t xseq = 0;
+  int cur_head = -1;
 
   for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
     const int64_t node = wid / H;
     const int head = (int)(wid - node * H);
     const int hoff = head * C;
-    float4 xr_v[VPL], att_v[VPL], acc[VPL];
-    load_row<float, VPL>(xr + node * ld_x + hoff, lane, c4, xr_v);
-    load_row_f32<VPL>(att + hoff, lane, c4, att_v);
+    if (head != cur_head) {
+      for (int v = lane; v < c4; v += 32) sts_f4(att_s + 16u * v, Vec4<float>::ld(att + hoff + 4 * v));
+      cur_head = head;
+      __syncwarp();
+    }
+    if (leader) {
+      ring_expect(xbar, row_bytes);
+      ring_copy(xr_s, xr + node * ld_x + hoff, row_bytes, xbar, pol_keep);
+    }
+    float4 acc[VPL];
 #pragma unroll
     for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
     const int beg = rowptr[node], end = rowptr[node + 1];
+    const bool single = end - beg <= 32;  // whole segment in one batch: alpha is written once, normalised
     float m_run = -INFINITY, s_run = 0.f;
+    bool xr_ready = false;
+    int keep_eid = 0;
+    float keep_logit = 0.f;
 
     for (int base = beg; base < end; base += 32) {
       const int cnt = min(32, end - base);
@@ -488,30 +529,31 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
                       row_bytes);
       }
       for (int t = 0; t < cnt; ++t) {
-        const uint32_t s = ring.seq + t;
+        const uint32_t q = ring.seq + t;
         const float m0 = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
         const int tn = t + RING < cnt ? t + RING : t;
         const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
         const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
-        ring.wait(s);
-        float4 x0[VPL], p0[VPL];
-        lds_row<VPL>(ring.slot(s), lane, c4, x0);
-        lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, p0);
-        __syncwarp();  // every lane has read the slot -> it may be refilled
-        if (leader && t + RING < cnt)
-          ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
-                      row_bytes);
+        if (!xr_ready) {
+          ring_wait(xbar, xseq & 1u);
+          xr_ready = true;
+        }
+        ring.wait(q);
+        const uint32_t sx = ring.slot(q) + l16, sp = sx + row_bytes;
+        // logit = att . (leaky(s*m)*m),  s = x_r[i] + x_l[j] + e_proj[e]   (mgat_v2_conv.py:262-270)
         float2 part2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
-          float4 sv = p4_add(p4_add(xr_v[k], x0[k]), p0[k]);
-          if (MASKED) sv = p4_scale(sv, m0);
-          float4 w = p4_leaky(sv, slope);
-          if (MASKED) w = p4_scale(w, m0);
-          part2 = p4_dot_acc(w, att_v[k], part2);
+          if (col_active<VPL, CT>(k, lane, c4)) {
+            float4 sv = p4_add(p4_add(lds_f4(xr_s + l16 + 512u * k), lds_f4(sx + 512u * k)), lds_f4(sp + 512u * k));
+            if (MASKED) sv = p4_scale(sv, m0);
+            float4 w = p4_leaky(sv, slope);
+            if (MASKED) w = p4_scale(w, m0);
+            part2 = p4_dot_acc(w, lds_f4(att_s + l16 + 512u * k), part2);
+          }
         }
         const float part0 = warp_sum(p2_sum(part2));
-        if (part0 > m_run) {  // new running max: rescale (exp(0) = 1 otherwise, so skipping is exact)
+        if (part0 > m_run) {
           const float sc = expf(m_run - part0);
           s_run *= sc;
 #pragma unroll
@@ -522,206 +564,352 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
         s_run += pe;
         const float pm = MASKED ? pe * m0 : pe;
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) acc[k] = p4_fma_s(x0[k], pm, acc[k]);
+        for (int k = 0; k < VPL; ++k)
+          if (col_active<VPL, CT>(k, lane, c4)) acc[k] = p4_fma_s(lds_f4(sx + 512u * k), pm, acc[k]);
         if (lane == t) my_logit = part0;
+        __syncwarp();  // every lane is done with the slot
+        if (leader && t + RING < cnt)
+          ring.issue2(q + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
+                      row_bytes);
       }
       ring.seq += cnt;
-      if (lane < cnt) alpha[(int64_t)my_eid * H + head] = my_logit;  // raw logit, normalised below
+      if (single) {
+        keep_eid = my_eid;
+        keep_logit = my_logit;
+      } else if (lane < cnt) {
+        alpha[(int64_t)my_eid * H + head] = my_logit;
+      }
     }
+    if (!xr_ready) ring_wait(xbar, xseq & 1u);  // node without in-edges: still consume the x_r copy
+    ++xseq;
+    __syncwarp();  // the x_r row is free for the next task's copy
 
-    const float inv = 1.f / (s_run + 1e-16f);  // PyG softmax epsilon (mgat_v2_conv.py:272)
+    const float inv = 1.f / (s_run + 1e-16f);
     float* orow = out + node * ld_out + hoff;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      const int v = lane + 32 * k;
-      if (v < c4) {
+      if (col_active<VPL, CT>(k, lane, c4)) {
+        const int v = lane + 32 * k;
         float4 o = f4_scale(acc[k], inv);
         if (bias != nullptr) o = f4_add(o, Vec4<float>::ld(bias + hoff + 4 * v));
         Vec4<float>::st(orow + 4 * v, o);
       }
     }
-    for (int base = beg; base < end; base += 32) {
-      if (base + lane < end) {
-        const int64_t idx = (int64_t)eid[base + lane] * H + head;
-        alpha[idx] = expf(alpha[idx] - m_run) * inv;
+    if (single) {
+      if (lane < end - beg) alpha[(int64_t)keep_eid * H + head] = expf(keep_logit - m_run) * inv;
+    } else {
+      for (int base = beg; base < end; base += 32) {
+        if (base + lane < end) {
+          const int64_t idx = (int64_t)eid[base + lane] * H + head;
+          alpha[idx] = expf(alpha[idx] - m_run) * inv;
+        }
       }
     }
   }
 }
 
-template <int VPL, bool MASKED>
-__global__ void __launch_bounds__(EDGE_WARPS * 32, 4)
+// ------------------------------------------------------------------------------------------
+// backward, pass 1 (dst-major).  Warp w: head = w % H, column = w / H; column c owns the nodes
+// [c*K, (c+1)*K).  The g_att partial of a warp stays in registers over its K nodes and is written to
+// gatt_part[w, :]; gat_att_reduce* folds the partials in a fixed order (deterministic).
+// smem per warp: [slot0][slot1][x_r row][att row]; barriers: RING + 1 (x_r).
+//
+// Per (node, head): sweep 1 accumulates dot = sum_e a_e m_e t_e with t_e = <G, x_l[src_e]>, sweep 2
+// produces the per-edge gradients from gl_e = a_e (m_e t_e - dot) (see the note in
+// gat_edge_bwd_dst_kernel on why both must use the very same t_e roundings).  Segments of <= 32 edges
+// (the usual case) keep t_e in lane e's register and run both sweeps as ONE stream of 2*deg ring items,
+// so the x_l|e_proj copies of sweep 2 are already in flight while sweep 1 drains; longer segments take
+// the two-loop path that recomputes the bit-identical t_e.
+// ------------------------------------------------------------------------------------------
+template <int VPL, bool MASKED, int CT, int HT>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 6)
 gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const float* __restrict__ xl,
                              const float* __restrict__ xr, int64_t ld_x, const float* __restrict__ ep,
                              const float* __restrict__ att, const float* __restrict__ emask,
                              const float* __restrict__ alpha, const int* __restrict__ rowptr,
                              const int* __restrict__ nbr, const int* __restrict__ eid, float* __restrict__ g_xr,
                              int64_t ld_gx, float* __restrict__ g_ep, float* __restrict__ gatt_part,
-                             float* __restrict__ gm_h, int64_t N, int H, int C, float slope) {
+                             float* __restrict__ gm_h, int64_t N, int H_, int C_, float slope, int K) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t wid0 = (int64_t)blockIdx.x * EDGE_WARPS + warp;
-  const int64_t nwarps = (int64_t)gridDim.x * EDGE_WARPS;  // multiple of H by construction
+  const int64_t wid0 = (int64_t)blockIdx.x * EDGE_WARPS + warp;  // gridDim.x*EDGE_WARPS is a multiple of H
   const int head = (int)(wid0 % H);
+  const int64_t col = wid0 / H;
   const int c4 = C >> 2;
-  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
   const int64_t HC = (int64_t)H * C;
   const int hoff = head * C;
+  const uint32_t wbytes = ring_warp_bytes(C, 2);
   WarpRing ring;
-  ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
-            smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
+  ring.init(smem_addr_u32(ring_smem) + warp * wbytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * (RING + 1), 2 * row_bytes, lane, 1);
+  const uint32_t xr_s = ring.data + 2 * RING * row_bytes, att_s = xr_s + row_bytes;
+  const uint32_t xbar = ring.extra_bar(0);
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-  const bool leader = warp_elect_one();  // issues the bulk copies (see warp_elect_one)
+  const bool leader = warp_elect_one();
+  uint32_t xseq = 0;
 
-  float4 att_v[VPL], gatt[VPL];
-  load_row_f32<VPL>(att + hoff, lane, c4, att_v);
+  for (int v = lane; v < c4; v += 32) sts_f4(att_s + 16u * v, Vec4<float>::ld(att + hoff + 4 * v));
+  __syncwarp();
+  float4 gatt[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) gatt[k] = f4_zero();
 
-  for (int64_t node = wid0 / H; node < N; node += nwarps / H) {
-    float4 G[VPL], xr_v[VPL], gxr[VPL];
+  const int64_t node_end = min(N, (col + 1) * (int64_t)K);
+  for (int64_t node = col * K; node < node_end; ++node) {
+    if (leader) {
+      ring_expect(xbar, row_bytes);
+      ring_copy(xr_s, xr + node * ld_x + hoff, row_bytes, xbar, pol_keep);
+    }
+    float4 G[VPL], gxr[VPL];
     load_row<float, VPL>(gout + node * ld_g + hoff, lane, c4, G);
-    load_row<float, VPL>(xr + node * ld_x + hoff, lane, c4, xr_v);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) gxr[k] = f4_zero();
     const int beg = rowptr[node], end = rowptr[node + 1];
+    const int deg = end - beg;
+    bool xr_ready = false;
 
-    // sweep 1: dot = sum_e a_e m_e <G, x_l[src_e]>  (see the note in gat_edge_bwd_dst_kernel)
-    float dot = 0.f;
-    for (int base = beg; base < end; base += 32) {
-      const int cnt = min(32, end - base);
-      int my_src = 0;
-      float my_am = 0.f;
-      if (lane < cnt) {
-        my_src = nbr[base + lane];
-        const int e = eid[base + lane];
-        my_am = alpha[(int64_t)e * H + head];
-        if (MASKED) my_am *= emask[e];
-      }
-      const int npre = min(RING, cnt);
-      for (int t = 0; t < npre; ++t) {
-        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
-        if (leader) ring.issue1(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
-      }
-      for (int t = 0; t < cnt; ++t) {
-        const uint32_t s = ring.seq + t;
-        const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
-        const int jn = __shfl_sync(ISG_FULL_MASK, my_src, t + RING < cnt ? t + RING : t);
-        ring.wait(s);
-        float4 xv[VPL];
-        lds_row<VPL>(ring.slot(s), lane, c4, xv);
-        __syncwarp();
-        if (leader && t + RING < cnt) ring.issue1(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, row_bytes);
-        float2 pp2 = make_float2(0.f, 0.f);
+    // t_e = <G, x_l row in the slot>; one fixed instruction sequence for every use
+    auto row_dot = [&](uint32_t sx) -> float {
+      float2 pp2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) pp2 = p4_dot_acc(G[k], xv[k], pp2);
-        const float pp = warp_sum(p2_sum(pp2));  // sweep 2 repeats exactly this sequence
-        dot = fmaf(am, pp, dot);
+      for (int k = 0; k < VPL; ++k)
+        if (col_active<VPL, CT>(k, lane, c4)) pp2 = p4_dot_acc(G[k], lds_f4(sx + 512u * k), pp2);
+      return warp_sum(p2_sum(pp2));
+    };
+    // per-edge gradients; returns the per-head edge-mask gradient (MASKED only)
+    auto edge_grad = [&](uint32_t sx, uint32_t sp, float tt, float a, float m, float dot, int e) -> float {
+      if (!xr_ready) {
+        ring_wait(xbar, xseq & 1u);
+        xr_ready = true;
       }
-      ring.seq += cnt;
-    }
-
-    // sweep 2: per-edge gradients (recomputes the bit-identical t_e)
-    for (int base = beg; base < end; base += 32) {
-      const int cnt = min(32, end - base);
-      int my_src = 0, my_eid = 0;
-      float my_m = 1.f, my_a = 0.f, my_gm = 0.f;
-      if (lane < cnt) {
-        my_src = nbr[base + lane];
-        my_eid = eid[base + lane];
-        if (MASKED) my_m = emask[my_eid];
-        my_a = alpha[(int64_t)my_eid * H + head];
-      }
-      const int npre = min(RING, cnt);
-      for (int t = 0; t < npre; ++t) {
-        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
-        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
-        if (leader)
-          ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff, pol_stream,
-                      row_bytes);
-      }
-      for (int t = 0; t < cnt; ++t) {
-        const uint32_t s = ring.seq + t;
-        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
-        const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
-        const float a = __shfl_sync(ISG_FULL_MASK, my_a, t);
-        const int tn = t + RING < cnt ? t + RING : t;
-        const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
-        const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
-        ring.wait(s);
-        float4 xv[VPL], pv[VPL];
-        lds_row<VPL>(ring.slot(s), lane, c4, xv);
-        lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, pv);
-        __syncwarp();
-        if (leader && t + RING < cnt)
-          ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
-                      row_bytes);
-        float2 tp2 = make_float2(0.f, 0.f);
+      const float gl = a * (m * tt - dot);  // d loss / d logit[e,h]
+      const float glmm = MASKED ? gl * m * m : gl;
+      float2 av2 = make_float2(0.f, 0.f);  // sum_c att*v (edge-mask gradient, see below)
+      float* gerow = g_ep + (int64_t)e * HC + hoff + 4 * lane;
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) tp2 = p4_dot_acc(G[k], xv[k], tp2);
-        const float tt = warp_sum(p2_sum(tp2));
-        const float gl = a * (m * tt - dot);  // d loss / d logit[e,h]
-        const float glmm = MASKED ? gl * m * m : gl;
-        float2 av2 = make_float2(0.f, 0.f);  // sum_c att*v (edge-mask gradient, see below)
-        float* gerow = g_ep + (int64_t)e * HC + hoff;
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const float4 sx = p4_add(p4_add(xr_v[k], xv[k]), pv[k]);
-          const float4 u = MASKED ? p4_scale(sx, m) : sx;
+      for (int k = 0; k < VPL; ++k) {
+        if (col_active<VPL, CT>(k, lane, c4)) {
+          const float4 sxv =
+              p4_add(p4_add(lds_f4(xr_s + l16 + 512u * k), lds_f4(sx + 512u * k)), lds_f4(sp + 512u * k));
+          const float4 u = MASKED ? p4_scale(sxv, m) : sxv;
           const float4 v = p4_leaky(u, slope);
+          const float4 at = lds_f4(att_s + l16 + 512u * k);
           // g_att += gl * (v*m);  g_s = gl*m*m * att * leaky'(u)
           gatt[k] = p4_fma_s(MASKED ? p4_scale(v, m) : v, gl, gatt[k]);
           const float4 lk = make_float4(u.x > 0.f ? 1.f : slope, u.y > 0.f ? 1.f : slope, u.z > 0.f ? 1.f : slope,
                                         u.w > 0.f ? 1.f : slope);
-          const float4 gs = p4_scale(p4_mul(att_v[k], lk), glmm);
+          const float4 gs = p4_scale(p4_mul(at, lk), glmm);
           gxr[k] = p4_add(gxr[k], gs);
-          if (MASKED) av2 = p4_dot_acc(att_v[k], v, av2);
-          const int v4 = lane + 32 * k;
-          if (v4 < c4) Vec4<float>::st_stream(gerow + 4 * v4, gs);
-        }
-        // d/dm of logit = sum_c att*(dw/dm): w = leaky(s*m)*m  =>  gw*v + gu*s = 2*gl*att*v per channel
-        // (gu*s = gw*m*leaky'(u)*s = gw*v), so the per-head edge-mask gradient is 2*gl*sum_c att*v + t*a.
-        const float gmpart = MASKED ? 2.f * gl * p2_sum(av2) : 0.f;
-        if (MASKED) {
-          const float gm = warp_sum(gmpart) + tt * a;
-          if (lane == t) my_gm = gm;
+          if (MASKED) av2 = p4_dot_acc(at, v, av2);
+          Vec4<float>::st_stream(gerow + 128 * k, gs);
         }
       }
-      ring.seq += cnt;
-      if (MASKED && lane < cnt) gm_h[(int64_t)my_eid * H + head] = my_gm;
+      // d/dm of logit = sum_c att*(dw/dm): w = leaky(s*m)*m  =>  gw*v + gu*s = 2*gl*att*v per channel
+      // (gu*s = gw*m*leaky'(u)*s = gw*v), so the per-head edge-mask gradient is 2*gl*sum_c att*v + t*a.
+      return MASKED ? warp_sum(2.f * gl * p2_sum(av2)) + tt * a : 0.f;
+    };
+
+    if (deg <= 32) {
+      int my_src = 0, my_eid = 0;
+      float my_m = 1.f, my_a = 0.f, my_t = 0.f, my_gm = 0.f;
+      if (lane < deg) {
+        my_src = nbr[beg + lane];
+        my_eid = eid[beg + lane];
+        if (MASKED) my_m = emask[my_eid];
+        my_a = alpha[(int64_t)my_eid * H + head];
+      }
+      const float my_am = MASKED ? my_a * my_m : my_a;
+      const int items = 2 * deg;  // item i < deg: sweep-1 edge i (x_l only); i >= deg: sweep-2 edge i-deg
+      auto issue_item = [&](int i) {  // all lanes call (shuffles); the elected lane issues
+        const int t = i < deg ? i : i - deg;
+        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (leader) {
+          if (i < deg)
+            ring.issue1(ring.seq + i, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
+          else
+            ring.issue2(ring.seq + i, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff,
+                        pol_stream, row_bytes);
+        }
+      };
+      for (int i = 0; i < min(RING, items); ++i) issue_item(i);
+      float dot = 0.f;
+      for (int t = 0; t < deg; ++t) {
+        const uint32_t s = ring.seq + t;
+        const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+        ring.wait(s);
+        const float pp = row_dot(ring.slot(s) + l16);  // warp_sum inside: every lane is past its slot reads
+        if (t + RING < items) issue_item(t + RING);
+        if (lane == t) my_t = pp;
+        dot = fmaf(am, pp, dot);
+      }
+      for (int t = 0; t < deg; ++t) {
+        const uint32_t s = ring.seq + deg + t;
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+        const float a = __shfl_sync(ISG_FULL_MASK, my_a, t);
+        const float tt = __shfl_sync(ISG_FULL_MASK, my_t, t);
+        ring.wait(s);
+        const uint32_t sx = ring.slot(s) + l16;
+        const float gm = edge_grad(sx, sx + row_bytes, tt, a, m, dot, e);
+        __syncwarp();
+        if (deg + t + RING < items) issue_item(deg + t + RING);
+        if (MASKED && lane == t) my_gm = gm;
+      }
+      ring.seq += items;
+      if (MASKED && lane < deg) gm_h[(int64_t)my_eid * H + head] = my_gm;
+    } else {
+      // sweep 1
+      float dot = 0.f;
+      for (int base = beg; base < end; base += 32) {
+        const int cnt = min(32, end - base);
+        int my_src = 0;
+        float my_am = 0.f;
+        if (lane < cnt) {
+          my_src = nbr[base + lane];
+          const int e = eid[base + lane];
+          my_am = alpha[(int64_t)e * H + head];
+          if (MASKED) my_am *= emask[e];
+        }
+        const int npre = min(RING, cnt);
+        for (int t = 0; t < npre; ++t) {
+          const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+          if (leader) ring.issue1(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
+        }
+        for (int t = 0; t < cnt; ++t) {
+          const uint32_t s = ring.seq + t;
+          const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+          const int jn = __shfl_sync(ISG_FULL_MASK, my_src, t + RING < cnt ? t + RING : t);
+          ring.wait(s);
+          const float pp = row_dot(ring.slot(s) + l16);
+          if (leader && t + RING < cnt) ring.issue1(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, row_bytes);
+          dot = fmaf(am, pp, dot);
+        }
+        ring.seq += cnt;
+      }
+      // sweep 2 (recomputes the bit-identical t_e)
+      for (int base = beg; base < end; base += 32) {
+        const int cnt = min(32, end - base);
+        int my_src = 0, my_eid = 0;
+        float my_m = 1.f, my_a = 0.f, my_gm = 0.f;
+        if (lane < cnt) {
+          my_src = nbr[base + lane];
+          my_eid = eid[base + lane];
+          if (MASKED) my_m = emask[my_eid];
+          my_a = alpha[(int64_t)my_eid * H + head];
+        }
+        const int npre = min(RING, cnt);
+        for (int t = 0; t < npre; ++t) {
+          const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+          const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+          if (leader)
+            ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff,
+                        pol_stream, row_bytes);
+        }
+        for (int t = 0; t < cnt; ++t) {
+          const uint32_t s = ring.seq + t;
+          const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+          const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+          const float a = __shfl_sync(ISG_FULL_MASK, my_a, t);
+          const int tn = t + RING < cnt ? t + RING : t;
+          const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
+          const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+          ring.wait(s);
+          const uint32_t sx = ring.slot(s) + l16;
+          const float tt = row_dot(sx);
+          const float gm = edge_grad(sx, sx + row_bytes, tt, a, m, dot, e);
+          __syncwarp();
+          if (leader && t + RING < cnt)
+            ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
+                        row_bytes);
+          if (MASKED && lane == t) my_gm = gm;
+        }
+        ring.seq += cnt;
+        if (MASKED && lane < cnt) gm_h[(int64_t)my_eid * H + head] = my_gm;
+      }
     }
+    if (!xr_ready) ring_wait(xbar, xseq & 1u);
+    ++xseq;
+    __syncwarp();
     float* grow = g_xr + node * ld_gx + hoff;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int v4 = lane + 32 * k;
-      if (v4 < c4) Vec4<float>::st(grow + 4 * v4, gxr[k]);
-    }
+    for (int k = 0; k < VPL; ++k)
+      if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(grow + 4 * (lane + 32 * k), gxr[k]);
   }
   float* prow = gatt_part + wid0 * C;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v4 = lane + 32 * k;
-    if (v4 < c4) Vec4<float>::st(prow + 4 * v4, gatt[k]);
+  for (int k = 0; k < VPL; ++k)
+    if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(prow + 4 * (lane + 32 * k), gatt[k]);
+}
+
+// g_att = column sums of gatt_part viewed as [rows, H*C] (row = column index of the dst kernel), two
+// fixed-order stages: slabs of GR_ROWS rows -> part2 [parts2, H*C], then part2 -> g_att with GR2_LANES
+// row lanes per column and a fixed-order shared-memory fold.
+constexpr int GR_ROWS = 16;
+constexpr int GR2_LANES = 16;
+__global__ void __launch_bounds__(64)
+gat_att_reduce1_kernel(const float* __restrict__ part, int64_t rows, int cols, float* __restrict__ part2) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.y * GR_ROWS, r1 = min(rows, r0 + GR_ROWS);
+  float4 v[GR_ROWS];
+#pragma unroll
+  for (int u = 0; u < GR_ROWS; ++u) v[u] = (r0 + u < r1) ? Vec4<float>::ld(part + (r0 + u) * cols + c) : f4_zero();
+  float4 s = v[0];
+#pragma unroll
+  for (int u = 1; u < GR_ROWS; ++u) s = f4_add(s, v[u]);
+  Vec4<float>::st(part2 + (int64_t)blockIdx.y * cols + c, s);
+}
+__global__ void __launch_bounds__(64 * GR2_LANES)
+gat_att_reduce2_kernel(const float* __restrict__ part2, int nparts, int cols, float* __restrict__ g_att) {
+  __shared__ float4 red[GR2_LANES][64];
+  const int c = (blockIdx.x * 64 + threadIdx.x) * 4;
+  float4 s = f4_zero();
+  if (c < cols) {
+    int p = threadIdx.y;
+    for (; p + 3 * GR2_LANES < nparts; p += 4 * GR2_LANES) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = Vec4<float>::ld(part2 + (int64_t)(p + u * GR2_LANES) * cols + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s = f4_add(s, v[u]);
+    }
+    for (; p < nparts; p += GR2_LANES) s = f4_add(s, Vec4<float>::ld(part2 + (int64_t)p * cols + c));
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < GR2_LANES; ++y) t = f4_add(t, red[y][threadIdx.x]);
+    Vec4<float>::st(g_att + c, t);
   }
 }
 
-template <int VPL, bool MASKED>
-__global__ void __launch_bounds__(EDGE_WARPS * 32)
+// ------------------------------------------------------------------------------------------
+// backward, pass 2 (src-major): g_xl[j] = sum_{e: src = j} ( g_eproj[e] + G[dst_e] * alpha*m ).
+// ------------------------------------------------------------------------------------------
+template <int VPL, bool MASKED, int CT, int HT>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 7)
 gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const float* __restrict__ g_ep,
                              const float* __restrict__ emask, const float* __restrict__ alpha,
                              const int* __restrict__ colptr, const int* __restrict__ nbr,
                              const int* __restrict__ eid, float* __restrict__ g_xl, int64_t ld_gx, int64_t NH,
-                             int H, int C) {
+                             int H_, int C_) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2;
-  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
   const int64_t HC = (int64_t)H * C;
+  const uint32_t wbytes = ring_warp_bytes(C, 0);
   WarpRing ring;
-  ring.init(smem_addr_u32(ring_smem) + warp * RING * 2 * row_bytes,
-            smem_addr_u32(ring_smem) + EDGE_WARPS * RING * 2 * row_bytes + warp * RING * 8, 2 * row_bytes, lane);
+  ring.init(smem_addr_u32(ring_smem) + warp * wbytes, smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * RING,
+            2 * row_bytes, lane, 0);
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-  const bool leader = warp_elect_one();  // issues the bulk copies (see warp_elect_one)
+  const bool leader = warp_elect_one();
 
   for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
     const int64_t node = wid / H;
@@ -756,31 +944,44 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
         const int in_ = __shfl_sync(ISG_FULL_MASK, my_dst, tn);
         const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
         ring.wait(s);
-        float4 gv[VPL], Gv[VPL];
-        lds_row<VPL>(ring.slot(s), lane, c4, gv);
-        lds_row<VPL>(ring.slot(s) + row_bytes, lane, c4, Gv);
+        const uint32_t sg = ring.slot(s) + l16, sG = sg + row_bytes;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+          if (col_active<VPL, CT>(k, lane, c4))
+            acc[k] = p4_add(acc[k], p4_fma_s(lds_f4(sG + 512u * k), am, lds_f4(sg + 512u * k)));
         __syncwarp();
         if (leader && t + RING < cnt)
           ring.issue2(s + RING, g_ep + (int64_t)en * HC + hoff, pol_stream, gout + (int64_t)in_ * ld_g + hoff,
                       pol_keep, row_bytes);
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) acc[k] = p4_add(acc[k], p4_fma_s(Gv[k], am, gv[k]));
       }
       ring.seq += cnt;
     }
     float* grow = g_xl + node * ld_gx + hoff;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int v4 = lane + 32 * k;
-      if (v4 < c4) Vec4<float>::st(grow + 4 * v4, acc[k]);
-    }
+    for (int k = 0; k < VPL; ++k)
+      if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(grow + 4 * (lane + 32 * k), acc[k]);
   }
 }
 
-inline size_t ring_smem_bytes(int C) { return (size_t)EDGE_WARPS * RING * (2 * (size_t)C * 4 + 8); }
-inline int ring_ctas_per_sm(int C) {
-  int n = (int)((200 * 1024) / ring_smem_bytes(C));
-  return n < 1 ? 1 : (n > 6 ? 6 : n);
+// Columns of the dst-major backward: K nodes per column, sized for ~6 waves of resident CTAs so that the
+// hardware block scheduler evens out the degree imbalance; K and the grid depend on (N, H) only.
+struct BwdRingPlan {
+  int K;
+  int64_t cols, blocks, warps, parts2;
+};
+inline BwdRingPlan bwd_ring_plan(int64_t N, int H) {
+  BwdRingPlan p;
+  if (N < 1) N = 1;
+  if (H < 1) H = 1;
+  const int64_t target_cols = (int64_t)ISG_NUM_SMS * 6 * 6;
+  p.K = (int)(N / target_cols);
+  if (p.K < 1) p.K = 1;
+  p.cols = (N + p.K - 1) / p.K;
+  p.blocks = (p.cols * H + EDGE_WARPS - 1) / EDGE_WARPS;
+  while ((p.blocks * EDGE_WARPS) % H != 0) ++p.blocks;
+  p.warps = p.blocks * EDGE_WARPS;
+  p.parts2 = (p.warps / H + GR_ROWS - 1) / GR_ROWS;
+  return p;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -829,13 +1030,15 @@ int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* 
                     const int* dst_eid, void* out, int64_t ld_out, float* alpha, int64_t N, int H, int C,
                     float slope, cudaStream_t stream) {
   const int64_t NH = N * H;
-  const size_t smem = ring_smem_bytes(C);
-  auto kern = gat_edge_fwd_ring_kernel<VPL, MASKED>;
+  const size_t smem = ring_smem_bytes(C, 2, 1);
+  // the reference shape (C = 300, H = 4) runs the build with C and H as compile-time constants
+  const bool ref_shape = VPL == 3 && C == 300 && H == 4;
+  auto kern = ref_shape ? gat_edge_fwd_ring_kernel<VPL, MASKED, VPL == 3 ? 300 : 0, VPL == 3 ? 4 : 0>
+                        : gat_edge_fwd_ring_kernel<VPL, MASKED, 0, 0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  int64_t blocks = ceil_div(NH, EDGE_WARPS);
-  const int64_t cap = (int64_t)ISG_NUM_SMS * ring_ctas_per_sm(C);
-  if (blocks > cap) blocks = cap;
+  // one CTA per EDGE_WARPS (node, head) tasks: the block scheduler balances the degree spread
+  const int64_t blocks = ceil_div(NH, (int64_t)EDGE_WARPS);
   kern<<<(unsigned)blocks, EDGE_WARPS * 32, smem, stream>>>(
       (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, bias, emask, dst_ptr, dst_nbr,
       dst_eid, (float*)out, ld_out, alpha, NH, H, C, slope);
@@ -849,27 +1052,32 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
                     const int* dst_ptr, const int* dst_nbr, const int* dst_eid, const int* src_ptr,
                     const int* src_nbr, const int* src_eid, void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj,
                     float* g_att, float* g_emask, int64_t N, int64_t E, int H, int C, float slope,
-                    float* gatt_part, float* gm_h, int blocks, cudaStream_t stream) {
-  const size_t smem = ring_smem_bytes(C);
-  auto kd = gat_edge_bwd_dst_ring_kernel<VPL, MASKED>;
-  auto ks = gat_edge_bwd_src_ring_kernel<VPL, MASKED>;
-  cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    float* gatt_part, float* gatt_part2, float* gm_h, const BwdRingPlan& plan, cudaStream_t stream) {
+  const size_t smem_d = ring_smem_bytes(C, 2, 1), smem_s = ring_smem_bytes(C, 0, 0);
+  const bool ref_shape = VPL == 3 && C == 300 && H == 4;
+  auto kd = ref_shape ? gat_edge_bwd_dst_ring_kernel<VPL, MASKED, VPL == 3 ? 300 : 0, VPL == 3 ? 4 : 0>
+                      : gat_edge_bwd_dst_ring_kernel<VPL, MASKED, 0, 0>;
+  auto ks = ref_shape ? gat_edge_bwd_src_ring_kernel<VPL, MASKED, VPL == 3 ? 300 : 0, VPL == 3 ? 4 : 0>
+                      : gat_edge_bwd_src_ring_kernel<VPL, MASKED, 0, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
   if (e != cudaSuccess) return (int)e;
-  kd<<<blocks, EDGE_WARPS * 32, smem, stream>>>((const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r,
-                                                ld_x, (const float*)e_proj, att, emask, alpha, dst_ptr, dst_nbr,
-                                                dst_eid, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H,
-                                                C, slope);
+  kd<<<(unsigned)plan.blocks, EDGE_WARPS * 32, smem_d, stream>>>(
+      (const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, emask, alpha,
+      dst_ptr, dst_nbr, dst_eid, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H, C, slope, plan.K);
   ISG_CHECK_LAUNCH();
-  gat_att_reduce_kernel<<<dim3(ceil_div(C, 32), H), dim3(32, 8), 0, stream>>>(
-      gatt_part, (int64_t)blocks * EDGE_WARPS, H, C, g_att);
+  const int HC = H * C;
+  const int64_t rows = plan.warps / H;
+  gat_att_reduce1_kernel<<<dim3(ceil_div(HC / 4, 64), (unsigned)plan.parts2), 64, 0, stream>>>(gatt_part, rows, HC,
+                                                                                           gatt_part2);
+  ISG_CHECK_LAUNCH();
+  gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)plan.parts2, HC,
+                                                                                   g_att);
   ISG_CHECK_LAUNCH();
   const int64_t NH = N * H;
-  int64_t sb = ceil_div(NH, EDGE_WARPS);
-  const int64_t cap = (int64_t)ISG_NUM_SMS * ring_ctas_per_sm(C);
-  if (sb > cap) sb = cap;
-  ks<<<(unsigned)sb, EDGE_WARPS * 32, smem, stream>>>((const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha,
-                                                      src_ptr, src_nbr, src_eid, (float*)g_xl, ld_gx, NH, H, C);
+  ks<<<(unsigned)ceil_div(NH, (int64_t)EDGE_WARPS), EDGE_WARPS * 32, smem_s, stream>>>(
+      (const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, (float*)g_xl, ld_gx,
+      NH, H, C);
   ISG_CHECK_LAUNCH();
   if (MASKED && E > 0) {
     gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
@@ -968,9 +1176,13 @@ extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, 
 }
 
 extern "C" size_t isg_gat_edge_bwd_workspace_bytes(int64_t N, int64_t E, int H, int C) {
+  // max over the two layouts (register-load kernels: persistent grid; ring kernels: BwdRingPlan)
   const int blocks = bwd_grid_blocks(N > 0 ? N : 1, H > 0 ? H : 1);
-  return align256((size_t)blocks * EDGE_WARPS * (size_t)C * sizeof(float)) +
-         align256((size_t)E * (size_t)H * sizeof(float));
+  const BwdRingPlan plan = bwd_ring_plan(N, H);
+  const size_t a = align256((size_t)blocks * EDGE_WARPS * (size_t)C * sizeof(float));
+  const size_t b = align256((size_t)plan.warps * (size_t)C * sizeof(float)) +
+                   align256((size_t)plan.parts2 * (size_t)(H > 0 ? H : 1) * (size_t)C * sizeof(float));
+  return (a > b ? a : b) + align256((size_t)E * (size_t)H * sizeof(float));
 }
 
 extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r,
@@ -1015,13 +1227,17 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
   return edge_mask ? launch_bwd_ring<V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,     \
                                               dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,     \
                                               g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,    \
-                                              gatt_part, gm_h, blocks, stream)                               \
+                                              rp_part, rp_part2, rp_gmh, rplan, stream)                      \
                    : launch_bwd_ring<V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,    \
                                                dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,    \
                                                g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,   \
-                                               gatt_part, gm_h, blocks, stream)
+                                               rp_part, rp_part2, rp_gmh, rplan, stream)
     if (((uintptr_t)x_l & 15) || ((uintptr_t)g_out & 15) || ((uintptr_t)e_proj & 15) || ((uintptr_t)g_eproj & 15))
       return ISG_EUNSUPPORTED;
+    const BwdRingPlan rplan = bwd_ring_plan(N, H);
+    float* rp_part = (float*)workspace;
+    float* rp_part2 = (float*)((char*)workspace + align256((size_t)rplan.warps * (size_t)C * sizeof(float)));
+    float* rp_gmh = (float*)((char*)rp_part2 + align256((size_t)rplan.parts2 * (size_t)H * (size_t)C * sizeof(float)));
     switch (vpl) {
       case 1: ISG_BWD_RING(1);
       case 2: ISG_BWD_RING(2);

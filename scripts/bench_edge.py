@@ -49,6 +49,12 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7, bf16=False):
         nb = min(chunk_graphs, B - done)
         g = synth.make_topology(nb, mean_nodes=mn, mean_edges=me, seed=seed + done, max_nodes=None)
         ei, batch = g["edge_index"].to(dev), g["batch"].to(dev)
+        if os.environ.get("BENCH_SORT_DEGREE"):  # experiment: relabel nodes by descending in-degree
+            deg = torch.bincount(ei[1], minlength=batch.numel())
+            order = torch.argsort(deg, descending=True, stable=True)
+            rank = torch.empty_like(order); rank[order] = torch.arange(order.numel(), device=dev)
+            ei = rank[ei]
+            print("max/mean in-degree", int(deg.max()), float(deg.float().mean()), file=sys.stderr)
         N, E = int(batch.numel()), int(ei.shape[1])
         gi = GraphIndex(ei, batch, nb)
         gen = torch.Generator(device=dev).manual_seed(seed)
