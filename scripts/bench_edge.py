@@ -124,6 +124,8 @@ def main():
     pk, src = peak()
     points = [(4096, 10, 50), (4096, 20, 150), (4096, 50, 600), (4096, 100, 1500), (4096, 200, 4000)] \
         if args.sweep else [(256, 20, 150), (1024, 20, 150)]
+    if os.environ.get("BENCH_POINT"):  # e.g. BENCH_POINT=1024,100,1500
+        points = [tuple(int(v) for v in os.environ["BENCH_POINT"].split(","))]
     for B, mn, me in points:
         # keep e_proj + g_eproj of one chunk under ~40 GB
         chunk = max(1, min(B, int(40e9 / (2 * 4 * HC * me))))
