@@ -56,7 +56,8 @@ if "--traffic" in sys.argv:
         name = r[ik]
         mb = float(r[ir].replace(",", "")) + float(r[iw].replace(",", ""))
         key = None
-        for frag in ("gat_edge_fwd", "gat_edge_bwd_dst", "gat_edge_bwd_src", "gat_att_reduce", "gm_head_sum"):
+        for frag in ("gat_edge_fwd", "gat_edge_bwd_dst", "gat_edge_bwd_src", "gat_att_reduce_kernel",
+                     "gat_att_reduce1", "gat_att_reduce2", "gm_head_sum"):
             if frag in name:
                 key = frag
         if key:
@@ -68,5 +69,6 @@ if "--traffic" in sys.argv:
         res["isg_gat_edge_fwd"] = avg["gat_edge_fwd"]
     if "gat_edge_bwd_dst" in avg and "gat_edge_bwd_src" in avg:
         res["isg_gat_edge_bwd"] = sum(avg.get(k, 0.0) for k in ("gat_edge_bwd_dst", "gat_edge_bwd_src",
-                                                                 "gat_att_reduce", "gm_head_sum"))
+                                                                 "gat_att_reduce_kernel", "gat_att_reduce1",
+                                                                 "gat_att_reduce2", "gm_head_sum"))
     json.dump(res, open(out_path, "w"), indent=1)
