@@ -67,6 +67,116 @@ class GradAllReduce:
         self.unpack()
 
 
+class OverlappedGradAllReduce(GradAllReduce):
+    """Bucketed variant that overlaps the collective with the backward pass (what DDP's reducer does for the
+    reference, main.py:85-94): the parameters are cut into buckets in the order their gradients are produced;
+    a post-accumulate-grad hook packs each finished bucket into its slice of the flat buffer and issues its
+    all-reduce on a communication stream while the backward pass of the earlier layers is still running.
+
+    Protocol per step:   backward()  ->  finish()        (finish joins the communication stream and unpacks)
+    The first backward is a RECORDING pass (nothing is overlapped): it observes which parameters receive a
+    gradient and in which order; parameters that never do (36 MGAT tensors) are left out of the buckets and
+    keep contributing zeros, like DDP's unused-parameter handling.  The set must not change afterwards.
+    Works under CUDA-graph capture: the communication stream forks from / joins the capturing stream."""
+
+    def __init__(self, module, process_group=None, bucket_bytes=8 << 20):
+        super().__init__(module, process_group)
+        from . import ops
+
+        ops.set_side_stream_with_dist(False)  # the hooks read gradients DURING backward: no side-stream producers
+        self.bucket_bytes = int(bucket_bytes)
+        self._index = {p: i for i, p in enumerate(self.params)}
+        self._offsets, off = [], 0
+        for p in self.params:
+            self._offsets.append(off)
+            off += p.numel()
+        self._order = []        # recording pass: parameter indices in gradient-ready order
+        self._buckets = None    # list of dicts: params (indices), lo, hi (flat range)
+        self._bucket_of = {}
+        self._pending = []
+        self._launched = 0
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    # ---- recording pass -> buckets
+    def _build_buckets(self):
+        # the flat buffer is re-laid-out in gradient-ready order so that every bucket is one contiguous slice
+        order = self._order + [i for i in range(len(self.params)) if i not in set(self._order)]
+        self.views, self._offsets, off = [None] * len(self.params), [0] * len(self.params), 0
+        for i in order:
+            p = self.params[i]
+            self._offsets[i] = off
+            self.views[i] = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.flat.zero_()
+        self._buckets, cur = [], None
+        for i in self._order:
+            nbytes = self.params[i].numel() * 4
+            if cur is None or cur["bytes"] >= self.bucket_bytes:
+                cur = {"params": [], "lo": self._offsets[i], "hi": self._offsets[i], "bytes": 0}
+                self._buckets.append(cur)
+            cur["params"].append(i)
+            cur["hi"] = self._offsets[i] + self.params[i].numel()
+            cur["bytes"] += nbytes
+        self._bucket_of = {i: b for b, bk in enumerate(self._buckets) for i in bk["params"]}
+        self._reset()
+
+    def _reset(self):
+        self._pending = [len(bk["params"]) for bk in self._buckets]
+        self._launched = 0
+
+    # ---- hooks
+    def _on_grad(self, p):
+        i = self._index[p]
+        if self._buckets is None:
+            self._order.append(i)
+            return
+        b = self._bucket_of.get(i)
+        if b is None:
+            raise RuntimeError("a parameter outside the recorded set received a gradient; "
+                               "OverlappedGradAllReduce needs a static set of used parameters")
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        bk = self._buckets[b]
+        torch._foreach_copy_([self.views[i] for i in bk["params"]], [self.params[i].grad for i in bk["params"]])
+        self._launched += 1
+        if self.world == 1:
+            return
+        chunk = self.flat[bk["lo"]:bk["hi"]]
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+                chunk.mul_(1.0 / self.world)
+        else:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            chunk.mul_(1.0 / self.world)
+
+    def finish(self):
+        """Call after backward(): completes the step's reduction and writes the averaged gradients back."""
+        if self._buckets is None:  # recording pass: reduce everything now, unoverlapped, and build the buckets
+            if not self._order:
+                raise RuntimeError("finish() before any backward pass")
+            self.all_reduce_mean()
+            self._build_buckets()
+            return
+        if self._launched != len(self._buckets):
+            raise RuntimeError(f"{len(self._buckets) - self._launched} gradient bucket(s) never completed: "
+                               "the set of used parameters changed after the recording pass")
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        used = [i for bk in self._buckets for i in bk["params"]]
+        torch._foreach_copy_([self.params[i].grad for i in used], [self.views[i] for i in used])
+        self._reset()
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def shard_graphs(num_graphs_total, rank, world):
     """Contiguous, balanced split of whole graphs across ranks (DistributedSampler analogue,
     datasets/build.py:44-49, without shuffling): returns (first_graph, num_graphs) of this rank."""

@@ -12,12 +12,28 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _loss_of(model, O, synth, first, count, Btot, C):
+    """Loss of `model` on this rank's slice of the shared global batch (same construction as run() below)."""
+    b = synth.make_batch(Btot, channels=C, mean_nodes=6, mean_edges=24, seed=7)
+    keep_g = (b["batch"] >= first) & (b["batch"] < first + count)
+    node_ids = keep_g.nonzero().flatten()
+    remap = torch.full((b["batch"].numel(),), -1, dtype=torch.int64)
+    remap[node_ids] = torch.arange(node_ids.numel())
+    ei = b["edge_index"]
+    keep_e = keep_g[ei[0]]
+    h, _, _, _ = model(b["x"][node_ids], remap[ei[:, keep_e]], b["instr_vectors"][:, first:first + count],
+                       b["global_language_feats"][first:first + count], b["edge_attr"][keep_e],
+                       b["batch"][node_ids] - first)
+    per_graph = torch.zeros(count).index_add_(0, b["batch"][node_ids] - first, (h * h).mean(dim=1))
+    return per_graph.sum() / Btot
+
+
 def _worker(rank, world, port, ret):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import isg_oracle as O
     from isg_b200 import synth
-    from isg_b200.dp import GradAllReduce, shard_graphs
+    from isg_b200.dp import GradAllReduce, OverlappedGradAllReduce, shard_graphs
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -55,6 +71,22 @@ def _worker(rank, world, port, ret):
     # DDP averages; our loss is already normalised by the global batch, so undo the mean -> sum
     red.all_reduce_mean()
     grads = {k: (p.grad * world if p.grad is not None else None) for k, p in model.named_ref_parameters()}
+    # bucketed / overlapped reducer: recording pass, then two hooked passes; must give the same averages
+    model2, _ = run(first, count)
+    ored = OverlappedGradAllReduce(model2, bucket_bytes=16 << 10)
+    for it in range(3):
+        for p in model2.parameters():
+            p.grad = None
+        loss2 = _loss_of(model2, O, synth, first, count, Btot, C)
+        loss2.backward()
+        ored.finish()
+    worst_o = 0.0
+    for (k, p), (k2, p2) in zip(model.named_ref_parameters(), model2.named_ref_parameters()):
+        assert k == k2 and (p.grad is None) == (p2.grad is None), k
+        if p.grad is not None:
+            worst_o = max(worst_o, float((p.grad - p2.grad).abs().max()) / (float(p.grad.abs().max()) or 1.0))
+    ret[f"overlap_worst_{rank}"] = worst_o
+    ret[f"overlap_buckets_{rank}"] = len(ored._buckets)
     if rank == 0:
         ref_model, ref_loss = run(0, Btot)
         ref_loss.backward()
@@ -83,6 +115,10 @@ def test_two_rank_gradient_allreduce_matches_single_rank():
     assert ret["worst"] < 1e-4, dict(ret)
     assert ret["n_none"] == 40  # 36 never-used MGAT parameters + layer-3 node_nn/ques_nn (masking off)
     assert ret["bucket"] > 0
+    # the hooked, bucketed reducer reproduces the flat one (same sums, different grouping of the collective)
+    for r in range(2):
+        assert ret[f"overlap_worst_{r}"] < 1e-6, dict(ret)
+        assert ret[f"overlap_buckets_{r}"] >= 2
 
 
 def test_shard_graphs_is_a_partition():
