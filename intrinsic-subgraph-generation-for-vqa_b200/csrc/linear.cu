@@ -186,14 +186,14 @@ extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const f
   if (M < 0 || Nout <= 0 || K <= 0) return ISG_EINVAL;
   if (M == 0) return ISG_OK;
   if (!x || !w || !y) return ISG_EINVAL;
-  if (mode < 0 || mode > 4 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
+  if (mode < 0 || mode > 2 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
   if (K % 4 || Nout % 4 || ldx % 4 || ldy % 4 || (z_pre && ldz % 4)) return ISG_EUNSUPPORTED;
   if (mode != 0) {
     isg::TcGemm t{};
     t.A = (const float*)x; t.lda = ldx; t.B = (const float*)w; t.ldb = K; t.C = (float*)y; t.ldc = ldy;
     t.rows = M; t.cols = Nout; t.R = K; t.a_mn = 0; t.b_mn = 0; t.epi = 0; t.splits = 1;
     t.r_chunk = ((int64_t)K + 31) / 32 * 32;
-    t.bias = bias; t.Z = (float*)z_pre; t.ldz = ldz; t.act = act; t.split3 = (mode == 1) ? 1 : (mode == 3 ? 3 : (mode == 4 ? 4 : 0));
+    t.bias = bias; t.Z = (float*)z_pre; t.ldz = ldz; t.act = act; t.split3 = (mode == 1) ? 1 : 0;
     return isg::tc_gemm(t, stream_);
   }
   GemmArgs g{};
@@ -212,14 +212,14 @@ extern "C" int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, con
   if (M < 0 || Nout <= 0 || K <= 0) return ISG_EINVAL;
   if (M == 0) return ISG_OK;
   if (!g_y || !w || !g_x) return ISG_EINVAL;
-  if (mode < 0 || mode > 4 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
+  if (mode < 0 || mode > 2 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
   if (K % 4 || Nout % 4 || ldg % 4 || ldgx % 4 || (z_prev && ldz % 4)) return ISG_EUNSUPPORTED;
   if (mode != 0) {
     isg::TcGemm t{};
     t.A = (const float*)g_y; t.lda = ldg; t.B = (const float*)w; t.ldb = K; t.C = (float*)g_x; t.ldc = ldgx;
     t.rows = M; t.cols = K; t.R = Nout; t.a_mn = 0; t.b_mn = 1; t.epi = 1; t.splits = 1;
     t.r_chunk = ((int64_t)Nout + 31) / 32 * 32;
-    t.Zprev = (const float*)z_prev; t.ldz = ldz; t.accumulate = accumulate; t.split3 = (mode == 1) ? 1 : (mode == 3 ? 3 : (mode == 4 ? 4 : 0));
+    t.Zprev = (const float*)z_prev; t.ldz = ldz; t.accumulate = accumulate; t.split3 = (mode == 1) ? 1 : 0;
     return isg::tc_gemm(t, stream_);
   }
   GemmArgs g{};
@@ -245,7 +245,7 @@ extern "C" int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int
                                 int64_t M, int Nout, int K, int mode, int dtype, void* workspace, size_t ws_bytes,
                                 void* stream_) {
   if (M < 0 || Nout <= 0 || K <= 0 || !g_w) return ISG_EINVAL;
-  if (mode < 0 || mode > 4 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
+  if (mode < 0 || mode > 2 || dtype != ISG_F32) return ISG_EUNSUPPORTED;
   if (K % 4 || Nout % 4 || ldg % 4 || ldx % 4) return ISG_EUNSUPPORTED;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (M == 0) {
@@ -262,7 +262,7 @@ extern "C" int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int
     const int ts = isg::tc_wgrad_splits(M, Nout, K, &chunk);
     t.A = (const float*)g_y; t.lda = ldg; t.B = (const float*)x; t.ldb = ldx;
     t.rows = Nout; t.cols = K; t.R = M; t.a_mn = 1; t.b_mn = 1; t.epi = 2; t.splits = ts; t.r_chunk = chunk;
-    t.split3 = (mode == 1) ? 1 : (mode == 3 ? 3 : (mode == 4 ? 4 : 0));
+    t.split3 = (mode == 1) ? 1 : 0;
     if (ts > 1) { t.C = (float*)workspace; t.ldc = K; t.c_split_stride = (int64_t)Nout * K; }
     else { t.C = g_w; t.ldc = K; t.c_split_stride = 0; }
     const int rc = isg::tc_gemm(t, stream_);

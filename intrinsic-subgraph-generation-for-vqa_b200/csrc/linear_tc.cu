@@ -87,8 +87,6 @@ struct TcArgs {
   const float* Zprev;
   int act;
   int accumulate;
-  int split3;    // 1: 3xTF32 (lo planes in smem, correction accumulator), 0: single-pass TF32
-  int write_hi;  // verification only: also write the truncated hi back (results are bit-identical)
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -276,7 +274,10 @@ __device__ __forceinline__ float4 lo_part(float4 v) {
 }
 
 // ------------------------------------------------------------------------------ the kernel
-template <bool A_MN, bool B_MN, int EPI>
+// SPLIT (mode 1 vs mode 2), PAIR (cluster of two sharing the B tile by multicast) and FULLBN (BN == 128) are
+// compile-time: the per-k-block role loops are latency chains in which every runtime conditional costs ~1 %
+// (measured by bisecting an instrumented build), so the hot instantiation carries none.
+template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcArgs g) {
@@ -284,16 +285,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t CL = cluster_nctarank();  // 1 (plain launch) or 2 (cluster pair sharing the B tile)
+  constexpr uint32_t CL = PAIR ? 2u : 1u;  // plain launch, or a cluster pair sharing the B tile
   const uint32_t cta_rank = cluster_ctarank();
 
-  const int S = g.stages;
-  const int BN = g.BN;
+  const int S = SPLIT ? TS_STAGES : g.stages;  // mode 1: smem ring == TMEM A ring
+  const int BN = FULLBN ? MAX_BN : g.BN;
   const uint32_t b_tile_bytes = (uint32_t)BN * (BK * 4);
   // stage layout: mode 1 [A raw 8K][B BN*64][B_lo BN*64] (A goes on to TMEM); mode 2 [A 8K][B BN*64]
   const uint32_t off_b_hi = A_TILE_BYTES;
   const uint32_t off_b_lo = off_b_hi + b_tile_bytes;
-  const uint32_t epi_base = smem_base + (uint32_t)S * g.stage_bytes;
+  // stage size: a compile-time constant in the hot instantiation (A 8 KiB + B 8 KiB + B_lo 8 KiB)
+  const uint32_t stage_bytes = (SPLIT && FULLBN) ? (uint32_t)(A_TILE_BYTES + 2 * MAX_BN * BK * 4) : (uint32_t)g.stage_bytes;
+  const uint32_t epi_base = smem_base + (uint32_t)S * stage_bytes;
   const uint32_t bar_base = epi_base + EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto conv_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -360,7 +363,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int num_kb = tile_kb(t);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
+        const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t fb = full_bar(stage);
         mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + b_tile_bytes);
         const int r0 = (int)(r_beg + (int64_t)kb * BK);
@@ -402,6 +405,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t idesc_ts = idesc & ~(1u << 15);
     const uint32_t a_kstep = A_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);  // descriptor units of 16 B
     const uint32_t b_kstep = B_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);
+    const uint64_t a_hi0 = make_desc(smem_base, A_MN), b_hi0 = make_desc(smem_base + off_b_hi, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t gchunk = 0;
@@ -411,7 +415,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tp = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       const uint32_t d_corr = tmem_base + TM_CORR;  // single stage: drained once per tile by the epilogue
-      if (g.split3) {
+      if (SPLIT) {
         mbar_wait(cempty_bar(0), (uint32_t)(it & 1) ^ 1u);
         tc_fence_after();
       }
@@ -423,11 +427,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t d_main = tmem_base + TM_MAIN + 128u * ms;
         const int kb1 = min(num_kb, kb0 + DRAIN_KB);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(g.split3 ? conv_bar(stage) : full_bar(stage), phase);
+          mbar_wait(SPLIT ? conv_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
-          const uint64_t b_hi = make_desc(sa + off_b_hi, B_MN), b_lo = make_desc(sa + off_b_lo, B_MN);
-          if (g.split3) {
+          // descriptors of stage s = those of stage 0 + s * stage_bytes/16 (the 14-bit address field cannot
+          // carry: all operand addresses are below 227 KiB)
+          const uint32_t sdelta = (uint32_t)stage * (stage_bytes >> 4);
+          const uint64_t b_hi = b_hi0 + sdelta, b_lo = b_hi + (b_tile_bytes >> 4);
+          if (SPLIT) {
             const uint32_t a_t = tmem_base + TM_A + 32u * (uint32_t)stage;  // hi at +0, lo at +16
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -437,7 +443,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               umma_tf32_ts(d_corr, a_t + 16u + 8u * k, b_hi + bk, idesc_ts, 1u);
             }
           } else {
-            const uint64_t a_hi = make_desc(sa, A_MN);
+            const uint64_t a_hi = a_hi0 + sdelta;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t ak = (uint64_t)(a_kstep * k), bk = (uint64_t)(b_kstep * k);
@@ -451,14 +457,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         umma_commit(mfull_bar(ms));  // chunk partial complete -> epilogue drains it
       }
-      if (g.split3) umma_commit(cfull_bar(0));
+      if (SPLIT) umma_commit(cfull_bar(0));
     }
    }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================================== lo-plane splitters (mode 1)
     // (A software-pipelined variant that prefetched the next k-block's operands while the TMEM stores drained
     // measured 5-9 % SLOWER; the straightforward per-k-block sequence below is the faster one.)
-    if (g.split3) {
+    if (SPLIT) {
       const int tid = threadIdx.x - 128;
       const int nb = (int)(b_tile_bytes / 16);  // <= 512 float4
       int stage = 0;
@@ -467,13 +473,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int num_kb = tile_kb(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          const uint32_t sa = smem_base + (uint32_t)stage * g.stage_bytes;
-          if (g.write_hi == 2) {  // timing experiment only (mode 4): skip the split work, results are garbage
-            tc_fence_before();
-            mbar_arrive(conv_bar(stage));
-            if (++stage == S) { stage = 0; phase ^= 1u; }
-            continue;
-          }
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           // ---- A: row `tid` of the tile -> 16 k-values -> TMEM (hi = raw, lo = exact remainder)
           float av[16];
           if (!A_MN) {
@@ -497,7 +497,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = tid + 128 * u;
-            vb[u] = i < nb ? lds_f4(sa + off_b_hi + (uint32_t)i * 16u) : f4_zero();
+            vb[u] = (FULLBN || i < nb) ? lds_f4(sa + off_b_hi + (uint32_t)i * 16u) : f4_zero();
           }
           const uint32_t a_t = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + TM_A + 32u * (uint32_t)stage;
           tmem_st16(a_t, av);
@@ -508,10 +508,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = tid + 128 * u;
-            if (i < nb) {
-              sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(vb[u]));
-              if (g.write_hi) sts_f4(sa + off_b_hi + (uint32_t)i * 16u, hi_part(vb[u]));
-            }
+            if (FULLBN || i < nb) sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(vb[u]));
           }
           tmem_st_wait();
           tc_fence_before();
@@ -561,7 +558,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(mempty_bar(ms));  // this warp is done with the chunk's TMEM stage
       }
-      if (g.split3) {
+      if (SPLIT) {
         mbar_wait(cfull_bar(0), (uint32_t)(it & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_sel + TM_CORR + 64u * half;
@@ -669,13 +666,17 @@ int pick_bn(int cols, bool mn_major) {
 
 template <bool A_MN, bool B_MN, int EPI>
 int launch(const isg::TcGemm& p, cudaStream_t stream) {
+  if (p.split3 != 0 && p.split3 != 1) return ISG_EUNSUPPORTED;
   TcArgs g{};
   g.C = p.C; g.ldc = p.ldc; g.rows = p.rows; g.cols = p.cols; g.R = p.R;
   g.BN = pick_bn(p.cols, B_MN);
   g.stage_bytes = A_TILE_BYTES + (p.split3 ? 2 : 1) * g.BN * BK * 4;
   g.stages = (SMEM_LIMIT - 1024 - EPI_BYTES - BAR_BYTES) / g.stage_bytes;
   if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
-  if (p.split3 && g.stages > TS_STAGES) g.stages = TS_STAGES;  // one TMEM A slot per smem stage
+  if (p.split3) {  // one TMEM A slot per smem stage
+    if (g.stages < TS_STAGES) return ISG_EUNSUPPORTED;
+    g.stages = TS_STAGES;
+  }
   if (g.stages < 2) return ISG_EUNSUPPORTED;
   g.m_tiles = ceil_div(p.rows, BM);
   g.n_tiles = ceil_div(p.cols, g.BN);
@@ -683,17 +684,14 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   g.r_chunk = p.r_chunk;
   g.c_split_stride = p.c_split_stride;
   g.bias = p.bias; g.Z = p.Z; g.ldz = p.ldz; g.Zprev = p.Zprev; g.act = p.act; g.accumulate = p.accumulate;
-  g.split3 = p.split3 ? 1 : 0;
-  g.write_hi = p.split3 == 3 ? 1 : (p.split3 == 4 ? 2 : 0);
   if (p.rows >= (1ll << 31) || p.R >= (1ll << 31)) return ISG_EUNSUPPORTED;  // TMA coordinates are int32
 
   // cluster pairs whenever there are at least two M tiles to pair and the B tile splits evenly
   // Measured (B200, c3 step): the single-pass mode is bound by L2->SM operand traffic and gains 1.33x from the
   // pair (0.160 -> 0.120 ms on [39809,300]x[300,1200]); the 3xTF32 mode is bound by its splitter / MMA chain
-  // and runs 1.7 % SLOWER as pairs (lock-step coupling), so it launches single CTAs unless ISG_TC_CLUSTER is set.
+  // and runs 1.7 % SLOWER as pairs (lock-step coupling), so it always launches single CTAs.
   static const bool env_no_cluster = getenv("ISG_TC_NO_CLUSTER") != nullptr;
-  static const bool env_cluster = getenv("ISG_TC_CLUSTER") != nullptr;
-  const bool want_pair = (p.split3 == 0 || env_cluster) && !p.no_cluster && !env_no_cluster;
+  const bool want_pair = p.split3 == 0 && !p.no_cluster && !env_no_cluster;
   const bool pair = want_pair && g.m_tiles >= 2 && (B_MN ? ((g.BN / 32) % 2 == 0) : true);
   const int CLh = pair ? 2 : 1;
 
@@ -707,7 +705,12 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   if (rc != ISG_OK) return rc;
 
   const int smem = 1024 + g.stages * g.stage_bytes + EPI_BYTES + BAR_BYTES;
-  auto kern = tc_gemm_kernel<A_MN, B_MN, EPI>;
+  // instantiations: mode 1 single CTA (BN == 128 specialised, generic BN), mode 2 single CTA, mode 2 pair
+  const bool fullbn = g.BN == MAX_BN;
+  auto kern = p.split3 ? (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true>
+                                 : tc_gemm_kernel<A_MN, B_MN, EPI, true, false, false>)
+                       : (pair ? tc_gemm_kernel<A_MN, B_MN, EPI, false, true, false>
+                               : tc_gemm_kernel<A_MN, B_MN, EPI, false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   const int m_groups = (g.m_tiles + CLh - 1) / CLh;

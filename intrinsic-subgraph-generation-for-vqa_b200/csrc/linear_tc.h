@@ -27,7 +27,7 @@ struct TcGemm {
   int act;
   int accumulate;
   int no_cluster;  // 1: launch single CTAs (no B-tile multicast pairs); debugging / A-B comparison
-  int split3;      // 1 = 3xTF32 (fp32-grade), 0 = single-pass TF32, 3 = 3xTF32 with an explicit hi write-back (verification only)
+  int split3;      // 1 = 3xTF32 (fp32-grade), 0 = single-pass TF32
 };
 
 int tc_gemm(const TcGemm& p, void* stream);
