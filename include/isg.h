@@ -229,12 +229,16 @@ int isg_attn_pool_bwd(const float* g_out, const float* g_gate, const float* x, c
  *   wgrad: g_W = g_y^T x (deterministic split over M; bias gradient = isg_colsum(g_y))
  * x [M,K] pitch ldx; W [Nout,K] dense; y [M,Nout] pitch ldy.
  * `mode`: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 split (fp32-grade), 2 = tcgen05 single-pass TF32
- *         (3 = mode 1 with an explicit hi write-back, verification only).
+ * `w_lo` (fwd, dgrad; optional, mode 1 only): the weight's lo plane  w - tf32_trunc(w)  from isg_split_lo, [Nout,K]
+ *         dense like W.  When given, the kernel fetches it by TMA instead of splitting the weight tile in its
+ *         per-k-block loop (one small kernel per weight and step instead of work on the GEMM's critical chain);
+ *         NULL keeps the in-kernel split.  Results are bit-identical either way.
  * ------------------------------------------------------------------------------------- */
-int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias,
+int isg_split_lo(const float* w, int64_t n /* multiple of 4 */, float* w_lo, void* stream);
+int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* w_lo /* or NULL */, const float* bias,
                    void* y, int64_t ldy, void* z_pre /* or NULL */, int64_t ldz,
                    int64_t M, int Nout, int K, int act, int mode, int dtype, void* stream);
-int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w,
+int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, const float* w_lo /* or NULL */,
                      const void* z_prev /* or NULL */, int64_t ldz,
                      void* g_x, int64_t ldgx, int accumulate,
                      int64_t M, int Nout, int K, int mode, int dtype, void* stream);

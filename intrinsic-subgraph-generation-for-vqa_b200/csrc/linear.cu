@@ -180,7 +180,27 @@ inline int wgrad_splits(int64_t M, int Nout, int K) {
 
 }  // namespace
 
-extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
+// w_lo[i] = w[i] - tf32_trunc(w[i]) (exact): the lo plane of the 3xTF32 split, produced once per weight and step
+__global__ void split_lo_kernel(const float* __restrict__ w, int64_t n4, float* __restrict__ w_lo) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = Vec4<float>::ld(w + 4 * i);
+  const float4 h = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xffffe000u), __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                               __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+  Vec4<float>::st(w_lo + 4 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+}
+
+extern "C" int isg_split_lo(const float* w, int64_t n, float* w_lo, void* stream_) {
+  if (n < 0) return ISG_EINVAL;
+  if (n == 0) return ISG_OK;
+  if (!w || !w_lo) return ISG_EINVAL;
+  if (n % 4 || ((uintptr_t)w & 15) || ((uintptr_t)w_lo & 15)) return ISG_EUNSUPPORTED;
+  split_lo_kernel<<<(unsigned)isg::ceil_div(n / 4, (int64_t)256), 256, 0, (cudaStream_t)stream_>>>(w, n / 4, w_lo);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* w_lo, const float* bias, void* y, int64_t ldy,
                               void* z_pre, int64_t ldz, int64_t M, int Nout, int K, int act, int mode, int dtype,
                               void* stream_) {
   if (M < 0 || Nout <= 0 || K <= 0) return ISG_EINVAL;
@@ -194,6 +214,7 @@ extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const f
     t.rows = M; t.cols = Nout; t.R = K; t.a_mn = 0; t.b_mn = 0; t.epi = 0; t.splits = 1;
     t.r_chunk = ((int64_t)K + 31) / 32 * 32;
     t.bias = bias; t.Z = (float*)z_pre; t.ldz = ldz; t.act = act; t.split3 = (mode == 1) ? 1 : 0;
+    t.B_lo = (mode == 1) ? w_lo : nullptr;
     return isg::tc_gemm(t, stream_);
   }
   GemmArgs g{};
@@ -206,7 +227,7 @@ extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const f
   return ISG_OK;
 }
 
-extern "C" int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, const void* z_prev, int64_t ldz,
+extern "C" int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, const float* w_lo, const void* z_prev, int64_t ldz,
                                 void* g_x, int64_t ldgx, int accumulate, int64_t M, int Nout, int K, int mode,
                                 int dtype, void* stream_) {
   if (M < 0 || Nout <= 0 || K <= 0) return ISG_EINVAL;
@@ -220,6 +241,7 @@ extern "C" int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, con
     t.rows = M; t.cols = K; t.R = Nout; t.a_mn = 0; t.b_mn = 1; t.epi = 1; t.splits = 1;
     t.r_chunk = ((int64_t)Nout + 31) / 32 * 32;
     t.Zprev = (const float*)z_prev; t.ldz = ldz; t.accumulate = accumulate; t.split3 = (mode == 1) ? 1 : 0;
+    t.B_lo = (mode == 1) ? w_lo : nullptr;
     return isg::tc_gemm(t, stream_);
   }
   GemmArgs g{};

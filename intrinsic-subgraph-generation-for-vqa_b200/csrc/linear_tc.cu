@@ -277,10 +277,12 @@ __device__ __forceinline__ float4 lo_part(float4 v) {
 // SPLIT (mode 1 vs mode 2), PAIR (cluster of two sharing the B tile by multicast) and FULLBN (BN == 128) are
 // compile-time: the per-k-block role loops are latency chains in which every runtime conditional costs ~1 %
 // (measured by bisecting an instrumented build), so the hot instantiation carries none.
-template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN>
+// BLO: the lo plane of B comes pre-split from global memory (a second tensor map): the splitter warps then only
+// move A into tensor memory — no shared-memory stores and no generic->async proxy fence on the per-k-block chain.
+template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN, bool BLO>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcArgs g) {
+               const __grid_constant__ CUtensorMap map_blo, const TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -365,7 +367,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t fb = full_bar(stage);
-        mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + b_tile_bytes);
+        mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + (BLO ? 2u : 1u) * b_tile_bytes);
         const int r0 = (int)(r_beg + (int64_t)kb * BK);
         if (!A_MN) {
           tma_load_2d(sa, &map_a, fb, r0, m0);
@@ -376,9 +378,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (CL == 1) {
           if (!B_MN) {
             tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0);
+            if (BLO) tma_load_2d(sa + off_b_lo, &map_blo, fb, r0, n0);
           } else {
             for (int c = 0; c < BN / 32; ++c)
               tma_load_2d(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + 32 * c, r0);
+            if (BLO)
+              for (int c = 0; c < BN / 32; ++c)
+                tma_load_2d(sa + off_b_lo + c * (BK * 128), &map_blo, fb, n0 + 32 * c, r0);
           }
         } else {
           // this CTA fetches half of the B tile and multicasts it into both CTAs of the pair
@@ -494,10 +500,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < 16; ++k) av[k] = lds_f1(ca + (uint32_t)k * 128u + (((ml >> 3) ^ ((uint32_t)k & 3u)) << 5));
           }
           float4 vb[4];
+          if (!BLO) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = tid + 128 * u;
-            vb[u] = (FULLBN || i < nb) ? lds_f4(sa + off_b_hi + (uint32_t)i * 16u) : f4_zero();
+            for (int u = 0; u < 4; ++u) {
+              const int i = tid + 128 * u;
+              vb[u] = (FULLBN || i < nb) ? lds_f4(sa + off_b_hi + (uint32_t)i * 16u) : f4_zero();
+            }
           }
           const uint32_t a_t = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + TM_A + 32u * (uint32_t)stage;
           tmem_st16(a_t, av);
@@ -505,14 +513,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 16; ++k) al[k] = lo1(av[k]);
           tmem_st16(a_t + 16u, al);
+          if (!BLO) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = tid + 128 * u;
-            if (FULLBN || i < nb) sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(vb[u]));
+            for (int u = 0; u < 4; ++u) {
+              const int i = tid + 128 * u;
+              if (FULLBN || i < nb) sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(vb[u]));
+            }
           }
           tmem_st_wait();
           tc_fence_before();
-          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          if (!BLO) fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
           mbar_arrive(conv_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -703,14 +713,25 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   if (!B_MN) rc = make_map(&mb, p.B, p.R, p.cols, p.ldb, BK, g.BN / CLh, false);
   else rc = make_map(&mb, p.B, p.cols, p.R, p.ldb, 32, BK, true);
   if (rc != ISG_OK) return rc;
+  const bool blo = p.split3 && p.B_lo != nullptr;
+  CUtensorMap mblo = mb;
+  if (blo) {
+    if (!B_MN) rc = make_map(&mblo, p.B_lo, p.R, p.cols, p.ldb, BK, g.BN, false);
+    else rc = make_map(&mblo, p.B_lo, p.cols, p.R, p.ldb, 32, BK, true);
+    if (rc != ISG_OK) return rc;
+  }
 
   const int smem = 1024 + g.stages * g.stage_bytes + EPI_BYTES + BAR_BYTES;
   // instantiations: mode 1 single CTA (BN == 128 specialised, generic BN), mode 2 single CTA, mode 2 pair
   const bool fullbn = g.BN == MAX_BN;
-  auto kern = p.split3 ? (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true>
-                                 : tc_gemm_kernel<A_MN, B_MN, EPI, true, false, false>)
-                       : (pair ? tc_gemm_kernel<A_MN, B_MN, EPI, false, true, false>
-                               : tc_gemm_kernel<A_MN, B_MN, EPI, false, false, false>);
+  // (+ the pre-split-B variants of mode 1; wgrad's B is an activation and is always split in the kernel)
+  constexpr bool CAN_BLO = !A_MN;
+  auto kern = p.split3 ? (blo && CAN_BLO ? (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, CAN_BLO>
+                                                   : tc_gemm_kernel<A_MN, B_MN, EPI, true, false, false, CAN_BLO>)
+                                         : (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, false>
+                                                   : tc_gemm_kernel<A_MN, B_MN, EPI, true, false, false, false>))
+                       : (pair ? tc_gemm_kernel<A_MN, B_MN, EPI, false, true, false, false>
+                               : tc_gemm_kernel<A_MN, B_MN, EPI, false, false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   const int m_groups = (g.m_tiles + CLh - 1) / CLh;
@@ -729,7 +750,7 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, ma, mb, g);
+  e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mblo, g);
   if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   return ISG_OK;

@@ -10,6 +10,8 @@ struct TcGemm {
   int64_t lda;
   const float* B;  // b_mn == 0: [cols, R] R-contiguous;  b_mn == 1: [R, cols] cols-contiguous
   int64_t ldb;
+  const float* B_lo;  // optional (mode 1): B - tf32_trunc(B), same layout and pitch as B, fetched by TMA instead of
+                      // being produced by the splitter warps (isg_split_lo); NULL = split B inside the kernel
   float* C;        // [rows, cols] (+ split * c_split_stride)
   int64_t ldc;
   int64_t rows;

@@ -29,25 +29,39 @@ def _c(t):
 # ------------------------------------------------------------------------------------------
 # dense projections (kernel d)
 # ------------------------------------------------------------------------------------------
-def linear_fwd_raw(x, w, b, act, want_pre, mode=None):
+# Rows from which the mode-1 dgrad takes the weight's lo plane pre-split (isg_split_lo, one ~3 us kernel per weight
+# and step) instead of splitting the weight tile inside the GEMM's k-loop.  Measured on [39809,1200]x[1200,300]:
+# dgrad 216 -> 202 us (its B tile is MN-major: 128-byte TMA rows).  The forward product is NOT pre-split: its
+# K-major weight tile has 64-byte rows and the extra TMA requests cost more than the split saves (202 -> 243 us).
+PRESPLIT_MIN_ROWS = 1024
+
+
+def split_lo(w):
+    """w - tf32_trunc(w) (exact), the lo plane of the 3xTF32 split of a dense fp32 weight."""
+    w_lo = torch.empty_like(w)
+    L.call("isg_split_lo", L.ptr(w), w.numel(), L.ptr(w_lo), L.stream())
+    return w_lo
+
+
+def linear_fwd_raw(x, w, b, act, want_pre, mode=None, w_lo=None):
     lib = L.load()
     mode = _GEMM_MODE if mode is None else mode
     M, K = x.shape
     Nout = w.shape[0]
     y = torch.empty(M, Nout, dtype=x.dtype, device=x.device)
     z = torch.empty(M, Nout, dtype=x.dtype, device=x.device) if want_pre else None
-    L.call("isg_linear_fwd", L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(y), Nout, L.ptr(z), Nout, M, Nout, K,
-                               act, mode, L.dtype_code(x), L.stream())
+    L.call("isg_linear_fwd", L.ptr(x), x.stride(0), L.ptr(w), L.ptr(w_lo), L.ptr(b), L.ptr(y), Nout, L.ptr(z), Nout,
+                               M, Nout, K, act, mode, L.dtype_code(x), L.stream())
     return y, z
 
 
-def linear_dgrad_raw(gy, w, z_prev=None, out=None, accumulate=False, mode=None):
+def linear_dgrad_raw(gy, w, z_prev=None, out=None, accumulate=False, mode=None, w_lo=None):
     lib = L.load()
     mode = _GEMM_MODE if mode is None else mode
     M, Nout = gy.shape
     K = w.shape[1]
     gx = out if out is not None else torch.empty(M, K, dtype=gy.dtype, device=gy.device)
-    L.call("isg_linear_dgrad", L.ptr(gy), gy.stride(0), L.ptr(w), L.ptr(z_prev), K, L.ptr(gx), gx.stride(0),
+    L.call("isg_linear_dgrad", L.ptr(gy), gy.stride(0), L.ptr(w), L.ptr(w_lo), L.ptr(z_prev), K, L.ptr(gx), gx.stride(0),
                                  1 if accumulate else 0, M, Nout, K, mode, L.dtype_code(gy), L.stream())
     return gx
 
@@ -165,7 +179,7 @@ class LinearAct(torch.autograd.Function):
     node_nn / ques_nn (models/masking.py:137,152)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, mode=None):
+    def forward(ctx, x, w, b, act, mode=None, bwd_mode=None):
         L.require_cuda(x, w, b)
         x, w = _c(x), _c(w)
         b = _c(b) if b is not None else None
@@ -173,6 +187,9 @@ class LinearAct(torch.autograd.Function):
         y, z = linear_fwd_raw(x, w, b, act, want_pre=(act != L.ACT_NONE), mode=mode)
         ctx.act = act
         ctx.mode = mode
+        # gradients never feed a discrete decision: a projection forced to strict-fp32 FFMA in the forward pass
+        # (the sampler's gate) still runs its backward products on the tensor cores in the global fp32-grade mode
+        ctx.bwd_mode = _GEMM_MODE if (mode == 0 and bwd_mode is None) else (mode if bwd_mode is None else bwd_mode)
         ctx.has_bias = b is not None
         ctx.save_for_backward(x, w, z)
         return y
@@ -184,15 +201,19 @@ class LinearAct(torch.autograd.Function):
             gy = gelu_bwd(_c(gy), z)
         elif gy.stride(1) != 1 or gy.stride(0) % 4 != 0:
             gy = gy.contiguous()  # column views of a wider buffer are consumed through their pitch
-        gx = linear_dgrad_raw(gy, w, mode=ctx.mode) if ctx.needs_input_grad[0] else None
-        gw = linear_wgrad_raw(gy, x, mode=ctx.mode) if ctx.needs_input_grad[1] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            w_lo = split_lo(w) if (ctx.bwd_mode == 1 and gy.shape[0] >= PRESPLIT_MIN_ROWS and w.numel() % 4 == 0) else None
+            gx = linear_dgrad_raw(gy, w, mode=ctx.bwd_mode, w_lo=w_lo)
+        gw = linear_wgrad_raw(gy, x, mode=ctx.bwd_mode) if ctx.needs_input_grad[1] else None
         gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def linear(x, w, b=None, act=L.ACT_NONE, mode=None):
-    """mode=None -> the global projection mode (set_gemm_mode / ISG_GEMM_MODE)."""
-    return LinearAct.apply(x, w, b, act, mode)
+def linear(x, w, b=None, act=L.ACT_NONE, mode=None, bwd_mode=None):
+    """mode=None -> the global projection mode (set_gemm_mode / ISG_GEMM_MODE); bwd_mode=None -> the backward
+    products use `mode`, except that a forward forced to mode 0 falls back to the global mode for its gradients."""
+    return LinearAct.apply(x, w, b, act, mode, bwd_mode)
 
 
 # ------------------------------------------------------------------------------------------

@@ -560,6 +560,29 @@ def test_linear_fwd_dgrad_wgrad(M, K, Nout, act, mode, tol):
     assert util.rel_err(bc.grad, bo.grad) <= max(tol, 1e-5)
 
 
+@pytest.mark.parametrize("M,K,Nout", [(1500, 300, 1200), (4910, 1200, 600), (257, 300, 300)])
+def test_linear_tc_presplit_weight_lo_is_bit_identical(M, K, Nout):
+    """isg_split_lo + the w_lo argument of isg_linear_fwd / _dgrad (weight lo plane fetched by TMA) must give exactly
+    the bits of the in-kernel split: same products, same accumulation order."""
+    from isg_b200 import lib as L
+    from isg_b200 import ops
+
+    g = torch.Generator().manual_seed(M + Nout)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(Nout, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(Nout, generator=g).to(DEV)
+    gy = torch.randn(M, Nout, generator=g).to(DEV)
+    w_lo = ops.split_lo(w)
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(w_lo, w - hi) and torch.equal(hi + w_lo, w)
+    y0, z0 = ops.linear_fwd_raw(x, w, b, L.ACT_GELU, True, mode=1)
+    y1, z1 = ops.linear_fwd_raw(x, w, b, L.ACT_GELU, True, mode=1, w_lo=w_lo)
+    assert torch.equal(y0, y1) and torch.equal(z0, z1)
+    gx0 = ops.linear_dgrad_raw(gy, w, mode=1)
+    gx1 = ops.linear_dgrad_raw(gy, w, mode=1, w_lo=w_lo)
+    assert torch.equal(gx0, gx1)
+
+
 def test_linear_tc_pitched_views_and_long_reduction():
     """tcgen05 path on column views of a wider buffer (x_l | x_r share one pitch) and on a reduction long
     enough to need many wgrad splits (E = 40k rows, BASELINE config 3 size)."""
