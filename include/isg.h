@@ -229,13 +229,18 @@ int isg_attn_pool_bwd(const float* g_out, const float* g_gate, const float* x, c
  *   wgrad: g_W = g_y^T x (deterministic split over M; bias gradient = isg_colsum(g_y))
  * x [M,K] pitch ldx; W [Nout,K] dense; y [M,Nout] pitch ldy.
  * `mode`: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 split (fp32-grade), 2 = tcgen05 single-pass TF32
- * `w_lo` (fwd, dgrad; optional, mode 1 only): the weight's lo plane  w - tf32_trunc(w)  from isg_split_lo, [Nout,K]
- *         dense like W.  When given, the kernel fetches it by TMA instead of splitting the weight tile in its
- *         per-k-block loop (one small kernel per weight and step instead of work on the GEMM's critical chain);
- *         NULL keeps the in-kernel split.  Results are bit-identical either way.
+ * Optional pre-split weight planes (mode 1 only; NULL keeps the in-kernel split; results are bit-identical):
+ *   dgrad  `w_lo`  = w - tf32_trunc(w), [Nout,K] dense, from isg_split_lo;
+ *   fwd    `w_t`, `w_t_lo` = the transposed weight [K,Nout] dense and its lo plane, from isg_transpose_split
+ *          (both or neither).  The kernel then fetches the lo plane by TMA instead of splitting the weight tile in
+ *          its per-k-block loop, and the forward product reads the weight as an MN-major operand (128-byte TMA rows
+ *          instead of 64-byte ones).  One small kernel per weight and step instead of work on the GEMM's critical chain.
  * ------------------------------------------------------------------------------------- */
 int isg_split_lo(const float* w, int64_t n /* multiple of 4 */, float* w_lo, void* stream);
-int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* w_lo /* or NULL */, const float* bias,
+int isg_transpose_split(const float* w /* [Nout,K] */, int Nout, int K, float* w_t /* [K,Nout] */,
+                        float* w_t_lo /* [K,Nout] */, void* stream);
+int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* w_t /* or NULL */,
+                   const float* w_t_lo /* or NULL */, const float* bias,
                    void* y, int64_t ldy, void* z_pre /* or NULL */, int64_t ldz,
                    int64_t M, int Nout, int K, int act, int mode, int dtype, void* stream);
 int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, const float* w_lo /* or NULL */,

@@ -200,7 +200,38 @@ extern "C" int isg_split_lo(const float* w, int64_t n, float* w_lo, void* stream
   return ISG_OK;
 }
 
-extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* w_lo, const float* bias, void* y, int64_t ldy,
+// w_t[k, n] = w[n, k] and w_t_lo = w_t - tf32_trunc(w_t): the weight as an MN-major B operand for the forward
+// product (128-byte TMA rows instead of the 64-byte rows of the K-major [Nout, K] tile) plus its lo plane.
+// 32x32 shared-memory tile transpose; w [Nout, K] dense, outputs [K, Nout] dense.
+__global__ void transpose_split_kernel(const float* __restrict__ w, int Nout, int K, float* __restrict__ w_t,
+                                       float* __restrict__ w_t_lo) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    tile[r][threadIdx.x] = (n < Nout && k < K) ? w[(int64_t)n * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, n = n0 + threadIdx.x;
+    if (k < K && n < Nout) {
+      const float v = tile[threadIdx.x][r];
+      w_t[(int64_t)k * Nout + n] = v;
+      w_t_lo[(int64_t)k * Nout + n] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    }
+  }
+}
+
+extern "C" int isg_transpose_split(const float* w, int Nout, int K, float* w_t, float* w_t_lo, void* stream_) {
+  if (Nout <= 0 || K <= 0) return ISG_EINVAL;
+  if (!w || !w_t || !w_t_lo) return ISG_EINVAL;
+  transpose_split_kernel<<<dim3(isg::ceil_div(K, 32), isg::ceil_div(Nout, 32)), dim3(32, 8), 0, (cudaStream_t)stream_>>>(
+      w, Nout, K, w_t, w_t_lo);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const float* w_t, const float* w_t_lo, const float* bias, void* y, int64_t ldy,
                               void* z_pre, int64_t ldz, int64_t M, int Nout, int K, int act, int mode, int dtype,
                               void* stream_) {
   if (M < 0 || Nout <= 0 || K <= 0) return ISG_EINVAL;
@@ -214,7 +245,10 @@ extern "C" int isg_linear_fwd(const void* x, int64_t ldx, const void* w, const f
     t.rows = M; t.cols = Nout; t.R = K; t.a_mn = 0; t.b_mn = 0; t.epi = 0; t.splits = 1;
     t.r_chunk = ((int64_t)K + 31) / 32 * 32;
     t.bias = bias; t.Z = (float*)z_pre; t.ldz = ldz; t.act = act; t.split3 = (mode == 1) ? 1 : 0;
-    t.B_lo = (mode == 1) ? w_lo : nullptr;
+    if (mode == 1 && w_t && w_t_lo) {  // transposed, pre-split weight: MN-major B operand, lo plane by TMA
+      if (((uintptr_t)w_t & 15) || ((uintptr_t)w_t_lo & 15)) return ISG_EUNSUPPORTED;
+      t.B = w_t; t.ldb = Nout; t.b_mn = 1; t.B_lo = w_t_lo;
+    }
     return isg::tc_gemm(t, stream_);
   }
   GemmArgs g{};

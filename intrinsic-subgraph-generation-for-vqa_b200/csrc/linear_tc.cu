@@ -40,6 +40,7 @@
 //   warp 2       TMEM allocation, 512 columns.  mode 1: main[2 chunk stages] 0..255, correction 256..383,
 //                A ring (4 slots x {hi 16, lo 16} columns) 384..511; mode 2: main[2] only, SS operands
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -654,6 +655,14 @@ int make_map(CUtensorMap* m, const float* base, int64_t dim0, int64_t dim1, int6
              bool mn_major) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return ISG_EUNSUPPORTED;
+  // cuTensorMapEncodeTiled is a DRIVER call and needs a current context.  A thread that has only ever been handed
+  // cached allocations (an autograd worker whose first CUDA action is this GEMM) has none bound yet and the encode
+  // fails with CUDA_ERROR_INVALID_CONTEXT; one runtime call per thread binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    if (cudaFree(nullptr) != cudaSuccess) return ISG_EINVAL;
+    ctx_bound = true;
+  }
   if (((uintptr_t)base & 15) || (ld % 4)) return ISG_EUNSUPPORTED;
   cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
@@ -663,6 +672,10 @@ int make_map(CUtensorMap* m, const float* base, int64_t dim0, int64_t dim1, int6
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && getenv("ISG_TC_VERBOSE"))
+    fprintf(stderr, "[isg] cuTensorMapEncodeTiled failed: CUresult %d base %p dims %llu x %llu pitch %llu B box %u x %u mn %d\n",
+            (int)r, (const void*)base, (unsigned long long)dims[0], (unsigned long long)dims[1],
+            (unsigned long long)strides[0], box[0], box[1], (int)mn_major);
   return r == CUDA_SUCCESS ? ISG_OK : ISG_EINVAL;
 }
 
@@ -763,6 +776,7 @@ namespace isg {
 int tc_gemm(const TcGemm& p, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!p.a_mn && !p.b_mn && p.epi == 0) return launch<false, false, EPI_FWD>(p, stream);
+  if (!p.a_mn && p.b_mn && p.epi == 0) return launch<false, true, EPI_FWD>(p, stream);  // fwd on a transposed weight
   if (!p.a_mn && p.b_mn && p.epi == 1) return launch<false, true, EPI_DGRAD>(p, stream);
   if (p.a_mn && p.b_mn && p.epi == 2) return launch<true, true, EPI_PLAIN>(p, stream);
   return ISG_EUNSUPPORTED;

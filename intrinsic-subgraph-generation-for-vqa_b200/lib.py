@@ -50,7 +50,8 @@ SIGNATURES = {
     "isg_attn_pool_fwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "isg_attn_pool_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "isg_split_lo": (_I32, [_P, _I64, _P, _P]),
-    "isg_linear_fwd": (_I32, [_P, _I64, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
+    "isg_transpose_split": (_I32, [_P, _I32, _I32, _P, _P, _P]),
+    "isg_linear_fwd": (_I32, [_P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
     "isg_linear_dgrad": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I64, _I32, _I64, _I32, _I32, _I32, _I32, _P]),
     "isg_linear_wgrad_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "isg_linear_wgrad": (_I32, [_P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
@@ -84,7 +85,7 @@ KERNELS_PER_CALL = {
     "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_imle_bwd": 1,
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
-    "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
+    "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_transpose_split": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
     "isg_gelu_bwd": 1, "isg_colsum": 2,
 }
 launch_count = 0
@@ -127,7 +128,8 @@ def call(name, *args):
     else:
         rc = fn(*args)
     if rc != 0:
-        check(rc)
+        msg = load().isg_error_string(int(rc)).decode()
+        raise RuntimeError(f"{name}{tuple(args)} failed with code {rc}: {msg}")
     launch_count += KERNELS_PER_CALL.get(name, 0)
 
 

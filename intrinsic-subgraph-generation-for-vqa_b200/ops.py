@@ -43,15 +43,24 @@ def split_lo(w):
     return w_lo
 
 
-def linear_fwd_raw(x, w, b, act, want_pre, mode=None, w_lo=None):
+def transpose_split(w):
+    """(w^T, w^T - tf32_trunc(w^T)) as dense [K, Nout] tensors: the forward product's pre-split MN-major weight."""
+    Nout, K = w.shape
+    w_t = torch.empty(K, Nout, dtype=torch.float32, device=w.device)
+    w_t_lo = torch.empty(K, Nout, dtype=torch.float32, device=w.device)
+    L.call("isg_transpose_split", L.ptr(w), Nout, K, L.ptr(w_t), L.ptr(w_t_lo), L.stream())
+    return w_t, w_t_lo
+
+
+def linear_fwd_raw(x, w, b, act, want_pre, mode=None, w_t=None, w_t_lo=None):
     lib = L.load()
     mode = _GEMM_MODE if mode is None else mode
     M, K = x.shape
     Nout = w.shape[0]
     y = torch.empty(M, Nout, dtype=x.dtype, device=x.device)
     z = torch.empty(M, Nout, dtype=x.dtype, device=x.device) if want_pre else None
-    L.call("isg_linear_fwd", L.ptr(x), x.stride(0), L.ptr(w), L.ptr(w_lo), L.ptr(b), L.ptr(y), Nout, L.ptr(z), Nout,
-                               M, Nout, K, act, mode, L.dtype_code(x), L.stream())
+    L.call("isg_linear_fwd", L.ptr(x), x.stride(0), L.ptr(w), L.ptr(w_t), L.ptr(w_t_lo), L.ptr(b), L.ptr(y), Nout,
+                               L.ptr(z), Nout, M, Nout, K, act, mode, L.dtype_code(x), L.stream())
     return y, z
 
 
@@ -184,7 +193,10 @@ class LinearAct(torch.autograd.Function):
         x, w = _c(x), _c(w)
         b = _c(b) if b is not None else None
         mode = _GEMM_MODE if mode is None else mode
-        y, z = linear_fwd_raw(x, w, b, act, want_pre=(act != L.ACT_NONE), mode=mode)
+        w_t = w_t_lo = None
+        if mode == 1 and x.shape[0] >= PRESPLIT_MIN_ROWS and w.shape[0] % 4 == 0:
+            w_t, w_t_lo = transpose_split(w)
+        y, z = linear_fwd_raw(x, w, b, act, want_pre=(act != L.ACT_NONE), mode=mode, w_t=w_t, w_t_lo=w_t_lo)
         ctx.act = act
         ctx.mode = mode
         # gradients never feed a discrete decision: a projection forced to strict-fp32 FFMA in the forward pass

@@ -39,7 +39,7 @@ def timed_call(name, *args):
     e.record()
     torch.cuda.synchronize()
     if name == "isg_linear_fwd":
-        M, Nout, K, mode = args[10], args[11], args[12], args[14]
+        M, Nout, K, mode = args[11], args[12], args[13], args[15]
     elif name == "isg_linear_dgrad":
         M, Nout, K, mode = args[9], args[10], args[11], args[12]
     elif name == "isg_linear_wgrad":

@@ -61,5 +61,5 @@ def test_argument_validation_without_gpu():
     lib = L.load()
     assert lib.isg_gat_edge_fwd(None, None, 0, None, None, None, None, None, None, None, None, 0, None, 4, 4, 4,
                                 301, 0.2, 0, None) == -2  # C % 4 != 0 -> ISG_EUNSUPPORTED
-    assert lib.isg_linear_fwd(None, 0, None, None, None, None, 0, None, 0, -1, 4, 4, 0, 0, 0, None) == -1
+    assert lib.isg_linear_fwd(None, 0, None, None, None, None, None, 0, None, 0, -1, 4, 4, 0, 0, 0, None) == -1
     assert lib.isg_csr_build(None, -1, 4, None, None, None, None, None, None, None, None, 0, None) == -1

@@ -562,8 +562,9 @@ def test_linear_fwd_dgrad_wgrad(M, K, Nout, act, mode, tol):
 
 @pytest.mark.parametrize("M,K,Nout", [(1500, 300, 1200), (4910, 1200, 600), (257, 300, 300)])
 def test_linear_tc_presplit_weight_lo_is_bit_identical(M, K, Nout):
-    """isg_split_lo + the w_lo argument of isg_linear_fwd / _dgrad (weight lo plane fetched by TMA) must give exactly
-    the bits of the in-kernel split: same products, same accumulation order."""
+    """isg_split_lo / isg_transpose_split + the pre-split weight arguments of isg_linear_dgrad / _fwd (lo plane fetched
+    by TMA; forward on the transposed, MN-major weight) must give exactly the bits of the in-kernel split: same
+    products, same accumulation order."""
     from isg_b200 import lib as L
     from isg_b200 import ops
 
@@ -576,7 +577,9 @@ def test_linear_tc_presplit_weight_lo_is_bit_identical(M, K, Nout):
     hi = (w.view(torch.int32) & -8192).view(torch.float32)
     assert torch.equal(w_lo, w - hi) and torch.equal(hi + w_lo, w)
     y0, z0 = ops.linear_fwd_raw(x, w, b, L.ACT_GELU, True, mode=1)
-    y1, z1 = ops.linear_fwd_raw(x, w, b, L.ACT_GELU, True, mode=1, w_lo=w_lo)
+    w_t, w_t_lo = ops.transpose_split(w)
+    assert torch.equal(w_t, w.t().contiguous()) and torch.equal(w_t_lo, w_lo.t().contiguous())
+    y1, z1 = ops.linear_fwd_raw(x, w, b, L.ACT_GELU, True, mode=1, w_t=w_t, w_t_lo=w_t_lo)
     assert torch.equal(y0, y1) and torch.equal(z0, z1)
     gx0 = ops.linear_dgrad_raw(gy, w, mode=1)
     gx1 = ops.linear_dgrad_raw(gy, w, mode=1, w_lo=w_lo)
