@@ -783,18 +783,29 @@ int tc_gemm(const TcGemm& p, void* stream_) {
 }
 
 int tc_wgrad_splits(int64_t M, int Nout, int K, int64_t* r_chunk) {
-  // The reduction over rows is split for parallelism only (accuracy is handled by the in-kernel chunk
-  // drain): one wave of tiles, every split at least 32 k-blocks long; partials are summed in a fixed order.
-  const int tiles = ceil_div(Nout, BM) * ceil_div(K, pick_bn(K, true));
-  int64_t s = ISG_NUM_SMS / tiles;
-  const int64_t max_by_len = (M + 32 * BK - 1) / (32 * BK);
-  if (s > max_by_len) s = max_by_len;
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  int64_t chunk = (M + s - 1) / s;
+  // The reduction over rows is split for parallelism only (accuracy is handled by the in-kernel chunk drain);
+  // partials are summed in a fixed order.  With t output tiles and s splits the persistent grid runs
+  // ceil(t*s / SMs) waves of M/s rows each (+ a per-tile prologue/epilogue worth ~256 rows): pick the s that
+  // minimises that, every split at least 32 k-blocks long.  (One wave of floor(SMs / t) splits — the first
+  // heuristic — left 19-23 % of the SMs idle on the [E,1200]x[E,300] and [N,2400]x[N,300] gradients.)
+  const int64_t tiles = (int64_t)ceil_div(Nout, BM) * ceil_div(K, pick_bn(K, true));
+  int64_t max_s = (M + 32 * BK - 1) / (32 * BK);
+  if (max_s > 64) max_s = 64;
+  if (max_s < 1) max_s = 1;
+  int64_t best_s = 1;
+  double best_cost = 0.0;
+  for (int64_t s = 1; s <= max_s; ++s) {
+    const int64_t waves = (tiles * s + ISG_NUM_SMS - 1) / ISG_NUM_SMS;
+    const double cost = (double)waves * ((double)M / (double)s + 256.0);
+    if (s == 1 || cost < best_cost * 0.995) {  // prefer fewer splits on near-ties (fewer partials to reduce)
+      best_cost = cost;
+      best_s = s;
+    }
+  }
+  int64_t chunk = (M + best_s - 1) / best_s;
   chunk = ((chunk + BK - 1) / BK) * BK;
   if (chunk < BK) chunk = BK;
-  s = (M + chunk - 1) / chunk;  // every split non-empty
+  int64_t s = (M + chunk - 1) / chunk;  // every split non-empty
   if (s < 1) s = 1;
   *r_chunk = chunk;
   return (int)s;
