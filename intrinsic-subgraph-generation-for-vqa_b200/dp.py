@@ -29,15 +29,20 @@ class GradAllReduce:
             off += p.numel()
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.nbytes = self.numel * 4
+        self._zeroed = None  # indices of the parameters whose (gradient-less) slices are known to hold zeros
+        # NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and scale afterwards
+        self._avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
 
     def pack(self):
         """grads -> flat bucket (zeros where a parameter has no gradient)."""
         have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
-        none = [v for v, p in zip(self.views, self.params) if p.grad is None]
+        none = tuple(i for i, p in enumerate(self.params) if p.grad is None)
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-        for v in none:
-            v.zero_()
+        if none != self._zeroed:  # zero slices stay zero through sum / average: only re-zero when the set changes
+            for i in none:
+                self.views[i].zero_()
+            self._zeroed = none
 
     def unpack(self):
         """flat bucket -> .grad of every parameter that had one (others stay None, like DDP)."""
@@ -54,12 +59,17 @@ class GradAllReduce:
         if self.stream is not None and async_op:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-                self.flat.mul_(1.0 / self.world)
+                self._reduce(self.flat)
             return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / self.world)
+        self._reduce(self.flat)
         self.unpack()
+
+    def _reduce(self, buf):
+        if self._avg:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.mul_(1.0 / self.world)
 
     def wait(self):
         if self.stream is not None:
@@ -108,6 +118,7 @@ class OverlappedGradAllReduce(GradAllReduce):
             self.views[i] = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.flat.zero_()
+        self._zeroed = None
         self._buckets, cur = [], None
         for i in self._order:
             nbytes = self.params[i].numel() * 4
@@ -148,11 +159,9 @@ class OverlappedGradAllReduce(GradAllReduce):
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
-                chunk.mul_(1.0 / self.world)
+                self._reduce(chunk)
         else:
-            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
-            chunk.mul_(1.0 / self.world)
+            self._reduce(chunk)
 
     def finish(self):
         """Call after backward(): completes the step's reduction and writes the averaged gradients back."""
