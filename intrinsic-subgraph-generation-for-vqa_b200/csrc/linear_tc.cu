@@ -51,10 +51,14 @@ namespace {
 using namespace isg;
 
 constexpr int BM = 128;      // UMMA M (cta_group::1)
-constexpr int BK = 16;       // fp32 elements per k-block
+#ifndef ISG_TC_BK
+#define ISG_TC_BK 16
+#endif
+constexpr int BK = ISG_TC_BK;  // fp32 elements per k-block: 16 (64-byte K-major rows, SWIZZLE_64B) or 32 (128-byte, SWIZZLE_128B)
+static_assert(BK == 16 || BK == 32, "BK must be 16 or 32");
 constexpr int UMMA_K = 8;    // kind::tf32
 constexpr int MAX_BN = 128;
-constexpr int DRAIN_KB = 8;  // k-blocks per accumulator chunk (K = 128 -> 16 truncating steps per chain)
+constexpr int DRAIN_KB = 128 / BK;  // k-blocks per accumulator chunk (K = 128 -> 16 truncating steps per chain)
 constexpr int NTHREADS = 512;
 constexpr int A_TILE_BYTES = BM * BK * 4;          // 8 KiB
 constexpr int EPI_WARPS = 8;
@@ -65,8 +69,8 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_MAIN = 0, TM_CORR = 256;     // column bases; main stage s adds 128*s
-constexpr uint32_t TM_A = 384;                     // mode 1: A ring, slot s at TM_A + 32*s (hi 16 cols, lo 16 cols)
-constexpr int TS_STAGES = 4;                       // A-ring slots == smem stages in mode 1
+constexpr uint32_t TM_A = 384;                     // mode 1: A ring, slot s at TM_A + 2*BK*s (hi BK cols, lo BK cols)
+constexpr int TS_STAGES = 128 / (2 * BK);          // A-ring slots == smem stages in mode 1 (4 at BK=16, 2 at BK=32)
 
 enum Epi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_PLAIN = 2 };
 
@@ -258,8 +262,9 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
 //             4 k-rows 512 B apart (SBO).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
   const uint64_t lbo = mn_major ? (uint64_t)((BK * 128) >> 4) : 1ull;
-  const uint64_t sbo = 512 >> 4;
-  const uint64_t layout = mn_major ? 1ull : 4ull;
+  // K-major: 8-row groups of BK*4-byte rows; swizzle mode = row length (64B: code 4, 128B: code 2)
+  const uint64_t sbo = mn_major ? (512 >> 4) : ((8 * BK * 4) >> 4);
+  const uint64_t layout = mn_major ? 1ull : (BK == 16 ? 4ull : 2ull);
   return (uint64_t)((saddr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
@@ -441,13 +446,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sdelta = (uint32_t)stage * (stage_bytes >> 4);
           const uint64_t b_hi = b_hi0 + sdelta, b_lo = b_hi + (b_tile_bytes >> 4);
           if (SPLIT) {
-            const uint32_t a_t = tmem_base + TM_A + 32u * (uint32_t)stage;  // hi at +0, lo at +16
+            const uint32_t a_t = tmem_base + TM_A + (uint32_t)(2 * BK) * (uint32_t)stage;  // hi at +0, lo at +BK
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t bk = (uint64_t)(b_kstep * k);
               umma_tf32_ts(d_main, a_t + 8u * k, b_hi + bk, idesc_ts, (kb > kb0 || k > 0) ? 1u : 0u);
               umma_tf32_ts(d_corr, a_t + 8u * k, b_lo + bk, idesc_ts, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(d_corr, a_t + 16u + 8u * k, b_hi + bk, idesc_ts, 1u);
+              umma_tf32_ts(d_corr, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_ts, 1u);
             }
           } else {
             const uint64_t a_hi = a_hi0 + sdelta;
@@ -473,7 +478,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // measured 5-9 % SLOWER; the straightforward per-k-block sequence below is the faster one.)
     if (SPLIT) {
       const int tid = threadIdx.x - 128;
-      const int nb = (int)(b_tile_bytes / 16);  // <= 512 float4
+      const int nb = (int)(b_tile_bytes / 16);  // <= 32*BK float4
       int stage = 0;
       uint32_t phase = 0;
       for (int t = work0; t < total_tiles; t += work_stride) {
@@ -481,44 +486,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-          // ---- A: row `tid` of the tile -> 16 k-values -> TMEM (hi = raw, lo = exact remainder)
-          float av[16];
-          if (!A_MN) {
-            // K-major tile: row of 64 B, SWIZZLE_64B: 16-byte chunk c sits at c ^ ((row >> 1) & 3)
-            const uint32_t rowa = sa + (uint32_t)tid * 64u;
-            const uint32_t x = ((uint32_t)tid >> 1) & 3u;
+          // ---- A: row `tid` of the tile -> BK k-values -> TMEM (hi = raw, lo = exact remainder), 16 at a time
+          const uint32_t a_t = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + TM_A + (uint32_t)(2 * BK) * (uint32_t)stage;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float4 v = lds_f4(rowa + (((uint32_t)c ^ x) << 4));
-              av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+          for (int hh = 0; hh < BK / 16; ++hh) {
+            float av[16];
+            if (!A_MN) {
+              // K-major tile: rows of BK*4 bytes; 16-byte chunk c of row r sits at c ^ (r & 7) (SWIZZLE_128B, BK = 32)
+              // or c ^ ((r >> 1) & 3) (SWIZZLE_64B, BK = 16)
+              const uint32_t rowa = sa + (uint32_t)tid * (uint32_t)(BK * 4);
+              const uint32_t x = BK == 16 ? (((uint32_t)tid >> 1) & 3u) : ((uint32_t)tid & 7u);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 v = lds_f4(rowa + ((((uint32_t)(4 * hh + c)) ^ x) << 4));
+                av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+              }
+            } else {
+              // MN-major tile: chunk (tid / 32) of [BK k-rows][128 B], 32-byte swizzle atoms:
+              // element (ml, k) sits at k*128 + (((ml >> 3) ^ (k & 3)) << 5) + ((ml & 7) << 2)
+              const uint32_t ml = (uint32_t)tid & 31u;
+              const uint32_t ca = sa + ((uint32_t)tid >> 5) * (BK * 128u) + ((ml & 7u) << 2) + (uint32_t)hh * (16u * 128u);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) av[k] = lds_f1(ca + (uint32_t)k * 128u + (((ml >> 3) ^ ((uint32_t)k & 3u)) << 5));
             }
-          } else {
-            // MN-major tile: chunk (tid / 32) of [16 k-rows][128 B], 32-byte swizzle atoms:
-            // element (ml, k) sits at k*128 + (((ml >> 3) ^ (k & 3)) << 5) + ((ml & 7) << 2)
-            const uint32_t ml = (uint32_t)tid & 31u;
-            const uint32_t ca = sa + ((uint32_t)tid >> 5) * (BK * 128u) + ((ml & 7u) << 2);
+            tmem_st16(a_t + 16u * hh, av);
+            float al[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) av[k] = lds_f1(ca + (uint32_t)k * 128u + (((ml >> 3) ^ ((uint32_t)k & 3u)) << 5));
+            for (int k = 0; k < 16; ++k) al[k] = lo1(av[k]);
+            tmem_st16(a_t + (uint32_t)BK + 16u * hh, al);
           }
-          float4 vb[4];
           if (!BLO) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BK / 4; ++u) {  // b_tile_bytes / 16 / 128 float4 per thread at BN = 128
               const int i = tid + 128 * u;
-              vb[u] = (FULLBN || i < nb) ? lds_f4(sa + off_b_hi + (uint32_t)i * 16u) : f4_zero();
-            }
-          }
-          const uint32_t a_t = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + TM_A + 32u * (uint32_t)stage;
-          tmem_st16(a_t, av);
-          float al[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) al[k] = lo1(av[k]);
-          tmem_st16(a_t + 16u, al);
-          if (!BLO) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = tid + 128 * u;
-              if (FULLBN || i < nb) sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(vb[u]));
+              if (FULLBN || i < nb) sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(lds_f4(sa + off_b_hi + (uint32_t)i * 16u)));
             }
           }
           tmem_st_wait();
@@ -670,7 +671,8 @@ int make_map(CUtensorMap* m, const float* base, int64_t dim0, int64_t dim1, int6
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                            : (BK == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS && getenv("ISG_TC_VERBOSE"))
     fprintf(stderr, "[isg] cuTensorMapEncodeTiled failed: CUresult %d base %p dims %llu x %llu pitch %llu B box %u x %u mn %d\n",
