@@ -51,26 +51,49 @@ namespace {
 using namespace isg;
 
 constexpr int BM = 128;      // UMMA M (cta_group::1)
+// Default ("wide") build: 32-wide k-blocks (128-byte K-major rows) with FOUR A slots in tensor memory.  To make room
+// the two correction products accumulate into the main accumulator (no separate correction accumulator: 48 instead
+// of 16 truncating steps per drained chunk -> 1.4-2.0e-6 instead of 6.5e-7 against fp64, the FFMA kernel's range)
+// and the epilogue staging tile is halved so that four 48 KiB stages fit.  Halves the synchronisation rounds per
+// reduction element: fwd 0.188 -> 0.157, dgrad 0.204 -> 0.155, wgrad 0.215 -> 0.162 ms on [39809,300]x[300,1200].
+// -DISG_TC_NARROW builds the previous kernel (16-wide k-blocks, separate correction accumulator, 6.5e-7).
+#if !defined(ISG_TC_NARROW) && !defined(ISG_TC_BK)
+#define ISG_TC_WIDE 1
+#endif
+#ifdef ISG_TC_WIDE
+#define ISG_TC_BK 32
+#define ISG_TC_MERGE 1
+#else
+#define ISG_TC_MERGE 0
+#endif
 #ifndef ISG_TC_BK
 #define ISG_TC_BK 16
 #endif
+constexpr bool MERGE = ISG_TC_MERGE != 0;
 constexpr int BK = ISG_TC_BK;  // fp32 elements per k-block: 16 (64-byte K-major rows, SWIZZLE_64B) or 32 (128-byte, SWIZZLE_128B)
 static_assert(BK == 16 || BK == 32, "BK must be 16 or 32");
 constexpr int UMMA_K = 8;    // kind::tf32
 constexpr int MAX_BN = 128;
-constexpr int DRAIN_KB = 128 / BK;  // k-blocks per accumulator chunk (K = 128 -> 16 truncating steps per chain)
+#ifndef ISG_TC_DRAIN_K
+#define ISG_TC_DRAIN_K 128
+#endif
+// k-blocks per accumulator chunk (K = 128): 16 truncating steps per chain with a separate correction accumulator,
+// 48 with the merged one.  Measured with the merged accumulator: K = 64 -> 1.1e-6 but fwd 0.157 -> 0.184 ms,
+// K = 32 -> 8e-7 and 0.207 ms; the drain is not free, so the chunk stays at 128.
+constexpr int DRAIN_KB = ISG_TC_DRAIN_K / BK;
 constexpr int NTHREADS = 512;
 constexpr int A_TILE_BYTES = BM * BK * 4;          // 8 KiB
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_ROW_BYTES = 144;                 // 32 floats + 16 B pad (conflict-free float4 transpose)
-constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_ROW_BYTES;
+constexpr int EPI_ROWS = MERGE ? 16 : 32;           // rows staged per pass by one epilogue warp
+constexpr int EPI_BYTES = EPI_WARPS * EPI_ROWS * EPI_ROW_BYTES;
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_MAIN = 0, TM_CORR = 256;     // column bases; main stage s adds 128*s
-constexpr uint32_t TM_A = 384;                     // mode 1: A ring, slot s at TM_A + 2*BK*s (hi BK cols, lo BK cols)
-constexpr int TS_STAGES = 128 / (2 * BK);          // A-ring slots == smem stages in mode 1 (4 at BK=16, 2 at BK=32)
+constexpr uint32_t TM_A = MERGE ? 256 : 384;       // mode 1: A ring, slot s at TM_A + 2*BK*s (hi BK cols, lo BK cols)
+constexpr int TS_STAGES = (512 - (int)TM_A) / (2 * BK);  // A-ring slots == smem stages in mode 1
 
 enum Epi { EPI_FWD = 0, EPI_DGRAD = 1, EPI_PLAIN = 2 };
 
@@ -427,7 +450,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tp = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       const uint32_t d_corr = tmem_base + TM_CORR;  // single stage: drained once per tile by the epilogue
-      if (SPLIT) {
+      if (SPLIT && !MERGE) {
         mbar_wait(cempty_bar(0), (uint32_t)(it & 1) ^ 1u);
         tc_fence_after();
       }
@@ -451,8 +474,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t bk = (uint64_t)(b_kstep * k);
               umma_tf32_ts(d_main, a_t + 8u * k, b_hi + bk, idesc_ts, (kb > kb0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(d_corr, a_t + 8u * k, b_lo + bk, idesc_ts, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(d_corr, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_ts, 1u);
+              umma_tf32_ts(MERGE ? d_main : d_corr, a_t + 8u * k, b_lo + bk, idesc_ts,
+                           (MERGE || kb > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(MERGE ? d_main : d_corr, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_ts, 1u);
             }
           } else {
             const uint64_t a_hi = a_hi0 + sdelta;
@@ -469,7 +493,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         umma_commit(mfull_bar(ms));  // chunk partial complete -> epilogue drains it
       }
-      if (SPLIT) umma_commit(cfull_bar(0));
+      if (SPLIT && !MERGE) umma_commit(cfull_bar(0));
     }
    }
   } else if (warp >= 4 && warp < 8) {
@@ -534,7 +558,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================================================================== epilogue (8 warps)
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 8) >> 2;  // column half: [64*half, 64*half + 64)
-    const uint32_t stg = epi_base + (uint32_t)(warp - 8) * 32 * EPI_ROW_BYTES;
+    const uint32_t stg = epi_base + (uint32_t)(warp - 8) * EPI_ROWS * EPI_ROW_BYTES;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     uint32_t gchunk = 0;
     int it = 0;
@@ -570,7 +594,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(mempty_bar(ms));  // this warp is done with the chunk's TMEM stage
       }
-      if (SPLIT) {
+      if (SPLIT && !MERGE) {
         mbar_wait(cfull_bar(0), (uint32_t)(it & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_sel + TM_CORR + 64u * half;
@@ -591,18 +615,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int cc = 0; cc < 2; ++cc) {
         const int c0 = 64 * half + 32 * cc;
         if (n0 + c0 >= n_lim) continue;  // warp-uniform
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts_f4(stg + lane * EPI_ROW_BYTES + j * 16,
-                 make_float4(acc[32 * cc + 4 * j], acc[32 * cc + 4 * j + 1], acc[32 * cc + 4 * j + 2],
-                             acc[32 * cc + 4 * j + 3]));
-        __syncwarp();
         const int col = n0 + c0 + (lane & 7) * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int rh = 0; rh < 32 / EPI_ROWS; ++rh) {  // EPI_ROWS rows of the warp's 32 per pass
+        __syncwarp();
+        if (EPI_ROWS == 32 || (lane >> 4) == rh) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts_f4(stg + (lane & (EPI_ROWS - 1)) * EPI_ROW_BYTES + j * 16,
+                   make_float4(acc[32 * cc + 4 * j], acc[32 * cc + 4 * j + 1], acc[32 * cc + 4 * j + 2],
+                               acc[32 * cc + 4 * j + 3]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < EPI_ROWS / 4; ++i) {
           const int rl = i * 4 + (lane >> 3);
-          const int64_t row = m0 + rl;
+          const int64_t row = m0 + rh * EPI_ROWS + rl;
           float4 v = lds_f4(stg + rl * EPI_ROW_BYTES + (lane & 7) * 16);
           if (row < g.rows && col < n_lim) {
             if (EPI == EPI_FWD) {
@@ -619,6 +647,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             Vec4<float>::st(Cb + row * g.ldc + col, v);
           }
+        }
         }
       }
     }
