@@ -29,11 +29,13 @@ def _c(t):
 # ------------------------------------------------------------------------------------------
 # dense projections (kernel d)
 # ------------------------------------------------------------------------------------------
-# Rows from which the mode-1 dgrad takes the weight's lo plane pre-split (isg_split_lo, one ~3 us kernel per weight
-# and step) instead of splitting the weight tile inside the GEMM's k-loop.  Measured on [39809,1200]x[1200,300]:
-# dgrad 216 -> 202 us (its B tile is MN-major: 128-byte TMA rows).  The forward product is NOT pre-split: its
-# K-major weight tile has 64-byte rows and the extra TMA requests cost more than the split saves (202 -> 243 us).
-PRESPLIT_MIN_ROWS = 1024
+# Pre-split weight planes (isg_split_lo / isg_transpose_split, one ~3 us kernel per weight and step): the GEMM fetches
+# the weight's lo plane by TMA instead of splitting the weight tile inside its k-loop.  With the 16-wide k-block
+# kernel (-DISG_TC_NARROW) this paid off from ~1000 rows (dgrad 216 -> 202 us; forward on the transposed, MN-major
+# weight 202 -> 179 us on [39809,300]x[300,1200]); with the default 32-wide kernel the operand rows are 128 bytes
+# either way and the extra L2 traffic and launches cost slightly more than the split saves (5.17-5.21 vs 5.24-5.29
+# ms per c3 step), so it is off unless ISG_PRESPLIT_MIN_ROWS is set.
+PRESPLIT_MIN_ROWS = int(os.environ.get("ISG_PRESPLIT_MIN_ROWS", str(1 << 62)))
 
 
 def split_lo(w):
