@@ -228,7 +228,8 @@ int isg_attn_pool_bwd(const float* g_out, const float* g_gate, const float* x, c
  *   dgrad: g_x = (g_y W) [* gelu'(z_prev) if z_prev != NULL]
  *   wgrad: g_W = g_y^T x (deterministic split over M; bias gradient = isg_colsum(g_y))
  * x [M,K] pitch ldx; W [Nout,K] dense; y [M,Nout] pitch ldy.
- * `mode`: 0 = fp32 FFMA, 1 = tcgen05 3xTF32 split (fp32-grade), 2 = tcgen05 single-pass TF32
+ * `mode`: 0 = fp32 FFMA (0.8-1.7e-6 vs fp64), 1 = tcgen05 3xTF32 split (fp32-grade: 1.4-2.0e-6; 6.5e-7 in the
+ *         -DISG_TC_NARROW build), 2 = tcgen05 single-pass TF32 (~8e-4)
  * Optional pre-split weight planes (mode 1 only; NULL keeps the in-kernel split; results are bit-identical):
  *   dgrad  `w_lo`  = w - tf32_trunc(w), [Nout,K] dense, from isg_split_lo;
  *   fwd    `w_t`, `w_t_lo` = the transposed weight [K,Nout] dense and its lo plane, from isg_transpose_split
