@@ -237,8 +237,8 @@ def main_isg(args, rank, world, local_rank):
     # Multi-GPU training: one flat all-reduce after each replay of the captured step (default).  --overlap buckets
     # the collective, issues it from gradient hooks during the backward pass and captures it into the step's CUDA
     # graph (isg_b200.dp.OverlappedGradAllReduce; the process group must then exist before the capture).  Measured
-    # on 2 GPUs: 7.13 vs 7.20 ms/step, but the eager e2e path loses 11 % to the hooks and the process hung in
-    # teardown after printing its line, so it stays opt-in.
+    # on 2 GPUs (r1i): 5.47-5.48 vs 5.43 ms/step — the bucket collectives compete with the persistent GEMM CTAs for
+    # SMs and nothing is gained at this scale, so it stays opt-in (8 GPUs not measured).
     overlap = world > 1 and train and args.overlap and not args.no_graph
     reducer = None
     if overlap:
@@ -387,15 +387,28 @@ def main_isg(args, rank, world, local_rank):
     else:
         ms = ms_eager
     clk = clocks.stop() if rank == 0 else None
+    n_buckets = len(reducer._buckets) if overlap else 0
+    if overlap:
+        # the eager passes below (breakdown, e2e) use the flat reducer: the per-bucket hooks cost host time there
+        reducer.remove_hooks()
+        reducer = GradAllReduce(model)
+        overlap = False
     # kernel-family breakdown of one extra (untimed) step, for DESIGN.md / the JSON line
     ms_b, _, tall = timed(lambda: step(resident, noise_d), 2, None if not args.breakdown else list(L.KERNELS_PER_CALL))
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
-    if rank != 0:
+    def teardown():
+        # a communicator whose collectives were captured into a CUDA graph must outlive that graph
         if world > 1:
+            torch.cuda.synchronize()
+            if graph is not None:
+                graph.reset()
             dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return
     graphs = B * world * args.steps
     value = graphs / (ms / 1e3)
@@ -451,7 +464,7 @@ def main_isg(args, rank, world, local_rank):
                    "channels": CHANNELS, "heads": HEADS, "layers": LAYERS, "sample_k": K_SAMPLE,
                    "step": "MGAT forward+backward" + (
                        (" + NCCL gradient all-reduce (42 MB in %d buckets, issued by gradient hooks during backward, "
-                        "captured in the step graph)" % len(reducer._buckets)) if overlap else
+                        "captured in the step graph)" % n_buckets) if n_buckets else
                        " + NCCL gradient all-reduce (42 MB flat bucket after the step)" if world > 1 else "")
                    if train else "MGAT forward (no_grad)",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
@@ -475,8 +488,7 @@ def main_isg(args, rank, world, local_rank):
         line["breakdown_step_ms"] = ms_b / 2
     out_stream.write(json.dumps(line) + "\n")
     out_stream.flush()
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():
