@@ -560,6 +560,24 @@ def test_linear_fwd_dgrad_wgrad(M, K, Nout, act, mode, tol):
     assert util.rel_err(bc.grad, bo.grad) <= max(tol, 1e-5)
 
 
+def test_linear_tc_3xtf32_error_bound_vs_fp64():
+    """The default projection mode is documented as fp32-grade: 1.4-2.0e-6 against fp64 for the three products of a
+    [9600,300]x[300,1200] layer (include/isg.h); the FFMA kernel sits at 0.8-1.7e-6."""
+    from isg_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    M, K, Nout = 9600, 300, 1200
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(Nout, K, generator=g) / math.sqrt(K)).to(DEV)
+    gy = torch.randn(M, Nout, generator=g).to(DEV)
+    x64, w64, gy64 = x.double(), w.double(), gy.double()
+    y, _ = ops.linear_fwd_raw(x, w, None, 0, False, mode=1)
+    gx = ops.linear_dgrad_raw(gy, w, mode=1)
+    gw = ops.linear_wgrad_raw(gy, x, mode=1)
+    for got, ref in ((y, x64 @ w64.t()), (gx, gy64 @ w64), (gw, gy64.t() @ x64)):
+        assert util.rel_err(got, ref) <= 3e-6
+
+
 @pytest.mark.parametrize("M,K,Nout", [(1500, 300, 1200), (4910, 1200, 600), (257, 300, 300)])
 def test_linear_tc_presplit_weight_lo_is_bit_identical(M, K, Nout):
     """isg_split_lo / isg_transpose_split + the pre-split weight arguments of isg_linear_dgrad / _fwd (lo plane fetched
