@@ -79,7 +79,7 @@ constexpr int MAX_BN = 128;
 #endif
 // k-blocks per accumulator chunk (K = 128): 16 truncating steps per chain with a separate correction accumulator,
 // 48 with the merged one.  Measured with the merged accumulator: K = 64 -> 1.1e-6 but fwd 0.157 -> 0.184 ms,
-// K = 32 -> 8e-7 and 0.207 ms; the drain is not free, so the chunk stays at 128.
+// K = 32 -> 8e-7 and 0.207 ms; K = 256 -> 2.4-3.1e-6 and no faster (0.160 ms): the chunk stays at 128.
 constexpr int DRAIN_KB = ISG_TC_DRAIN_K / BK;
 constexpr int NTHREADS = 512;
 constexpr int A_TILE_BYTES = BM * BK * 4;          // 8 KiB
