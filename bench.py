@@ -117,14 +117,15 @@ def edge_study(points=((4096, 20, 150),), reps=10):
     return out
 
 
-def measured_traffic(kernel_key):
-    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture
-    (profiles/edge_traffic.json, written by scripts/ncu_summary.py --traffic); None if absent."""
+def measured_traffic(kernel_key, workload):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture of THIS workload
+    (profiles/edge_traffic.json: {workload: {entry point: bytes}}, written by scripts/ncu_summary.py --traffic);
+    None when no capture of this workload is committed."""
     p = os.path.join(ROOT, "profiles", "edge_traffic.json")
     if not os.path.exists(p):
         return None
     try:
-        return json.load(open(p)).get(kernel_key)
+        return json.load(open(p)).get(workload, {}).get(kernel_key)
     except Exception:
         return None
 
@@ -176,21 +177,84 @@ def run_cpu_port(sampler, train, B, steps, warmup, seed=3407):
             "N": int(b["x"].shape[0]), "E": int(b["edge_index"].shape[1])}
 
 
+def run_cpu_reference(sampler, train, B, steps, warmup, seed=3407):
+    """The reference's OWN MGAT (models/mgat.py + mgat_v2_conv.py + masking.py + sampling/**, unmodified files
+    staged into the git-ignored oracle/_ref/ by oracle/stage_reference.py, or /root/reference where it exists),
+    executed on the host cores on the pure-torch shim of its missing PyG wheels.  Same synthetic batch, weights
+    and injected noise as the GPU arm.  Returns None when no reference tree is available (-> the port)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_loader as rl
+    from isg_b200 import synth
+
+    if not rl.available():
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    with rl.scratch_cwd():
+        rl.load()
+        from ISubGVQA.models.mgat import MGAT as RefMGAT
+
+        model = RefMGAT(channels=CHANNELS, num_ins=LAYERS, heads=HEADS, use_instr=True,
+                        masking_thresholds=[1.0, 1.0, 1.0, 0.1], use_topk=True, interpretable_mode=False,
+                        sampler_type=sampler, sample_k=K_SAMPLE, nb_samples=1, alpha=1.0, beta=10.0, tau=1.0)
+    model.load_state_dict(synth.make_state_dict(CHANNELS, HEADS, LAYERS, seed))
+    model.train(train)
+    if sampler == "aimle":  # same warmed-up beta as the GPU arm (the state object lives in the decorator's closure)
+        for cell in model.convs[3].mask.sampler_train.__closure__:
+            if type(cell.cell_contents).__name__ == "AdaptiveTargetDistribution":
+                cell.cell_contents.beta = 1.0
+    b = make_inputs(B, seed)
+    if sampler in ("imle", "aimle"):
+        noise = synth.gumbel_noise(B, b["nmax"], 0.3, seed)
+    else:
+        noise = synth.gumbel_noise(B, b["nmax"], 1.0, seed)[:, 0, :, 0].contiguous()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ctx = rl.inject_noise(noise) if sampler in ("imle", "aimle") else rl.inject_device_gumbel(noise)
+        with rl.scratch_cwd(), ctx:
+            if train:
+                x = b["x"].clone().requires_grad_(True)
+                ea = b["edge_attr"].clone().requires_grad_(True)
+                model.zero_grad()
+                h, _, _, _ = model(x, b["edge_index"], b["instr_vectors"], b["global_language_feats"], ea,
+                                   b["batch"], return_masks=True)
+                (h * h).mean().backward()
+            else:
+                with torch.no_grad():
+                    model(b["x"], b["edge_index"], b["instr_vectors"], b["global_language_feats"], b["edge_attr"],
+                          b["batch"], return_masks=True)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "N": int(b["x"].shape[0]), "E": int(b["edge_index"].shape[1]), "root": rl.REFERENCE_ROOT}
+
+
+def run_cpu_arm(sampler, train, B, steps, warmup):
+    """-> (result, kind, description): the reference's own code when its files are available, else the port."""
+    r = run_cpu_reference(sampler, train, B, steps, warmup)
+    if r is not None:
+        return r, "reference", ("the reference's own MGAT (unmodified models/*.py + sampling/**, staged by "
+                                "oracle/stage_reference.py) on the pure-torch shim of its PyG wheels")
+    return run_cpu_port(sampler, train, B, steps, warmup), "port", "oracle/isg_oracle.py OracleMGAT (CPU port)"
+
+
 def main_reference(args, rank, world):
-    desc, sampler, train, _ = WORKLOADS[args.workload]
+    desc, sampler, train, B = WORKLOADS[args.workload]
     if rank != 0:
         return
-    sample_B = 64
-    r = run_cpu_port(sampler, train, sample_B, args.steps, args.warmup)
+    r, kind, what = run_cpu_arm(sampler, train, B, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "sample": f"{sample_B} graphs per step "
-                   f"(N={r['N']}, E={r['E']}), CPU only"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": f"oracle/isg_oracle.py OracleMGAT, {sample_B}-graph batches of the same "
-                                   f"workload, {args.steps} steps after {args.warmup} warm-up"},
+        "config": {"workload": f"{args.workload}: {desc}", "graphs_per_gpu": B, "nodes": r["N"], "edges": r["E"],
+                   "channels": CHANNELS, "heads": HEADS, "layers": LAYERS, "sample_k": K_SAMPLE,
+                   "sample": f"the full {B}-graph batch of the workload per step, CPU only"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind,
+                         "sample": f"{what}; {B}-graph batches (N={r['N']}, E={r['E']}) of the same workload, "
+                                   f"{args.steps} steps after {args.warmup} warm-up, all host threads"},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -233,7 +297,7 @@ def main_isg(args, rank, world, local_rank):
     model.load_state_dict(synth.make_state_dict(CHANNELS, HEADS, LAYERS, 3407))  # same weights on every rank
     model.to(dev).train(train)
     if sampler == "aimle":
-        model.convs[3].mask.sampler_train.target._init[0] = 1.0  # warmed-up beta (beta0 = 0 gives zero grads)
+        model.convs[3].mask.sampler_train.target.beta = 1.0  # warmed-up beta (beta0 = 0 gives zero grads)
     # Multi-GPU training: one flat all-reduce after each replay of the captured step (default).  --overlap buckets
     # the collective, issues it from gradient hooks during the backward pass and captures it into the step's CUDA
     # graph (isg_b200.dp.OverlappedGradAllReduce; the process group must then exist before the capture).  Measured
@@ -426,7 +490,7 @@ def main_isg(args, rank, world, local_rank):
         ach = alg / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst + att_reduce + gat_edge_bwd_src)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic("isg_gat_edge_bwd"),
+                "traffic": measured_traffic("isg_gat_edge_bwd", args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
                 "launches_timed": calls}
     elif "isg_gat_edge_fwd" in tsum:
@@ -435,7 +499,7 @@ def main_isg(args, rank, world, local_rank):
         alg = (3 * fwd_b_un + fwd_b_m) / 4.0
         ach = alg / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "isg_gat_edge_fwd (gat_edge_fwd_kernel)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("isg_gat_edge_fwd"),
+                "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("isg_gat_edge_fwd", args.workload),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms, "launches_timed": calls}
     edge_fwd = None
@@ -446,11 +510,10 @@ def main_isg(args, rank, world, local_rank):
                     "frac": alg / (tot / calls * 1e-3) / 1e9 / peak}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sample_B = 64
-        r = run_cpu_port(sampler, train, sample_B, 3, 1)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"oracle/isg_oracle.py OracleMGAT on {sample_B}-graph batches (N={r['N']}, E={r['E']}) of "
-                         f"the same workload, 3 steps after 1 warm-up, {r['ms_per_step']:.0f} ms/step"}
+        r, kind, what = run_cpu_arm(sampler, train, B, 2, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind,
+               "sample": f"{what}; the workload's own {B}-graph batch (N={r['N']}, E={r['E']}), 2 steps after 1 "
+                         f"warm-up, {r['ms_per_step']:.0f} ms/step"}
     study = None
     if world == 1 and not args.no_edge_study:
         del resident, flush

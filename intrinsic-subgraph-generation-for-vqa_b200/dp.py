@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 
 class GradAllReduce:
-    def __init__(self, module, process_group=None):
+    def __init__(self, module, process_group=None, always_exchange=False):
         from . import ops
 
         ops.set_side_stream_with_dist(True)  # gradients are read after backward() has returned (and joined)
@@ -29,26 +29,54 @@ class GradAllReduce:
             off += p.numel()
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.nbytes = self.numel * 4
-        self._zeroed = None  # indices of the parameters whose (gradient-less) slices are known to hold zeros
+        self._none_seen = None    # this rank's gradient-less parameter indices at the last used-set exchange
+        self._global_used = None  # per parameter: did ANY rank produce a gradient (exchanged when the set changes)
+        self.always_exchange = bool(always_exchange)
         # NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and scale afterwards
         self._avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
 
+    def _local_unused(self):
+        return tuple(i for i, p in enumerate(self.params) if p.grad is None)
+
+    def _exchange_used_set(self, none):
+        """DDP(find_unused_parameters=True) semantics need the GLOBAL picture: a parameter that got no gradient
+        here but did on another rank must still receive the averaged gradient, and one that no rank used keeps
+        .grad = None.  The used-bitmap is all-reduced (MAX) whenever this rank's gradient-less set changes — one
+        small collective plus a host read on the first step and never again while the set is static.  Every rank
+        must take this branch in the same step (true when usage is decided by configuration; data-dependent usage
+        needs the exchange on every step: pass always_exchange=True)."""
+        used = torch.ones(len(self.params), dtype=torch.float32, device=self.flat.device)
+        if none:
+            used[list(none)] = 0.0
+        if self.world > 1:
+            dist.all_reduce(used, op=dist.ReduceOp.MAX, group=self.group)
+        self._global_used = tuple(bool(v) for v in used.cpu().tolist())
+        self._none_seen = none
+
     def pack(self):
-        """grads -> flat bucket (zeros where a parameter has no gradient)."""
+        """grads -> flat bucket.  A parameter without a gradient on this rank contributes zeros; its slice is
+        re-zeroed on EVERY pack (after a reduce it holds the other ranks' average, not zeros)."""
+        none = self._local_unused()
+        if self.always_exchange or none != self._none_seen:
+            self._exchange_used_set(none)
         have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
-        none = tuple(i for i, p in enumerate(self.params) if p.grad is None)
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-        if none != self._zeroed:  # zero slices stay zero through sum / average: only re-zero when the set changes
-            for i in none:
-                self.views[i].zero_()
-            self._zeroed = none
+        if none:
+            torch._foreach_zero_([self.views[i] for i in none])
 
     def unpack(self):
-        """flat bucket -> .grad of every parameter that had one (others stay None, like DDP)."""
-        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
-        if have:
-            torch._foreach_copy_([g for _, g in have], [v for v, _ in have])
+        """flat bucket -> .grad.  Parameters some rank used get the averaged gradient (materialised here when this
+        rank had none); parameters no rank used keep .grad = None, like DDP."""
+        dst, src = [], []
+        for i, (v, p) in enumerate(zip(self.views, self.params)):
+            if p.grad is not None:
+                dst.append(p.grad)
+                src.append(v)
+            elif self._global_used is not None and self._global_used[i]:
+                p.grad = v.clone()
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def all_reduce_mean(self, async_op=False):
         """Averages gradients across ranks.  With async_op=True the collective runs on a side stream;
@@ -93,7 +121,7 @@ class OverlappedGradAllReduce(GradAllReduce):
         super().__init__(module, process_group)
         from . import ops
 
-        ops.set_side_stream_with_dist(False)  # the hooks read gradients DURING backward: no side-stream producers
+        ops.forbid_side_stream(True)  # the hooks read gradients DURING backward: no side-stream producers
         self.bucket_bytes = int(bucket_bytes)
         self._index = {p: i for i, p in enumerate(self.params)}
         self._offsets, off = [], 0
@@ -118,7 +146,6 @@ class OverlappedGradAllReduce(GradAllReduce):
             self.views[i] = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.flat.zero_()
-        self._zeroed = None
         self._buckets, cur = [], None
         for i in self._order:
             nbytes = self.params[i].numel() * 4
@@ -181,6 +208,10 @@ class OverlappedGradAllReduce(GradAllReduce):
         self._reset()
 
     def remove_hooks(self):
+        from . import ops
+
+        if self._hooks:
+            ops.forbid_side_stream(False)
         for h in self._hooks:
             h.remove()
         self._hooks = []

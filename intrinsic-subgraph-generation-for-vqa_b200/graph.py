@@ -9,7 +9,7 @@ from . import lib as L
 
 class GraphIndex:
     __slots__ = ("edge_index", "batch", "N", "E", "B", "dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr",
-                 "src_eid", "status", "graph_ptr", "batch32", "_nmax_dev", "_nmax", "_key")
+                 "src_eid", "status", "graph_ptr", "batch32", "_nmax_dev", "_nmax", "_key", "_keepalive")
 
     def __init__(self, edge_index, batch, num_graphs, num_nodes=None):
         L.require_cuda(edge_index, batch)
@@ -44,6 +44,7 @@ class GraphIndex:
                                   L.ptr(self._nmax_dev), st)
         self._nmax = None
         self._key = None
+        self._keepalive = None
 
     @property
     def nmax(self):
@@ -68,13 +69,20 @@ _CACHE_SIZE = 4
 
 
 def get_graph_index(edge_index, batch, num_graphs):
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), batch.data_ptr(),
-           batch._version, int(batch.numel()), int(num_graphs), edge_index.device)
+    """The key is the identity of the caller's storage (address, offset, strides, version counter).  The cache
+    entry keeps the caller's tensors alive, so the allocator cannot hand the same address to a different batch
+    while the entry exists; inputs that had to be copied to become contiguous are indexed but never cached."""
+    if not (edge_index.is_contiguous() and batch.is_contiguous()):
+        return GraphIndex(edge_index, batch, num_graphs)
+    key = (edge_index.data_ptr(), edge_index.storage_offset(), edge_index._version, tuple(edge_index.shape),
+           batch.data_ptr(), batch.storage_offset(), batch._version, int(batch.numel()), int(num_graphs),
+           edge_index.device)
     for gi in _cache:
         if gi._key == key:
             return gi
     gi = GraphIndex(edge_index, batch, num_graphs)
     gi._key = key
+    gi._keepalive = (edge_index, batch)
     _cache.insert(0, gi)
     del _cache[_CACHE_SIZE:]
     return gi

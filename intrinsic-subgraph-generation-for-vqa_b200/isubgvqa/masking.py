@@ -92,6 +92,9 @@ class MaskingModel(torch.nn.Module):
             self.sampler_train, self.sampler_val = get_aimle_samplers(
                 sample_k=sample_k, device=None, nb_samples=nb_samples, alpha=alpha, tau=tau,
                 noise_source=noise_source)
+            # adaptive beta / gradient-norm EMA as a persistent buffer: checkpointed with the model (the reference
+            # loses it on resume, target_aimle.py:101-109) and moved by .to(device)
+            self.sampler_train.target.bind(self, "aimle_state")
         elif sampler_type == "simple":
             self.sampler = EdgeSIMPLEBatched(k=sample_k, device="cuda", policy="edge_candid")
         elif sampler_type == "gumbel":
@@ -99,6 +102,16 @@ class MaskingModel(torch.nn.Module):
         self.injected_noise = None
         self.injected_dropout_mask = None
         self.last_theta = None
+
+    OPTIONAL_STATE_KEYS = ("aimle_state",)  # absent from checkpoints written by the reference
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        before = len(missing_keys)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+        optional = {prefix + k for k in self.OPTIONAL_STATE_KEYS}
+        missing_keys[before:] = [k for k in missing_keys[before:] if k not in optional]
 
     def reset_parameters(self):
         for seq in (self.gate_nn, self.node_nn, self.ques_nn):

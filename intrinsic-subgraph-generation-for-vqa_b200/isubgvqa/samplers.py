@@ -70,7 +70,10 @@ class TargetDistribution:
 class AdaptiveTargetDistribution:
     """target_aimle.py:87-162.  The reference keeps beta / grad_norm as Python attributes and pays
     three .item() syncs per backward; here they live in an 8-double device vector that
-    isg_aimle_bwd updates in place."""
+    isg_aimle_bwd updates in place: [beta, grad_norm, previous_beta_update, alpha, beta_update_step,
+    grad_norm_decay_rate, target_norm, beta_update_momentum].  When the distribution belongs to a
+    MaskingModel the vector is that module's persistent buffer `aimle_state` (bind()), so it follows
+    .to(device) and is part of state_dict(); standalone it is created lazily on first use."""
 
     def __init__(self, initial_alpha=1.0, initial_beta=1.0, initial_grad_norm=1.0, beta_update_step=0.0001,
                  beta_update_momentum=0.0, grad_norm_decay_rate=0.9, target_norm=1.0):
@@ -78,28 +81,61 @@ class AdaptiveTargetDistribution:
                       float(beta_update_step), float(grad_norm_decay_rate), float(target_norm),
                       float(beta_update_momentum)]
         self._state = None
+        self._owner = None  # (module, buffer name)
+
+    def bind(self, module, name):
+        """Keep the state in `module`'s registered buffer `name` (float64[8])."""
+        module.register_buffer(name, torch.tensor(self._init, dtype=torch.float64), persistent=True)
+        self._owner = (module, name)
+        self._state = None
+
+    def _buffer(self):
+        module, name = self._owner
+        buf = getattr(module, name)
+        if buf.dtype != torch.float64:  # module.float()/.half() casts floating buffers; the kernel needs doubles
+            buf = buf.double()
+            setattr(module, name, buf)
+        return buf
 
     def state(self, device):
+        if self._owner is not None:
+            buf = self._buffer()
+            if buf.device != torch.device(device):
+                raise RuntimeError(f"AIMLE state lives on {buf.device} but theta is on {device}: move the module")
+            return buf
         if self._state is None or self._state.device != torch.device(device):
             init = self._init if self._state is None else self._state.cpu().tolist()
             self._state = torch.tensor(init, dtype=torch.float64, device=device)
         return self._state
 
     def _get(self, i):
+        if self._owner is not None:
+            return float(self._buffer()[i].item())
         return self._init[i] if self._state is None else float(self._state[i].item())
 
-    alpha = property(lambda self: self._get(3))
-    beta = property(lambda self: self._get(0))
-    grad_norm = property(lambda self: self._get(1))
-    previous_beta_update = property(lambda self: self._get(2))
+    def _set(self, i, value):
+        self._init[i] = float(value)
+        if self._owner is not None:
+            self._buffer()[i] = float(value)
+        elif self._state is not None:
+            self._state[i] = float(value)
+
+    alpha = property(lambda self: self._get(3), lambda self, v: self._set(3, v))
+    beta = property(lambda self: self._get(0), lambda self, v: self._set(0, v))
+    grad_norm = property(lambda self: self._get(1), lambda self, v: self._set(1, v))
+    previous_beta_update = property(lambda self: self._get(2), lambda self, v: self._set(2, v))
 
     def state_dict(self):
         """Not part of the reference (its AIMLE state is lost on resume); offered so
-        callers can checkpoint it."""
+        callers of a standalone distribution can checkpoint it."""
+        if self._owner is not None:
+            return {"state": self._buffer().cpu().tolist()}
         return {"state": self._init if self._state is None else self._state.cpu().tolist()}
 
     def load_state_dict(self, sd):
         self._init = list(sd["state"])
+        if self._owner is not None:
+            self._buffer().copy_(torch.tensor(self._init, dtype=torch.float64))
         self._state = None
 
 

@@ -99,15 +99,25 @@ _join_pending = False
 _side_ok = False  # set per step by MGAT.forward: only when no parameter has a .grad to accumulate into
 
 
-_side_with_dist = False
+_side_forbidden = 0  # >0 while some consumer reads gradients DURING backward (see forbid_side_stream)
+_side_dist_ok = False
+
+
+def forbid_side_stream(on):
+    """A consumer that reads parameter gradients from hooks DURING the backward pass (DistributedDataParallel's
+    reducer, isg_b200.dp.OverlappedGradAllReduce) would see a side-stream gradient before it is joined.  Such a
+    consumer calls forbid_side_stream(True) for its lifetime and forbid_side_stream(False) when it goes away;
+    the ban is a counter, independent of whether a process group exists."""
+    global _side_forbidden
+    _side_forbidden = max(0, _side_forbidden + (1 if on else -1))
 
 
 def set_side_stream_with_dist(ok):
-    """torch.distributed wrappers that consume gradients DURING backward (DistributedDataParallel's bucket hooks)
-    would read a side-stream gradient before it is joined, so once a process group exists the side stream is off
-    unless the caller states that gradients are only read after backward() returns (isg_b200.dp.GradAllReduce)."""
-    global _side_with_dist
-    _side_with_dist = bool(ok)
+    """With a torch.distributed process group present and nobody vouching for it, the side stream stays off (a
+    stock DistributedDataParallel wrapper may be reading gradients during backward).  isg_b200.dp.GradAllReduce
+    reads gradients only after backward() has returned and joined, and says so here."""
+    global _side_dist_ok
+    _side_dist_ok = bool(ok)
 
 
 def allow_side_stream(ok):
@@ -116,7 +126,9 @@ def allow_side_stream(ok):
     accumulation into an existing .grad would run on the main stream without waiting — so the caller
     vouches for the former once per step."""
     global _side_ok
-    if ok and not _side_with_dist and torch.distributed.is_available() and torch.distributed.is_initialized():
+    if _side_forbidden > 0:
+        ok = False
+    elif ok and not _side_dist_ok and torch.distributed.is_available() and torch.distributed.is_initialized():
         ok = False
     _side_ok = bool(ok)
 
@@ -269,6 +281,9 @@ class GateTheta(torch.autograd.Function):
         dbl = 1 if double_gather else 0
         if q.shape[0] != (gi.B if dbl else xn.shape[0]):
             raise ValueError("GateTheta: q must be [B,D] with double_gather, [N,D] without")
+        if dbl and gi.B > xn.shape[0]:
+            # batch[batch[n]] uses a graph id as a node index: the reference raises here too (masking.py:151-153)
+            raise IndexError(f"double gather needs num_graphs <= num_nodes, got B={gi.B}, N={xn.shape[0]}")
         theta = torch.empty(xn.shape[0], 1, dtype=torch.float32, device=xn.device)
         L.call("isg_gate_theta_fwd", L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), xn.shape[0], xn.shape[1], dbl,
                                             L.ptr(theta), L.stream())
@@ -496,6 +511,7 @@ class GumbelTopk(torch.autograd.Function):
         theta = _c(theta)
         gumbel = _noise2d(gumbel, gi)
         N = theta.shape[0]
+        k = max(1, min(int(k), gi.nmax))  # local_k = min(k, Nmax), gumbel_scheme.py:54
         mask = torch.empty(N, 1, dtype=torch.float32, device=theta.device)
         saved = torch.empty(gi.B, k, gi.nmax, dtype=torch.float32, device=theta.device)
         L.call("isg_gumbel_topk_fwd", L.ptr(theta), L.ptr(gumbel), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k, tau,
@@ -530,12 +546,18 @@ class SimpleTopk(torch.autograd.Function):
         if g.shape[1] != npad:
             raise ValueError(f"SIMPLE noise has {g.shape[1]} slots per graph, expected n_pad = {npad}")
         g = _c(g.to(torch.float32))
+        k = max(1, min(int(k), gi.nmax))  # local_k = min(k, Nmax), simple_scheme.py:81
         mask = torch.empty(theta.shape[0], 1, dtype=torch.float32, device=theta.device)
         marg = torch.empty(gi.B, gi.nmax, dtype=torch.float32, device=theta.device)
-        L.call("isg_simple_marginals_fwd", L.ptr(theta), L.ptr(g), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
-               L.ptr(mask), L.ptr(marg), L.stream())
         ctx.gi, ctx.k = gi, k
         ctx.save_for_backward(theta)
+        if npad == 1:
+            # one slot per graph and k = 1: the only 1-subset is certain (marginal 1, sample 1, zero gradient)
+            mask.fill_(1.0)
+            marg.fill_(1.0)
+            return mask, marg
+        L.call("isg_simple_marginals_fwd", L.ptr(theta), L.ptr(g), L.ptr(gi.graph_ptr), gi.B, gi.nmax, k,
+               L.ptr(mask), L.ptr(marg), L.stream())
         return mask, marg
 
     @staticmethod
@@ -544,6 +566,8 @@ class SimpleTopk(torch.autograd.Function):
         gi = ctx.gi
         dy = _c(dy)
         dmarg = _c(dmarg) if dmarg is not None else None
+        if gi.nmax <= 1:
+            return torch.zeros_like(theta), None, None, None
         g = torch.empty_like(theta)
         L.call("isg_simple_marginals_bwd", L.ptr(dy), L.ptr(dmarg), L.ptr(theta), L.ptr(gi.graph_ptr), gi.B,
                gi.nmax, ctx.k, L.ptr(g), L.stream())

@@ -14,8 +14,21 @@ import contextlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("ISG_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "shim")
+
+
+def _find_root():
+    """/root/reference in the authoring container; on the GPU box the unmodified hot-path files staged by
+    oracle/stage_reference.py into the git-ignored oracle/_ref/ (they travel with the gpurun snapshot)."""
+    env = os.environ.get("ISG_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", os.path.join(_HERE, "_ref")]:
+        if os.path.isdir(os.path.join(cand, "ISubGVQA", "models")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _injected_noise = []  # FIFO of tensors consumed by the patched GumbelDistribution.sample
 

@@ -130,3 +130,49 @@ def test_shard_graphs_is_a_partition():
             assert spans[0][0] == 0 and sum(c for _, c in spans) == total
             for (f0, c0), (f1, _) in zip(spans, spans[1:]):
                 assert f0 + c0 == f1
+
+
+def _worker_uneven(rank, world, port, ret):
+    """Rank 1 never uses `b`; rank 0 does.  DDP(find_unused_parameters=True) semantics: both ranks end up with
+    the averaged gradient for `b` (rank 1 contributing zeros), on every step — a stale slice from the previous
+    all-reduce must not leak into the next one — and `c`, which nobody uses, keeps .grad = None."""
+    sys.path.insert(0, ROOT)
+    from isg_b200.dp import GradAllReduce
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.full((3,), 2.0))
+            self.b = torch.nn.Parameter(torch.full((2,), 3.0))
+            self.c = torch.nn.Parameter(torch.zeros(4))
+
+    m = M()
+    red = GradAllReduce(m)
+    ok = True
+    for step in range(3):
+        for p in m.parameters():
+            p.grad = None
+        loss = (m.a * (step + 1)).sum()
+        if rank == 0:
+            loss = loss + (m.b * 10.0 * (step + 1)).sum()
+        loss.backward()
+        red.all_reduce_mean()
+        ok &= torch.allclose(m.a.grad, torch.full((3,), float(step + 1)))
+        ok &= m.b.grad is not None and torch.allclose(m.b.grad, torch.full((2,), 5.0 * (step + 1)))
+        ok &= m.c.grad is None
+    ret[f"ok_{rank}"] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_unused_parameter_sets_that_differ_between_ranks():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_uneven, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["ok_0"] and ret["ok_1"], dict(ret)

@@ -155,6 +155,8 @@ def _run_edge_cuda(d, H, C, fused_pitch=False):
     (2, 6, 30, 512, 1, True, True),
     (2, 40, 900, 300, 4, True, False),  # in-degree > 32 -> multi-chunk online softmax
     (64, 20, 150, 300, 4, True, False),  # BASELINE config 1 size
+    (4, 200, 4000, 300, 4, True, False),  # BASELINE config 5's high-degree end: 200 objects / 4000 edges per graph
+    (3, 100, 1500, 300, 4, False, False),  # config 5, 100 objects / 1500 edges
 ])
 def test_edge_fwd_bwd_matches_oracle(B, mn, me, C, H, masked, gen):
     d = _edge_case(B, mn, me, C, H, masked, seed=B * 100 + C, general_mask=gen)

@@ -134,7 +134,7 @@ def run_cuda_case(cfg, step_count=None, device="cuda", capture=False):
     model.to(device)
     model.train(train)
     if cfg.get("aimle_beta0") is not None:
-        model.convs[3].mask.sampler_train.target._init[0] = float(cfg["aimle_beta0"])
+        model.convs[3].mask.sampler_train.target.beta = float(cfg["aimle_beta0"])
     N = b["x"].shape[0]
     ei, batch = b["edge_index"].to(device), b["batch"].to(device)
     outs = []
