@@ -62,6 +62,12 @@ int isg_csr_build(const int64_t* edge_index /* [2,E] */, int64_t num_edges, int6
 int isg_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
                   int32_t* graph_ptr, int32_t* batch32, int32_t* nmax, void* stream);
 
+/* crossing (1 int32, device) = number of edges whose endpoints lie in different graphs or out of range.
+ * PyG batches (datasets/gqa.py:237-272, Batch.from_data_list) never have such edges; 0 is the precondition
+ * of the single-launch edge backward (isg_gat_edge_bwd with graph_ptr != NULL). */
+int isg_graph_closure(const int64_t* edge_index /* [2,E] */, int64_t num_edges, const int64_t* batch,
+                      int64_t num_nodes, int32_t* crossing, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * (b) fused edge kernel = MaskingGATv2Conv.message (models/mgat_v2_conv.py:243-279) + PyG
  * propagate gathers + torch_geometric.utils.softmax (:272) + sum aggregation + bias (:231-232).
@@ -85,8 +91,12 @@ int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void*
  * Outputs: g_xl,g_xr [N,HC] pitch ld_gx; g_eproj [E,HC]; g_att [H*C] fp32;
  *          g_edge_mask [E] fp32 (NULL iff edge_mask NULL).
  * Two deterministic passes: dst-major (g_eproj, g_xr, g_att, g_edge_mask) then src-major
- * (g_xl) — no floating-point atomics. */
-size_t isg_gat_edge_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int heads, int channels);
+ * (g_xl) — no floating-point atomics.  With batch32 / graph_ptr / nmax given (fp32, and every edge inside
+ * one graph: isg_graph_closure == 0) the two passes run as block roles of ONE launch, ordered so that the
+ * src role reads g_eproj out of L2 instead of DRAM; results are bit-identical to the two-launch form.
+ * batch32 == NULL or graph_ptr == NULL or nmax <= 0 selects the two-launch form. */
+size_t isg_gat_edge_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t num_graphs, int heads,
+                                        int channels);
 int isg_gat_edge_bwd(const void* g_out, int64_t ld_g,
                      const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj,
                      const float* att, const float* bias, const float* edge_mask,
@@ -97,6 +107,8 @@ int isg_gat_edge_bwd(const void* g_out, int64_t ld_g,
                      float* g_att, float* g_edge_mask,
                      int64_t num_nodes, int64_t num_edges, int heads, int channels,
                      float negative_slope, int dtype,
+                     const int32_t* batch32 /* [N] or NULL */, const int32_t* graph_ptr /* [B+1] or NULL */,
+                     int64_t num_graphs, int nmax,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* NodeMaskToEdgeMask (sampling/node_edge_masks.py:5-19).

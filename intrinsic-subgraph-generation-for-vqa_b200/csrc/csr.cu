@@ -231,6 +231,32 @@ extern "C" int isg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, in
   return ISG_OK;
 }
 
+// crossing += #edges whose endpoints lie in different graphs (or out of range).  `crossing` must be zeroed by the
+// caller's memset below.
+__global__ void graph_closure_kernel(const int64_t* __restrict__ ei, int64_t E, const int64_t* __restrict__ batch,
+                                     int64_t N, int* __restrict__ crossing) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (e < E) {
+    const int64_t s = ei[e], d = ei[E + e];
+    bad = s < 0 || s >= N || d < 0 || d >= N || batch[s] != batch[d];
+  }
+  const unsigned m = __ballot_sync(ISG_FULL_MASK, bad);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(crossing, __popc(m));
+}
+
+extern "C" int isg_graph_closure(const int64_t* edge_index, int64_t E, const int64_t* batch, int64_t N,
+                                 int32_t* crossing, void* stream_) {
+  if (E < 0 || N < 0 || !crossing || (E > 0 && (!edge_index || !batch))) return ISG_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaError_t err = cudaMemsetAsync(crossing, 0, sizeof(int), stream);
+  if (err != cudaSuccess) return (int)err;
+  if (E == 0) return ISG_OK;
+  graph_closure_kernel<<<isg::ceil_div(E, 256), 256, 0, stream>>>(edge_index, E, batch, N, crossing);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
 extern "C" int isg_graph_ptr(const int64_t* batch, int64_t N, int64_t B, int32_t* graph_ptr,
                              int32_t* batch32, int32_t* nmax, void* stream_) {
   if (N < 0 || B < 0 || !graph_ptr || !nmax || (N > 0 && (!batch || !batch32))) return ISG_EINVAL;

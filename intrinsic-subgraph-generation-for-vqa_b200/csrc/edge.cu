@@ -963,6 +963,328 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// backward, ONE launch (fp32 ring path, graph-closed edge sets): the dst-major and the src-major pass above as
+// two block ROLES of the same kernel, interleaved so that g_eproj is consumed out of L2.
+//
+// Run as two launches, the src pass re-reads all of g_eproj (E x H*C floats: 191 MB at the c3 size, more than
+// the 126 MB L2) from DRAM — 216 of the 700 MB the two-pass backward moves for 501 MB of algorithmic traffic.
+// Here every block draws a ticket t from a global counter (tickets follow the order in which blocks actually
+// start, which blockIdx does not guarantee):   t even -> dst block t/2,   t odd -> src block (t-1)/2 - LAG,
+// so the src block of a node starts ~2*LAG tickets after the dst block of the same node.  A src task needs
+// the g_eproj rows of all out-edges of its node, which are written by the dst tasks of the nodes of the SAME
+// graph (edges never leave a graph — checked when the GraphIndex is built); each dst task bumps its graph's
+// completion counter with release semantics and the src task acquires it (spinning only if the lag was too
+// short).  LAG >= Nmax guarantees that every dst task a src task can wait for has already been ticketed, i.e.
+// is running or finished: no deadlock.  The g_eproj rows in flight between the two roles are
+// ~(LAG + resident blocks / 2) nodes' worth (~40 MB at the default lag), so the src role finds them in L2.
+// Arithmetic, task granularity ((node, head) per warp) and summation orders are exactly those of the two-pass
+// kernels: results are bit-identical to them and independent of the schedule.
+// sync[0] = ticket counter, sync[1 + g] = finished dst tasks of graph g; zeroed by a memset before the launch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int VPL, bool MASKED, int CT, int HT>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 6)
+gat_edge_bwd_fused_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const float* __restrict__ xl,
+                               const float* __restrict__ xr, int64_t ld_x, const float* __restrict__ ep,
+                               const float* __restrict__ att, const float* __restrict__ emask,
+                               const float* __restrict__ alpha, const int* __restrict__ rowptr,
+                               const int* __restrict__ nbr, const int* __restrict__ eid,
+                               const int* __restrict__ colptr, const int* __restrict__ snbr,
+                               const int* __restrict__ seid, const int* __restrict__ batch32,
+                               const int* __restrict__ graph_ptr, float* __restrict__ g_xl,
+                               float* __restrict__ g_xr, int64_t ld_gx, float* __restrict__ g_ep,
+                               float* __restrict__ gatt_part, float* __restrict__ gm_h, int* __restrict__ sync,
+                               int64_t NH, int64_t nblocks_role, int lag_blocks, int H_, int C_, float slope) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  __shared__ int s_ticket;
+  const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int ticket = s_ticket;
+  const bool src_role = (ticket & 1) != 0;
+  const int64_t blk = src_role ? (int64_t)(ticket >> 1) - lag_blocks : (int64_t)(ticket >> 1);
+  if (blk < 0 || blk >= nblocks_role) return;
+  const int64_t wid = blk * EDGE_WARPS + warp;
+  if (wid >= NH) return;  // warp-uniform; nothing below synchronises across warps
+  const int64_t node = wid / H;
+  const int head = (int)(wid - node * H);
+  const int c4 = C >> 2;
+  const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
+  const int64_t HC = (int64_t)H * C;
+  const int hoff = head * C;
+  const uint32_t wbytes = ring_warp_bytes(C, 2);
+  WarpRing ring;
+  ring.init(smem_addr_u32(ring_smem) + warp * wbytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * (RING + 1), 2 * row_bytes, lane, 1);
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const bool leader = warp_elect_one();
+  const int graph = batch32[node];
+
+  if (src_role) {
+    // ---- wait until every dst task of this node's graph has published its g_eproj rows
+    const int need = (graph_ptr[graph + 1] - graph_ptr[graph]) * H;
+    if (lane == 0) {
+      uint32_t spins = 0;
+      while (ld_acquire_gpu(sync + 1 + graph) < need) {
+        __nanosleep(100);
+        if (++spins > (1u << 23)) __trap();  // a lost signal must fail loudly, not hang the GPU
+      }
+    }
+    __syncwarp();
+    __threadfence();          // order the acquire before this warp's reads (all lanes)
+    fence_proxy_async_all();  // ... including the bulk copies (async proxy) of data written by generic stores
+    float4 acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
+    const int beg = colptr[node], end = colptr[node + 1];
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_dst = 0, my_eid = 0;
+      float my_am = 0.f;
+      if (lane < cnt) {
+        my_dst = snbr[base + lane];
+        my_eid = seid[base + lane];
+        my_am = alpha[(int64_t)my_eid * H + head];
+        if (MASKED) my_am *= emask[my_eid];
+      }
+      const int npre = min(RING, cnt);
+      for (int t = 0; t < npre; ++t) {
+        const int i = __shfl_sync(ISG_FULL_MASK, my_dst, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (leader)
+          ring.issue2(ring.seq + t, g_ep + (int64_t)e * HC + hoff, pol_stream, gout + (int64_t)i * ld_g + hoff,
+                      pol_keep, row_bytes);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t s = ring.seq + t;
+        const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+        const int tn = t + RING < cnt ? t + RING : t;
+        const int in_ = __shfl_sync(ISG_FULL_MASK, my_dst, tn);
+        const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+        ring.wait(s);
+        const uint32_t sg = ring.slot(s) + l16, sG = sg + row_bytes;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+          if (col_active<VPL, CT>(k, lane, c4))
+            acc[k] = p4_add(acc[k], p4_fma_s(lds_f4(sG + 512u * k), am, lds_f4(sg + 512u * k)));
+        __syncwarp();
+        if (leader && t + RING < cnt)
+          ring.issue2(s + RING, g_ep + (int64_t)en * HC + hoff, pol_stream, gout + (int64_t)in_ * ld_g + hoff,
+                      pol_keep, row_bytes);
+      }
+      ring.seq += cnt;
+    }
+    float* grow = g_xl + node * ld_gx + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(grow + 4 * (lane + 32 * k), acc[k]);
+    return;
+  }
+
+  // ---- dst role: one (node, head) task — the body of gat_edge_bwd_dst_ring_kernel with K = 1
+  const uint32_t xr_s = ring.data + 2 * RING * row_bytes, att_s = xr_s + row_bytes;
+  const uint32_t xbar = ring.extra_bar(0);
+  for (int v = lane; v < c4; v += 32) sts_f4(att_s + 16u * v, Vec4<float>::ld(att + hoff + 4 * v));
+  __syncwarp();
+  float4 gatt[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) gatt[k] = f4_zero();
+  {
+    if (leader) {
+      ring_expect(xbar, row_bytes);
+      ring_copy(xr_s, xr + node * ld_x + hoff, row_bytes, xbar, pol_keep);
+    }
+    float4 G[VPL], gxr[VPL];
+    load_row<float, VPL>(gout + node * ld_g + hoff, lane, c4, G);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) gxr[k] = f4_zero();
+    const int beg = rowptr[node], end = rowptr[node + 1];
+    const int deg = end - beg;
+    bool xr_ready = false;
+
+    auto row_dot = [&](uint32_t sx) -> float {
+      float2 pp2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        if (col_active<VPL, CT>(k, lane, c4)) pp2 = p4_dot_acc(G[k], lds_f4(sx + 512u * k), pp2);
+      return warp_sum(p2_sum(pp2));
+    };
+    auto edge_grad = [&](uint32_t sx, uint32_t sp, float tt, float a, float m, float dot, int e) -> float {
+      if (!xr_ready) {
+        ring_wait(xbar, 0u);
+        xr_ready = true;
+      }
+      const float gl = a * (m * tt - dot);
+      const float glmm = MASKED ? gl * m * m : gl;
+      float2 av2 = make_float2(0.f, 0.f);
+      float* gerow = g_ep + (int64_t)e * HC + hoff + 4 * lane;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (col_active<VPL, CT>(k, lane, c4)) {
+          const float4 sxv =
+              p4_add(p4_add(lds_f4(xr_s + l16 + 512u * k), lds_f4(sx + 512u * k)), lds_f4(sp + 512u * k));
+          const float4 u = MASKED ? p4_scale(sxv, m) : sxv;
+          const float4 v = p4_leaky(u, slope);
+          const float4 at = lds_f4(att_s + l16 + 512u * k);
+          gatt[k] = p4_fma_s(MASKED ? p4_scale(v, m) : v, gl, gatt[k]);
+          const float4 lk = make_float4(u.x > 0.f ? 1.f : slope, u.y > 0.f ? 1.f : slope, u.z > 0.f ? 1.f : slope,
+                                        u.w > 0.f ? 1.f : slope);
+          const float4 gs = p4_scale(p4_mul(at, lk), glmm);
+          gxr[k] = p4_add(gxr[k], gs);
+          if (MASKED) av2 = p4_dot_acc(at, v, av2);
+          Vec4<float>::st_stream(gerow + 128 * k, gs);  // L1 no-allocate only: the row stays in L2 for the src role
+        }
+      }
+      return MASKED ? warp_sum(2.f * gl * p2_sum(av2)) + tt * a : 0.f;
+    };
+
+    if (deg <= 32) {
+      int my_src = 0, my_eid = 0;
+      float my_m = 1.f, my_a = 0.f, my_t = 0.f, my_gm = 0.f;
+      if (lane < deg) {
+        my_src = nbr[beg + lane];
+        my_eid = eid[beg + lane];
+        if (MASKED) my_m = emask[my_eid];
+        my_a = alpha[(int64_t)my_eid * H + head];
+      }
+      const float my_am = MASKED ? my_a * my_m : my_a;
+      const int items = 2 * deg;
+      auto issue_item = [&](int i) {
+        const int t = i < deg ? i : i - deg;
+        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (leader) {
+          if (i < deg)
+            ring.issue1(ring.seq + i, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
+          else
+            ring.issue2(ring.seq + i, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff,
+                        pol_stream, row_bytes);
+        }
+      };
+      for (int i = 0; i < min(RING, items); ++i) issue_item(i);
+      float dot = 0.f;
+      for (int t = 0; t < deg; ++t) {
+        const uint32_t s = ring.seq + t;
+        const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+        ring.wait(s);
+        const float pp = row_dot(ring.slot(s) + l16);
+        if (t + RING < items) issue_item(t + RING);
+        if (lane == t) my_t = pp;
+        dot = fmaf(am, pp, dot);
+      }
+      for (int t = 0; t < deg; ++t) {
+        const uint32_t s = ring.seq + deg + t;
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+        const float a = __shfl_sync(ISG_FULL_MASK, my_a, t);
+        const float tt = __shfl_sync(ISG_FULL_MASK, my_t, t);
+        ring.wait(s);
+        const uint32_t sx = ring.slot(s) + l16;
+        const float gm = edge_grad(sx, sx + row_bytes, tt, a, m, dot, e);
+        __syncwarp();
+        if (deg + t + RING < items) issue_item(deg + t + RING);
+        if (MASKED && lane == t) my_gm = gm;
+      }
+      ring.seq += items;
+      if (MASKED && lane < deg) gm_h[(int64_t)my_eid * H + head] = my_gm;
+    } else {
+      float dot = 0.f;
+      for (int base = beg; base < end; base += 32) {
+        const int cnt = min(32, end - base);
+        int my_src = 0;
+        float my_am = 0.f;
+        if (lane < cnt) {
+          my_src = nbr[base + lane];
+          const int e = eid[base + lane];
+          my_am = alpha[(int64_t)e * H + head];
+          if (MASKED) my_am *= emask[e];
+        }
+        const int npre = min(RING, cnt);
+        for (int t = 0; t < npre; ++t) {
+          const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+          if (leader) ring.issue1(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
+        }
+        for (int t = 0; t < cnt; ++t) {
+          const uint32_t s = ring.seq + t;
+          const float am = __shfl_sync(ISG_FULL_MASK, my_am, t);
+          const int jn = __shfl_sync(ISG_FULL_MASK, my_src, t + RING < cnt ? t + RING : t);
+          ring.wait(s);
+          const float pp = row_dot(ring.slot(s) + l16);
+          if (leader && t + RING < cnt) ring.issue1(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, row_bytes);
+          dot = fmaf(am, pp, dot);
+        }
+        ring.seq += cnt;
+      }
+      for (int base = beg; base < end; base += 32) {
+        const int cnt = min(32, end - base);
+        int my_src = 0, my_eid = 0;
+        float my_m = 1.f, my_a = 0.f, my_gm = 0.f;
+        if (lane < cnt) {
+          my_src = nbr[base + lane];
+          my_eid = eid[base + lane];
+          if (MASKED) my_m = emask[my_eid];
+          my_a = alpha[(int64_t)my_eid * H + head];
+        }
+        const int npre = min(RING, cnt);
+        for (int t = 0; t < npre; ++t) {
+          const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+          const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+          if (leader)
+            ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff,
+                        pol_stream, row_bytes);
+        }
+        for (int t = 0; t < cnt; ++t) {
+          const uint32_t s = ring.seq + t;
+          const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+          const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+          const float a = __shfl_sync(ISG_FULL_MASK, my_a, t);
+          const int tn = t + RING < cnt ? t + RING : t;
+          const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
+          const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+          ring.wait(s);
+          const uint32_t sx = ring.slot(s) + l16;
+          const float tt = row_dot(sx);
+          const float gm = edge_grad(sx, sx + row_bytes, tt, a, m, dot, e);
+          __syncwarp();
+          if (leader && t + RING < cnt)
+            ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
+                        row_bytes);
+          if (MASKED && lane == t) my_gm = gm;
+        }
+        ring.seq += cnt;
+        if (MASKED && lane < cnt) gm_h[(int64_t)my_eid * H + head] = my_gm;
+      }
+    }
+    if (!xr_ready) ring_wait(xbar, 0u);
+    __syncwarp();
+    float* grow = g_xr + node * ld_gx + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(grow + 4 * (lane + 32 * k), gxr[k]);
+  }
+  float* prow = gatt_part + wid * C;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+    if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(prow + 4 * (lane + 32 * k), gatt[k]);
+  // publish: every lane orders its own g_eproj stores (also towards the async proxy that will read them),
+  // then one lane signals the graph's counter
+  __threadfence();
+  fence_proxy_async_all();
+  __syncwarp();
+  if (lane == 0) red_release_gpu_add(sync + 1 + graph, 1);
+}
+
 // Columns of the dst-major backward: K nodes per column, sized for ~6 waves of resident CTAs so that the
 // hardware block scheduler evens out the degree imbalance; K and the grid depend on (N, H) only.
 struct BwdRingPlan {
@@ -1086,6 +1408,57 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
   return ISG_OK;
 }
 
+// Lag between the dst role and the src role of a node, in blocks (see gat_edge_bwd_fused_ring_kernel): at least the
+// blocks that hold Nmax nodes (deadlock freedom) and by default 640, which lets the ~888 resident blocks of dst
+// work drain before the matching src blocks start while keeping the in-flight g_eproj rows (~40 MB) inside L2.
+inline int fused_lag_blocks(int nmax, int H) {
+  static const int env = [] {
+    const char* v = getenv("ISG_EDGE_LAG_BLOCKS");
+    return v ? atoi(v) : 0;
+  }();
+  const int need = (int)(((int64_t)nmax * H + EDGE_WARPS - 1) / EDGE_WARPS) + 1;
+  const int want = env > 0 ? env : 640;
+  return want > need ? want : need;
+}
+
+template <int VPL, bool MASKED>
+int launch_bwd_fused(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r, int64_t ld_x,
+                     const void* e_proj, const float* att, const float* emask, const float* alpha,
+                     const int* dst_ptr, const int* dst_nbr, const int* dst_eid, const int* src_ptr,
+                     const int* src_nbr, const int* src_eid, const int* batch32, const int* graph_ptr, int64_t B,
+                     int nmax, void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att, float* g_emask,
+                     int64_t N, int64_t E, int H, int C, float slope, float* gatt_part, float* gatt_part2,
+                     float* gm_h, int* sync, cudaStream_t stream) {
+  const size_t smem = ring_smem_bytes(C, 2, 1);
+  const bool ref_shape = VPL == 3 && C == 300 && H == 4;
+  auto kf = ref_shape ? gat_edge_bwd_fused_ring_kernel<VPL, MASKED, VPL == 3 ? 300 : 0, VPL == 3 ? 4 : 0>
+                      : gat_edge_bwd_fused_ring_kernel<VPL, MASKED, 0, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  if ((e = cudaMemsetAsync(sync, 0, (size_t)(1 + B) * sizeof(int), stream)) != cudaSuccess) return (int)e;
+  const int64_t NH = N * H;
+  const int64_t nb = ceil_div(NH, (int64_t)EDGE_WARPS);
+  const int lag = fused_lag_blocks(nmax, H);
+  const int64_t grid = 2 * (nb + lag);
+  if (grid >= (int64_t)INT32_MAX) return ISG_EUNSUPPORTED;
+  kf<<<(unsigned)grid, EDGE_WARPS * 32, smem, stream>>>(
+      (const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, emask, alpha,
+      dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, batch32, graph_ptr, (float*)g_xl, (float*)g_xr, ld_gx,
+      (float*)g_eproj, gatt_part, gm_h, sync, NH, nb, lag, H, C, slope);
+  ISG_CHECK_LAUNCH();
+  const int HC = H * C;
+  const int64_t parts2 = (N + GR_ROWS - 1) / GR_ROWS;  // gatt_part viewed as [N rows, H*C]
+  gat_att_reduce1_kernel<<<dim3(ceil_div(HC / 4, 64), (unsigned)parts2), 64, 0, stream>>>(gatt_part, N, HC, gatt_part2);
+  ISG_CHECK_LAUNCH();
+  gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)parts2, HC, g_att);
+  ISG_CHECK_LAUNCH();
+  if (MASKED && E > 0) {
+    gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
+    ISG_CHECK_LAUNCH();
+  }
+  return ISG_OK;
+}
+
 template <typename T, int VPL>
 int launch_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj, const float* att,
                const float* bias, const float* emask, const int* dst_ptr, const int* dst_nbr,
@@ -1175,14 +1548,23 @@ extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, 
   return ISG_EUNSUPPORTED;
 }
 
-extern "C" size_t isg_gat_edge_bwd_workspace_bytes(int64_t N, int64_t E, int H, int C) {
-  // max over the two layouts (register-load kernels: persistent grid; ring kernels: BwdRingPlan)
-  const int blocks = bwd_grid_blocks(N > 0 ? N : 1, H > 0 ? H : 1);
-  const BwdRingPlan plan = bwd_ring_plan(N, H);
+extern "C" size_t isg_gat_edge_bwd_workspace_bytes(int64_t N, int64_t E, int64_t B, int H, int C) {
+  // max over the three layouts (register-load kernels: persistent grid; two-launch ring kernels: BwdRingPlan;
+  // single-launch ring kernel: one g_att partial per (node, head) + the ticket / per-graph counters)
+  if (N < 0) N = 0;
+  if (B < 0) B = 0;
+  const int h = H > 0 ? H : 1;
+  const int blocks = bwd_grid_blocks(N > 0 ? N : 1, h);
+  const BwdRingPlan plan = bwd_ring_plan(N, h);
   const size_t a = align256((size_t)blocks * EDGE_WARPS * (size_t)C * sizeof(float));
   const size_t b = align256((size_t)plan.warps * (size_t)C * sizeof(float)) +
-                   align256((size_t)plan.parts2 * (size_t)(H > 0 ? H : 1) * (size_t)C * sizeof(float));
-  return (a > b ? a : b) + align256((size_t)E * (size_t)H * sizeof(float));
+                   align256((size_t)plan.parts2 * (size_t)h * (size_t)C * sizeof(float));
+  const size_t c = align256((size_t)(N + EDGE_WARPS) * (size_t)h * (size_t)C * sizeof(float)) +
+                   align256((size_t)((N + GR_ROWS - 1) / GR_ROWS) * (size_t)h * (size_t)C * sizeof(float)) +
+                   align256((size_t)(1 + B) * sizeof(int));
+  size_t m = a > b ? a : b;
+  m = m > c ? m : c;
+  return m + align256((size_t)E * (size_t)h * sizeof(float));
 }
 
 extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r,
@@ -1192,6 +1574,7 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
                                 const int32_t* src_ptr, const int32_t* src_nbr, const int32_t* src_eid,
                                 void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att,
                                 float* g_edge_mask, int64_t N, int64_t E, int H, int C, float slope, int dtype,
+                                const int32_t* batch32, const int32_t* graph_ptr, int64_t B, int nmax,
                                 void* workspace, size_t ws_bytes, void* stream_) {
   if (N < 0 || E < 0 || H <= 0 || C <= 0) return ISG_EINVAL;
   if (C % 4 != 0 || C > 512 || ld_x % 4 != 0 || ld_out % 4 != 0 || ld_g % 4 != 0 || ld_gx % 4 != 0)
@@ -1207,7 +1590,8 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
       (E > 0 && (!e_proj || !alpha || !g_eproj || !dst_nbr || !dst_eid || !src_nbr || !src_eid)))
     return ISG_EINVAL;
   if ((edge_mask != nullptr) != (g_edge_mask != nullptr)) return ISG_EINVAL;
-  if (ws_bytes < isg_gat_edge_bwd_workspace_bytes(N, E, H, C) || !workspace) return ISG_EWORKSPACE;
+  if (B < 0) return ISG_EINVAL;
+  if (ws_bytes < isg_gat_edge_bwd_workspace_bytes(N, E, B, H, C) || !workspace) return ISG_EWORKSPACE;
   const int blocks = bwd_grid_blocks(N, H);
   float* gatt_part = (float*)workspace;
   float* gm_h = (float*)((char*)workspace + align256((size_t)blocks * EDGE_WARPS * (size_t)C * sizeof(float)));
@@ -1234,6 +1618,29 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
                                                rp_part, rp_part2, rp_gmh, rplan, stream)
     if (((uintptr_t)x_l & 15) || ((uintptr_t)g_out & 15) || ((uintptr_t)e_proj & 15) || ((uintptr_t)g_eproj & 15))
       return ISG_EUNSUPPORTED;
+    if (batch32 && graph_ptr && nmax > 0 && B > 0) {
+      float* fp_part = (float*)workspace;
+      float* fp_part2 = (float*)((char*)workspace + align256((size_t)(N + EDGE_WARPS) * (size_t)H * (size_t)C * sizeof(float)));
+      int* fp_sync = (int*)((char*)fp_part2 +
+                            align256((size_t)((N + GR_ROWS - 1) / GR_ROWS) * (size_t)H * (size_t)C * sizeof(float)));
+      float* fp_gmh = (float*)((char*)fp_sync + align256((size_t)(1 + B) * sizeof(int)));
+#define ISG_BWD_FUSED(V)                                                                                         \
+  return edge_mask ? launch_bwd_fused<V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha, dst_ptr, \
+                                               dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, batch32, graph_ptr, B,  \
+                                               nmax, g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C,    \
+                                               slope, fp_part, fp_part2, fp_gmh, fp_sync, stream)                   \
+                   : launch_bwd_fused<V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha, dst_ptr, \
+                                                dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, batch32, graph_ptr, B, \
+                                                nmax, g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C,   \
+                                                slope, fp_part, fp_part2, fp_gmh, fp_sync, stream)
+      switch (vpl) {
+        case 1: ISG_BWD_FUSED(1);
+        case 2: ISG_BWD_FUSED(2);
+        case 3: ISG_BWD_FUSED(3);
+        case 4: ISG_BWD_FUSED(4);
+      }
+#undef ISG_BWD_FUSED
+    }
     const BwdRingPlan rplan = bwd_ring_plan(N, H);
     float* rp_part = (float*)workspace;
     float* rp_part2 = (float*)((char*)workspace + align256((size_t)rplan.warps * (size_t)C * sizeof(float)));

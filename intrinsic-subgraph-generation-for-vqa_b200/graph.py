@@ -9,7 +9,7 @@ from . import lib as L
 
 class GraphIndex:
     __slots__ = ("edge_index", "batch", "N", "E", "B", "dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr",
-                 "src_eid", "status", "graph_ptr", "batch32", "_nmax_dev", "_nmax", "_key", "_keepalive")
+                 "src_eid", "status", "graph_ptr", "batch32", "_nmax_dev", "_nmax", "_closed", "_key", "_keepalive")
 
     def __init__(self, edge_index, batch, num_graphs, num_nodes=None):
         L.require_cuda(edge_index, batch)
@@ -39,10 +39,13 @@ class GraphIndex:
                                   L.ptr(self.src_eid), L.ptr(self.status), L.ptr(ws), ws_bytes, st)
         self.graph_ptr = torch.empty(B + 1, **i32)
         self.batch32 = torch.empty(max(N, 1), **i32)
-        self._nmax_dev = torch.empty(1, **i32)
+        self._nmax_dev = torch.empty(2, **i32)  # [nmax, number of edges that leave their graph]
         L.call("isg_graph_ptr", L.ptr(self.batch), N, B, L.ptr(self.graph_ptr), L.ptr(self.batch32),
                                   L.ptr(self._nmax_dev), st)
+        L.call("isg_graph_closure", L.ptr(self.edge_index), E, L.ptr(self.batch), N,
+               self._nmax_dev.data_ptr() + 4, st)
         self._nmax = None
+        self._closed = None
         self._key = None
         self._keepalive = None
 
@@ -51,12 +54,28 @@ class GraphIndex:
         """Max nodes per graph as a Python int.  One device->host read per batch (the reference
         syncs here too: to_dense_batch's int(num_nodes.max()), models/masking.py:162)."""
         if self._nmax is None:
-            self._nmax = int(self._nmax_dev.item())
+            self._read_host()
         return self._nmax
 
-    def set_nmax(self, nmax):
-        """Lets a data loader that already knows the graph sizes skip the device->host read."""
+    @property
+    def closed(self):
+        """True when no edge leaves its graph (always so for PyG batches).  Read together with nmax."""
+        if self._closed is None:
+            self._read_host()
+        return self._closed
+
+    def _read_host(self):
+        nmax, crossing = self._nmax_dev.tolist()
+        if self._nmax is None:
+            self._nmax = int(nmax)
+        if self._closed is None:
+            self._closed = crossing == 0
+
+    def set_nmax(self, nmax, closed=True):
+        """Lets a data loader that already knows the graph sizes (and that its edges stay inside their graphs)
+        skip the device->host read."""
         self._nmax = int(nmax)
+        self._closed = bool(closed)
 
     def check_indices(self):
         bad = int(self.status.item())

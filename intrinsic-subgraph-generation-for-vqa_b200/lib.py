@@ -26,9 +26,11 @@ SIGNATURES = {
     "isg_graph_ptr": (_I32, [_P, _I64, _I64, _P, _P, _P, _P]),
     "isg_gat_edge_fwd": (_I32, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32,
                                 _F, _I32, _P]),
-    "isg_gat_edge_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
+    "isg_graph_closure": (_I32, [_P, _I64, _P, _I64, _P, _P]),
+    "isg_gat_edge_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32, _I32]),
     "isg_gat_edge_bwd": (_I32, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P,
-                                _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _I32, _P, _SZ, _P]),
+                                _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _I32, _P, _P, _I64, _I32,
+                                _P, _SZ, _P]),
     "isg_node_edge_mask_fwd": (_I32, [_P, _P, _I64, _P, _P]),
     "isg_node_edge_mask_bwd": (_I32, [_P, _P, _P, _I64, _P, _P]),
     "isg_topk_mask_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
@@ -81,7 +83,7 @@ def load():
 
 # kernels launched per C-ABI call (memsets excluded); used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
-    "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 3,
+    "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_graph_closure": 1, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 3,
     "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_imle_bwd": 1,
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,

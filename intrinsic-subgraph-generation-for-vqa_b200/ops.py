@@ -7,6 +7,7 @@ import torch
 
 from . import lib as L
 
+_EDGE_BWD_FUSED = os.environ.get("ISG_EDGE_BWD_FUSED", "1") != "0"  # 0: always the two-launch edge backward
 _DEBUG_EDGE_BWD = None  # diagnostics: set to a list to capture GatEdge.backward inputs/outputs
 # projection arithmetic: 1 = tcgen05 3xTF32 with bounded accumulation chains (default; measured 6.5e-7 relative
 # against fp64, i.e. at or below the FFMA kernel's error), 0 = fp32 FFMA, 2 = tcgen05 single-pass TF32 (~8e-4)
@@ -387,14 +388,17 @@ class GatEdge(torch.autograd.Function):
         g_ep = torch.empty(gi.E, HC, dtype=e_proj.dtype, device=dev)
         g_att = torch.empty(att.shape, dtype=torch.float32, device=dev)
         g_em = torch.empty(gi.E, 1, dtype=torch.float32, device=dev) if em is not None else None
-        nbytes = lib.isg_gat_edge_bwd_workspace_bytes(N, gi.E, H, C)
+        nbytes = lib.isg_gat_edge_bwd_workspace_bytes(N, gi.E, gi.B, H, C)
         ws = L.workspace(nbytes, dev)
+        fused = _EDGE_BWD_FUSED and gi.closed  # single launch needs every edge inside one graph
         L.call("isg_gat_edge_bwd", L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), 2 * HC,
                                      L.ptr(e_proj), L.ptr(att), L.ptr(bias), L.ptr(em), L.ptr(alpha), L.ptr(out), HC,
                                      L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr),
                                      L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(g_xl), L.ptr(g_xr), 2 * HC,
                                      L.ptr(g_ep), L.ptr(g_att), L.ptr(g_em), N, gi.E, H, C, ctx.slope,
-                                     L.dtype_code(xlr), L.ptr(ws), nbytes, L.stream())
+                                     L.dtype_code(xlr), L.ptr(gi.batch32) if fused else None,
+                                     L.ptr(gi.graph_ptr) if fused else None, gi.B, gi.nmax if fused else 0,
+                                     L.ptr(ws), nbytes, L.stream())
         # the column-sum kernel is fp32-only: bf16 storage converts g_out once (N x HC, small next to the edge pass)
         g_bias = colsum(g_out if g_out.dtype == torch.float32 else g_out.float()) if ctx.has_bias else None
         if _DEBUG_EDGE_BWD is not None:

@@ -73,7 +73,8 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7, bf16=False):
         gep = torch.empty(E, HC, device=dev, dtype=fdt)
         gatt = torch.empty(HC, device=dev)
         gem = torch.empty(E, device=dev) if masked else None
-        wsb = lib.isg_gat_edge_bwd_workspace_bytes(N, E, H, C)
+        wsb = lib.isg_gat_edge_bwd_workspace_bytes(N, E, nb, H, C)
+        fused = os.environ.get("ISG_EDGE_BWD_FUSED", "1") != "0" and gi.closed and not bf16
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
         st = L.stream()
 
@@ -87,7 +88,8 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7, bf16=False):
                    ep.data_ptr(), att.data_ptr(), bias.data_ptr(), L.ptr(em), alpha.data_ptr(), out.data_ptr(), HC,
                    L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr), L.ptr(gi.src_nbr),
                    L.ptr(gi.src_eid), gxlr.data_ptr(), gxlr.data_ptr() + HC * es, 2 * HC, gep.data_ptr(),
-                   gatt.data_ptr(), L.ptr(gem), N, E, H, C, 0.2, code, ws.data_ptr(), wsb, st)
+                   gatt.data_ptr(), L.ptr(gem), N, E, H, C, 0.2, code, L.ptr(gi.batch32) if fused else None,
+                   L.ptr(gi.graph_ptr) if fused else None, nb, gi.nmax if fused else 0, ws.data_ptr(), wsb, st)
 
         for fn, key in ((fwd, "fwd_ms"), (bwd, "bwd_ms")):
             for _ in range(3):

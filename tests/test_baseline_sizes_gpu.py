@@ -9,11 +9,14 @@ The oracle port runs ~250 graphs/s on a few host cores, so each case costs secon
 Gradients are checked twice.  (1) Teacher-forced: the oracle is re-run with the edge kernel's forward inputs
 (x_l, x_r, e_proj of every layer) replaced by the CUDA values, so both sides evaluate leaky_relu on identical
 pre-activations: every tensor must then agree to 1e-4 (or agree with the fp64 replay of the same step).
-(2) Un-forced: against the free-running fp32 oracle, for EVERY input and parameter gradient, with an explicit
-outlier budget — leaky_relu's derivative jumps at 0 and among ~1.9e8 pre-activations per step a few lie
-within fp32 rounding of 0, where any two fp32 evaluation orders pick different slopes; each such flip moves a
-handful of gradient rows by more than 1e-4 of the tensor scale.  The budget bounds how many elements may do
-that (OUTLIER_FRAC) and by how much (OUTLIER_MAX); everything else is held to 1e-4."""
+(2) Un-forced, every input and parameter gradient, against the EXACT gradient: the free-running oracle in fp64
+(discrete sampler decisions replayed).  leaky_relu's derivative jumps at 0; of the ~1.9e8 pre-activations of a
+256-graph step ~1e2 lie within fp32 rounding of 0, where ANY fp32 evaluation — the reference's own included —
+picks the other slope than exact arithmetic does, and each such flip moves whole gradient rows by 1e-3..1e-2 of
+their scale (measured: the free-running fp32 oracle and the CUDA path differ from each other by up to 5e-2 of
+a tensor's max on single elements at this size).  No fp32 implementation can be held to 1e-4 against another
+one there, so the bar is: the CUDA gradients are as close to the exact ones as the reference's fp32 arithmetic
+is — per tensor, relative L2 error <= UNFORCED_FACTOR x the fp32 oracle's (floor UNFORCED_FLOOR)."""
 import pytest
 import torch
 
@@ -22,31 +25,30 @@ from isg_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-OUTLIER_FRAC = 2e-3   # at most 0.2 % of a tensor's elements may miss 1e-4 (relative to the tensor's max) ...
-OUTLIER_MAX = 2e-2    # ... and none by more than 2 % of the tensor's max
+UNFORCED_FACTOR = 4.0   # CUDA-vs-exact relative L2 error may be at most this multiple of the fp32 oracle's ...
+UNFORCED_FLOOR = 2e-4   # ... or this, whichever is larger
 
 
-def _outliers(a, b, rtol=util.RTOL):
+def _rel_l2(a, b):
     a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
-    scale = float(b.abs().max()) or 1.0
-    d = (a - b).abs() / scale
-    return float((d > rtol).double().mean()), float(d.max())
+    return float((a - b).norm()) / (float(b.norm()) or 1.0)
 
 
-def _check_unforced(got, free, names=("gx", "g_edge_attr", "g_instr", "g_glf")):
-    report = {}
+def _check_unforced(got, free32, exact, names=("gx", "g_edge_attr", "g_instr", "g_glf")):
+    """got: CUDA; free32: free-running fp32 oracle; exact: free-running fp64 oracle (sampler decisions replayed)."""
+    rows = {}
     for key in names:
-        report[key] = _outliers(got[key], free[key])
-    for name, w in free["param_grads"].items():
+        rows[key] = (_rel_l2(got[key], exact[key]), _rel_l2(free32[key], exact[key]))
+    for name, w in exact["param_grads"].items():
         g = got["param_grads"].get(name)
         if w is None:
             assert g is None or float(g.abs().max()) == 0.0, name
             continue
         assert g is not None, name
-        report[name] = _outliers(g, w)
-    bad = {k: v for k, v in report.items() if v[0] > OUTLIER_FRAC or v[1] > OUTLIER_MAX}
-    assert not bad, f"un-forced gradient check: (fraction > 1e-4, worst) = {bad}"
-    return report
+        rows[name] = (_rel_l2(g, w), _rel_l2(free32["param_grads"][name], w))
+    bad = {k: v for k, v in rows.items() if v[0] > max(UNFORCED_FLOOR, UNFORCED_FACTOR * v[1])}
+    assert not bad, f"un-forced gradients, relative L2 error vs fp64 (cuda, fp32 oracle): {bad}"
+    return rows
 
 
 def test_c3_training_step_matches_oracle_at_256_graphs():
@@ -60,9 +62,12 @@ def test_c3_training_step_matches_oracle_at_256_graphs():
     want = util.run_oracle_case(cfg, teacher=[got["teacher"]])[0]
     exact = util.run_oracle_case(cfg, dtype=torch.float64, replay=[free["record"]], teacher=[got["teacher"]])[0]
     util.compare_step(got, want, "aimle", exact=exact)
-    report = _check_unforced(got, free)
-    worst = max(report.items(), key=lambda kv: kv[1][1])
-    print(f"c3 un-forced: worst tensor {worst[0]} (frac>1e-4 {worst[1][0]:.2e}, max {worst[1][1]:.2e})")
+    truth = util.run_oracle_case(cfg, dtype=torch.float64, replay=[free["record"]])[0]
+    rows = _check_unforced(got, free, truth)
+    worst = max(rows.items(), key=lambda kv: kv[1][0])
+    print(f"c3 un-forced vs fp64: worst tensor {worst[0]}: cuda {worst[1][0]:.2e}, fp32 oracle {worst[1][1]:.2e}; "
+          f"median cuda {sorted(v[0] for v in rows.values())[len(rows) // 2]:.2e}, "
+          f"median fp32 oracle {sorted(v[1] for v in rows.values())[len(rows) // 2]:.2e}")
 
 
 def test_c2_inference_matches_oracle_at_1024_graphs():

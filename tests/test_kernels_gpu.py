@@ -168,6 +168,45 @@ def test_edge_fwd_bwd_matches_oracle(B, mn, me, C, H, masked, gen):
         assert util.rel_err(got["g_mask"], want["g_mask"]) <= RTOL
 
 
+@pytest.mark.parametrize("B,mn,me,masked", [(64, 20, 150, True), (256, 20, 150, False), (5, 60, 1200, True),
+                                            (1, 9, 40, False)])
+def test_edge_bwd_single_launch_is_bit_identical_to_two_pass(B, mn, me, masked):
+    """The single-launch backward (dst / src block roles ordered by tickets, g_eproj consumed from L2) does the
+    same arithmetic in the same order as the two-launch form: every output bit-identical, run to run as well."""
+    from isg_b200 import ops
+
+    d = _edge_case(B, mn, me, 300, 4, masked, seed=31 + B)
+    keys = ("out", "alpha", "g_x_l", "g_x_r", "g_e_proj", "g_att", "g_bias") + (("g_mask",) if masked else ())
+    prev = ops._EDGE_BWD_FUSED
+    try:
+        ops._EDGE_BWD_FUSED = False
+        two = _run_edge_cuda(d, 4, 300)
+        ops._EDGE_BWD_FUSED = True
+        one = _run_edge_cuda(d, 4, 300)
+        again = _run_edge_cuda(d, 4, 300)
+    finally:
+        ops._EDGE_BWD_FUSED = prev
+    for k in keys:
+        assert torch.equal(one[k], two[k]), k
+        assert torch.equal(one[k], again[k]), k
+
+
+def test_edge_bwd_falls_back_when_edges_leave_their_graph():
+    """An edge between two graphs breaks the precondition of the single-launch backward; GraphIndex.closed
+    reports it and the two-launch form runs (results still match the oracle)."""
+    d = _edge_case(6, 10, 50, 300, 4, True, seed=5)
+    ei = d["edge_index"].clone()
+    ei[0, 3] = d["x_l"].shape[0] - 1  # source in the last graph, destination in the first
+    d["edge_index"] = ei
+    gi = _gi(ei, d["batch"], int(d["batch"].max()) + 1)
+    assert gi.closed is False
+    want = _run_edge_oracle(d, 4, 300)
+    got = _run_edge_cuda(d, 4, 300)
+    for k in ("out", "g_x_l", "g_x_r", "g_e_proj", "g_att", "g_mask"):
+        assert util.rel_err(got[k], want[k]) <= RTOL, k
+    assert _gi(_edge_case(6, 10, 50, 300, 4, True, seed=5)["edge_index"], d["batch"], 6).closed is True
+
+
 def test_edge_fused_pitch_and_isolated_nodes():
     d = _edge_case(3, 9, 50, 300, 4, True, seed=77)
     # append two nodes without any edge: out must equal the bias there, grads zero
