@@ -134,6 +134,19 @@ int isg_topk_mask_fwd(const float* theta, const float* noise, const int32_t* gra
                       int64_t num_graphs, int nmax, int k, float tau,
                       float* mask, float* z_dense, void* stream);
 
+/* Fused sampler forward for IMLE / AIMLE — one launch for models/masking.py:151-176 + mgat_v2_conv.py:166-171:
+ * theta[n] = gelu(<xn[n], q[...]>/sqrt(D)) * keep[n]  (isg_gate_theta_fwd semantics, bit-identical),
+ * z = MAP(theta_dense + noise*tau), mask [N], z_dense [B,Nmax], and — when edge_mask != NULL — the
+ * NodeMaskToEdgeMask forward edge_mask[e] = mask[src]*mask[dst] (sampling/node_edge_masks.py:5-12) over the
+ * dst-sorted CSR.  The edge-mask part needs every edge inside one graph (isg_graph_closure == 0).
+ * Backward: isg_imle_bwd / isg_aimle_bwd, isg_gate_theta_bwd, isg_node_edge_mask_bwd as before. */
+int isg_sampler_fused_fwd(const float* xn, const float* q, const float* keep /* [N] or NULL */,
+                          const float* noise /* [B,Nmax] or NULL */, const int32_t* batch32,
+                          const int32_t* graph_ptr, const int32_t* dst_ptr, const int32_t* dst_nbr,
+                          const int32_t* dst_eid, int64_t num_graphs, int dim, int double_gather, int nmax, int k,
+                          float tau, float* theta, float* mask, float* z_dense, float* edge_mask /* [E] or NULL */,
+                          void* stream);
+
 /* IMLE backward (wrapper.py:124-172, target.py:44-48):
  * z' = MAP(alpha*theta - beta*dy + noise*tau_target);  g_theta = z - z'   (ragged [N]). */
 int isg_imle_bwd(const float* dy, const float* theta, const float* noise, const float* z_dense,
@@ -186,23 +199,29 @@ int isg_simple_marginals_bwd(const float* dy, const float* d_marginals, const fl
  * ------------------------------------------------------------------------------------- */
 
 /* instruction gating  y = gelu(x * ins[batch])  (models/mgat_v2_conv.py:156-157).
- * bwd: g_x [N,D] and g_ins [B,D] (segmented sum per graph, deterministic). */
+ * bwd: g_x [N,D] and g_ins [B,D] (segmented sum per graph, deterministic).  g_residual [N,D] or NULL is added
+ * to g_x (the gradient that reaches x through the layer's residual connection, models/mgat.py:172);
+ * accumulate_ins != 0 adds to g_ins instead of overwriting it. */
 int isg_instr_gate_fwd(const float* x, const float* ins, const int32_t* batch32,
                        int64_t num_nodes, int dim, float* y, void* stream);
 int isg_instr_gate_bwd(const float* g_y, const float* x, const float* ins,
                        const int32_t* graph_ptr, int64_t num_graphs, int dim,
+                       const float* g_residual, int accumulate_ins,
                        float* g_x, float* g_ins, void* stream);
 
 /* gate logits (models/masking.py:151-155).  double_gather = 1: q is [B,D] (one row per graph) and
  * theta[n] = gelu(<xn[n], q[batch[batch[n]]]> / sqrt(D)) — the double gather that results from
  * models/mgat_v2_conv.py:166-168 passing imle_att[batch] into a forward that indexes [batch] again.
  * double_gather = 0: q is [N,D] and theta[n] = gelu(<xn[n], q[batch[n]]> / sqrt(D)) (MaskingModel.forward
- * called directly with a per-node u).  bwd: g_xn [N,D], g_q (same shape as q). */
+ * called directly with a per-node u).  keep [N] or NULL: the dropout keep-mask of models/masking.py:159
+ * (0 or 1/(1-p)), multiplied into theta (and into g_theta in the backward).
+ * bwd: g_xn [N,D], g_q (same shape as q). */
 int isg_gate_theta_fwd(const float* xn, const float* q, const int32_t* batch32,
-                       int64_t num_nodes, int dim, int double_gather, float* theta, void* stream);
+                       int64_t num_nodes, int dim, int double_gather, const float* keep, float* theta,
+                       void* stream);
 int isg_gate_theta_bwd(const float* g_theta, const float* xn, const float* q,
                        const int32_t* batch32, const int32_t* graph_ptr,
-                       int64_t num_nodes, int64_t num_graphs, int dim, int double_gather,
+                       int64_t num_nodes, int64_t num_graphs, int dim, int double_gather, const float* keep,
                        float* g_xn, float* g_q, float* scratch /* [N] */, void* stream);
 
 /* scatter-SDPA + GraphNorm + residual (models/mgat.py:168-172; utils/scatter_scaled_dot_product.py:6-15;
@@ -273,6 +292,23 @@ int isg_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_t n, void* 
 size_t isg_colsum_workspace_bytes(int64_t rows, int cols);
 int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, float* out,
                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Layer executor: one call runs every kernel of one MGAT layer — the body of the loop in MGAT.forward
+ * (models/mgat.py:131-177: MaskingGATv2Conv.forward models/mgat_v2_conv.py:138-241 incl. MaskingModel.forward
+ * models/masking.py:132-199, x_proj, scatter-SDPA, GraphNorm, residual) — and one more its backward, in the
+ * order of the entry points above.  Arguments are three flat arrays indexed by NAMED slots (csrc/executor.cu
+ * lists them: D_* dims int64, F_* scalars double, P_* device pointers); isg_layer_slot(name) returns a slot's
+ * index (-1 if unknown) and isg_layer_slot_count(0|1|2) the length of the dims | scalars | ptrs array.
+ * Activations are written to caller-provided buffers (P_XG ... P_EMASK) by the forward and read back by the
+ * backward; the backward's temporaries live in P_WS (isg_mgat_layer_bwd_workspace_bytes(dims) bytes, passed in
+ * D_WS_BYTES).  Unused pointer slots are NULL.
+ * ------------------------------------------------------------------------------------- */
+int isg_layer_slot(const char* name);
+int isg_layer_slot_count(int which);
+size_t isg_mgat_layer_bwd_workspace_bytes(const int64_t* dims);
+int isg_mgat_layer_fwd(const int64_t* dims, const double* scalars, void* const* ptrs, void* stream);
+int isg_mgat_layer_bwd(const int64_t* dims, const double* scalars, void* const* ptrs, void* stream);
 
 #ifdef __cplusplus
 }

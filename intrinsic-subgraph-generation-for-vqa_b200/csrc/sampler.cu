@@ -316,6 +316,71 @@ gumbel_topk_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s
   for (int i = lane; i < nb; i += 32) g_theta[n0 + i] = A[i];
 }
 
+// ---- fused forward (IMLE / AIMLE): gate logit -> dropout -> + tau*noise -> per-graph top-k -> node mask ->
+// edge mask, ONE launch (SURVEY.md §8d "fused variant"; reference: models/masking.py:151-176 followed by
+// mgat_v2_conv.py:166-171 / sampling/node_edge_masks.py:5-12).  One warp per graph: the logits of the graph's
+// nodes are warp dot products <xn[n], q[batch[batch[n]]]> in exactly the order of gate_theta_fwd_kernel
+// (segment.cu), so theta — and hence the mask — is bit-identical to the unfused kernels; the graph's mask stays
+// in shared memory for the edge-mask pass over the graph's in-edges (needs every edge inside one graph).
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+sampler_fused_fwd_kernel(const float* __restrict__ xn, const float* __restrict__ q, const float* __restrict__ keep,
+                         const float* __restrict__ noise, const int* __restrict__ batch, const int* __restrict__ gptr,
+                         const int* __restrict__ dst_ptr, const int* __restrict__ dst_nbr,
+                         const int* __restrict__ dst_eid, int64_t B, int D, int dbl, int nmax, int k, float tau,
+                         float* __restrict__ theta, float* __restrict__ mask, float* __restrict__ zd,
+                         float* __restrict__ emask) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * SAMP_WARPS + warp;
+  if (b >= B) return;
+  float* orig = smem + (size_t)warp * 2 * nmax;
+  float* work = orig + nmax;
+  const int n0 = gptr[b], nb = gptr[b + 1] - n0;
+  const float rs = sqrtf((float)D);
+  for (int i = 0; i < nb; ++i) {
+    const int n = n0 + i;
+    const int qi = dbl ? batch[batch[n]] : batch[n];  // quirk Q1: double gather (see gate_theta_fwd_kernel)
+    const float* xr = xn + (int64_t)n * D;
+    const float* qr = q + (int64_t)qi * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s = fmaf(xr[c], qr[c], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float g = gelu_f(s / rs);
+      const float th = keep ? __fmul_rn(g, keep[n]) : g;
+      theta[n] = th;
+      orig[i] = th;
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < nmax; i += 32) {
+    const float th = (i < nb) ? orig[i] : 0.f;
+    const float nz = noise ? noise[b * nmax + i] : 0.f;
+    const float sc = __fadd_rn(th, __fmul_rn(nz, tau));
+    orig[i] = sc;
+    work[i] = sc;
+  }
+  __syncwarp();
+  const bool all = k >= nmax;
+  const float thr = all ? 0.f : kth_largest_warp(work, nmax, k, lane);
+  for (int i = lane; i < nmax; i += 32) {
+    const float z = (all || orig[i] >= thr) ? 1.f : 0.f;
+    zd[b * nmax + i] = z;
+    work[i] = z;
+    if (i < nb) mask[n0 + i] = z;
+  }
+  __syncwarp();
+  if (emask != nullptr && nb > 0) {  // edge_mask[e] = mask[src] * mask[dst] over the in-edges of the graph's nodes
+    const int p0 = dst_ptr[n0], p1 = dst_ptr[n0 + nb];
+    int node = 0;  // lanes walk the edge range; the owning node is found by advancing over dst_ptr
+    for (int p = p0 + lane; p < p1; p += 32) {
+      while (dst_ptr[n0 + node + 1] <= p) ++node;
+      const int src = dst_nbr[p] - n0;
+      emask[dst_eid[p]] = __fmul_rn(work[src], work[node]);
+    }
+  }
+}
+
 inline int check_samp(const int32_t* gptr, int64_t B, int nmax, int k) {
   if (B < 0 || nmax < 0 || k < 0) return ISG_EINVAL;
   if (B > 0 && !gptr) return ISG_EINVAL;
@@ -344,6 +409,26 @@ extern "C" int isg_topk_mask_fwd(const float* theta, const float* noise, const i
   if ((rc = set_smem(topk_mask_fwd_kernel, smem))) return rc;
   topk_mask_fwd_kernel<<<isg::ceil_div(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream_>>>(
       theta, noise, gptr, B, nmax, k, tau, mask, z_dense);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_sampler_fused_fwd(const float* xn, const float* q, const float* keep, const float* noise,
+                                     const int32_t* batch32, const int32_t* gptr, const int32_t* dst_ptr,
+                                     const int32_t* dst_nbr, const int32_t* dst_eid, int64_t B, int D,
+                                     int double_gather, int nmax, int k, float tau, float* theta, float* mask,
+                                     float* z_dense, float* edge_mask, void* stream_) {
+  int rc = check_samp(gptr, B, nmax, k);
+  if (rc) return rc;
+  if (D <= 0) return ISG_EINVAL;
+  if (B == 0 || nmax == 0) return ISG_OK;
+  if (!xn || !q || !batch32 || !theta || !mask || !z_dense || k < 1) return ISG_EINVAL;
+  if (edge_mask && (!dst_ptr || !dst_nbr || !dst_eid)) return ISG_EINVAL;
+  const size_t smem = (size_t)SAMP_WARPS * 2 * nmax * sizeof(float);
+  if ((rc = set_smem(sampler_fused_fwd_kernel, smem))) return rc;
+  sampler_fused_fwd_kernel<<<isg::ceil_div(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream_>>>(
+      xn, q, keep, noise, batch32, gptr, dst_ptr, dst_nbr, dst_eid, B, D, double_gather, nmax, k, tau, theta, mask,
+      z_dense, edge_mask);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

@@ -32,7 +32,8 @@ __global__ void instr_gate_fwd_kernel(const float* __restrict__ x, const float* 
 // one CTA per graph; thread c loops over the graph's nodes (coalesced across c)
 __global__ void instr_gate_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                       const float* __restrict__ ins, const int* __restrict__ gptr, int D,
-                                      float* __restrict__ gx, float* __restrict__ gins) {
+                                      const float* __restrict__ gres, int acc_ins, float* __restrict__ gx,
+                                      float* __restrict__ gins) {
   const int b = blockIdx.x;
   const int n0 = gptr[b], n1 = gptr[b + 1];
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
@@ -42,10 +43,11 @@ __global__ void instr_gate_bwd_kernel(const float* __restrict__ gy, const float*
       const int64_t o = (int64_t)n * D + c;
       const float xv = x[o];
       const float gp = gy[o] * gelu_grad_f(xv * iv);
-      gx[o] = gp * iv;
+      gx[o] = gres ? __fadd_rn(__fmul_rn(gp, iv), gres[o]) : gp * iv;  // + the residual branch's gradient
       acc = fmaf(gp, xv, acc);
     }
-    gins[(int64_t)b * D + c] = acc;
+    const int64_t oi = (int64_t)b * D + c;
+    gins[oi] = acc_ins ? gins[oi] + acc : acc;
   }
 }
 
@@ -53,7 +55,7 @@ __global__ void instr_gate_bwd_kernel(const float* __restrict__ gy, const float*
 // warp per node
 __global__ void gate_theta_fwd_kernel(const float* __restrict__ xn, const float* __restrict__ q,
                                       const int* __restrict__ batch, int64_t N, int D, int dbl,
-                                      float* __restrict__ theta) {
+                                      const float* __restrict__ keep, float* __restrict__ theta) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
@@ -63,14 +65,17 @@ __global__ void gate_theta_fwd_kernel(const float* __restrict__ xn, const float*
   float s = 0.f;
   for (int c = lane; c < D; c += 32) s = fmaf(xr[c], qr[c], s);
   s = warp_sum(s);
-  if (lane == 0) theta[n] = gelu_f(s / sqrtf((float)D));
+  if (lane == 0) {
+    const float th = gelu_f(s / sqrtf((float)D));
+    theta[n] = keep ? __fmul_rn(th, keep[n]) : th;  // dropout keep-mask (0 or 1/(1-p)), masking.py:159
+  }
 }
 
 // g_xn: warp per node (recomputes the pre-activation)
 __global__ void gate_theta_bwd_xn_kernel(const float* __restrict__ gth, const float* __restrict__ xn,
                                          const float* __restrict__ q, const int* __restrict__ batch,
-                                         int64_t N, int D, int dbl, float* __restrict__ gxn,
-                                         float* __restrict__ gpre) {
+                                         int64_t N, int D, int dbl, const float* __restrict__ keep,
+                                         float* __restrict__ gxn, float* __restrict__ gpre) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
@@ -81,7 +86,8 @@ __global__ void gate_theta_bwd_xn_kernel(const float* __restrict__ gth, const fl
   for (int c = lane; c < D; c += 32) s = fmaf(xr[c], qr[c], s);
   s = warp_sum(s);
   const float rs = 1.0f / sqrtf((float)D);
-  const float gp = gth[n] * gelu_grad_f(s * rs) * rs;  // d loss / d <xn,q>
+  const float gth_n = keep ? __fmul_rn(gth[n], keep[n]) : gth[n];
+  const float gp = gth_n * gelu_grad_f(s * rs) * rs;  // d loss / d <xn,q>
   for (int c = lane; c < D; c += 32) gxn[n * D + c] = gp * qr[c];
   if (lane == 0) gpre[n] = gp;
 }
@@ -436,8 +442,8 @@ attn_pool_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ 
   }
 }
 
-__global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ z,
-                                float* __restrict__ gz, int64_t n) {
+// gz may alias gy (the layer executor runs it in place): no __restrict__ on those two
+__global__ void gelu_bwd_kernel(const float* gy, const float* __restrict__ z, float* gz, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) gz[i] = gy[i] * gelu_grad_f(z[i]);
 }
@@ -509,33 +515,35 @@ extern "C" int isg_instr_gate_fwd(const float* x, const float* ins, const int32_
 }
 
 extern "C" int isg_instr_gate_bwd(const float* g_y, const float* x, const float* ins, const int32_t* gptr,
-                                  int64_t B, int D, float* g_x, float* g_ins, void* stream_) {
+                                  int64_t B, int D, const float* g_residual, int accumulate_ins, float* g_x,
+                                  float* g_ins, void* stream_) {
   if (B < 0 || D <= 0) return ISG_EINVAL;
   if (B == 0) return ISG_OK;
   if (!g_y || !x || !ins || !gptr || !g_x || !g_ins) return ISG_EINVAL;
-  instr_gate_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, x, ins, gptr, D, g_x, g_ins);
+  instr_gate_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, x, ins, gptr, D, g_residual,
+                                                                        accumulate_ins, g_x, g_ins);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
 
 extern "C" int isg_gate_theta_fwd(const float* xn, const float* q, const int32_t* batch32, int64_t N, int D,
-                                  int double_gather, float* theta, void* stream_) {
+                                  int double_gather, const float* keep, float* theta, void* stream_) {
   if (N < 0 || D <= 0) return ISG_EINVAL;
   if (N == 0) return ISG_OK;
   if (!xn || !q || !batch32 || !theta) return ISG_EINVAL;
-  gate_theta_fwd_kernel<<<isg::ceil_div(N * 32, 128), 128, 0, (cudaStream_t)stream_>>>(xn, q, batch32, N, D, double_gather, theta);
+  gate_theta_fwd_kernel<<<isg::ceil_div(N * 32, 128), 128, 0, (cudaStream_t)stream_>>>(xn, q, batch32, N, D, double_gather, keep, theta);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
 
 extern "C" int isg_gate_theta_bwd(const float* g_theta, const float* xn, const float* q, const int32_t* batch32,
                                   const int32_t* gptr, int64_t N, int64_t B, int D, int double_gather,
-                                  float* g_xn, float* g_q, float* scratch, void* stream_) {
+                                  const float* keep, float* g_xn, float* g_q, float* scratch, void* stream_) {
   if (N < 0 || B < 0 || D <= 0) return ISG_EINVAL;
   if (N == 0 || B == 0) return ISG_OK;
   if (!g_theta || !xn || !q || !batch32 || !gptr || !g_xn || !g_q || !scratch) return ISG_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
-  gate_theta_bwd_xn_kernel<<<isg::ceil_div(N * 32, 128), 128, 0, stream>>>(g_theta, xn, q, batch32, N, D, double_gather, g_xn, scratch);
+  gate_theta_bwd_xn_kernel<<<isg::ceil_div(N * 32, 128), 128, 0, stream>>>(g_theta, xn, q, batch32, N, D, double_gather, keep, g_xn, scratch);
   ISG_CHECK_LAUNCH();
   gate_theta_bwd_q_kernel<<<(unsigned)(double_gather ? B : N), 320, 0, stream>>>(scratch, xn, gptr, (int)B, D, double_gather, g_q);
   ISG_CHECK_LAUNCH();

@@ -2,7 +2,6 @@
 import math
 
 import torch
-import torch.nn.functional as F
 
 from .. import lib as L
 from .. import ops
@@ -123,7 +122,7 @@ class MaskingModel(torch.nn.Module):
     def forward_fused(self, x, u_graph, gi):
         xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)
         q = ops.linear(u_graph, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)
-        theta = ops.GateTheta.apply(xn, q, gi, True)
+        theta = ops.GateTheta.apply(xn, q, gi, True, self._keep_mask(x.shape[0], x.device))
         return self._sample(theta, gi)
 
     def forward(self, x, u, batch, edge_index, size=None, use_all_instrs=True):
@@ -135,14 +134,57 @@ class MaskingModel(torch.nn.Module):
         gi = get_graph_index(edge_index, batch, num_graphs)
         xn = ops.linear(x, self.node_nn[0].weight, self.node_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)
         q = ops.linear(u, self.ques_nn[0].weight, self.ques_nn[0].bias, L.ACT_GELU, self.GATE_GEMM_MODE)  # u [N,D]
-        theta = ops.GateTheta.apply(xn, q, gi, False)  # q[batch] (masking.py:152)
+        theta = ops.GateTheta.apply(xn, q, gi, False, self._keep_mask(x.shape[0], x.device))  # q[batch] (:152)
         return self._sample(theta, gi)
+
+    DROPOUT_P = 0.2  # masking.py:159 / :196 — dropout on theta, training only
+
+    def _keep_mask(self, N, device):
+        """The keep-mask F.dropout(theta, p=0.2) would draw — Bernoulli(1-p) / (1-p) on the device generator —
+        or the injected one; it is applied inside the gate-logit kernel.  None in eval mode."""
+        drop, self.injected_dropout_mask = self.injected_dropout_mask, None
+        if not self.training:
+            return None
+        if drop is not None:
+            return drop
+        keep = torch.empty(N, 1, dtype=torch.float32, device=device).bernoulli_(1.0 - self.DROPOUT_P)
+        return keep.mul_(1.0 / (1.0 - self.DROPOUT_P))
+
+    def executor_spec(self, gi, device, N):
+        """What the layer executor (csrc/executor.cu) needs to run this layer's sampler: the random draws of this
+        step (noise, dropout keep-mask — injected ones take precedence) and the sampler's constants."""
+        from .executor import SAMPLER_CODE
+
+        noise, self.injected_noise = self.injected_noise, None
+        keep = self._keep_mask(N, device)
+        if keep is not None:
+            keep = keep.to(device=device, dtype=torch.float32).contiguous()
+        st = self.sampler_type
+        spec = dict(code=SAMPLER_CODE[st], keep=keep)
+        if st in ("imle", "aimle"):
+            sampler = self.sampler_train if self.training else self.sampler_val
+            nz = ops._noise2d(sampler._noise(gi.B, gi.nmax, device, noise), gi)
+            spec.update(k=int(sampler.k), noise=nz, tau_in=sampler.tau_in, tau_tgt=sampler.tau_tgt)
+            if st == "imle":
+                spec.update(alpha=float(sampler.target.alpha), beta=float(sampler.target.beta))
+            else:
+                state, adaptive = sampler._state(device)
+                spec.update(state=state, adaptive=adaptive)
+        elif st == "gumbel":
+            g = noise if noise is not None else self.sampler._gumbel(gi.B, gi.nmax, device)
+            spec.update(k=max(1, min(int(self.sampler.k), gi.nmax)), noise=ops._noise2d(g, gi),
+                        gumbel_tau=float(self.sampler.tau))
+        else:  # simple
+            npad = L.load().isg_simple_npad(gi.nmax)
+            g = noise if noise is not None else self.sampler._gumbel(gi.B, npad, device)
+            g = g.reshape(gi.B, -1)
+            if g.shape[1] != npad:
+                raise ValueError(f"SIMPLE noise has {g.shape[1]} slots per graph, expected n_pad = {npad}")
+            spec.update(k=max(1, min(int(self.sampler.k), gi.nmax)), noise=g.to(torch.float32).contiguous())
+        return spec
 
     def _sample(self, theta, gi):
         noise, self.injected_noise = self.injected_noise, None
-        drop, self.injected_dropout_mask = self.injected_dropout_mask, None
-        if self.training:  # masking.py:159 / :196 — dropout p=0.2 on theta
-            theta = theta * drop if drop is not None else F.dropout(theta, p=0.2, training=True)
         self.last_theta = theta
         if not self.use_topk:  # masking.py:195-198
             return (torch.sigmoid(theta) > 0.5).to(dtype=theta.dtype)

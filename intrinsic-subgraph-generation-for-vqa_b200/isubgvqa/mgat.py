@@ -1,10 +1,22 @@
 """Mirror of ISubGVQA/models/mgat.py (MGAT)."""
 import torch
 
+import os
+
 from .. import lib as L
 from .. import ops
 from ..graph import get_graph_index
+from . import executor
 from .mgat_v2_conv import MaskingGATv2Conv
+
+# 1 (default): MGAT.forward runs the layer executor (one C call per layer and direction, isubgvqa/executor.py);
+# 0: the per-operator path below (one autograd Function per kernel family), kept as the cross-check.
+_USE_EXECUTOR = os.environ.get("ISG_EXECUTOR", "1") != "0"
+
+
+def set_executor(on):
+    global _USE_EXECUTOR
+    _USE_EXECUTOR = bool(on)
 
 
 class GraphNormParams(torch.nn.Module):
@@ -69,6 +81,18 @@ class MGAT(torch.nn.Module):
             params = self.__dict__["_param_list"] = list(self.parameters())
         ops.allow_side_stream(all(p.grad is None for p in params))
         gi = get_graph_index(edge_index, batch, instr_vectors.shape[1])
+        if _USE_EXECUTOR and executor.supported(self, explainer):
+            masked = [c for c in self.convs if c.mask.masking_threshold != 1.0]
+            if masked and gi.B > x.shape[0]:  # batch[batch[n]] (quirk Q1): the reference raises here too
+                raise IndexError(f"double gather needs num_graphs <= num_nodes, got B={gi.B}, N={x.shape[0]}")
+            if not any(c.mask.sampler_type == "simple" for c in masked) or gi.nmax > 1:
+                for conv in self.convs:
+                    executor.ensure_stacked(conv)
+                specs = [c.mask.executor_spec(gi, x.device, x.shape[0]) if c.mask.masking_threshold != 1.0 else None
+                         for c in self.convs]
+                h, mask = executor.MgatFunction.apply(self, gi, specs, ops.gemm_mode(), x, edge_attr, instr_vectors,
+                                                      global_language_feats, *executor.flat_params(self))
+                return h, mask, [], []
         h = x
         mask = None
         if self.use_global_mask:

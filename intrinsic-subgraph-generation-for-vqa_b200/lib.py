@@ -34,6 +34,8 @@ SIGNATURES = {
     "isg_node_edge_mask_fwd": (_I32, [_P, _P, _I64, _P, _P]),
     "isg_node_edge_mask_bwd": (_I32, [_P, _P, _P, _I64, _P, _P]),
     "isg_topk_mask_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "isg_sampler_fused_fwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _F, _P, _P, _P,
+                                     _P, _P]),
     "isg_imle_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _P, _P]),
     "isg_aimle_workspace_bytes": (_SZ, []),
     "isg_aimle_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _I32, _P, _P, _P, _SZ, _P]),
@@ -43,9 +45,9 @@ SIGNATURES = {
     "isg_simple_marginals_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "isg_simple_marginals_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "isg_instr_gate_fwd": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
-    "isg_instr_gate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
-    "isg_gate_theta_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
-    "isg_gate_theta_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "isg_instr_gate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _I32, _P, _P, _P]),
+    "isg_gate_theta_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "isg_gate_theta_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "isg_sdpa_graphnorm_fwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "isg_sdpa_graphnorm_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P,
                                       _P]),
@@ -60,6 +62,11 @@ SIGNATURES = {
     "isg_gelu_bwd": (_I32, [_P, _P, _P, _I64, _P]),
     "isg_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
     "isg_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
+    "isg_layer_slot": (_I32, [ctypes.c_char_p]),
+    "isg_layer_slot_count": (_I32, [_I32]),
+    "isg_mgat_layer_bwd_workspace_bytes": (_SZ, [_P]),
+    "isg_mgat_layer_fwd": (_I32, [_P, _P, _P, _P]),
+    "isg_mgat_layer_bwd": (_I32, [_P, _P, _P, _P]),
 }
 
 
@@ -84,7 +91,7 @@ def load():
 # kernels launched per C-ABI call (memsets excluded); used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
     "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_graph_closure": 1, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 3,
-    "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_imle_bwd": 1,
+    "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_sampler_fused_fwd": 1, "isg_imle_bwd": 1,
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
     "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_transpose_split": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,

@@ -7,7 +7,18 @@ import torch
 
 from . import lib as L
 
-_EDGE_BWD_FUSED = os.environ.get("ISG_EDGE_BWD_FUSED", "1") != "0"  # 0: always the two-launch edge backward
+# Edge backward as one launch (dst / src block roles, g_eproj consumed from L2) or as two launches.  Measured on
+# B200 (profiles/r2b_edge_fused_vs_two_pass.txt): the single launch wins where segments are long — 12 % / 19 % /
+# 25 % at 12 / 15 / 20 edges per node (batch 4096) — and loses 9-28 % at GQA's 5-8 edges per node, where both forms
+# are bound by per-task start-up latency rather than DRAM traffic.  None = pick by mean degree; True / False force.
+_EDGE_BWD_FUSED = {"1": True, "0": False}.get(os.environ.get("ISG_EDGE_BWD_FUSED", ""), None)
+EDGE_BWD_FUSED_MIN_DEGREE = 10.0
+
+
+def edge_bwd_fused(gi):
+    """Whether GatEdge.backward runs the single-launch form for this batch (needs every edge inside one graph)."""
+    want = _EDGE_BWD_FUSED if _EDGE_BWD_FUSED is not None else gi.E >= EDGE_BWD_FUSED_MIN_DEGREE * max(gi.N, 1)
+    return bool(want) and gi.closed
 _DEBUG_EDGE_BWD = None  # diagnostics: set to a list to capture GatEdge.backward inputs/outputs
 # projection arithmetic: 1 = tcgen05 3xTF32 with bounded accumulation chains (default; measured 6.5e-7 relative
 # against fp64, i.e. at or below the FFMA kernel's error), 0 = fp32 FFMA, 2 = tcgen05 single-pass TF32 (~8e-4)
@@ -268,17 +279,19 @@ class InstrGate(torch.autograd.Function):
         gx = torch.empty_like(x)
         gins = torch.empty_like(ins)
         L.call("isg_instr_gate_bwd", L.ptr(gy), L.ptr(x), L.ptr(ins), L.ptr(gi.graph_ptr), gi.B, x.shape[1],
-                                            L.ptr(gx), L.ptr(gins), L.stream())
+                                            None, 0, L.ptr(gx), L.ptr(gins), L.stream())
         return gx, gins, None
 
 
 class GateTheta(torch.autograd.Function):
-    """theta = gelu(<xn, q[batch[batch]]> / sqrt(D))  (models/masking.py:151-155, double gather via
-    models/mgat_v2_conv.py:166-168).  q is [B, D] (one row per graph)."""
+    """theta = gelu(<xn, q[batch[batch]]> / sqrt(D)) [* keep]  (models/masking.py:151-155, double gather via
+    models/mgat_v2_conv.py:166-168; keep [N,1] = the dropout keep-mask of masking.py:159, 0 or 1/(1-p), folded
+    into the kernel).  q is [B, D] (one row per graph)."""
 
     @staticmethod
-    def forward(ctx, xn, q, gi, double_gather):
+    def forward(ctx, xn, q, gi, double_gather, keep=None):
         xn, q = _c(xn), _c(q)
+        keep = _c(keep.to(torch.float32)) if keep is not None else None
         dbl = 1 if double_gather else 0
         if q.shape[0] != (gi.B if dbl else xn.shape[0]):
             raise ValueError("GateTheta: q must be [B,D] with double_gather, [N,D] without")
@@ -287,23 +300,23 @@ class GateTheta(torch.autograd.Function):
             raise IndexError(f"double gather needs num_graphs <= num_nodes, got B={gi.B}, N={xn.shape[0]}")
         theta = torch.empty(xn.shape[0], 1, dtype=torch.float32, device=xn.device)
         L.call("isg_gate_theta_fwd", L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), xn.shape[0], xn.shape[1], dbl,
-                                            L.ptr(theta), L.stream())
+                                            L.ptr(keep), L.ptr(theta), L.stream())
         ctx.gi, ctx.dbl = gi, dbl
-        ctx.save_for_backward(xn, q)
+        ctx.save_for_backward(xn, q, keep)
         return theta
 
     @staticmethod
     def backward(ctx, gth):
-        xn, q = ctx.saved_tensors
+        xn, q, keep = ctx.saved_tensors
         gi = ctx.gi
         gth = _c(gth)
         gxn = torch.empty_like(xn)
         gq = torch.empty_like(q)
         scratch = torch.empty(xn.shape[0], dtype=torch.float32, device=xn.device)
         L.call("isg_gate_theta_bwd", L.ptr(gth), L.ptr(xn), L.ptr(q), L.ptr(gi.batch32), L.ptr(gi.graph_ptr),
-                                            xn.shape[0], gi.B, xn.shape[1], ctx.dbl, L.ptr(gxn), L.ptr(gq),
-                                            L.ptr(scratch), L.stream())
-        return gxn, gq, None, None
+                                            xn.shape[0], gi.B, xn.shape[1], ctx.dbl, L.ptr(keep), L.ptr(gxn),
+                                            L.ptr(gq), L.ptr(scratch), L.stream())
+        return gxn, gq, None, None, None
 
 
 class SdpaGraphNormResidual(torch.autograd.Function):
@@ -390,7 +403,7 @@ class GatEdge(torch.autograd.Function):
         g_em = torch.empty(gi.E, 1, dtype=torch.float32, device=dev) if em is not None else None
         nbytes = lib.isg_gat_edge_bwd_workspace_bytes(N, gi.E, gi.B, H, C)
         ws = L.workspace(nbytes, dev)
-        fused = _EDGE_BWD_FUSED and gi.closed  # single launch needs every edge inside one graph
+        fused = edge_bwd_fused(gi)
         L.call("isg_gat_edge_bwd", L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), 2 * HC,
                                      L.ptr(e_proj), L.ptr(att), L.ptr(bias), L.ptr(em), L.ptr(alpha), L.ptr(out), HC,
                                      L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr),

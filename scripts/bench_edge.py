@@ -74,7 +74,8 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7, bf16=False):
         gatt = torch.empty(HC, device=dev)
         gem = torch.empty(E, device=dev) if masked else None
         wsb = lib.isg_gat_edge_bwd_workspace_bytes(N, E, nb, H, C)
-        fused = os.environ.get("ISG_EDGE_BWD_FUSED", "1") != "0" and gi.closed and not bf16
+        from isg_b200 import ops
+        fused = ops.edge_bwd_fused(gi) and not bf16
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
         st = L.stream()
 

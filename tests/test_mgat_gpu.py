@@ -73,6 +73,60 @@ def test_cuda_matches_oracle_at_baseline_sizes(sampler, train, B):
     assert util.rel_err(got["gx"], free["gx"]) <= 2e-2
 
 
+@pytest.mark.parametrize("sampler,train,k", [("imle", True, 2), ("aimle", True, 2), ("gumbel", True, 2),
+                                             ("simple", True, 2), ("imle", False, 3), ("gumbel", False, 2)])
+def test_layer_executor_matches_per_operator_path(sampler, train, k):
+    """MGAT.forward through the layer executor (one C call per layer and direction, the default) against the
+    per-operator autograd Functions on the same inputs: the forward runs the same kernels (h and the mask are
+    bit-identical); the backward differs only in where a few small additions happen (<= 1e-5)."""
+    cfg = dict(sampler=sampler, train=train, channels=300, num_graphs=12, mean_nodes=14, mean_edges=90, k=k,
+               seed=515, steps=2, aimle_beta0=2.0 if sampler == "aimle" else None)
+    fast = util.run_cuda_case(cfg, executor=True)
+    slow = util.run_cuda_case(cfg, executor=False)
+    for a, b in zip(fast, slow):
+        assert torch.equal(a["h"], b["h"]) and torch.equal(a["mask"], b["mask"])
+        for key in ("gx", "g_edge_attr", "g_instr", "g_glf"):
+            assert util.rel_err(a[key], b[key]) <= 1e-5, key
+        assert set(a["param_grads"]) == set(b["param_grads"])
+        for name, g in b["param_grads"].items():
+            if g is None:
+                assert a["param_grads"][name] is None, name
+            else:
+                assert util.rel_err(a["param_grads"][name], g) <= 1e-5, name
+
+
+def test_layer_executor_accumulates_into_existing_grads_and_external_mask_gradient():
+    """Two backward passes without zero_grad add up (the flat gradient buffer is fresh per backward), and a
+    gradient that reaches the returned node mask from OUTSIDE MGAT (the pooling layer multiplies by it,
+    models/isubgvqa.py:280-287) is routed into the sampler's perturbation gradient like in the per-operator path."""
+    from isg_b200.isubgvqa import MGAT
+    from isg_b200.isubgvqa import mgat as mgat_mod
+
+    b = synth.make_batch(6, mean_nodes=9, mean_edges=40, seed=3)
+    args = [b[k].cuda() for k in ("x", "edge_index", "instr_vectors", "global_language_feats", "edge_attr", "batch")]
+    noise = util.case_noise("imle", 6, b["nmax"], 3).cuda()
+    res = {}
+    for fast in (True, False):
+        mgat_mod.set_executor(fast)
+        try:
+            m = MGAT(channels=300, num_ins=4, heads=4, use_instr=True, masking_thresholds=[1.0, 1.0, 1.0, 0.1],
+                     use_topk=True, interpretable_mode=False, sampler_type="imle", sample_k=2)
+            m.load_state_dict(synth.make_state_dict(seed=3))
+            m.cuda().eval()
+            for _ in range(2):
+                m.convs[3].mask.injected_noise = noise
+                h, mask, _, _ = m(*args, return_masks=True)
+                w = torch.linspace(-1, 1, mask.numel(), device="cuda").view_as(mask)
+                (util.loss_fn(h) + (mask * w).sum() + (h * mask).mean()).backward()
+            res[fast] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        finally:
+            mgat_mod.set_executor(True)
+    assert set(res[True]) == set(res[False])
+    for k, g in res[False].items():
+        assert util.rel_err(res[True][k], g) <= 1e-5, k
+    assert float(res[True]["convs.3.mask.node_nn.0.weight"].abs().max()) > 0
+
+
 def test_full_size_inference_properties():
     """BASELINE config 2 (B=1024, Gumbel, eval, no_grad): too slow for the CPU oracle inside the GPU
     suite -> size-independent properties: finite outputs, mask ~ k-hot per graph, determinism."""

@@ -120,10 +120,23 @@ def run_oracle_fp64_arbiter(cfg):
     return o32, o64
 
 
-def run_cuda_case(cfg, step_count=None, device="cuda", capture=False):
+def run_cuda_case(cfg, step_count=None, device="cuda", capture=False, executor=True):
     """Runs the CUDA drop-in (isg_b200.isubgvqa.MGAT) on a golden config.  capture=True also returns the
-    edge kernel's forward inputs of every layer (`teacher` dict for run_oracle_case)."""
+    edge kernel's forward inputs of every layer (`teacher` dict for run_oracle_case).  executor=True (the
+    default configuration of the package) runs MGAT.forward through the layer executor, False through the
+    per-operator autograd Functions."""
     from isg_b200.isubgvqa import MGAT
+    from isg_b200.isubgvqa import mgat as mgat_mod
+
+    prev_exec = mgat_mod._USE_EXECUTOR
+    mgat_mod.set_executor(executor)
+    try:
+        return _run_cuda_case(cfg, step_count, device, capture, executor, MGAT)
+    finally:
+        mgat_mod.set_executor(prev_exec)
+
+
+def _run_cuda_case(cfg, step_count, device, capture, executor, MGAT):
 
     C, B, seed, sampler, train = cfg["channels"], cfg["num_graphs"], cfg["seed"], cfg["sampler"], cfg["train"]
     b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
@@ -146,8 +159,9 @@ def run_cuda_case(cfg, step_count=None, device="cuda", capture=False):
         iv = b["instr_vectors"].to(device).requires_grad_(True)
         gl = b["global_language_feats"].to(device).requires_grad_(True)
         model.zero_grad()
+        model.capture_activations = {} if (capture and executor) else None
         for conv in model.convs:
-            conv.debug_tensors = {} if capture else None
+            conv.debug_tensors = {} if (capture and not executor) else None
             if conv.mask.masking_threshold != 1.0:
                 conv.mask.injected_noise = noise
                 conv.mask.injected_dropout_mask = drop.to(device) if drop is not None else None
@@ -156,7 +170,9 @@ def run_cuda_case(cfg, step_count=None, device="cuda", capture=False):
         loss.backward()
         pg = {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in model.named_parameters()}
         teacher = None
-        if capture:
+        if capture and executor:
+            teacher = {k: v.detach().cpu() for k, v in model.capture_activations.items()}
+        elif capture:
             teacher = {f"{n}.{i}": conv.debug_tensors[n].detach().cpu() for i, conv in enumerate(model.convs)
                        for n in ("x_l", "x_r", "e_proj")}
         outs.append(dict(h=h.detach().cpu(), mask=mask.detach().cpu(), loss=float(loss.detach()), gx=x.grad.cpu(),
