@@ -97,6 +97,58 @@ def edge_bytes(N, E, masked, s=4):
     return fwd, bwd
 
 
+def gemm_flops(N, E, B, train):
+    """Algorithmic FLOPs of the dense projections per step: per layer forward
+    2*300*1200*(2N + E) + 2N*(1200*600 + 600*300), the masked layer adds 2*(N + B)*300*300; the backward
+    (dgrad + wgrad of every projection) is twice the forward."""
+    D, HC, HID = CHANNELS, HEADS * CHANNELS, CHANNELS * (HEADS // 2)
+    fwd = LAYERS * (2 * D * HC * (2 * N + E) + 2 * N * (HC * HID + HID * D)) + 2 * (N + B) * D * D
+    return fwd * (3 if train else 1)
+
+
+def sampler_bytes(N, E, B, nmax):
+    """Algorithmic HBM bytes of the fused sampler forward (gate dot + dropout + noise + top-k + node mask + edge
+    mask, one launch): xn [N,D] + q [B,D] + keep/theta/mask [N] each + noise/z_dense [B,Nmax] each + graph_ptr +
+    the dst-sorted CSR (ptr, nbr, eid) + edge_mask [E]."""
+    return 4 * (N * CHANNELS + B * CHANNELS + 3 * N + 2 * B * nmax + (B + 1) + (N + 1) + 3 * E)
+
+
+def sampler_study(N, E, B, nmax, gi, dev, reps=50):
+    """The fused sampler forward timed alone (L2 flushed between launches): SURVEY.md §8d asks for its achieved
+    GB/s 'honestly' — it is latency-bound at every BASELINE size (~20 B per node)."""
+    from isg_b200 import lib as L
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    xn = torch.randn(N, CHANNELS, device=dev, generator=g)
+    q = torch.randn(B, CHANNELS, device=dev, generator=g)
+    keep = (torch.rand(N, device=dev, generator=g) > 0.2).float() / 0.8
+    noise = torch.randn(B, nmax, device=dev, generator=g) * 0.3
+    theta, mask, em = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(E, device=dev)
+    zd = torch.empty(B, nmax, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = L.stream()
+
+    def run():
+        L.call("isg_sampler_fused_fwd", xn.data_ptr(), q.data_ptr(), keep.data_ptr(), noise.data_ptr(),
+               gi.batch32.data_ptr(), gi.graph_ptr.data_ptr(), gi.dst_ptr.data_ptr(), gi.dst_nbr.data_ptr(),
+               gi.dst_eid.data_ptr(), B, CHANNELS, 1, nmax, K_SAMPLE, 1.0, theta.data_ptr(), mask.data_ptr(),
+               zd.data_ptr(), em.data_ptr(), st)
+
+    for _ in range(5):
+        run()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def edge_study(points=((4096, 20, 150),), reps=10):
     """BASELINE config 5 (edge-kernel roofline study), one point by default: the fused edge kernels timed alone
     at batch 4096 (scripts/bench_edge.py runs the whole 10-200 objects / 50-4000 edges sweep)."""
@@ -406,8 +458,6 @@ def main_isg(args, rank, world, local_rank):
         for _ in range(max(args.warmup, 3)):
             step_core(resident, noise_d)
     torch.cuda.synchronize()
-    edge_names = ["isg_gat_edge_fwd", "isg_gat_edge_bwd"]
-
     # The resident-input step is launch-bound on the host (~180 kernel launches + autograd bookkeeping take
     # about as long as the GPU needs for them), so forward+backward is captured ONCE into a CUDA graph and the
     # timed region replays it (the NCCL all-reduce, if any, is issued eagerly after each replay): identical
@@ -441,11 +491,14 @@ def main_isg(args, rank, world, local_rank):
         if reducer is not None and not overlap:
             reducer.all_reduce_mean()
 
+    from isg_b200.isubgvqa import mgat as mgat_mod
+
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    launches_per_step = None
-    ms_eager, launches, tsum = timed(lambda: step(resident, noise_d), args.steps, edge_names)
+    # (1) eager step through the layer executor (what a caller of the nn.Module gets with resident inputs)
+    ms_eager, launches, _ = timed(lambda: step(resident, noise_d), args.steps)
+    # (2) value: the same step replayed from the captured graph
     if graph is not None:
         ms, _, _ = timed(graphed_step, args.steps)
     else:
@@ -457,8 +510,17 @@ def main_isg(args, rank, world, local_rank):
         reducer.remove_hooks()
         reducer = GradAllReduce(model)
         overlap = False
-    # kernel-family breakdown of one extra (untimed) step, for DESIGN.md / the JSON line
-    ms_b, _, tall = timed(lambda: step(resident, noise_d), 2, None if not args.breakdown else list(L.KERNELS_PER_CALL))
+    # (3) per-kernel CUDA events for the roofline blocks: the same K steps through the per-operator path, where
+    # every kernel family is its own C-ABI call that lib.call can bracket with events on the launching stream
+    # (the executor issues them from C).  Same kernels, same order, same step.
+    kernel_names = ["isg_gat_edge_fwd", "isg_gat_edge_bwd", "isg_linear_fwd", "isg_linear_dgrad", "isg_linear_wgrad"]
+    mgat_mod.set_executor(False)
+    for _ in range(2):
+        step(resident, noise_d)
+    _, _, tsum = timed(lambda: step(resident, noise_d), args.steps,
+                       kernel_names if not args.breakdown else list(L.KERNELS_PER_CALL))
+    tall = tsum
+    mgat_mod.set_executor(True)
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -488,7 +550,7 @@ def main_isg(args, rank, world, local_rank):
         per_launch_ms = tot / calls
         alg = (3 * bwd_b_un + bwd_b_m) / 4.0  # 3 unmasked layers + 1 masked layer per step
         ach = alg / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst + att_reduce + gat_edge_bwd_src)",
+        roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst_ring + gat_att_reduce1/2 + gat_edge_bwd_src_ring)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": measured_traffic("isg_gat_edge_bwd", args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
@@ -508,6 +570,40 @@ def main_isg(args, rank, world, local_rank):
         alg = (3 * fwd_b_un + fwd_b_m) / 4.0
         edge_fwd = {"ms_per_launch": tot / calls, "achieved_GBps": alg / (tot / calls * 1e-3) / 1e9,
                     "frac": alg / (tot / calls * 1e-3) / 1e9 / peak}
+    # projections: tensor-pipe roofline.  useful = algorithmic fp32 FLOPs / summed launch time of all isg_linear_*
+    # calls; issued = 3x that in mode 1 (three TF32 products per fp32 product).  Peak: MEASURED_PEAKS.json has no TF32
+    # entry; kind::tf32 runs at half the bf16 rate, so peak = bf16_tflops_sustained / 2 (kernels timed inside a step).
+    roof_gemm = None
+    lin = [tsum[k] for k in ("isg_linear_fwd", "isg_linear_dgrad", "isg_linear_wgrad") if k in tsum]
+    if lin:
+        lin_ms = sum(t for _, t in lin) / args.steps
+        fl = gemm_flops(N, E, B, train)
+        useful = fl / (lin_ms * 1e-3) / 1e12
+        mult = {0: 1.0, 1: 3.0, 2: 1.0}[args.gemm_mode]
+        pk_tf = None
+        try:
+            pk_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]) / 2.0
+        except Exception:
+            pass
+        roof_gemm = {"bound": "tensor", "kernel": "tc_gemm_kernel (all isg_linear_fwd/dgrad/wgrad launches of the step)",
+                     "achieved": useful * mult, "achieved_useful_fp32": useful, "peak": pk_tf, "unit": "TFLOP/s",
+                     "frac": (useful * mult / pk_tf) if pk_tf else None,
+                     "frac_useful": (useful / pk_tf) if pk_tf else None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 rate)",
+                     "algorithmic_flops_per_step": fl, "ms_per_step": lin_ms,
+                     "launches_per_step": sum(c for c, _ in lin) // args.steps,
+                     "tensor_pipe_active_pct_ncu": measured_traffic("tc_gemm_tensor_pipe_pct", args.workload)}
+    samp = None
+    if world == 1 and sampler in ("imle", "aimle"):
+        from isg_b200.graph import get_graph_index
+
+        gi = get_graph_index(resident["edge_index"], resident["batch"], B)
+        t_ms = sampler_study(N, E, B, nmax, gi, dev)
+        sb = sampler_bytes(N, E, B, nmax)
+        samp = {"kernel": "sampler_fused_fwd_kernel (gate dot + dropout + tau*noise + top-k + node mask + edge mask, "
+                          "one launch)", "ms_per_launch": t_ms, "algorithmic_bytes_per_launch": sb,
+                "achieved_GBps": sb / (t_ms * 1e-3) / 1e9, "frac": sb / (t_ms * 1e-3) / 1e9 / peak,
+                "note": "latency-bound at this size (SURVEY.md section 8d): one warp per graph, ~20 nodes each"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r, kind, what = run_cpu_arm(sampler, train, B, 2, 1)
@@ -533,8 +629,11 @@ def main_isg(args, rank, world, local_rank):
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
                          f"~{(4 * 4 * HEADS * CHANNELS * (3 * E + 8 * N)) / 1e9:.2f} GB also exceeds the 126 MB L2",
                    "gemm_mode": gemm_desc,
-                   "cuda_graph": ("value: K replays of one captured step (eager: %.3f ms/step); roofline kernel times "
-                                  "and e2e are eager" % (ms_eager / args.steps)) if graph is not None else "off", "optimizer": "out of scope (SURVEY.md §8 f4)"},
+                   "host_path": "layer executor: one C call per MGAT layer and direction (isg_mgat_layer_fwd/_bwd)",
+                   "cuda_graph": ("value: K replays of one captured step; the same step issued eagerly through the "
+                                  "nn.Module takes %.3f ms/step; e2e is eager" % (ms_eager / args.steps))
+                   if graph is not None else "off",
+                   "optimizer": "not in the timed step (SURVEY.md section 8 f4: isg_b200.optim)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "what": "pinned host batch -> H2D + CSR build on a copy stream one batch ahead (isg_b200.loader."
@@ -542,13 +641,15 @@ def main_isg(args, rank, world, local_rank):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roof,
+        "roofline_gemm": roof_gemm,
+        "sampler": samp,
         "edge_fwd": edge_fwd,
         "edge_roofline_study": study,
         "cpu_baseline": cpu,
     }
     if args.breakdown:
-        line["breakdown_ms_per_step"] = {k: round(v[1] / 2, 4) for k, v in sorted(tall.items(), key=lambda kv: -kv[1][1])}
-        line["breakdown_step_ms"] = ms_b / 2
+        line["breakdown_ms_per_step"] = {k: round(v[1] / args.steps, 4)
+                                         for k, v in sorted(tall.items(), key=lambda kv: -kv[1][1])}
     out_stream.write(json.dumps(line) + "\n")
     out_stream.flush()
     teardown()

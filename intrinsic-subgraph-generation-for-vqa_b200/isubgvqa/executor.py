@@ -190,6 +190,28 @@ def _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, ins_ptr, glf, edge_attr, s
         p[s.P_AIMLE_STATE] = spec["state"].data_ptr() if spec.get("state") is not None else 0
 
 
+def kernel_launches(spec, gi, backward):
+    """Kernels one isg_mgat_layer_fwd / _bwd call launches (memsets excluded) — mirrors csrc/executor.cu; used
+    for bench.py's gpu_launches claim."""
+    K = L.KERNELS_PER_CALL
+    masked = spec is not None
+    if not backward:
+        n = K["isg_instr_gate_fwd"] + 4 * K["isg_linear_fwd"] + K["isg_gat_edge_fwd"] + K["isg_sdpa_graphnorm_fwd"]
+        if masked:
+            n += 2 * K["isg_linear_fwd"]
+            if spec["code"] in (1, 2) and gi.closed:
+                n += K["isg_sampler_fused_fwd"]
+            else:
+                n += K["isg_gate_theta_fwd"] + 1 + K["isg_node_edge_mask_fwd"]
+        return n
+    n = (K["isg_sdpa_graphnorm_bwd"] + 7 * K["isg_colsum"] + K["isg_gelu_bwd"] + 4 * K["isg_linear_dgrad"] +
+         4 * K["isg_linear_wgrad"] + K["isg_gat_edge_bwd"] + K["isg_instr_gate_bwd"])
+    if masked:
+        n += 1 + K["isg_node_edge_mask_bwd"] + (3 if spec["code"] == 2 else 1) + K["isg_gate_theta_bwd"] + \
+            2 * (K["isg_gelu_bwd"] + K["isg_linear_dgrad"] + K["isg_linear_wgrad"] + K["isg_colsum"])
+    return n
+
+
 class MgatFunction(torch.autograd.Function):
     """(x, edge_attr, instr_vectors, global_language_feats, *parameters) -> (h, mask of the last layer or None)."""
 
@@ -208,7 +230,7 @@ class MgatFunction(torch.autograd.Function):
             d, f, p = _arrays()
             _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, iv.data_ptr() + i * B * pl.D * 4, glf, edge_attr,
                          specs[i], ap, gemm_mode)
-            L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st)
+            L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, False))
             x_in_ptr = ap + pl.act[i]["P_H_OUT"]
         ctx.model, ctx.gi, ctx.specs, ctx.pl, ctx.gemm_mode, ctx.arena = model, gi, specs, pl, gemm_mode, arena
         ctx.save_for_backward(x, edge_attr, iv, glf, *params)
@@ -294,7 +316,7 @@ class MgatFunction(torch.autograd.Function):
                     continue
                 slot = {"W_L": "P_G_W_LR", "B_L": "P_G_B_LR"}.get(name, "P_G_" + name)
                 p[getattr(s, slot)] = gp + 4 * pl.grad_off[(i, name)]
-            L.call("isg_mgat_layer_bwd", _p(d), _p(f), _p(p), st)
+            L.call("isg_mgat_layer_bwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, True))
             g_in_ptr = out.data_ptr()
             if hook is not None:
                 lo, hi = pl.layer_span[i]
