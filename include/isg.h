@@ -294,6 +294,38 @@ int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, float* out,
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * SURVEY.md section 8 row f2 — scene-graph encoding layer in front of MGAT: torch_geometric MetaLayer(EdgeModel,
+ * NodeModel) (models/scene_graph_encoder.py:107-146) and the GraphNorm SceneGraphEncoder.forward evaluates in
+ * float64 on the CPU (:99-102).  The [300, 900] / [300, 600] weights of the concatenated inputs are split by
+ * column block; the node blocks are applied per NODE by isg_linear_fwd and gathered here.
+ * ------------------------------------------------------------------------------------- */
+
+/* z[e] = a[src[e]] + b[dst[e]] + q[e]  (a, b: [N,D] or NULL; q [E,D]; edge_index [2,E] int64);  y = act(z).
+ * z_pre [E,D] or NULL receives z (for the GELU backward). */
+int isg_gather_add_act_fwd(const float* a, const float* b, const float* q, const int64_t* edge_index,
+                           int64_t num_edges, int dim, int act, float* z_pre, float* y, void* stream);
+
+/* out[n] = sum over p in [ptr[n], ptr[n+1]) of in[eid[p]]  (x 1/max(deg,1) if mean != 0): torch_scatter.scatter_mean
+ * by destination (scene_graph_encoder.py:141) over the dst-sorted CSR, and the transposes of the two gathers above
+ * (over the dst- / src-sorted CSR) in the backward.  Deterministic (fixed CSR order). */
+int isg_segment_sum(const float* in /* [E,D] */, const int32_t* ptr, const int32_t* eid, int64_t num_nodes, int dim,
+                    int mean, float* out /* [N,D] */, void* stream);
+
+/* out[e] = in[idx[e]] (x 1/max(deg(idx[e]),1) if ptr != NULL): backward of the segment mean. */
+int isg_gather_rows(const float* in /* [N,D] */, const int64_t* idx /* [E] */, const int32_t* ptr /* [N+1] or NULL */,
+                    int64_t num_edges, int dim, float* out /* [E,D] */, void* stream);
+
+/* GraphNorm (eps 1e-5) with float64 statistics and arithmetic, result rounded to float once — what
+ * scene_graph_encoder.py:99-102 computes through a CPU DoubleTensor round trip.  Saves mean, rstd [B,D] double.
+ * bwd: g_x [N,D] and per-graph partials of g_weight / g_bias / g_mean_scale [B,D] (summed by isg_colsum). */
+int isg_graphnorm64_fwd(const float* x, const float* weight, const float* bias, const float* mean_scale,
+                        const int32_t* graph_ptr, int64_t num_graphs, int dim, double eps,
+                        float* y, double* mean, double* rstd, void* stream);
+int isg_graphnorm64_bwd(const float* g_y, const float* x, const float* weight, const float* mean_scale,
+                        const double* mean, const double* rstd, const int32_t* graph_ptr, int64_t num_graphs, int dim,
+                        float* g_x, float* gw_part, float* gb_part, float* gms_part, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Layer executor: one call runs every kernel of one MGAT layer — the body of the loop in MGAT.forward
  * (models/mgat.py:131-177: MaskingGATv2Conv.forward models/mgat_v2_conv.py:138-241 incl. MaskingModel.forward
  * models/masking.py:132-199, x_proj, scatter-SDPA, GraphNorm, residual) — and one more its backward, in the

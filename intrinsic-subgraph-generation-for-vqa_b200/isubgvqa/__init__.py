@@ -4,12 +4,13 @@ arithmetic done by libisg.so.  `install()` makes the reference's own import stat
 modules, so main.py / training / eval run unchanged."""
 import sys
 
-from . import att_pooling, masking, mgat, mgat_v2_conv, node_edge_masks, samplers  # noqa: F401
+from . import att_pooling, masking, mgat, mgat_v2_conv, node_edge_masks, samplers, scene_graph_encoder  # noqa: F401
 from .att_pooling import GlobalAttention  # noqa: F401
 from .masking import MaskingModel, get_aimle_samplers, get_imle_samplers  # noqa: F401
 from .mgat import MGAT  # noqa: F401
 from .mgat_v2_conv import MaskingGATv2Conv  # noqa: F401
 from .node_edge_masks import NodeMaskToEdgeMask  # noqa: F401
+from .scene_graph_encoder import GraphNorm64, SceneGraphEncodingLayer, encode_scene_graph  # noqa: F401
 
 _ALIASES = {
     "ISubGVQA.models.mgat": mgat,

@@ -62,6 +62,11 @@ SIGNATURES = {
     "isg_gelu_bwd": (_I32, [_P, _P, _P, _I64, _P]),
     "isg_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
     "isg_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
+    "isg_gather_add_act_fwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "isg_segment_sum": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "isg_gather_rows": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
+    "isg_graphnorm64_fwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I32, ctypes.c_double, _P, _P, _P, _P]),
+    "isg_graphnorm64_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
     "isg_layer_slot": (_I32, [ctypes.c_char_p]),
     "isg_layer_slot_count": (_I32, [_I32]),
     "isg_mgat_layer_bwd_workspace_bytes": (_SZ, [_P]),
@@ -95,7 +100,8 @@ KERNELS_PER_CALL = {
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
     "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_transpose_split": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
-    "isg_gelu_bwd": 1, "isg_colsum": 2,
+    "isg_gelu_bwd": 1, "isg_colsum": 2, "isg_gather_add_act_fwd": 1, "isg_segment_sum": 1, "isg_gather_rows": 1,
+    "isg_graphnorm64_fwd": 1, "isg_graphnorm64_bwd": 1,
 }
 launch_count = 0
 _timing = None  # name -> list of (start_event, end_event) when enabled

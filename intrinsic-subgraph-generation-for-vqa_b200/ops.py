@@ -623,3 +623,95 @@ class AttnPool(torch.autograd.Function):
         L.call("isg_attn_pool_bwd", L.ptr(g_out), L.ptr(g_gate), L.ptr(x), L.ptr(m), L.ptr(q), L.ptr(gate),
                L.ptr(gi.graph_ptr), gi.B, x.shape[1], gi.nmax, L.ptr(g_x), L.ptr(g_m), L.ptr(g_q), L.stream())
         return g_x, g_m, g_q, None
+
+
+# ------------------------------------------------------------------------------------------
+# scene-graph encoding layer (csrc/sgenc.cu)
+# ------------------------------------------------------------------------------------------
+class GatherAddAct(torch.autograd.Function):
+    """y = act(a[src] + b[dst] + q): the first Linear of EdgeModel.edge_mlp / NodeModel.node_mlp_1 applied to the
+    concatenation [x[src], x[dst], e] / [x[src], e'] (models/scene_graph_encoder.py:118-120,138-140) with its
+    weight split by column block — a, b [N,D] are the per-NODE projections, q [E,D] the per-edge one (+ bias)."""
+
+    @staticmethod
+    def forward(ctx, a, b, q, gi, act):
+        L.require_cuda(q)
+        a = _c(a) if a is not None else None
+        b = _c(b) if b is not None else None
+        q = _c(q)
+        E, D = q.shape
+        y = torch.empty_like(q)
+        z = torch.empty_like(q) if act != L.ACT_NONE else None
+        L.call("isg_gather_add_act_fwd", L.ptr(a), L.ptr(b), L.ptr(q), L.ptr(gi.edge_index), E, D, act, L.ptr(z),
+               L.ptr(y), L.stream())
+        ctx.gi, ctx.act, ctx.has = gi, act, (a is not None, b is not None)
+        ctx.save_for_backward(z)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (z,) = ctx.saved_tensors
+        gi = ctx.gi
+        gz = gelu_bwd(_c(gy), z) if ctx.act == L.ACT_GELU else _c(gy)
+        D = gz.shape[1]
+        ga = gb = None
+        if ctx.has[0]:  # a was gathered by source: transpose = segment sum over the src-sorted CSR
+            ga = torch.empty(gi.N, D, dtype=torch.float32, device=gz.device)
+            L.call("isg_segment_sum", L.ptr(gz), L.ptr(gi.src_ptr), L.ptr(gi.src_eid), gi.N, D, 0, L.ptr(ga), L.stream())
+        if ctx.has[1]:
+            gb = torch.empty(gi.N, D, dtype=torch.float32, device=gz.device)
+            L.call("isg_segment_sum", L.ptr(gz), L.ptr(gi.dst_ptr), L.ptr(gi.dst_eid), gi.N, D, 0, L.ptr(gb), L.stream())
+        return ga, gb, gz, None, None
+
+
+class SegmentMeanByDst(torch.autograd.Function):
+    """torch_scatter.scatter_mean(m, col, dim=0, dim_size=N) (models/scene_graph_encoder.py:141) over the
+    dst-sorted CSR: deterministic, no atomics."""
+
+    @staticmethod
+    def forward(ctx, m, gi):
+        m = _c(m)
+        out = torch.empty(gi.N, m.shape[1], dtype=torch.float32, device=m.device)
+        L.call("isg_segment_sum", L.ptr(m), L.ptr(gi.dst_ptr), L.ptr(gi.dst_eid), gi.N, m.shape[1], 1, L.ptr(out),
+               L.stream())
+        ctx.gi = gi
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gi = ctx.gi
+        g = _c(g)
+        gm = torch.empty(gi.E, g.shape[1], dtype=torch.float32, device=g.device)
+        L.call("isg_gather_rows", L.ptr(g), gi.edge_index.data_ptr() + 8 * gi.E, L.ptr(gi.dst_ptr), gi.E, g.shape[1],
+               L.ptr(gm), L.stream())
+        return gm, None
+
+
+class GraphNorm64(torch.autograd.Function):
+    """GraphNorm evaluated in float64 on the device (models/scene_graph_encoder.py:99-102 does it through a CPU
+    DoubleTensor round trip every forward)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mean_scale, gi, eps):
+        x = _c(x)
+        N, D = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(gi.B, D, dtype=torch.float64, device=x.device)
+        rstd = torch.empty(gi.B, D, dtype=torch.float64, device=x.device)
+        L.call("isg_graphnorm64_fwd", L.ptr(x), L.ptr(weight), L.ptr(bias), L.ptr(mean_scale), L.ptr(gi.graph_ptr),
+               gi.B, D, float(eps), L.ptr(y), L.ptr(mean), L.ptr(rstd), L.stream())
+        ctx.gi = gi
+        ctx.save_for_backward(x, weight, mean_scale, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, mean_scale, mean, rstd = ctx.saved_tensors
+        gi = ctx.gi
+        g = _c(g)
+        D = x.shape[1]
+        gx = torch.empty_like(x)
+        parts = torch.empty(3, gi.B, D, dtype=torch.float32, device=x.device)
+        L.call("isg_graphnorm64_bwd", L.ptr(g), L.ptr(x), L.ptr(weight), L.ptr(mean_scale), L.ptr(mean), L.ptr(rstd),
+               L.ptr(gi.graph_ptr), gi.B, D, L.ptr(gx), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(parts[2]), L.stream())
+        return gx, colsum(parts[0]), colsum(parts[1]), colsum(parts[2]), None, None

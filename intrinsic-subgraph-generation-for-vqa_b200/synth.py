@@ -141,3 +141,27 @@ def make_state_dict(channels=300, heads=4, num_ins=4, seed=3407):
                 t = t + 1.0
         sd[k] = t
     return sd
+
+
+def sgenc_param_shapes(nf=300, ef=300, hd=300):
+    """state_dict layout of the reference's scene-graph encoding MetaLayer (models/scene_graph_encoder.py:107-146)."""
+    return {
+        "edge_model.edge_mlp.0.weight": (hd, 2 * nf + ef), "edge_model.edge_mlp.0.bias": (hd,),
+        "edge_model.edge_mlp.2.weight": (hd, hd), "edge_model.edge_mlp.2.bias": (hd,),
+        "node_model.node_mlp_1.0.weight": (hd, nf + hd), "node_model.node_mlp_1.0.bias": (hd,),
+        "node_model.node_mlp_1.2.weight": (hd, hd), "node_model.node_mlp_1.2.bias": (hd,),
+        "node_model.node_mlp_2.0.weight": (hd, nf + hd), "node_model.node_mlp_2.0.bias": (hd,),
+        "node_model.node_mlp_2.2.weight": (hd, hd), "node_model.node_mlp_2.2.bias": (hd,),
+    }
+
+
+def make_sgenc_state_dict(nf=300, ef=300, hd=300, seed=3407):
+    """Deterministic weights for the MetaLayer (torch.nn.Linear-style scale) + a GraphNorm (weight, bias, mean_scale)."""
+    g = torch.Generator().manual_seed(seed + 2)
+    sd = {}
+    for k, s in sgenc_param_shapes(nf, ef, hd).items():
+        a = 1.0 / (s[-1] ** 0.5) if len(s) == 2 else 0.05
+        sd[k] = (torch.rand(s, generator=g) * 2 - 1) * a
+    gn = {"weight": 1.0 + 0.1 * torch.randn(hd, generator=g), "bias": 0.1 * torch.randn(hd, generator=g),
+          "mean_scale": 1.0 + 0.1 * torch.randn(hd, generator=g)}
+    return sd, gn

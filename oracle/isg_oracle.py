@@ -186,6 +186,41 @@ def graph_norm(x, batch, weight, bias, mean_scale, num_graphs, eps=1e-5):
 
 
 # --------------------------------------------------------------------------------------
+# the scene-graph encoding layer in front of MGAT
+# --------------------------------------------------------------------------------------
+
+
+def scene_graph_meta_layer(x, edge_index, edge_attr, p):
+    """models/scene_graph_encoder.py:107-146 — torch_geometric.nn.MetaLayer(EdgeModel, NodeModel) with u=None:
+      e'  = edge_mlp(cat[x[src], x[dst], e])                       (:118-120; Linear(900,300) GELU Linear(300,300))
+      m   = node_mlp_1(cat[x[src], e'])                             (:138-140; Linear(600,300) GELU Linear(300,300))
+      agg = scatter_mean(m, dst, dim_size=N)                        (:141)
+      x'  = node_mlp_2(cat[x, agg])                                 (:142-143)
+    `p` maps the reference's state_dict keys (edge_model.edge_mlp.0.weight, ...) to tensors.  -> (x', e')."""
+    src, dst = edge_index[0], edge_index[1]
+    N = x.size(0)
+
+    def mlp(prefix, t):
+        t = F.linear(t, p[prefix + ".0.weight"], p[prefix + ".0.bias"])
+        return F.linear(F.gelu(t), p[prefix + ".2.weight"], p[prefix + ".2.bias"])
+
+    e2 = mlp("edge_model.edge_mlp", torch.cat([x[src], x[dst], edge_attr], 1))
+    m = mlp("node_model.node_mlp_1", torch.cat([x[src], e2], 1))
+    cnt = torch.bincount(dst, minlength=N).clamp(min=1).to(x.dtype).unsqueeze(-1)
+    agg = _seg_sum(m, dst, N) / cnt
+    x2 = mlp("node_model.node_mlp_2", torch.cat([x, agg], 1))
+    return x2, e2
+
+
+def scene_graph_encode(x, edge_index, edge_attr, batch, p, gn_weight, gn_bias, gn_mean_scale, num_graphs):
+    """models/scene_graph_encoder.py:91-104 — MetaLayer, then GraphNorm evaluated in float64 (the reference moves
+    x to the CPU as a DoubleTensor, normalises there and casts back, :99-102).  -> (x_encoded, edge_attr_encoded)."""
+    x2, e2 = scene_graph_meta_layer(x, edge_index, edge_attr, p)
+    y = graph_norm(x2.double(), batch, gn_weight, gn_bias, gn_mean_scale, num_graphs)  # fp32 params promote
+    return y.to(x2.dtype), e2
+
+
+# --------------------------------------------------------------------------------------
 # gate logits theta (MaskingModel.forward up to the sampler)
 # --------------------------------------------------------------------------------------
 

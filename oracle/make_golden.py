@@ -119,8 +119,46 @@ def run_reference(sampler, train, C, B, mn, me, k, seed, aimle_steps=1):
     return outs
 
 
+SGENC_CASES = [("sgenc_c300", 300, 6, 9, 40, 2024), ("sgenc_c64", 64, 9, 14, 90, 2025)]
+
+
+def run_reference_sgenc(C, B, mn, me, seed):
+    """the reference's own MetaLayer (get_gt_scene_graph_encoding_layer) followed by the
+    float64 GraphNorm of SceneGraphEncoder.forward (models/scene_graph_encoder.py:91-104)."""
+    with rl.scratch_cwd():
+        layer = rl.load_scene_graph_encoding_layer(C, C, C)
+    import torch_geometric
+
+    sd, gnp = synth.make_sgenc_state_dict(C, C, C, seed)
+    layer.load_state_dict(sd)
+    gn = torch_geometric.nn.norm.GraphNorm(C)
+    gn.load_state_dict(gnp)
+    b = synth.make_batch(B, channels=C, mean_nodes=mn, mean_edges=me, seed=seed)
+    x = b["x"].clone().requires_grad_(True)
+    ea = b["edge_attr"].clone().requires_grad_(True)
+    xe, ee, _ = layer(x=x, edge_index=b["edge_index"], edge_attr=ea, u=None, batch=b["batch"])
+    save = xe.dtype
+    xn = gn(xe.type(torch.DoubleTensor), b["batch"]).type(save)
+    w1 = torch.sin(torch.arange(xn.numel(), dtype=torch.float32)).view_as(xn)
+    w2 = torch.cos(torch.arange(ee.numel(), dtype=torch.float32)).view_as(ee)
+    ((xn * w1).sum() / xn.shape[0] + (ee * w2).sum() / ee.shape[0]).backward()
+    pg = {k: (p.grad.clone() if p.numel() <= 4096 else digest(p.grad)) for k, p in layer.named_parameters()}
+    pg.update({"graph_layer_norm." + k: p.grad.clone() for k, p in gn.named_parameters()})
+    return dict(x_encoded=xn.detach().clone(), edge_attr_encoded=ee.detach().clone(), gx=x.grad.clone(),
+                g_edge_attr=ea.grad.clone(), param_grads=pg)
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only0 = set(sys.argv[1:])
+    for name, C, B, mn, me, seed in SGENC_CASES:
+        if only0 and name not in only0:
+            continue
+        out = run_reference_sgenc(C, B, mn, me, seed)
+        path = os.path.join(GOLDEN_DIR, name + ".pt")
+        torch.save(dict(config=dict(kind="sgenc", channels=C, num_graphs=B, mean_nodes=mn, mean_edges=me, seed=seed),
+                        out=out, generator="oracle/make_golden.py", torch=torch.__version__), path)
+        print(name, tuple(out["x_encoded"].shape), os.path.getsize(path) // 1024, "KiB")
     with rl.scratch_cwd():
         rl.load()
     only = set(sys.argv[1:])

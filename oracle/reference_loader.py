@@ -139,3 +139,26 @@ def inject_device_gumbel(g):
     finally:
         torch.distributions.gumbel.Gumbel.sample = orig_sample
         simple_mod.gumbel_keys = orig_keys
+
+
+def load_scene_graph_encoding_layer(num_node_features=300, num_edge_features=300, hidden_dim=300):
+    """The reference's MetaLayer (models/scene_graph_encoder.py:107-146), built by its own factory function.
+    Harness patch (not an edit of the reference): models/scene_graph_encoder.py:5 imports
+    ..datasets.scene_graph.GQASceneGraphs at module level, which needs torchtext / GloVe / the GQA JSON files;
+    a stub module is registered under that name first — the factory function never touches it."""
+    import types
+
+    load()
+    name = "ISubGVQA.datasets.scene_graph"
+    if name not in sys.modules:
+        pkg = sys.modules.get("ISubGVQA.datasets")
+        if pkg is None:
+            pkg = types.ModuleType("ISubGVQA.datasets")
+            pkg.__path__ = []
+            sys.modules["ISubGVQA.datasets"] = pkg
+        stub = types.ModuleType(name)
+        stub.GQASceneGraphs = type("GQASceneGraphs", (), {})
+        sys.modules[name] = stub
+    from ISubGVQA.models.scene_graph_encoder import get_gt_scene_graph_encoding_layer
+
+    return get_gt_scene_graph_encoding_layer(num_node_features, num_edge_features, hidden_dim)

@@ -27,3 +27,34 @@ class TopKPooling(torch.nn.Module):
 
     def reset_parameters(self):
         self.select.reset_parameters()
+
+
+class MetaLayer(torch.nn.Module):
+    """torch_geometric.nn.MetaLayer (PyG 2.6.1) as used by models/scene_graph_encoder.py:145:
+        row, col = edge_index
+        edge_attr = edge_model(x[row], x[col], edge_attr, u, batch[row])      (if edge_model)
+        x = node_model(x, edge_index, edge_attr, u, batch)                    (if node_model)
+        u = global_model(x, edge_index, edge_attr, u, batch)                  (if global_model)
+        return x, edge_attr, u"""
+
+    def __init__(self, edge_model=None, node_model=None, global_model=None):
+        super().__init__()
+        self.edge_model = edge_model
+        self.node_model = node_model
+        self.global_model = global_model
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for item in (self.node_model, self.edge_model, self.global_model):
+            if hasattr(item, "reset_parameters"):
+                item.reset_parameters()
+
+    def forward(self, x, edge_index, edge_attr=None, u=None, batch=None):
+        row, col = edge_index[0], edge_index[1]
+        if self.edge_model is not None:
+            edge_attr = self.edge_model(x[row], x[col], edge_attr, u, batch if batch is None else batch[row])
+        if self.node_model is not None:
+            x = self.node_model(x, edge_index, edge_attr, u, batch)
+        if self.global_model is not None:
+            u = self.global_model(x, edge_index, edge_attr, u, batch)
+        return x, edge_attr, u

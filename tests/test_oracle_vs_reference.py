@@ -95,3 +95,44 @@ def test_global_attention_pool_matches_live_reference(golden_mod):
         torch.Tensor.cuda = orig_cuda
     for a, b in zip((o2, g2, x2.grad, u2.grad, m2.grad), want):
         assert util.rel_err(a, b) <= 1e-6
+
+
+def test_scene_graph_encoding_layer_restatement_matches_live_reference():
+    """oracle.scene_graph_encode vs the reference's own MetaLayer (built by
+    get_gt_scene_graph_encoding_layer, models/scene_graph_encoder.py:107-146) followed by the float64 GraphNorm
+    of SceneGraphEncoder.forward (:99-102), values and every gradient."""
+    import isg_oracle as O
+    from isg_b200 import synth
+
+    torch.manual_seed(11)
+    with rl.scratch_cwd():
+        layer = rl.load_scene_graph_encoding_layer(24, 24, 24)
+    import torch_geometric  # the shim (on sys.path once the reference is loaded)
+
+    gn = torch_geometric.nn.norm.GraphNorm(24)
+    with torch.no_grad():
+        gn.weight.uniform_(0.5, 1.5), gn.bias.normal_(0, 0.1), gn.mean_scale.uniform_(0.5, 1.5)
+    b = synth.make_batch(5, channels=24, mean_nodes=8, mean_edges=30, seed=9)
+    x = b["x"].clone().requires_grad_(True)
+    ea = b["edge_attr"].clone().requires_grad_(True)
+    xe, ee, _ = layer(x=x, edge_index=b["edge_index"], edge_attr=ea, u=None, batch=b["batch"])
+    save = xe.dtype
+    xn = gn(xe.type(torch.DoubleTensor), b["batch"]).type(save)  # scene_graph_encoder.py:99-102
+    w1, w2 = torch.randn_like(xn), torch.randn_like(ee)
+    ((xn * w1).sum() + (ee * w2).sum()).backward()
+    ref = dict(xn=xn.detach(), ee=ee.detach(), gx=x.grad.clone(), gea=ea.grad.clone(),
+               params={k: p.grad.clone() for k, p in layer.named_parameters()},
+               gn={k: p.grad.clone() for k, p in gn.named_parameters()})
+
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    g = {k: v.detach().clone().requires_grad_(True) for k, v in gn.state_dict().items()}
+    x2 = b["x"].clone().requires_grad_(True)
+    ea2 = b["edge_attr"].clone().requires_grad_(True)
+    yn, ye = O.scene_graph_encode(x2, b["edge_index"], ea2, b["batch"], p, g["weight"], g["bias"], g["mean_scale"], 5)
+    ((yn * w1).sum() + (ye * w2).sum()).backward()
+    assert util.rel_err(yn, ref["xn"]) <= 1e-6 and util.rel_err(ye, ref["ee"]) <= 1e-6
+    assert util.rel_err(x2.grad, ref["gx"]) <= 1e-5 and util.rel_err(ea2.grad, ref["gea"]) <= 1e-5
+    for k, w in ref["params"].items():
+        assert util.rel_err(p[k].grad, w) <= 1e-5, k
+    for k, w in ref["gn"].items():
+        assert util.rel_err(g[k].grad, w) <= 1e-5, k

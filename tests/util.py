@@ -13,7 +13,64 @@ RTOL = 1e-4  # BASELINE.json north_star: logits, answers and gradients within 1e
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+    """MGAT fixtures (the hot path proper)."""
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")) if not os.path.basename(p).startswith("sgenc_"))
+
+
+def sgenc_golden_files():
+    """Scene-graph encoding layer fixtures."""
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "sgenc_*.pt")))
+
+
+def sgenc_loss(xn, ee):
+    w1 = torch.sin(torch.arange(xn.numel(), dtype=torch.float32, device=xn.device)).view_as(xn)
+    w2 = torch.cos(torch.arange(ee.numel(), dtype=torch.float32, device=ee.device)).view_as(ee)
+    return (xn * w1.to(xn.dtype)).sum() / xn.shape[0] + (ee * w2.to(ee.dtype)).sum() / ee.shape[0]
+
+
+def run_oracle_sgenc(cfg, dtype=torch.float32):
+    import isg_oracle as O
+
+    C, B, seed = cfg["channels"], cfg["num_graphs"], cfg["seed"]
+    sd, gnp = synth.make_sgenc_state_dict(C, C, C, seed)
+    b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
+    p = {k: v.to(dtype).requires_grad_(True) for k, v in sd.items()}
+    g = {k: v.to(dtype).requires_grad_(True) for k, v in gnp.items()}
+    x = b["x"].to(dtype).requires_grad_(True)
+    ea = b["edge_attr"].to(dtype).requires_grad_(True)
+    xn, ee = O.scene_graph_encode(x, b["edge_index"], ea, b["batch"], p, g["weight"], g["bias"], g["mean_scale"], B)
+    sgenc_loss(xn, ee).backward()
+    pg = {k: v.grad for k, v in p.items()}
+    pg.update({"graph_layer_norm." + k: v.grad for k, v in g.items()})
+    return dict(x_encoded=xn.detach(), edge_attr_encoded=ee.detach(), gx=x.grad, g_edge_attr=ea.grad, param_grads=pg)
+
+
+def run_cuda_sgenc(cfg, device="cuda"):
+    from isg_b200.isubgvqa import GraphNorm64, SceneGraphEncodingLayer, encode_scene_graph
+
+    C, B, seed = cfg["channels"], cfg["num_graphs"], cfg["seed"]
+    sd, gnp = synth.make_sgenc_state_dict(C, C, C, seed)
+    b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
+    layer = SceneGraphEncodingLayer(C, C, C)
+    layer.load_state_dict(sd, strict=True)
+    gn = GraphNorm64(C)
+    gn.load_state_dict(gnp, strict=True)
+    layer.to(device), gn.to(device)
+    x = b["x"].to(device).requires_grad_(True)
+    ea = b["edge_attr"].to(device).requires_grad_(True)
+    xn, ee = encode_scene_graph(layer, gn, x, b["edge_index"].to(device), ea, b["batch"].to(device), B)
+    sgenc_loss(xn, ee).backward()
+    pg = {k: p.grad.detach().cpu() for k, p in layer.named_parameters()}
+    pg.update({"graph_layer_norm." + k: p.grad.detach().cpu() for k, p in gn.named_parameters()})
+    return dict(x_encoded=xn.detach().cpu(), edge_attr_encoded=ee.detach().cpu(), gx=x.grad.cpu(),
+                g_edge_attr=ea.grad.cpu(), param_grads=pg)
+
+
+def compare_sgenc(got, want, rtol=RTOL):
+    for key in ("x_encoded", "edge_attr_encoded", "gx", "g_edge_attr"):
+        assert rel_err(got[key], want[key]) <= rtol, (key, rel_err(got[key], want[key]))
+    for name, w in want["param_grads"].items():
+        check_param_grad(name, got["param_grads"].get(name), w, rtol)
 
 
 def load_golden(path):
