@@ -37,6 +37,7 @@ extern "C" {
 #define ISG_BF16 1
 
 #define ISG_ACT_NONE 0
+#define ISG_OPT_MAX_TENSORS 64 /* tensors per isg_grad_sq_partials / isg_adam_update call (passed by value) */
 #define ISG_ACT_GELU 1 /* exact erf GELU, torch.nn.GELU() default */
 
 int isg_version(void);
@@ -324,6 +325,28 @@ int isg_graphnorm64_fwd(const float* x, const float* weight, const float* bias, 
 int isg_graphnorm64_bwd(const float* g_y, const float* x, const float* weight, const float* mean_scale,
                         const double* mean, const double* rstd, const int32_t* graph_ptr, int64_t num_graphs, int dim,
                         float* g_x, float* gw_part, float* gb_part, float* gms_part, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SURVEY.md section 8 row f4 — optimizer tail of the training step (training/train_epoch.py:111-118:
+ * GradScaler.unscale_ + clip_grad_norm_(max_norm 2.0) + GradScaler.step(torch.optim.Adam) + update) without a
+ * host synchronisation.  Tensors are fp32, passed as arrays of <= ISG_OPT_MAX_TENSORS device pointers per call.
+ *   1. isg_grad_sq_partials  (per group)  partial[off + b] = sum over block b's 4096-element chunk of
+ *                                         (g * inv_scale)^2; *nonfinite |= any inf/nan      (isg_opt_blocks = #b)
+ *   2. isg_clip_finalize     (once)       state[0] = total norm, state[1] = min(1, max_norm / (norm + 1e-6)),
+ *                                         state[2] = found_inf, state[3] += 1 unless found_inf (step counter);
+ *                                         found_inf_out (or NULL) receives state[2] (GradScaler's per-device flag)
+ *   3. isg_adam_update       (per group)  torch.optim.Adam step on g * inv_scale * state[1]; no-op if found_inf.
+ * inv_scale / lr_dev: device scalars or NULL (1.0 / the host `lr`).  `nonfinite` must be zeroed by the caller.
+ * ------------------------------------------------------------------------------------- */
+int isg_opt_max_tensors(void);
+int64_t isg_opt_blocks(const int64_t* numel, int count);
+int isg_grad_sq_partials(const void* const* grads, const int64_t* numel, int count, const float* inv_scale,
+                         double* partial, int partial_off, int32_t* nonfinite, void* stream);
+int isg_clip_finalize(const double* partial, int nparts, const int32_t* nonfinite, float max_norm,
+                      float* state /* [4] */, float* found_inf_out, void* stream);
+int isg_adam_update(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                    const int64_t* numel, int count, const float* inv_scale, const float* state,
+                    const float* lr_dev, float lr, float beta1, float beta2, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Layer executor: one call runs every kernel of one MGAT layer — the body of the loop in MGAT.forward

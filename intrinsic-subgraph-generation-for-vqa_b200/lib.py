@@ -67,6 +67,11 @@ SIGNATURES = {
     "isg_gather_rows": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
     "isg_graphnorm64_fwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I32, ctypes.c_double, _P, _P, _P, _P]),
     "isg_graphnorm64_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "isg_opt_max_tensors": (_I32, []),
+    "isg_opt_blocks": (_I64, [_P, _I32]),
+    "isg_grad_sq_partials": (_I32, [_P, _P, _I32, _P, _P, _I32, _P, _P]),
+    "isg_clip_finalize": (_I32, [_P, _I32, _P, _F, _P, _P, _P]),
+    "isg_adam_update": (_I32, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _F, _F, _F, _F, _P]),
     "isg_layer_slot": (_I32, [ctypes.c_char_p]),
     "isg_layer_slot_count": (_I32, [_I32]),
     "isg_mgat_layer_bwd_workspace_bytes": (_SZ, [_P]),
@@ -101,7 +106,8 @@ KERNELS_PER_CALL = {
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
     "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_transpose_split": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
     "isg_gelu_bwd": 1, "isg_colsum": 2, "isg_gather_add_act_fwd": 1, "isg_segment_sum": 1, "isg_gather_rows": 1,
-    "isg_graphnorm64_fwd": 1, "isg_graphnorm64_bwd": 1,
+    "isg_graphnorm64_fwd": 1, "isg_graphnorm64_bwd": 1, "isg_grad_sq_partials": 1, "isg_clip_finalize": 1,
+    "isg_adam_update": 1,
 }
 launch_count = 0
 _timing = None  # name -> list of (start_event, end_event) when enabled
