@@ -410,15 +410,26 @@ def main_isg(args, rank, world, local_rank):
         # a new batch arrives as new device tensors: its CSR / graph_ptr are built afresh (on the copy stream)
         pending.append(prefetcher.stage(host, extra={"noise": noise_h}, nmax=nmax))
 
+    e2e_prof = {"stage_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0, "n": 0}
+
     def step_e2e():
         # public-API path, every step: pinned host batch -> H2D + CSR build (copy stream, one batch ahead of the
         # compute) -> MGAT fwd+bwd -> loss.item() + mask.cpu().  Each call issues exactly one batch of H2D copies.
+        t0 = time.perf_counter()
         if not pending:
             stage_next()
         t, ext = prefetcher.get(pending.pop(0))
         stage_next()
+        t1 = time.perf_counter()
         loss, mask = step(t, ext["noise"])
-        return float(loss.item()), mask.to("cpu")
+        t2 = time.perf_counter()
+        out = float(loss.item()), mask.to("cpu")
+        t3 = time.perf_counter()
+        e2e_prof["stage_ms"] += 1e3 * (t1 - t0)
+        e2e_prof["enqueue_ms"] += 1e3 * (t2 - t1)
+        e2e_prof["wait_ms"] += 1e3 * (t3 - t2)
+        e2e_prof["n"] += 1
+        return out
 
     def barrier():
         if world > 1:
@@ -521,8 +532,9 @@ def main_isg(args, rank, world, local_rank):
                        kernel_names if not args.breakdown else list(L.KERNELS_PER_CALL))
     tall = tsum
     mgat_mod.set_executor(True)
-    for _ in range(2):
+    for _ in range(3):
         step_e2e()
+    e2e_prof.update(stage_ms=0.0, enqueue_ms=0.0, wait_ms=0.0, n=0)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
     def teardown():
@@ -636,6 +648,8 @@ def main_isg(args, rank, world, local_rank):
                    "optimizer": "not in the timed step (SURVEY.md section 8 f4: isg_b200.optim)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
+                "host_ms_per_step": {k: round(e2e_prof[k] / max(e2e_prof["n"], 1), 3)
+                                     for k in ("stage_ms", "enqueue_ms", "wait_ms")},
                 "what": "pinned host batch -> H2D + CSR build on a copy stream one batch ahead (isg_b200.loader."
                         "DevicePrefetcher) -> MGAT fwd+bwd (eager) -> loss.item() + mask.cpu(), every step"},
         "gpu_launches": launches,

@@ -130,13 +130,18 @@ __global__ void csr_place_kernel(const int64_t* __restrict__ ei, int64_t E, int6
   }
 }
 
-// One thread per segment: ascending insertion sort of the edge ids (segments are node degrees:
-// ~7.5 on GQA graphs, nearly sorted already for the source ordering), then emit the neighbour.
+// One WARP per segment: ascending sort of the edge ids the atomics of csr_place_kernel left in arbitrary order
+// (=> the stable order of the reference's COO), then emit the neighbour.  Segments of <= 32 edges (every node of
+// a GQA graph at ~8 edges per node) are ranked in registers: lane i holds one id and counts the smaller ones with
+// 32 shuffles.  Longer segments (hub nodes, the 200-object sweep points) run a normalised bitonic network in
+// place — every compare-exchange ascending, so the virtual +inf padding beyond the segment end never moves —
+// O(d log^2 d / 32) per warp instead of the O(d^2) single-thread insertion sort this replaces.
 __global__ void csr_sort_segments_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t N,
                                          const int* __restrict__ dst_ptr, const int* __restrict__ src_ptr,
                                          int* __restrict__ dst_eid, int* __restrict__ src_eid,
                                          int* __restrict__ dst_nbr, int* __restrict__ src_nbr) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (t >= 2 * N) return;
   const bool by_src = t >= N;
   const int64_t node = by_src ? t - N : t;
@@ -144,17 +149,41 @@ __global__ void csr_sort_segments_kernel(const int64_t* __restrict__ ei, int64_t
   int* eid = by_src ? src_eid : dst_eid;
   int* nbr = by_src ? src_nbr : dst_nbr;
   const int64_t* other = by_src ? ei + E : ei;  // src ordering stores dst, dst ordering stores src
-  const int beg = ptr[node], end = ptr[node + 1];
-  for (int i = beg + 1; i < end; ++i) {
-    const int key = eid[i];
-    int j = i - 1;
-    while (j >= beg && eid[j] > key) {
-      eid[j + 1] = eid[j];
-      --j;
+  const int beg = ptr[node], deg = ptr[node + 1] - beg;
+  if (deg <= 0) return;
+  int* a = eid + beg;
+  if (deg <= 32) {
+    const int key = lane < deg ? a[lane] : 0x7fffffff;
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) rank += (__shfl_sync(ISG_FULL_MASK, key, j) < key) ? 1 : 0;  // ids are distinct
+    __syncwarp();
+    if (lane < deg) {
+      a[rank] = key;
+      nbr[beg + rank] = (int)other[key];
     }
-    eid[j + 1] = key;
+    return;
   }
-  for (int i = beg; i < end; ++i) nbr[i] = (int)other[eid[i]];
+  int n2 = 64;
+  while (n2 < deg) n2 <<= 1;
+  auto cmpswap = [&](int i, int partner) {
+    if (partner > i && partner < deg) {
+      const int x = a[i], y = a[partner];
+      if (x > y) {
+        a[i] = y;
+        a[partner] = x;
+      }
+    }
+  };
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int i = lane; i < deg; i += 32) cmpswap(i, i ^ (k - 1));
+    __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int i = lane; i < deg; i += 32) cmpswap(i, i ^ j);
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < deg; i += 32) nbr[beg + i] = (int)other[a[i]];
 }
 
 __global__ void graph_ptr_kernel(const int64_t* __restrict__ batch, int64_t N, int64_t B,
@@ -224,7 +253,7 @@ extern "C" int isg_csr_build(const int64_t* edge_index, int64_t E, int64_t N, in
     csr_place_kernel<<<eblocks, 256, 0, stream>>>(edge_index, E, N, dst_ptr, src_ptr, cur_dst, cur_src,
                                                   dst_eid, src_eid);
     ISG_CHECK_LAUNCH();
-    csr_sort_segments_kernel<<<isg::ceil_div(2 * N, 128), 128, 0, stream>>>(
+    csr_sort_segments_kernel<<<isg::ceil_div(2 * N * 32, 256), 256, 0, stream>>>(
         edge_index, E, N, dst_ptr, src_ptr, dst_eid, src_eid, dst_nbr, src_nbr);
     ISG_CHECK_LAUNCH();
   }
