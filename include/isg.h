@@ -66,6 +66,14 @@ int isg_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
 /* crossing (1 int32, device) = number of edges whose endpoints lie in different graphs or out of range.
  * PyG batches (datasets/gqa.py:237-272, Batch.from_data_list) never have such edges; 0 is the precondition
  * of the single-launch edge backward (isg_gat_edge_bwd with graph_ptr != NULL). */
+/* Task order of the edge kernels: dst_order / src_order [N] = node ids by DEcreasing in- / out-degree (counting sort
+ * over min(degree, 255); equal-degree nodes in unspecified order).  The edge kernels run one warp per (node, head);
+ * handing them the longest segments first removes the end-of-launch tail (the order never changes any result).
+ * No reference counterpart (PyG has no such schedule). */
+size_t isg_degree_order_workspace_bytes(void);
+int isg_degree_order(const int32_t* dst_ptr, const int32_t* src_ptr, int64_t num_nodes, int32_t* dst_order,
+                     int32_t* src_order, void* workspace, size_t workspace_bytes, void* stream);
+
 int isg_graph_closure(const int64_t* edge_index /* [2,E] */, int64_t num_edges, const int64_t* batch,
                       int64_t num_nodes, int32_t* crossing, void* stream);
 
@@ -78,12 +86,13 @@ int isg_graph_closure(const int64_t* edge_index /* [2,E] */, int64_t num_edges, 
  * x_l / x_r: [N, HC] with row pitch ld_x elements (they may be the two halves of one fused
  * projection); e_proj [E,HC] dense, ORIGINAL edge order; edge_mask [E] fp32 or NULL;
  * out [N,HC] pitch ld_out; alpha [E,H] fp32 in ORIGINAL edge order.
+ * dst_order / src_order [N] (isg_degree_order) or NULL: the order in which the (node, head) tasks are scheduled.
  * ------------------------------------------------------------------------------------- */
 int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj,
                      const float* att /* [H*C] */, const float* bias /* [H*C] or NULL */,
                      const float* edge_mask,
                      const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
-                     void* out, int64_t ld_out, float* alpha,
+                     const int32_t* dst_order /* or NULL */, void* out, int64_t ld_out, float* alpha,
                      int64_t num_nodes, int64_t num_edges, int heads, int channels,
                      float negative_slope, int dtype, void* stream);
 
@@ -103,7 +112,9 @@ int isg_gat_edge_bwd(const void* g_out, int64_t ld_g,
                      const float* att, const float* bias, const float* edge_mask,
                      const float* alpha, const void* out, int64_t ld_out,
                      const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
+                     const int32_t* dst_order /* or NULL */,
                      const int32_t* src_ptr, const int32_t* src_nbr, const int32_t* src_eid,
+                     const int32_t* src_order /* or NULL */,
                      void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj,
                      float* g_att, float* g_edge_mask,
                      int64_t num_nodes, int64_t num_edges, int heads, int channels,
@@ -293,6 +304,12 @@ int isg_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_t n, void* 
 size_t isg_colsum_workspace_bytes(int64_t rows, int cols);
 int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, float* out,
                void* workspace, size_t workspace_bytes, void* stream);
+/* n (<= 12) independent column sums in two launches: out[i][c] = sum_r in[i][r, c].  Bit-identical to n isg_colsum
+ * calls (same slabs, same fold order).  The arrays are host arrays.  Used by isg_mgat_layer_bwd for the bias /
+ * GraphNorm-affine gradients of one layer (models/mgat_v2_conv.py:63-103 biases, models/mgat.py:79-89,163). */
+size_t isg_colsum_multi_workspace_bytes(int n, const int64_t* rows, const int* cols);
+int isg_colsum_multi(int n, const float* const* in, const int64_t* ld, const int64_t* rows, const int* cols,
+                     float* const* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * SURVEY.md section 8 row f2 — scene-graph encoding layer in front of MGAT: torch_geometric MetaLayer(EdgeModel,

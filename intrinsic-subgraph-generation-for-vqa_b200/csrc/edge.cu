@@ -469,8 +469,8 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
                          const float* __restrict__ ep, const float* __restrict__ att,
                          const float* __restrict__ bias, const float* __restrict__ emask,
                          const int* __restrict__ rowptr, const int* __restrict__ nbr,
-                         const int* __restrict__ eid, float* __restrict__ out, int64_t ld_out,
-                         float* __restrict__ alpha, int64_t NH, int H_, int C_, float slope) {
+                         const int* __restrict__ eid, const int* __restrict__ order, float* __restrict__ out,
+                         int64_t ld_out, float* __restrict__ alpha, int64_t NH, int H_, int C_, float slope) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -489,8 +489,9 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
   int cur_head = -1;
 
   for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
-    const int64_t node = wid / H;
-    const int head = (int)(wid - node * H);
+    const int64_t slot = wid / H;
+    const int head = (int)(wid - slot * H);
+    const int64_t node = order ? order[slot] : slot;  // longest segments first (isg_degree_order)
     const int hoff = head * C;
     if (head != cur_head) {
       for (int v = lane; v < c4; v += 32) sts_f4(att_s + 16u * v, Vec4<float>::ld(att + hoff + 4 * v));
@@ -627,15 +628,19 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
                              const float* __restrict__ xr, int64_t ld_x, const float* __restrict__ ep,
                              const float* __restrict__ att, const float* __restrict__ emask,
                              const float* __restrict__ alpha, const int* __restrict__ rowptr,
-                             const int* __restrict__ nbr, const int* __restrict__ eid, float* __restrict__ g_xr,
-                             int64_t ld_gx, float* __restrict__ g_ep, float* __restrict__ gatt_part,
-                             float* __restrict__ gm_h, int64_t N, int H_, int C_, float slope, int K) {
+                             const int* __restrict__ nbr, const int* __restrict__ eid,
+                             const int* __restrict__ order, float* __restrict__ g_xr, int64_t ld_gx,
+                             float* __restrict__ g_ep, float* __restrict__ gatt_part, float* __restrict__ gm_h,
+                             int64_t N, int H_, int C_, float slope, int K) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t wid0 = (int64_t)blockIdx.x * EDGE_WARPS + warp;  // gridDim.x*EDGE_WARPS is a multiple of H
   const int head = (int)(wid0 % H);
-  const int64_t col = wid0 / H;
+  int64_t col = wid0 / H;
+  // K == 1 (one node per column): columns are taken in the order of isg_degree_order, longest segment first; the
+  // g_att partial row stays keyed by the NODE, so the fixed-order fold below does not depend on that order
+  if (order != nullptr && K == 1 && col < N) col = order[col];
   const int c4 = C >> 2;
   const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
   const int64_t HC = (int64_t)H * C;
@@ -838,7 +843,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
     for (int k = 0; k < VPL; ++k)
       if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(grow + 4 * (lane + 32 * k), gxr[k]);
   }
-  float* prow = gatt_part + wid0 * C;
+  float* prow = gatt_part + (col * H + head) * C;
 #pragma unroll
   for (int k = 0; k < VPL; ++k)
     if (col_active<VPL, CT>(k, lane, c4)) Vec4<float>::st(prow + 4 * (lane + 32 * k), gatt[k]);
@@ -896,8 +901,8 @@ __global__ void __launch_bounds__(EDGE_WARPS * 32, 7)
 gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const float* __restrict__ g_ep,
                              const float* __restrict__ emask, const float* __restrict__ alpha,
                              const int* __restrict__ colptr, const int* __restrict__ nbr,
-                             const int* __restrict__ eid, float* __restrict__ g_xl, int64_t ld_gx, int64_t NH,
-                             int H_, int C_) {
+                             const int* __restrict__ eid, const int* __restrict__ order, float* __restrict__ g_xl,
+                             int64_t ld_gx, int64_t NH, int H_, int C_) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -912,8 +917,9 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
   const bool leader = warp_elect_one();
 
   for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
-    const int64_t node = wid / H;
-    const int head = (int)(wid - node * H);
+    const int64_t slot = wid / H;
+    const int head = (int)(wid - slot * H);
+    const int64_t node = order ? order[slot] : slot;  // longest segments first (isg_degree_order)
     const int hoff = head * C;
     float4 acc[VPL];
 #pragma unroll
@@ -1349,8 +1355,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 template <int VPL, bool MASKED>
 int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj, const float* att,
                     const float* bias, const float* emask, const int* dst_ptr, const int* dst_nbr,
-                    const int* dst_eid, void* out, int64_t ld_out, float* alpha, int64_t N, int H, int C,
-                    float slope, cudaStream_t stream) {
+                    const int* dst_eid, const int* dst_order, void* out, int64_t ld_out, float* alpha, int64_t N,
+                    int H, int C, float slope, cudaStream_t stream) {
   const int64_t NH = N * H;
   const size_t smem = ring_smem_bytes(C, 2, 1);
   // the reference shape (C = 300, H = 4) runs the build with C and H as compile-time constants
@@ -1363,7 +1369,7 @@ int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* 
   const int64_t blocks = ceil_div(NH, (int64_t)EDGE_WARPS);
   kern<<<(unsigned)blocks, EDGE_WARPS * 32, smem, stream>>>(
       (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, bias, emask, dst_ptr, dst_nbr,
-      dst_eid, (float*)out, ld_out, alpha, NH, H, C, slope);
+      dst_eid, dst_order, (float*)out, ld_out, alpha, NH, H, C, slope);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -1371,10 +1377,11 @@ int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* 
 template <int VPL, bool MASKED>
 int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r, int64_t ld_x,
                     const void* e_proj, const float* att, const float* emask, const float* alpha,
-                    const int* dst_ptr, const int* dst_nbr, const int* dst_eid, const int* src_ptr,
-                    const int* src_nbr, const int* src_eid, void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj,
-                    float* g_att, float* g_emask, int64_t N, int64_t E, int H, int C, float slope,
-                    float* gatt_part, float* gatt_part2, float* gm_h, const BwdRingPlan& plan, cudaStream_t stream) {
+                    const int* dst_ptr, const int* dst_nbr, const int* dst_eid, const int* dst_order,
+                    const int* src_ptr, const int* src_nbr, const int* src_eid, const int* src_order, void* g_xl,
+                    void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att, float* g_emask, int64_t N, int64_t E,
+                    int H, int C, float slope, float* gatt_part, float* gatt_part2, float* gm_h,
+                    const BwdRingPlan& plan, cudaStream_t stream) {
   const size_t smem_d = ring_smem_bytes(C, 2, 1), smem_s = ring_smem_bytes(C, 0, 0);
   const bool ref_shape = VPL == 3 && C == 300 && H == 4;
   auto kd = ref_shape ? gat_edge_bwd_dst_ring_kernel<VPL, MASKED, VPL == 3 ? 300 : 0, VPL == 3 ? 4 : 0>
@@ -1386,7 +1393,8 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
   if (e != cudaSuccess) return (int)e;
   kd<<<(unsigned)plan.blocks, EDGE_WARPS * 32, smem_d, stream>>>(
       (const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, emask, alpha,
-      dst_ptr, dst_nbr, dst_eid, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H, C, slope, plan.K);
+      dst_ptr, dst_nbr, dst_eid, dst_order, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H, C, slope,
+      plan.K);
   ISG_CHECK_LAUNCH();
   const int HC = H * C;
   const int64_t rows = plan.warps / H;
@@ -1398,8 +1406,8 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
   ISG_CHECK_LAUNCH();
   const int64_t NH = N * H;
   ks<<<(unsigned)ceil_div(NH, (int64_t)EDGE_WARPS), EDGE_WARPS * 32, smem_s, stream>>>(
-      (const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, (float*)g_xl, ld_gx,
-      NH, H, C);
+      (const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, src_order,
+      (float*)g_xl, ld_gx, NH, H, C);
   ISG_CHECK_LAUNCH();
   if (MASKED && E > 0) {
     gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
@@ -1509,8 +1517,8 @@ inline int vpl_for(int C) { return (C / 4 + 31) / 32; }
 extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj,
                                 const float* att, const float* bias, const float* edge_mask,
                                 const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
-                                void* out, int64_t ld_out, float* alpha, int64_t N, int64_t E, int H, int C,
-                                float slope, int dtype, void* stream_) {
+                                const int32_t* dst_order, void* out, int64_t ld_out, float* alpha, int64_t N,
+                                int64_t E, int H, int C, float slope, int dtype, void* stream_) {
   if (N < 0 || E < 0 || H <= 0 || C <= 0) return ISG_EINVAL;
   if (C % 4 != 0 || C > 512 || ld_x % 4 != 0 || ld_out % 4 != 0) return ISG_EUNSUPPORTED;
   if (!(slope >= 0.f && slope <= 1.f)) return ISG_EUNSUPPORTED;  // leaky_relu evaluated as max(u, slope*u)
@@ -1525,9 +1533,9 @@ extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, 
   if (dtype == ISG_F32) {
 #define ISG_FWD_RING(V)                                                                                  \
   return edge_mask ? launch_fwd_ring<V, true>(x_l, x_r, ld_x, e_proj, att, bias, edge_mask, dst_ptr, dst_nbr, \
-                                              dst_eid, out, ld_out, alpha, N, H, C, slope, stream)       \
+                                              dst_eid, dst_order, out, ld_out, alpha, N, H, C, slope, stream) \
                    : launch_fwd_ring<V, false>(x_l, x_r, ld_x, e_proj, att, bias, edge_mask, dst_ptr, dst_nbr, \
-                                               dst_eid, out, ld_out, alpha, N, H, C, slope, stream)
+                                               dst_eid, dst_order, out, ld_out, alpha, N, H, C, slope, stream)
     if (((uintptr_t)x_l & 15) || ((uintptr_t)x_r & 15) || ((uintptr_t)e_proj & 15)) return ISG_EUNSUPPORTED;
     switch (vpl) {
       case 1: ISG_FWD_RING(1);
@@ -1571,7 +1579,8 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
                                 int64_t ld_x, const void* e_proj, const float* att, const float* bias,
                                 const float* edge_mask, const float* alpha, const void* out, int64_t ld_out,
                                 const int32_t* dst_ptr, const int32_t* dst_nbr, const int32_t* dst_eid,
-                                const int32_t* src_ptr, const int32_t* src_nbr, const int32_t* src_eid,
+                                const int32_t* dst_order, const int32_t* src_ptr, const int32_t* src_nbr,
+                                const int32_t* src_eid, const int32_t* src_order,
                                 void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att,
                                 float* g_edge_mask, int64_t N, int64_t E, int H, int C, float slope, int dtype,
                                 const int32_t* batch32, const int32_t* graph_ptr, int64_t B, int nmax,
@@ -1609,13 +1618,13 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
   if (dtype == ISG_F32) {
 #define ISG_BWD_RING(V)                                                                                        \
   return edge_mask ? launch_bwd_ring<V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,     \
-                                              dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,     \
-                                              g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,    \
-                                              rp_part, rp_part2, rp_gmh, rplan, stream)                      \
+                                              dst_ptr, dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, \
+                                              src_order, g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, \
+                                              H, C, slope, rp_part, rp_part2, rp_gmh, rplan, stream)          \
                    : launch_bwd_ring<V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,    \
-                                               dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, g_xl,    \
-                                               g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,   \
-                                               rp_part, rp_part2, rp_gmh, rplan, stream)
+                                               dst_ptr, dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, \
+                                               src_order, g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, \
+                                               H, C, slope, rp_part, rp_part2, rp_gmh, rplan, stream)
     if (((uintptr_t)x_l & 15) || ((uintptr_t)g_out & 15) || ((uintptr_t)e_proj & 15) || ((uintptr_t)g_eproj & 15))
       return ISG_EUNSUPPORTED;
     if (batch32 && graph_ptr && nmax > 0 && B > 0) {

@@ -31,7 +31,7 @@
 #define ISG_LAYER_PTRS(X)                                                                                      \
   /* graph index */                                                                                            \
   X(P_DST_PTR) X(P_DST_NBR) X(P_DST_EID) X(P_SRC_PTR) X(P_SRC_NBR) X(P_SRC_EID) X(P_GRAPH_PTR) X(P_BATCH32)      \
-  X(P_EDGE_INDEX)                                                                                              \
+  X(P_EDGE_INDEX) X(P_DST_ORDER) X(P_SRC_ORDER)                                                                  \
   /* inputs */                                                                                                 \
   X(P_X_IN) X(P_INS) X(P_GLF) X(P_EDGE_ATTR) X(P_NOISE) X(P_KEEP)                                                \
   /* parameters */                                                                                             \
@@ -99,8 +99,11 @@ BwdWs bwd_ws(const int64_t* d) {
   w.g_xn = take((size_t)N * D * 4);
   w.g_q = take((size_t)B * D * 4);
   w.scratch = take((size_t)N * 4);
-  w.colsum_bytes = max2(max2(isg_colsum_workspace_bytes(N, 2 * HC), isg_colsum_workspace_bytes(N, HID)),
-                        max2(isg_colsum_workspace_bytes(B, D), isg_colsum_workspace_bytes(N, D)));
+  {  // all column sums of the layer run as ONE batched call at the end of the backward (isg_colsum_multi)
+    const int64_t rows[9] = {B, B, B, N, N, N, N, N, B};
+    const int cols[9] = {D, D, D, D, HID, HC, 2 * HC, D, D};
+    w.colsum_bytes = isg_colsum_multi_workspace_bytes(9, rows, cols);
+  }
   w.colsum = take(w.colsum_bytes);
   w.wgrad_bytes = max2(max2(isg_linear_wgrad_workspace_bytes(E, HC, D), isg_linear_wgrad_workspace_bytes(N, 2 * HC, D)),
                        max2(max2(isg_linear_wgrad_workspace_bytes(N, HID, HC), isg_linear_wgrad_workspace_bytes(N, D, HID)),
@@ -210,7 +213,8 @@ extern "C" int isg_mgat_layer_fwd(const int64_t* d, const double* f, void* const
                       ISG_ACT_NONE, mode, ISG_F32, stream));  // :259
   CK(isg_gat_edge_fwd(xlr, xlr + HC, 2 * HC, p[P_EPROJ], ptr<const float>(p, P_ATT), ptr<const float>(p, P_BIAS), emask,
                       ptr<const int32_t>(p, P_DST_PTR), ptr<const int32_t>(p, P_DST_NBR),
-                      ptr<const int32_t>(p, P_DST_EID), p[P_OUT], HC, ptr<float>(p, P_ALPHA), N, E, H, D,
+                      ptr<const int32_t>(p, P_DST_EID), ptr<const int32_t>(p, P_DST_ORDER), p[P_OUT], HC,
+                      ptr<float>(p, P_ALPHA), N, E, H, D,
                       (float)f[F_SLOPE], ISG_F32, stream));  // :215,243-279
   // mgat.py:156 x_proj = Linear(HC, HID) GELU Linear(HID, D) GELU
   CK(isg_linear_fwd(p[P_OUT], HC, p[P_WP0], nullptr, nullptr, ptr<const float>(p, P_BP0), p[P_Y1], HID, p[P_Z1], HID, N,
@@ -252,8 +256,20 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
   const float* ins = ptr<const float>(p, P_INS);
   const float* g_h_out = ptr<const float>(p, P_G_H_OUT);
   const bool masked = d[D_MASKED] != 0;
+  // bias / affine gradients are column sums of tensors this backward leaves in its workspace: they are collected
+  // here and issued as one batched call (two launches) after the last producer
+  const float* cs_in[9];
+  float* cs_out[9];
+  int64_t cs_ld[9], cs_rows[9];
+  int cs_cols[9], cs_n = 0;
   auto colsum = [&](const float* t, int64_t rows, int cols, int slot) -> int {
-    return isg_colsum(t, cols, rows, cols, ptr<float>(p, slot), cs, w.colsum_bytes, stream_);
+    cs_in[cs_n] = t;
+    cs_out[cs_n] = ptr<float>(p, slot);
+    cs_ld[cs_n] = cols;
+    cs_rows[cs_n] = rows;
+    cs_cols[cs_n] = cols;
+    ++cs_n;
+    return ISG_OK;
   };
 
   // scatter-SDPA + GraphNorm + residual (mgat.py:168-172); the residual's share of g_h_in is added in the last step
@@ -283,8 +299,9 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
                       ptr<const float>(p, P_BIAS), masked ? ptr<const float>(p, P_EMASK) : nullptr,
                       ptr<const float>(p, P_ALPHA), p[P_OUT], HC, ptr<const int32_t>(p, P_DST_PTR),
                       ptr<const int32_t>(p, P_DST_NBR), ptr<const int32_t>(p, P_DST_EID),
-                      ptr<const int32_t>(p, P_SRC_PTR), ptr<const int32_t>(p, P_SRC_NBR),
-                      ptr<const int32_t>(p, P_SRC_EID), g_xlr, g_xlr + HC, 2 * HC, g_ep, ptr<float>(p, P_G_ATT),
+                      ptr<const int32_t>(p, P_DST_ORDER), ptr<const int32_t>(p, P_SRC_PTR),
+                      ptr<const int32_t>(p, P_SRC_NBR), ptr<const int32_t>(p, P_SRC_EID),
+                      ptr<const int32_t>(p, P_SRC_ORDER), g_xlr, g_xlr + HC, 2 * HC, g_ep, ptr<float>(p, P_G_ATT),
                       masked ? g_em : nullptr, N, E, H, D, (float)f[F_SLOPE], ISG_F32, fused ? batch32 : nullptr,
                       fused ? gptr : nullptr, B, fused ? nmax : 0, ws + w.edge, w.edge_bytes, stream_));
   CK(colsum(g_out, N, HC, P_G_BIAS));
@@ -347,6 +364,7 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
                         stream_));
     CK(colsum(g_q, B, D, P_G_BQ));
   }
+  CK(isg_colsum_multi(cs_n, cs_in, cs_ld, cs_rows, cs_cols, cs_out, cs, w.colsum_bytes, stream_));
   // gating + residual: g_x_in = g_xg * d gelu(x*ins)/dx + g_h_out;  g_ins += ...
   CK(isg_instr_gate_bwd(g_xg, ptr<const float>(p, P_X_IN), ins, gptr, B, D, g_h_out, 1, ptr<float>(p, P_G_X_IN),
                         ptr<float>(p, P_G_INS), stream_));

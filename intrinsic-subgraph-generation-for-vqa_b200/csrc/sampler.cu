@@ -318,11 +318,12 @@ gumbel_topk_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s
 
 // ---- fused forward (IMLE / AIMLE): gate logit -> dropout -> + tau*noise -> per-graph top-k -> node mask ->
 // edge mask, ONE launch (SURVEY.md §8d "fused variant"; reference: models/masking.py:151-176 followed by
-// mgat_v2_conv.py:166-171 / sampling/node_edge_masks.py:5-12).  One warp per graph: the logits of the graph's
-// nodes are warp dot products <xn[n], q[batch[batch[n]]]> in exactly the order of gate_theta_fwd_kernel
+// mgat_v2_conv.py:166-171 / sampling/node_edge_masks.py:5-12).  One CTA per graph: the logits of the graph's
+// nodes are warp dot products (one warp per node row) <xn[n], q[batch[batch[n]]]> in exactly the order of gate_theta_fwd_kernel
 // (segment.cu), so theta — and hence the mask — is bit-identical to the unfused kernels; the graph's mask stays
 // in shared memory for the edge-mask pass over the graph's in-edges (needs every edge inside one graph).
-__global__ void __launch_bounds__(SAMP_WARPS * 32)
+constexpr int FUSED_WARPS = 8;  // one CTA per graph: the gate dot products (one warp per node row) dominate
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
 sampler_fused_fwd_kernel(const float* __restrict__ xn, const float* __restrict__ q, const float* __restrict__ keep,
                          const float* __restrict__ noise, const int* __restrict__ batch, const int* __restrict__ gptr,
                          const int* __restrict__ dst_ptr, const int* __restrict__ dst_nbr,
@@ -331,13 +332,12 @@ sampler_fused_fwd_kernel(const float* __restrict__ xn, const float* __restrict__
                          float* __restrict__ emask) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b = (int64_t)blockIdx.x * SAMP_WARPS + warp;
-  if (b >= B) return;
-  float* orig = smem + (size_t)warp * 2 * nmax;
+  const int64_t b = blockIdx.x;
+  float* orig = smem;
   float* work = orig + nmax;
   const int n0 = gptr[b], nb = gptr[b + 1] - n0;
   const float rs = sqrtf((float)D);
-  for (int i = 0; i < nb; ++i) {
+  for (int i = warp; i < nb; i += FUSED_WARPS) {  // same per-row arithmetic order as gate_theta_fwd_kernel
     const int n = n0 + i;
     const int qi = dbl ? batch[batch[n]] : batch[n];  // quirk Q1: double gather (see gate_theta_fwd_kernel)
     const float* xr = xn + (int64_t)n * D;
@@ -352,28 +352,35 @@ sampler_fused_fwd_kernel(const float* __restrict__ xn, const float* __restrict__
       orig[i] = th;
     }
   }
-  __syncwarp();
-  for (int i = lane; i < nmax; i += 32) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < nmax; i += FUSED_WARPS * 32) {
     const float th = (i < nb) ? orig[i] : 0.f;
     const float nz = noise ? noise[b * nmax + i] : 0.f;
     const float sc = __fadd_rn(th, __fmul_rn(nz, tau));
     orig[i] = sc;
     work[i] = sc;
   }
-  __syncwarp();
+  __syncthreads();
   const bool all = k >= nmax;
-  const float thr = all ? 0.f : kth_largest_warp(work, nmax, k, lane);
-  for (int i = lane; i < nmax; i += 32) {
+  if (warp == 0 && !all) {
+    const float t = kth_largest_warp(work, nmax, k, lane);
+    __syncwarp();
+    if (lane == 0) work[0] = t;  // work[] is dead after the selection: slot 0 carries the threshold
+  }
+  __syncthreads();
+  const float thr = all ? 0.f : work[0];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nmax; i += FUSED_WARPS * 32) {
     const float z = (all || orig[i] >= thr) ? 1.f : 0.f;
     zd[b * nmax + i] = z;
     work[i] = z;
     if (i < nb) mask[n0 + i] = z;
   }
-  __syncwarp();
+  __syncthreads();
   if (emask != nullptr && nb > 0) {  // edge_mask[e] = mask[src] * mask[dst] over the in-edges of the graph's nodes
     const int p0 = dst_ptr[n0], p1 = dst_ptr[n0 + nb];
-    int node = 0;  // lanes walk the edge range; the owning node is found by advancing over dst_ptr
-    for (int p = p0 + lane; p < p1; p += 32) {
+    int node = 0;  // threads walk the edge range; the owning node is found by advancing over dst_ptr
+    for (int p = p0 + threadIdx.x; p < p1; p += FUSED_WARPS * 32) {
       while (dst_ptr[n0 + node + 1] <= p) ++node;
       const int src = dst_nbr[p] - n0;
       emask[dst_eid[p]] = __fmul_rn(work[src], work[node]);
@@ -424,9 +431,9 @@ extern "C" int isg_sampler_fused_fwd(const float* xn, const float* q, const floa
   if (B == 0 || nmax == 0) return ISG_OK;
   if (!xn || !q || !batch32 || !theta || !mask || !z_dense || k < 1) return ISG_EINVAL;
   if (edge_mask && (!dst_ptr || !dst_nbr || !dst_eid)) return ISG_EINVAL;
-  const size_t smem = (size_t)SAMP_WARPS * 2 * nmax * sizeof(float);
+  const size_t smem = (size_t)2 * nmax * sizeof(float);
   if ((rc = set_smem(sampler_fused_fwd_kernel, smem))) return rc;
-  sampler_fused_fwd_kernel<<<isg::ceil_div(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream_>>>(
+  sampler_fused_fwd_kernel<<<(unsigned)B, FUSED_WARPS * 32, smem, (cudaStream_t)stream_>>>(
       xn, q, keep, noise, batch32, gptr, dst_ptr, dst_nbr, dst_eid, B, D, double_gather, nmax, k, tau, theta, mask,
       z_dense, edge_mask);
   ISG_CHECK_LAUNCH();

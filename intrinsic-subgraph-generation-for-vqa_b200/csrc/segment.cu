@@ -29,7 +29,7 @@ __global__ void instr_gate_fwd_kernel(const float* __restrict__ x, const float* 
   Vec4<float>::st(y + idx * 4, o);
 }
 
-// one CTA per graph; thread c loops over the graph's nodes (coalesced across c)
+// one CTA per graph; thread c loops over the graph's nodes (coalesced across c) — any D
 __global__ void instr_gate_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                       const float* __restrict__ ins, const int* __restrict__ gptr, int D,
                                       const float* __restrict__ gres, int acc_ins, float* __restrict__ gx,
@@ -48,6 +48,65 @@ __global__ void instr_gate_bwd_kernel(const float* __restrict__ gy, const float*
     }
     const int64_t oi = (int64_t)b * D + c;
     gins[oi] = acc_ins ? gins[oi] + acc : acc;
+  }
+}
+
+// D % 4 == 0: float4 columns x IG_LANES row lanes (the serial walk above is a chain of ~20-40 dependent DRAM
+// round trips per thread: 32 us at the c3 size for 24 MB); per-lane partial sums of g_ins are folded in a fixed
+// order, so the result is deterministic.
+constexpr int IG_COLS = 80, IG_LANES = 4;
+__global__ void __launch_bounds__(IG_COLS * IG_LANES)
+instr_gate_bwd_v4_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ ins,
+                         const int* __restrict__ gptr, int D, const float* __restrict__ gres, int acc_ins,
+                         float* __restrict__ gx, float* __restrict__ gins) {
+  __shared__ float4 red[IG_LANES][IG_COLS];
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], n1 = gptr[b + 1];
+  const int cx = threadIdx.x % IG_COLS, ly = threadIdx.x / IG_COLS;
+  const int d4 = D >> 2;
+  for (int c0 = 0; c0 < d4; c0 += IG_COLS) {
+    const int c4 = c0 + cx;
+    float4 acc = f4_zero();
+    if (c4 < d4) {
+      const float4 iv = Vec4<float>::ld(ins + (int64_t)b * D + 4 * c4);
+      for (int n = n0 + ly; n < n1; n += IG_LANES) {
+        const int64_t o = (int64_t)n * D + 4 * c4;
+        const float4 xv = Vec4<float>::ld(x + o), g = Vec4<float>::ld(gy + o);
+        float4 gp, r;
+        gp.x = g.x * gelu_grad_f(xv.x * iv.x);
+        gp.y = g.y * gelu_grad_f(xv.y * iv.y);
+        gp.z = g.z * gelu_grad_f(xv.z * iv.z);
+        gp.w = g.w * gelu_grad_f(xv.w * iv.w);
+        if (gres) {
+          const float4 gr = Vec4<float>::ld(gres + o);
+          r.x = __fadd_rn(__fmul_rn(gp.x, iv.x), gr.x);
+          r.y = __fadd_rn(__fmul_rn(gp.y, iv.y), gr.y);
+          r.z = __fadd_rn(__fmul_rn(gp.z, iv.z), gr.z);
+          r.w = __fadd_rn(__fmul_rn(gp.w, iv.w), gr.w);
+        } else {
+          r.x = gp.x * iv.x;
+          r.y = gp.y * iv.y;
+          r.z = gp.z * iv.z;
+          r.w = gp.w * iv.w;
+        }
+        Vec4<float>::st(gx + o, r);
+        acc.x = fmaf(gp.x, xv.x, acc.x);
+        acc.y = fmaf(gp.y, xv.y, acc.y);
+        acc.z = fmaf(gp.z, xv.z, acc.z);
+        acc.w = fmaf(gp.w, xv.w, acc.w);
+      }
+    }
+    red[ly][cx] = acc;
+    __syncthreads();
+    if (ly == 0 && c4 < d4) {
+      float4 t = red[0][cx];
+#pragma unroll
+      for (int y = 1; y < IG_LANES; ++y) t = f4_add(t, red[y][cx]);
+      float* go = gins + (int64_t)b * D + 4 * c4;
+      if (acc_ins) t = f4_add(Vec4<float>::ld(go), t);
+      Vec4<float>::st(go, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -500,6 +559,78 @@ colsum_final_kernel(const float* __restrict__ part, int nparts, int cols, float*
   }
 }
 
+// ---- batched column sums: the bias / affine gradients of one layer's backward in two launches ----------------
+// (the layer executor used to issue up to nine isg_colsum calls = 18 latency-bound launches per layer, 0.43 ms of
+// the 5.3 ms c3 step).  Same slabs, same fold order as colsum_partial/final, so results are bit-identical.
+constexpr int CS_MAX_JOBS = 12;
+struct ColsumJob {
+  const float* in;
+  float* out;
+  float* part;
+  int64_t ld;
+  int64_t rows;
+  int cols, parts, cblocks, block0, fblock0;
+};
+struct ColsumBatch {
+  ColsumJob job[CS_MAX_JOBS];
+  int n;
+};
+
+__global__ void __launch_bounds__(64) colsum_multi_partial_kernel(const __grid_constant__ ColsumBatch batch) {
+  int j = 0;
+  while (j + 1 < batch.n && (int)blockIdx.x >= batch.job[j + 1].block0) ++j;
+  const ColsumJob& J = batch.job[j];
+  const int local = blockIdx.x - J.block0;
+  const int cb = local % J.cblocks, slab = local / J.cblocks;
+  const int c = (cb * 64 + threadIdx.x) * 4;
+  if (c >= J.cols) return;
+  const int64_t r0 = (int64_t)slab * CS_ROWS;
+  const int64_t r1 = min(J.rows, r0 + CS_ROWS);
+  const float* in = J.in;
+  const int64_t ld = J.ld;
+  float4 s = f4_zero();
+  int64_t r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = Vec4<float>::ld(in + (r + u) * ld + c);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
+  }
+  for (; r < r1; ++r) s = f4_add(s, Vec4<float>::ld(in + r * ld + c));
+  Vec4<float>::st(J.part + (int64_t)slab * J.cols + c, s);
+}
+
+__global__ void __launch_bounds__(64 * CS_LANES) colsum_multi_final_kernel(const __grid_constant__ ColsumBatch batch) {
+  __shared__ float4 red[CS_LANES][64];
+  int j = 0;
+  while (j + 1 < batch.n && (int)blockIdx.x >= batch.job[j + 1].fblock0) ++j;
+  const ColsumJob& J = batch.job[j];
+  const int c = ((blockIdx.x - J.fblock0) * 64 + threadIdx.x) * 4;
+  const int cols = J.cols, nparts = J.parts;
+  const float* part = J.part;
+  float4 s = f4_zero();
+  if (c < cols) {
+    int p = threadIdx.y;
+    for (; p + 3 * CS_LANES < nparts; p += 4 * CS_LANES) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = Vec4<float>::ld(part + (int64_t)(p + u * CS_LANES) * cols + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s = f4_add(s, v[u]);
+    }
+    for (; p < nparts; p += CS_LANES) s = f4_add(s, Vec4<float>::ld(part + (int64_t)p * cols + c));
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < CS_LANES; ++y) t = f4_add(t, red[y][threadIdx.x]);
+    Vec4<float>::st(J.out + c, t);
+  }
+}
+
 }  // namespace
 
 extern "C" int isg_instr_gate_fwd(const float* x, const float* ins, const int32_t* batch32, int64_t N, int D,
@@ -520,8 +651,14 @@ extern "C" int isg_instr_gate_bwd(const float* g_y, const float* x, const float*
   if (B < 0 || D <= 0) return ISG_EINVAL;
   if (B == 0) return ISG_OK;
   if (!g_y || !x || !ins || !gptr || !g_x || !g_ins) return ISG_EINVAL;
-  instr_gate_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, x, ins, gptr, D, g_residual,
-                                                                        accumulate_ins, g_x, g_ins);
+  const bool v4 = D % 4 == 0 && !(((uintptr_t)g_y | (uintptr_t)x | (uintptr_t)ins | (uintptr_t)g_x | (uintptr_t)g_ins |
+                                   (uintptr_t)g_residual) & 15);
+  if (v4)
+    instr_gate_bwd_v4_kernel<<<(unsigned)B, IG_COLS * IG_LANES, 0, (cudaStream_t)stream_>>>(
+        g_y, x, ins, gptr, D, g_residual, accumulate_ins, g_x, g_ins);
+  else
+    instr_gate_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, x, ins, gptr, D, g_residual,
+                                                                          accumulate_ins, g_x, g_ins);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -662,3 +799,54 @@ extern "C" int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, f
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
+
+extern "C" size_t isg_colsum_multi_workspace_bytes(int n, const int64_t* rows, const int* cols) {
+  if (n <= 0 || !rows || !cols) return 0;
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) total += (isg_colsum_workspace_bytes(rows[i], cols[i]) + 255) & ~(size_t)255;
+  return total;
+}
+
+extern "C" int isg_colsum_multi(int n, const float* const* in, const int64_t* ld, const int64_t* rows, const int* cols,
+                                float* const* out, void* workspace, size_t ws_bytes, void* stream_) {
+  if (n < 0 || n > CS_MAX_JOBS) return ISG_EINVAL;
+  if (n == 0) return ISG_OK;
+  if (!in || !ld || !rows || !cols || !out) return ISG_EINVAL;
+  if (ws_bytes < isg_colsum_multi_workspace_bytes(n, rows, cols) || !workspace) return ISG_EWORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ColsumBatch batch;
+  batch.n = 0;
+  int blocks = 0, fblocks = 0;
+  char* ws = (char*)workspace;
+  for (int i = 0; i < n; ++i) {
+    if (rows[i] < 0 || cols[i] <= 0 || !out[i]) return ISG_EINVAL;
+    if (rows[i] == 0) {
+      cudaError_t e = cudaMemsetAsync(out[i], 0, (size_t)cols[i] * sizeof(float), stream);
+      if (e != cudaSuccess) return (int)e;
+      continue;
+    }
+    if (!in[i]) return ISG_EINVAL;
+    if (cols[i] % 4 != 0 || ld[i] % 4 != 0 || ((uintptr_t)in[i] & 15) || ((uintptr_t)out[i] & 15)) return ISG_EUNSUPPORTED;
+    ColsumJob& J = batch.job[batch.n++];
+    J.in = in[i];
+    J.out = out[i];
+    J.part = (float*)ws;
+    ws += (isg_colsum_workspace_bytes(rows[i], cols[i]) + 255) & ~(size_t)255;
+    J.ld = ld[i];
+    J.rows = rows[i];
+    J.cols = cols[i];
+    J.parts = (int)((rows[i] + CS_ROWS - 1) / CS_ROWS);
+    J.cblocks = isg::ceil_div(cols[i] / 4, 64);
+    J.block0 = blocks;
+    J.fblock0 = fblocks;
+    blocks += J.cblocks * J.parts;
+    fblocks += J.cblocks;
+  }
+  if (batch.n == 0) return ISG_OK;
+  colsum_multi_partial_kernel<<<blocks, 64, 0, stream>>>(batch);
+  ISG_CHECK_LAUNCH();
+  colsum_multi_final_kernel<<<fblocks, dim3(64, CS_LANES), 0, stream>>>(batch);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+

@@ -4,12 +4,17 @@ sorted `batch` vector, and Nmax.  Built once per batch (the reference rebuilds g
 indices inside PyG on every one of the 4 layers: models/mgat_v2_conv.py:215)."""
 import torch
 
+import os
+
 from . import lib as L
+
+_EDGE_ORDER = os.environ.get("ISG_EDGE_ORDER", "1") != "0"  # A/B switch: "0" keeps the natural node order
 
 
 class GraphIndex:
     __slots__ = ("edge_index", "batch", "N", "E", "B", "dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr",
-                 "src_eid", "status", "graph_ptr", "batch32", "_nmax_dev", "_nmax", "_closed", "_key", "_keepalive")
+                 "src_eid", "dst_order", "src_order", "status", "graph_ptr", "batch32", "_nmax_dev", "_nmax", "_closed", "_key",
+                 "_keepalive")
 
     def __init__(self, edge_index, batch, num_graphs, num_nodes=None):
         L.require_cuda(edge_index, batch)
@@ -37,6 +42,14 @@ class GraphIndex:
         L.call("isg_csr_build", L.ptr(self.edge_index), E, N, L.ptr(self.dst_ptr), L.ptr(self.dst_nbr),
                                   L.ptr(self.dst_eid), L.ptr(self.src_ptr), L.ptr(self.src_nbr),
                                   L.ptr(self.src_eid), L.ptr(self.status), L.ptr(ws), ws_bytes, st)
+        # task order of the edge kernels: longest segments first (csrc/csr.cu, isg_degree_order)
+        self.dst_order = self.src_order = None
+        if _EDGE_ORDER:
+            self.dst_order = torch.empty(max(N, 1), **i32)
+            self.src_order = torch.empty(max(N, 1), **i32)
+            ows = L.workspace(lib.isg_degree_order_workspace_bytes(), dev)
+            L.call("isg_degree_order", L.ptr(self.dst_ptr), L.ptr(self.src_ptr), N, L.ptr(self.dst_order),
+                   L.ptr(self.src_order), L.ptr(ows), ows.numel(), st)
         self.graph_ptr = torch.empty(B + 1, **i32)
         self.batch32 = torch.empty(max(N, 1), **i32)
         self._nmax_dev = torch.empty(2, **i32)  # [nmax, number of edges that leave their graph]

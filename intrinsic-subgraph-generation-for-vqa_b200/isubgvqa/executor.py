@@ -169,8 +169,9 @@ def _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, ins_ptr, glf, edge_attr, s
     for name, t in (("P_DST_PTR", gi.dst_ptr), ("P_DST_NBR", gi.dst_nbr), ("P_DST_EID", gi.dst_eid),
                     ("P_SRC_PTR", gi.src_ptr), ("P_SRC_NBR", gi.src_nbr), ("P_SRC_EID", gi.src_eid),
                     ("P_GRAPH_PTR", gi.graph_ptr), ("P_BATCH32", gi.batch32), ("P_EDGE_INDEX", gi.edge_index),
+                    ("P_DST_ORDER", gi.dst_order), ("P_SRC_ORDER", gi.src_order),
                     ("P_GLF", glf), ("P_EDGE_ATTR", edge_attr)):
-        p[getattr(s, name)] = t.data_ptr()
+        p[getattr(s, name)] = t.data_ptr() if t is not None else 0
     p[s.P_X_IN], p[s.P_INS] = x_in_ptr, ins_ptr
     for name, t in layer_params(model, i):
         if name in ("W_R", "B_R"):
@@ -204,11 +205,11 @@ def kernel_launches(spec, gi, backward):
             else:
                 n += K["isg_gate_theta_fwd"] + 1 + K["isg_node_edge_mask_fwd"]
         return n
-    n = (K["isg_sdpa_graphnorm_bwd"] + 7 * K["isg_colsum"] + K["isg_gelu_bwd"] + 4 * K["isg_linear_dgrad"] +
+    n = (K["isg_sdpa_graphnorm_bwd"] + K["isg_colsum_multi"] + K["isg_gelu_bwd"] + 4 * K["isg_linear_dgrad"] +
          4 * K["isg_linear_wgrad"] + K["isg_gat_edge_bwd"] + K["isg_instr_gate_bwd"])
     if masked:
         n += 1 + K["isg_node_edge_mask_bwd"] + (3 if spec["code"] == 2 else 1) + K["isg_gate_theta_bwd"] + \
-            2 * (K["isg_gelu_bwd"] + K["isg_linear_dgrad"] + K["isg_linear_wgrad"] + K["isg_colsum"])
+            2 * (K["isg_gelu_bwd"] + K["isg_linear_dgrad"] + K["isg_linear_wgrad"])
     return n
 
 

@@ -24,11 +24,13 @@ SIGNATURES = {
     "isg_csr_workspace_bytes": (_SZ, [_I64, _I64]),
     "isg_csr_build": (_I32, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "isg_graph_ptr": (_I32, [_P, _I64, _I64, _P, _P, _P, _P]),
-    "isg_gat_edge_fwd": (_I32, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32,
+    "isg_gat_edge_fwd": (_I32, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32,
                                 _F, _I32, _P]),
+    "isg_degree_order_workspace_bytes": (_SZ, []),
+    "isg_degree_order": (_I32, [_P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "isg_graph_closure": (_I32, [_P, _I64, _P, _I64, _P, _P]),
     "isg_gat_edge_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32, _I32]),
-    "isg_gat_edge_bwd": (_I32, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P,
+    "isg_gat_edge_bwd": (_I32, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P,
                                 _P, _P, _I64, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _I32, _P, _P, _I64, _I32,
                                 _P, _SZ, _P]),
     "isg_node_edge_mask_fwd": (_I32, [_P, _P, _I64, _P, _P]),
@@ -62,6 +64,8 @@ SIGNATURES = {
     "isg_gelu_bwd": (_I32, [_P, _P, _P, _I64, _P]),
     "isg_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
     "isg_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
+    "isg_colsum_multi_workspace_bytes": (_SZ, [_I32, _P, _P]),
+    "isg_colsum_multi": (_I32, [_I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "isg_gather_add_act_fwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "isg_segment_sum": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "isg_gather_rows": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
@@ -100,12 +104,12 @@ def load():
 
 # kernels launched per C-ABI call (memsets excluded); used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
-    "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_graph_closure": 1, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 4,
+    "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_graph_closure": 1, "isg_degree_order": 3, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 4,
     "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_sampler_fused_fwd": 1, "isg_imle_bwd": 1,
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
     "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_transpose_split": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
-    "isg_gelu_bwd": 1, "isg_colsum": 2, "isg_gather_add_act_fwd": 1, "isg_segment_sum": 1, "isg_gather_rows": 1,
+    "isg_gelu_bwd": 1, "isg_colsum": 2, "isg_colsum_multi": 2, "isg_gather_add_act_fwd": 1, "isg_segment_sum": 1, "isg_gather_rows": 1,
     "isg_graphnorm64_fwd": 1, "isg_graphnorm64_bwd": 1, "isg_grad_sq_partials": 1, "isg_clip_finalize": 1,
     "isg_adam_update": 1,
 }

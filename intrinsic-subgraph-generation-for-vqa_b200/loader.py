@@ -41,8 +41,56 @@ class DevicePrefetcher:
         main.wait_event(ev)
         tensors = list(dev.values()) + list(ext.values())
         if gi is not None:
-            tensors += [getattr(gi, n) for n in ("dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr", "src_eid",
-                                                 "status", "graph_ptr", "batch32", "_nmax_dev")]
+            tensors += [t for t in (getattr(gi, n) for n in ("dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr", "src_eid",
+                                                 "dst_order", "src_order", "status", "graph_ptr", "batch32", "_nmax_dev")) if t is not None]
         for t in tensors:
             t.record_stream(main)  # allocated on the copy stream, consumed on the compute stream
         return dev, ext
+
+
+class HostResults:
+    """Device -> host read of each step's results without stalling the step behind it.
+
+    The reference's loop reads the loss with `.item()` right after `backward()` (training/train_epoch.py:120-133),
+    which idles the GPU while the host enqueues the next step.  Here every step's results are copied into pinned
+    host buffers on the compute stream (`push`), and the host picks them up `lag` steps later (`pop` waits on that
+    copy's event only): with lag 1 the host is always one step ahead of the GPU.  `drain()` returns whatever is
+    still in flight (call it after the last step)."""
+
+    def __init__(self, lag=1):
+        self.lag = int(lag)
+        self._inflight = []
+        self._free = []
+
+    def push(self, **tensors):
+        bufs = self._free.pop() if self._free else {}
+        out = {}
+        for k, t in tensors.items():
+            t = t.detach()
+            b = bufs.get(k)
+            if b is None or b.shape != t.shape or b.dtype != t.dtype:
+                b = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            b.copy_(t, non_blocking=True)
+            out[k] = b
+        ev = torch.cuda.Event()
+        ev.record()
+        self._inflight.append((out, ev))
+
+    def pop(self):
+        """Results of the step pushed `lag` steps ago, or None while fewer than lag + 1 steps are in flight."""
+        if len(self._inflight) <= self.lag:
+            return None
+        return self._take()
+
+    def drain(self):
+        res = []
+        while self._inflight:
+            res.append(self._take())
+        return res
+
+    def _take(self):
+        out, ev = self._inflight.pop(0)
+        ev.synchronize()
+        res = {k: (v.item() if v.dim() == 0 else v.clone()) for k, v in out.items()}
+        self._free.append(out)
+        return res

@@ -378,7 +378,8 @@ class GatEdge(torch.autograd.Function):
         alpha = torch.empty(gi.E, heads, dtype=torch.float32, device=xlr.device)
         L.call("isg_gat_edge_fwd", L.ptr(x_l), L.ptr(x_r), HC2, L.ptr(e_proj), L.ptr(att),
                                           L.ptr(bias), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr),
-                                          L.ptr(gi.dst_eid), L.ptr(out), HC, L.ptr(alpha), N, gi.E, heads, C,
+                                          L.ptr(gi.dst_eid), L.ptr(gi.dst_order), L.ptr(out), HC, L.ptr(alpha), N, gi.E,
+                                          heads, C,
                                           slope, L.dtype_code(xlr), L.stream())
         ctx.gi, ctx.heads, ctx.slope = gi, heads, slope
         ctx.has_bias = bias is not None
@@ -406,8 +407,9 @@ class GatEdge(torch.autograd.Function):
         fused = edge_bwd_fused(gi)
         L.call("isg_gat_edge_bwd", L.ptr(g_out), g_out.stride(0), L.ptr(x_l), L.ptr(x_r), 2 * HC,
                                      L.ptr(e_proj), L.ptr(att), L.ptr(bias), L.ptr(em), L.ptr(alpha), L.ptr(out), HC,
-                                     L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr),
-                                     L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(g_xl), L.ptr(g_xr), 2 * HC,
+                                     L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.dst_order),
+                                     L.ptr(gi.src_ptr), L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(gi.src_order),
+                                     L.ptr(g_xl), L.ptr(g_xr), 2 * HC,
                                      L.ptr(g_ep), L.ptr(g_att), L.ptr(g_em), N, gi.E, H, C, ctx.slope,
                                      L.dtype_code(xlr), L.ptr(gi.batch32) if fused else None,
                                      L.ptr(gi.graph_ptr) if fused else None, gi.B, gi.nmax if fused else 0,

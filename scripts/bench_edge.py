@@ -78,17 +78,18 @@ def run_point(B, mn, me, masked, reps, chunk_graphs, seed=7, bf16=False):
         fused = ops.edge_bwd_fused(gi) and not bf16
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
         st = L.stream()
+        order = (None, None) if os.environ.get("ISG_EDGE_ORDER", "1") == "0" else (gi.dst_order, gi.src_order)
 
         def fwd():
             L.call("isg_gat_edge_fwd", xlr.data_ptr(), xlr.data_ptr() + HC * es, 2 * HC, ep.data_ptr(), att.data_ptr(),
-                   bias.data_ptr(), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), out.data_ptr(),
-                   HC, alpha.data_ptr(), N, E, H, C, 0.2, code, st)
+                   bias.data_ptr(), L.ptr(em), L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(order[0]),
+                   out.data_ptr(), HC, alpha.data_ptr(), N, E, H, C, 0.2, code, st)
 
         def bwd():
             L.call("isg_gat_edge_bwd", gout.data_ptr(), HC, xlr.data_ptr(), xlr.data_ptr() + HC * es, 2 * HC,
                    ep.data_ptr(), att.data_ptr(), bias.data_ptr(), L.ptr(em), alpha.data_ptr(), out.data_ptr(), HC,
-                   L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(gi.src_ptr), L.ptr(gi.src_nbr),
-                   L.ptr(gi.src_eid), gxlr.data_ptr(), gxlr.data_ptr() + HC * es, 2 * HC, gep.data_ptr(),
+                   L.ptr(gi.dst_ptr), L.ptr(gi.dst_nbr), L.ptr(gi.dst_eid), L.ptr(order[0]), L.ptr(gi.src_ptr),
+                   L.ptr(gi.src_nbr), L.ptr(gi.src_eid), L.ptr(order[1]), gxlr.data_ptr(), gxlr.data_ptr() + HC * es, 2 * HC, gep.data_ptr(),
                    gatt.data_ptr(), L.ptr(gem), N, E, H, C, 0.2, code, L.ptr(gi.batch32) if fused else None,
                    L.ptr(gi.graph_ptr) if fused else None, nb, gi.nmax if fused else 0, ws.data_ptr(), wsb, st)
 

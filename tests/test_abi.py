@@ -59,7 +59,7 @@ def test_version_and_error_strings():
 def test_argument_validation_without_gpu():
     """Entry points validate arguments before touching the device: bad shapes return ISG_E* codes."""
     lib = L.load()
-    assert lib.isg_gat_edge_fwd(None, None, 0, None, None, None, None, None, None, None, None, 0, None, 4, 4, 4,
+    assert lib.isg_gat_edge_fwd(None, None, 0, None, None, None, None, None, None, None, None, None, 0, None, 4, 4, 4,
                                 301, 0.2, 0, None) == -2  # C % 4 != 0 -> ISG_EUNSUPPORTED
     assert lib.isg_linear_fwd(None, 0, None, None, None, None, None, 0, None, 0, -1, 4, 4, 0, 0, 0, None) == -1
     assert lib.isg_csr_build(None, -1, 4, None, None, None, None, None, None, None, None, 0, None) == -1

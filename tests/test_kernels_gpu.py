@@ -191,6 +191,34 @@ def test_edge_bwd_single_launch_is_bit_identical_to_two_pass(B, mn, me, masked):
         assert torch.equal(one[k], again[k]), k
 
 
+@pytest.mark.parametrize("B,mn,me,masked", [(64, 20, 150, True), (256, 20, 150, False), (3, 300, 20000, False)])
+def test_edge_task_order_longest_first_changes_no_bit(B, mn, me, masked):
+    """isg_degree_order: a permutation of the nodes by decreasing in- / out-degree (bins capped at 255); the edge
+    kernels scheduled in that order give bit-identical results to the natural node order."""
+    from isg_b200 import graph, ops
+
+    d = _edge_case(B, mn, me, 300, 4, masked, seed=11 + B)
+    gi = _gi(d["edge_index"], d["batch"], B)
+    N = gi.N
+    for order, ptr in ((gi.dst_order, gi.dst_ptr), (gi.src_order, gi.src_ptr)):
+        o = order.cpu().long()
+        assert torch.equal(torch.sort(o).values, torch.arange(N))
+        deg = (ptr[1:] - ptr[:-1]).cpu().long().clamp(max=255)[o]
+        assert bool((deg[1:] <= deg[:-1]).all())
+    keys = ("out", "alpha", "g_x_l", "g_x_r", "g_e_proj", "g_att", "g_bias") + (("g_mask",) if masked else ())
+    prev = ops._EDGE_BWD_FUSED
+    try:
+        ops._EDGE_BWD_FUSED = False  # the two-launch backward is the one that takes the order
+        with_order = _run_edge_cuda(d, 4, 300)
+        graph._EDGE_ORDER = False  # GraphIndex then carries no order: natural node order
+        natural = _run_edge_cuda(d, 4, 300)
+    finally:
+        ops._EDGE_BWD_FUSED = prev
+        graph._EDGE_ORDER = True
+    for k in keys:
+        assert torch.equal(with_order[k], natural[k]), k
+
+
 def test_edge_bwd_falls_back_when_edges_leave_their_graph():
     """An edge between two graphs breaks the precondition of the single-launch backward; GraphIndex.closed
     reports it and the two-launch form runs (results still match the oracle)."""
@@ -435,6 +463,64 @@ def test_instr_gate(D):
     assert util.rel_err(yc, yo) <= 1e-5
     assert util.rel_err(xc.grad, xo.grad) <= RTOL
     assert util.rel_err(ic.grad, io.grad) <= RTOL
+
+
+def test_colsum_multi_is_bit_identical_to_colsum():
+    """isg_colsum_multi (the layer backward's batched bias-gradient sums) == one isg_colsum per tensor, bit for bit,
+    including a zero-row job and a pitched input."""
+    import ctypes
+
+    from isg_b200 import lib as L
+
+    lib = L.load()
+    g = torch.Generator().manual_seed(5)
+    shapes = [(256, 300), (4910, 300), (4910, 600), (4910, 1200), (4910, 2400), (0, 300), (1, 300), (65, 304)]
+    wide = torch.randn(4910, 2400, generator=g).to(DEV)
+    ins = [torch.randn(r, c, generator=g).to(DEV) for r, c in shapes]
+    ins[3] = wide[:, 1200:]  # pitched view: ld = 2400
+    n = len(ins)
+    rows = np.array([t.shape[0] for t in ins], dtype=np.int64)
+    cols = np.array([t.shape[1] for t in ins], dtype=np.int32)
+    ld = np.array([t.stride(0) if t.shape[0] else t.shape[1] for t in ins], dtype=np.int64)
+    outs = [torch.full((c,), float("nan"), device=DEV) for c in cols]
+    pin = (ctypes.c_void_p * n)(*[t.data_ptr() for t in ins])
+    pout = (ctypes.c_void_p * n)(*[t.data_ptr() for t in outs])
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    nbytes = lib.isg_colsum_multi_workspace_bytes(n, vp(rows), vp(cols))
+    ws = L.workspace(nbytes, DEV)
+    L.call("isg_colsum_multi", n, pin, vp(ld), vp(rows), vp(cols), pout, L.ptr(ws), nbytes, L.stream())
+    for t, o in zip(ins, outs):
+        r, c = t.shape
+        want = torch.empty(c, device=DEV)
+        nb = lib.isg_colsum_workspace_bytes(r, c)
+        w1 = L.workspace(nb, DEV)
+        L.call("isg_colsum", L.ptr(t) if r else None, t.stride(0) if r else c, r, c, L.ptr(want), L.ptr(w1), nb, L.stream())
+        assert torch.equal(o, want), (r, c)
+        if r:
+            assert util.rel_err(o.cpu(), t.double().sum(0).float().cpu()) <= 1e-5
+    with pytest.raises(RuntimeError):  # too small a workspace is reported, not overrun
+        L.call("isg_colsum_multi", n, pin, vp(ld), vp(rows), vp(cols), pout, L.ptr(ws), 16, L.stream())
+
+
+def test_instr_gate_bwd_residual_and_accumulate_at_gqa_size():
+    """isg_instr_gate_bwd's vectorised kernel (float4 columns x 4 row lanes) with the residual gradient and the
+    accumulate flag the layer executor uses, against fp64 autograd."""
+    from isg_b200 import lib as L
+
+    B, D = 40, 300
+    batch, N, g = _node_case(B, 25, D, 3)
+    x, ins = torch.randn(N, D, generator=g), torch.randn(B, D, generator=g)
+    gy, gres, gins0 = torch.randn(N, D, generator=g), torch.randn(N, D, generator=g), torch.randn(B, D, generator=g)
+    xd, idd = x.double().requires_grad_(True), ins.double().requires_grad_(True)
+    y = torch.nn.functional.gelu(xd * idd[batch])
+    y.backward(gy.double())
+    gi = _gi(torch.zeros(2, 0, dtype=torch.int64), batch, B)
+    gx = torch.empty(N, D, device=DEV)
+    gins = gins0.to(DEV).clone()
+    L.call("isg_instr_gate_bwd", L.ptr(gy.to(DEV)), L.ptr(x.to(DEV)), L.ptr(ins.to(DEV)), L.ptr(gi.graph_ptr), B, D,
+           L.ptr(gres.to(DEV)), 1, L.ptr(gx), L.ptr(gins), L.stream())
+    assert util.rel_err(gx.cpu(), (xd.grad + gres.double()).float()) <= 1e-5
+    assert util.rel_err(gins.cpu(), (idd.grad + gins0.double()).float()) <= 1e-5
 
 
 @pytest.mark.parametrize("D", [16, 300])
