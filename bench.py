@@ -355,13 +355,20 @@ def main_isg(args, rank, world, local_rank):
     # graph (isg_b200.dp.OverlappedGradAllReduce; the process group must then exist before the capture).  Measured
     # on 2 GPUs (r1i): 5.47-5.48 vs 5.43 ms/step — the bucket collectives compete with the persistent GEMM CTAs for
     # SMs and nothing is gained at this scale, so it stays opt-in (8 GPUs not measured).
-    overlap = world > 1 and train and args.overlap and not args.no_graph
+    # Default since r2: isg_b200.dp.LayerGradAllReduce — .grad tensors are views of the executor's flat gradient
+    # buffer (no pack / unpack), each layer's slice is all-reduced on a communication stream as soon as that layer's
+    # backward has been issued, and the collectives are captured into the step's CUDA graph.  --dp-flat keeps the r1
+    # path (one flat all-reduce with pack / unpack after each replay), --overlap the r1 hook-based bucketing.
+    dp_mode = "none"
+    if world > 1 and train:
+        dp_mode = "hooks" if (args.overlap and not args.no_graph) else ("flat" if args.dp_flat else "layer")
+    overlap = dp_mode in ("hooks", "layer")  # the reduction is part of step_core (and of the captured graph)
     reducer = None
     if overlap:
-        from isg_b200.dp import OverlappedGradAllReduce
+        from isg_b200.dp import LayerGradAllReduce, OverlappedGradAllReduce
 
         dist.init_process_group("nccl", device_id=dev)
-        reducer = OverlappedGradAllReduce(model)
+        reducer = OverlappedGradAllReduce(model) if dp_mode == "hooks" else LayerGradAllReduce(model)
 
     keys = ("x", "edge_index", "instr_vectors", "global_language_feats", "edge_attr", "batch")
     host = {k: b[k].pin_memory() for k in keys}
@@ -543,10 +550,15 @@ def main_isg(args, rank, world, local_rank):
     else:
         ms = ms_eager
     clk = clocks.stop() if rank == 0 else None
-    n_buckets = len(reducer._buckets) if overlap else 0
+    n_buckets = len(reducer._buckets) if dp_mode == "hooks" else 0
+    layer_reducer = reducer if dp_mode == "layer" else None
     if overlap:
-        # the eager passes below (breakdown, e2e) use the flat reducer: the per-bucket hooks cost host time there
-        reducer.remove_hooks()
+        # the per-operator timing pass below has no layer executor underneath (and the per-bucket hooks cost host
+        # time in eager mode): it uses the flat reducer
+        if dp_mode == "hooks":
+            reducer.remove_hooks()
+        else:
+            reducer.detach()
         reducer = GradAllReduce(model)
         overlap = False
     # (3) per-kernel CUDA events for the roofline blocks: the same K steps through the per-operator path, where
@@ -560,6 +572,11 @@ def main_isg(args, rank, world, local_rank):
                        kernel_names if not args.breakdown else list(L.KERNELS_PER_CALL))
     tall = tsum
     mgat_mod.set_executor(True)
+    if layer_reducer is not None:  # e2e: the layer reducer again (eager, same hooks)
+        from isg_b200.dp import LayerGradAllReduce
+
+        reducer = LayerGradAllReduce(model)
+        overlap = True
     for _ in range(3):
         step_e2e()
     results.drain()
@@ -668,6 +685,8 @@ def main_isg(args, rank, world, local_rank):
                    "step": "MGAT forward+backward" + (
                        (" + NCCL gradient all-reduce (42 MB in %d buckets, issued by gradient hooks during backward, "
                         "captured in the step graph)" % n_buckets) if n_buckets else
+                       " + NCCL gradient all-reduce (in place on the executor's flat gradient buffer, one slice per "
+                       "layer issued during the backward pass, captured in the step graph)" if dp_mode == "layer" else
                        " + NCCL gradient all-reduce (42 MB flat bucket after the step)" if world > 1 else "")
                    if train else "MGAT forward (no_grad)",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
@@ -717,6 +736,8 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="multi-GPU (experimental): bucketed all-reduces issued during the backward pass and captured "
                          "in the step graph, instead of one flat all-reduce after the step")
+    ap.add_argument("--dp-flat", action="store_true",
+                    help="multi-GPU: the r1 reducer (flat 42 MB all-reduce with pack/unpack after each replay)")
     ap.add_argument("--no-edge-study", action="store_true", help="skip the batch-4096 edge-kernel roofline point")
     ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2],
                     help="projection arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32 (default), 2 tcgen05 1xTF32")

@@ -13,14 +13,14 @@ import torch.distributed as dist
 
 
 class GradAllReduce:
-    def __init__(self, module, process_group=None, always_exchange=False):
+    def __init__(self, module, process_group=None, always_exchange=False, params=None):
         from . import ops
 
         ops.set_side_stream_with_dist(True)  # gradients are read after backward() has returned (and joined)
-        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.params = [p for p in (module.parameters() if params is None else params) if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        dev = self.params[0].device
+        dev = self.params[0].device if self.params else torch.device("cpu")
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.views, off = [], 0
@@ -215,6 +215,109 @@ class OverlappedGradAllReduce(GradAllReduce):
         for h in self._hooks:
             h.remove()
         self._hooks = []
+
+
+class LayerGradAllReduce:
+    """Zero-copy, per-layer gradient averaging for an MGAT that runs through the layer executor
+    (isubgvqa/executor.py) — the drop-in for DistributedDataParallel(find_unused_parameters=True), main.py:85-94.
+
+    The executor writes every parameter gradient of the model into ONE flat fp32 buffer laid out in backward order
+    (layer L-1 first) and hands autograd views of it, so `.grad` already points INTO the bucket: there is no pack
+    and no unpack (the flat reducer copies 42 MB in and 42 MB out around its collective).  After each layer's
+    backward the executor calls back with that layer's slice; its all-reduce is issued on a communication stream
+    right away and runs while the earlier layers are still being differentiated — only layer 0's slice is exposed.
+    `finish()` (after backward()) joins the communication stream.  Parameters outside the executor's set (the
+    never-used gate_nn / gate_top / node_logits tensors, or anything else hanging off the module) go through a
+    small flat GradAllReduce with DDP's unused-parameter semantics.
+
+    The bucket is persistent (re-used every step) and is only handed out while every covered `.grad` is None —
+    with gradients being accumulated across backward passes autograd would add a view of the bucket to itself, so
+    the executor then falls back to a fresh buffer and the slices are reduced from there.
+    Works under CUDA-graph capture (the communication stream forks from / joins the capturing stream)."""
+
+    def __init__(self, model, process_group=None, overlap=True):
+        from . import ops
+        from .isubgvqa import executor
+
+        ops.set_side_stream_with_dist(True)
+        self.model = model
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.overlap = bool(overlap)
+        self.covered = executor.flat_params(model)
+        covered = {id(p) for p in self.covered}
+        rest = [p for p in model.parameters() if p.requires_grad and id(p) not in covered]
+        self.rest = GradAllReduce(model, process_group, params=rest) if rest else None
+        dev = self.covered[0].device
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        self._flat = None
+        self._slices = []      # (buffer, lo, hi, is-the-bucket) handed over during the current backward
+        self._issued = 0
+        self._fallback = None
+        self.nbytes = 4 * sum(p.numel() for p in self.covered)
+        model._isg_grad_bucket = self._bucket
+        model._isg_after_layer_backward = self._after_layer
+
+    def detach(self):
+        for name in ("_isg_grad_bucket", "_isg_after_layer_backward"):
+            if self.model.__dict__.get(name) is not None:
+                del self.model.__dict__[name]
+
+    # ---- executor callbacks
+    def _bucket(self, numel, device):
+        if any(p.grad is not None for p in self.covered):
+            return None  # accumulation step: autograd adds into the existing .grad, which may alias the bucket
+        if self._flat is None or self._flat.numel() != numel or self._flat.device != device:
+            self._flat = torch.empty(numel, dtype=torch.float32, device=device)
+        return self._flat
+
+    def _reduce(self, buf):
+        if self._avg:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.mul_(1.0 / self.world)
+
+    def _after_layer(self, layer, gflat, lo, hi):
+        mine = self._flat is not None and gflat.data_ptr() == self._flat.data_ptr()
+        self._slices.append((gflat, lo, hi, mine))
+        if self.world == 1 or not self.overlap or not mine:
+            return
+        chunk = gflat[lo:hi]
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self._reduce(chunk)
+        else:
+            self._reduce(chunk)
+        self._issued += 1
+
+    def finish(self):
+        """Call after backward(): every gradient is averaged when the current stream continues."""
+        slices, self._slices = self._slices, []
+        issued, self._issued = self._issued, 0
+        if not slices:
+            raise RuntimeError("finish() without a backward pass through the layer executor (is the executor "
+                               "enabled and the configuration supported?)")
+        if self.world > 1:
+            if not all(s[3] for s in slices):
+                # accumulation step: .grad = previous (already averaged, identical on every rank) + this rank's new
+                # values; averaging that sum across ranks is previous + mean(new) — the flat reducer does it
+                if self._fallback is None:
+                    self._fallback = GradAllReduce(self.model, self.group, params=self.covered)
+                self._fallback.all_reduce_mean()
+            elif issued:
+                if self.stream is not None:
+                    torch.cuda.current_stream().wait_stream(self.stream)
+            else:
+                buf = slices[0][0]
+                lo, hi = min(s[1] for s in slices), max(s[2] for s in slices)
+                self._reduce(buf[lo:hi])  # one collective over the whole (contiguous) bucket, in place
+        if self.rest is not None:
+            self.rest.all_reduce_mean()
+
+    all_reduce_mean = finish
 
 
 def shard_graphs(num_graphs_total, rank, world):

@@ -176,3 +176,83 @@ def test_unused_parameter_sets_that_differ_between_ranks():
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_worker_uneven, args=(2, port, ret), nprocs=2, join=True)
     assert ret["ok_0"] and ret["ok_1"], dict(ret)
+
+
+def _worker_layer(rank, world, port, ret):
+    """LayerGradAllReduce's host logic with the executor's two callbacks driven by hand (the executor itself
+    needs a GPU): the bucket is persistent and handed out only while every covered .grad is None; each layer slice
+    is averaged in place; an accumulation step (grads not cleared) goes through the flat fallback and yields
+    previous + mean(new); overlap=False reduces the whole bucket in finish()."""
+    sys.path.insert(0, ROOT)
+    from isg_b200.dp import LayerGradAllReduce
+    from isg_b200.isubgvqa import MGAT, executor
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = MGAT(channels=8, num_ins=4, heads=2, use_instr=True, masking_thresholds=[1.0, 1.0, 1.0, 0.1], use_topk=True,
+                 interpretable_mode=False, sampler_type="imle", sample_k=2)
+    ok = True
+    for overlap in (True, False):
+        red = LayerGradAllReduce(model, overlap=overlap)
+        covered = executor.flat_params(model)
+        numel = sum(p.numel() for p in covered)
+        L = len(model.convs)
+        spans, off = {}, 0
+        for i in reversed(range(L)):
+            n = sum(t.numel() for _n, t in executor.layer_params(model, i))
+            spans[i] = (off, off + n)
+            off += n
+        assert off == numel
+
+        def backward(scale):
+            """What MgatFunction.backward does with the two callbacks; returns the buffer it wrote."""
+            buf = model._isg_grad_bucket(numel, torch.device("cpu"))
+            fresh = buf is None
+            if fresh:
+                buf = torch.empty(numel)
+            for i in reversed(range(L)):
+                lo, hi = spans[i]
+                buf[lo:hi] = scale * (rank + 1) * (i + 1)
+                model._isg_after_layer_backward(i, buf, lo, hi)
+            o = 0
+            for i in reversed(range(L)):  # autograd: adopt the views (grad None) or accumulate into .grad
+                for _n, t in executor.layer_params(model, i):
+                    v = buf[o:o + t.numel()].view(t.shape)
+                    t.grad = v if t.grad is None else t.grad + v
+                    o += t.numel()
+            return buf, fresh
+
+        for p in model.parameters():
+            p.grad = None
+        buf, fresh = backward(1.0)
+        red.finish()
+        ok &= not fresh and buf.data_ptr() == red._flat.data_ptr()
+        mean_rank = (1 + world) / 2.0
+        for i in range(L):
+            lo, hi = spans[i]
+            ok &= bool(torch.allclose(buf[lo:hi], torch.full((hi - lo,), mean_rank * (i + 1))))
+        w = model.convs[2].lin_edge.weight
+        ok &= w.grad.data_ptr() >= buf.data_ptr() and bool(torch.allclose(w.grad, torch.full_like(w, mean_rank * 3)))
+        # accumulation step: grads are NOT cleared -> the bucket is withheld, the flat fallback reduces .grad
+        buf2, fresh2 = backward(10.0)
+        red.finish()
+        ok &= fresh2
+        ok &= bool(torch.allclose(w.grad, torch.full_like(w, mean_rank * 3 + 10.0 * mean_rank * 3)))
+        unused = [p for p in model.parameters() if p.requires_grad and all(p is not q for q in covered)]
+        ok &= len(unused) > 0 and all(p.grad is None for p in unused)  # nobody used them: stay None (DDP semantics)
+        red.detach()
+        ok &= "_isg_grad_bucket" not in model.__dict__
+    ret[f"ok_{rank}"] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_layer_grad_allreduce_in_place_and_accumulation():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker_layer, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["ok_0"] and ret["ok_1"], dict(ret)

@@ -92,12 +92,12 @@ def test_sharded_gradients_equal_single_batch():
     assert n_none == 40  # 36 never-used MGAT parameters + layer-3 node_nn / ques_nn (masking off)
 
 
-def _nccl_worker(rank, world, port, ret):
+def _nccl_worker(rank, world, port, ret, kind="flat"):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import torch.distributed as dist
 
-    from isg_b200.dp import GradAllReduce, shard_graphs
+    from isg_b200.dp import GradAllReduce, LayerGradAllReduce, shard_graphs
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -106,7 +106,7 @@ def _nccl_worker(rank, world, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     m = _model(dev)
     first, count = shard_graphs(BTOT, rank, world)
-    red = GradAllReduce(m)
+    red = GradAllReduce(m) if kind == "flat" else LayerGradAllReduce(m, overlap=(kind == "layer"))
     worst_steps = []
     for step in range(2):  # two steps: the second one must not see stale slices from the first all-reduce
         for p in m.parameters():
@@ -126,19 +126,50 @@ def _nccl_worker(rank, world, port, ret):
         ret["worst"] = max(w for w, _ in worst_steps)
         ret["n_none"] = worst_steps[0][1]
         ret["same"] = bool(all(torch.equal(both[0], b) for b in both))
+        if kind != "flat":  # zero-copy: .grad lives inside the reducer's persistent bucket
+            w = m.convs[1].lin_edge.weight.grad
+            lo = red._flat.data_ptr()
+            ret["in_place"] = bool(lo <= w.data_ptr() < lo + 4 * red._flat.numel())
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-def test_nccl_two_gpu_gradient_allreduce():
+@pytest.mark.parametrize("kind", ["flat", "layer", "layer_unoverlapped"])
+def test_nccl_two_gpu_gradient_allreduce(kind):
+    """kind: flat = GradAllReduce (pack / one collective / unpack); layer = LayerGradAllReduce (in place on the
+    executor's gradient buffer, one collective per layer issued during backward); layer_unoverlapped = the same
+    bucket reduced by one collective in finish()."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
 
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 33500 + (os.getpid() % 2000)
-    mp.spawn(_nccl_worker, args=(2, port, ret), nprocs=2, join=True)
+    port = 33500 + (os.getpid() % 2000) + {"flat": 0, "layer": 1, "layer_unoverlapped": 2}[kind]
+    mp.spawn(_nccl_worker, args=(2, port, ret, kind), nprocs=2, join=True)
     assert ret["worst"] <= 1e-4, dict(ret)
     assert ret["n_none"] == 40 and ret["same"], dict(ret)
+    assert kind == "flat" or ret["in_place"], dict(ret)
+
+
+def test_layer_reducer_single_gpu_is_a_no_op():
+    """world == 1, no process group: LayerGradAllReduce hands the executor its persistent bucket, finish() leaves the
+    gradients exactly as the plain backward produced them."""
+    from isg_b200.dp import LayerGradAllReduce
+
+    dev = torch.device("cuda")
+    m, ref = _model(dev), _model(dev)
+    red = LayerGradAllReduce(m)
+    for _ in range(2):
+        for p in m.parameters():
+            p.grad = None
+        _shard_loss(m, 0, BTOT, dev).backward()
+        red.finish()
+    _shard_loss(ref, 0, BTOT, dev).backward()
+    for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
+        assert (a.grad is None) == (b.grad is None), k
+        if a.grad is not None:
+            assert torch.equal(a.grad, b.grad), k
+    w = m.convs[0].lin_edge.weight.grad
+    assert red._flat.data_ptr() <= w.data_ptr() < red._flat.data_ptr() + 4 * red._flat.numel()

@@ -517,8 +517,10 @@ def test_instr_gate_bwd_residual_and_accumulate_at_gqa_size():
     gi = _gi(torch.zeros(2, 0, dtype=torch.int64), batch, B)
     gx = torch.empty(N, D, device=DEV)
     gins = gins0.to(DEV).clone()
-    L.call("isg_instr_gate_bwd", L.ptr(gy.to(DEV)), L.ptr(x.to(DEV)), L.ptr(ins.to(DEV)), L.ptr(gi.graph_ptr), B, D,
-           L.ptr(gres.to(DEV)), 1, L.ptr(gx), L.ptr(gins), L.stream())
+    gy_d, x_d, ins_d, gres_d = (t.to(DEV) for t in (gy, x, ins, gres))  # keep the device copies alive over the call
+    L.call("isg_instr_gate_bwd", L.ptr(gy_d), L.ptr(x_d), L.ptr(ins_d), L.ptr(gi.graph_ptr), B, D,
+           L.ptr(gres_d), 1, L.ptr(gx), L.ptr(gins), L.stream())
+    torch.cuda.synchronize()
     assert util.rel_err(gx.cpu(), (xd.grad + gres.double()).float()) <= 1e-5
     assert util.rel_err(gins.cpu(), (idd.grad + gins0.double()).float()) <= 1e-5
 
