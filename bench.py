@@ -368,7 +368,8 @@ def main_isg(args, rank, world, local_rank):
         from isg_b200.dp import LayerGradAllReduce, OverlappedGradAllReduce
 
         dist.init_process_group("nccl", device_id=dev)
-        reducer = OverlappedGradAllReduce(model) if dp_mode == "hooks" else LayerGradAllReduce(model)
+        reducer = (OverlappedGradAllReduce(model) if dp_mode == "hooks"
+                   else LayerGradAllReduce(model, overlap=args.dp_overlap))
 
     keys = ("x", "edge_index", "instr_vectors", "global_language_feats", "edge_attr", "batch")
     host = {k: b[k].pin_memory() for k in keys}
@@ -575,7 +576,7 @@ def main_isg(args, rank, world, local_rank):
     if layer_reducer is not None:  # e2e: the layer reducer again (eager, same hooks)
         from isg_b200.dp import LayerGradAllReduce
 
-        reducer = LayerGradAllReduce(model)
+        reducer = LayerGradAllReduce(model, overlap=args.dp_overlap)
         overlap = True
     for _ in range(3):
         step_e2e()
@@ -685,8 +686,10 @@ def main_isg(args, rank, world, local_rank):
                    "step": "MGAT forward+backward" + (
                        (" + NCCL gradient all-reduce (42 MB in %d buckets, issued by gradient hooks during backward, "
                         "captured in the step graph)" % n_buckets) if n_buckets else
-                       " + NCCL gradient all-reduce (in place on the executor's flat gradient buffer, one slice per "
-                       "layer issued during the backward pass, captured in the step graph)" if dp_mode == "layer" else
+                       (" + NCCL gradient all-reduce in place on the executor's flat gradient buffer (no pack/unpack), "
+                        + ("one slice per layer issued during the backward pass" if args.dp_overlap else
+                           "one 42 MB collective after the backward pass") + ", captured in the step graph")
+                       if dp_mode == "layer" else
                        " + NCCL gradient all-reduce (42 MB flat bucket after the step)" if world > 1 else "")
                    if train else "MGAT forward (no_grad)",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
@@ -736,6 +739,8 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="multi-GPU (experimental): bucketed all-reduces issued during the backward pass and captured "
                          "in the step graph, instead of one flat all-reduce after the step")
+    ap.add_argument("--dp-overlap", action="store_true",
+                    help="multi-GPU: issue each layer's all-reduce during the backward pass (communication stream)")
     ap.add_argument("--dp-flat", action="store_true",
                     help="multi-GPU: the r1 reducer (flat 42 MB all-reduce with pack/unpack after each replay)")
     ap.add_argument("--no-edge-study", action="store_true", help="skip the batch-4096 edge-kernel roofline point")

@@ -297,6 +297,31 @@ int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int64_t ldx,
                      int64_t M, int Nout, int K, int mode, int dtype,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (d), bf16 configuration (BASELINE.json config 3 "fp32 vs bf16"): the same projections with bf16 operands on
+ * tcgen05 kind::f16, fp32 accumulation — what torch.autocast(bfloat16) would give the reference's Linear layers
+ * (models/mgat_v2_conv.py:177,181,259, models/mgat.py:156; the reference imports autocast and never enters it,
+ * training/train_epoch.py:7).  Operands are bf16 with row pitches that are multiples of 8 elements (16 bytes;
+ * a 300-wide operand uses pitch 304); outputs are bf16 (out_dtype = ISG_BF16) or fp32 (ISG_F32).
+ *   fwd:   y = act(x W^T + b), optional pre-activation z (same dtype as y)      x [M,K], w [Nout,K]
+ *   dgrad: g_x = (g_y W) [* gelu'(z_prev)] [+= when accumulate, fp32 only]      g_y [M,Nout], w_t = W^T [K,Nout]
+ *   wgrad: g_W = g_y^T x, fp32, deterministic split over M                      g_y [M,Nout], x [M,K]
+ * isg_weights_to_bf16 produces the bf16 copies W [rows, ld_w] and W^T [cols, ld_t] of up to 24 fp32 weights
+ * [rows, cols] in one launch (pad columns zero); isg_to_bf16 converts an activation (pad columns zero). */
+int isg_to_bf16(const float* in, int64_t ld_in, int64_t rows, int cols, void* out_bf16, int64_t ld_out, void* stream);
+int isg_weights_to_bf16(int n, const float* const* w, const int* rows, const int* cols, void* const* w_bf16,
+                        const int* ld_w, void* const* w_t_bf16, const int* ld_t, void* stream);
+int isg_linear_bf16_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
+                        void* y, int64_t ldy, void* z_pre /* or NULL */, int64_t ldz,
+                        int64_t M, int Nout, int K, int act, int out_dtype, void* stream);
+int isg_linear_bf16_dgrad(const void* g_y, int64_t ldg, const void* w_t, int64_t ldwt,
+                          const void* z_prev /* or NULL, dtype of g_x */, int64_t ldz,
+                          void* g_x, int64_t ldgx, int accumulate,
+                          int64_t M, int Nout, int K, int out_dtype, void* stream);
+size_t isg_linear_bf16_wgrad_workspace_bytes(int64_t M, int Nout, int K);
+int isg_linear_bf16_wgrad(const void* g_y, int64_t ldg, const void* x, int64_t ldx, float* g_w /* [Nout,K] */,
+                          int64_t M, int Nout, int K, void* workspace, size_t workspace_bytes, void* stream);
+
 /* g = g_y * gelu'(z)  elementwise (backward of a GELU that closes a projection). */
 int isg_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_t n, void* stream);
 

@@ -61,6 +61,12 @@ SIGNATURES = {
     "isg_linear_dgrad": (_I32, [_P, _I64, _P, _P, _P, _I64, _P, _I64, _I32, _I64, _I32, _I32, _I32, _I32, _P]),
     "isg_linear_wgrad_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "isg_linear_wgrad": (_I32, [_P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _SZ, _P]),
+    "isg_to_bf16": (_I32, [_P, _I64, _I64, _I32, _P, _I64, _P]),
+    "isg_weights_to_bf16": (_I32, [_I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "isg_linear_bf16_fwd": (_I32, [_P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P]),
+    "isg_linear_bf16_dgrad": (_I32, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I64, _I32, _I32, _I32, _P]),
+    "isg_linear_bf16_wgrad_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "isg_linear_bf16_wgrad": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P, _SZ, _P]),
     "isg_gelu_bwd": (_I32, [_P, _P, _P, _I64, _P]),
     "isg_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
     "isg_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
@@ -109,7 +115,8 @@ KERNELS_PER_CALL = {
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
     "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_transpose_split": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
-    "isg_gelu_bwd": 1, "isg_colsum": 2, "isg_colsum_multi": 2, "isg_gather_add_act_fwd": 1, "isg_segment_sum": 1, "isg_gather_rows": 1,
+    "isg_to_bf16": 1, "isg_weights_to_bf16": 1, "isg_linear_bf16_fwd": 1, "isg_linear_bf16_dgrad": 1,
+    "isg_linear_bf16_wgrad": 2, "isg_gelu_bwd": 1, "isg_colsum": 2, "isg_colsum_multi": 2, "isg_gather_add_act_fwd": 1, "isg_segment_sum": 1, "isg_gather_rows": 1,
     "isg_graphnorm64_fwd": 1, "isg_graphnorm64_bwd": 1, "isg_grad_sq_partials": 1, "isg_clip_finalize": 1,
     "isg_adam_update": 1,
 }

@@ -1,0 +1,113 @@
+"""bf16 configuration (BASELINE.json config 3, second half): the tcgen05 kind::f16 projections against float64
+products of the SAME bf16-rounded operands.  With identical operands the only differences are fp32 accumulation
+order and the rounding of the output to its storage type, so the bars are: fp32 outputs <= 2e-5 of the tensor's
+scale, bf16 outputs <= 2^-8 (one bf16 ulp of the largest element: 3.9e-3)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from isg_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16_ULP = 2.0 ** -8
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _bf16_padded(t):
+    """[rows, cols] fp32 -> (bf16 device tensor [rows, pad8(cols)] with zero pad columns, the rounded values as f64)."""
+    rows, cols = t.shape
+    out = torch.zeros(rows, _pad8(cols), dtype=torch.bfloat16, device=DEV)
+    out[:, :cols] = t.to(DEV).to(torch.bfloat16)
+    return out, out[:, :cols].double().cpu()
+
+
+def _gelu_grad(z):
+    return 0.5 * (1 + torch.erf(z / 2 ** 0.5)) + z * torch.exp(-0.5 * z * z) / (2 * torch.pi) ** 0.5
+
+
+@pytest.mark.parametrize("M,K,Nout,act,out_bf16", [
+    (1, 300, 1200, 0, True), (37, 300, 2400, 0, True), (4910, 300, 1200, 0, True), (515, 1200, 600, 1, True),
+    (4910, 600, 300, 1, False), (129, 300, 300, 0, False), (3000, 64, 48, 1, True), (40000, 300, 1200, 0, True),
+])
+def test_linear_bf16_fwd_dgrad_wgrad(M, K, Nout, act, out_bf16):
+    lib = L.load()
+    g = torch.Generator().manual_seed(M + K + Nout)
+    x, w = torch.randn(M, K, generator=g), torch.randn(Nout, K, generator=g) / K ** 0.5
+    b, gy = torch.randn(Nout, generator=g) * 0.1, torch.randn(M, Nout, generator=g)
+    xb, xr = _bf16_padded(x)
+    gyb, gyr = _bf16_padded(gy)
+    # weights through isg_weights_to_bf16 (W and W^T in one launch)
+    w_d = w.to(DEV)
+    ldw, ldt = _pad8(K), _pad8(Nout)
+    wb = torch.full((Nout, ldw), float("nan"), dtype=torch.bfloat16, device=DEV)
+    wt = torch.full((K, ldt), float("nan"), dtype=torch.bfloat16, device=DEV)
+    arr = lambda v, ct: (ct * 1)(v)
+    L.call("isg_weights_to_bf16", 1, arr(w_d.data_ptr(), ctypes.c_void_p), arr(Nout, ctypes.c_int), arr(K, ctypes.c_int),
+           arr(wb.data_ptr(), ctypes.c_void_p), arr(ldw, ctypes.c_int), arr(wt.data_ptr(), ctypes.c_void_p),
+           arr(ldt, ctypes.c_int), L.stream())
+    wr = w.to(torch.bfloat16).double()
+    assert torch.equal(wb[:, :K].double().cpu(), wr) and torch.equal(wt[:, :Nout].double().cpu(), wr.t())
+    assert float(wb[:, K:].abs().sum()) == 0.0 and float(wt[:, Nout:].abs().sum()) == 0.0  # pad columns are zero
+    # ---- forward
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    code = L.BF16 if out_bf16 else L.F32
+    ldy = _pad8(Nout) if out_bf16 else Nout
+    y = torch.zeros(M, ldy, dtype=odt, device=DEV)
+    z = torch.zeros(M, ldy, dtype=odt, device=DEV) if act else None
+    b_d = b.to(DEV)
+    L.call("isg_linear_bf16_fwd", L.ptr(xb), xb.stride(0), L.ptr(wb), ldw, L.ptr(b_d), L.ptr(y), ldy, L.ptr(z), ldy, M,
+           Nout, K, act, code, L.stream())
+    z_ref = xr @ wr.t() + b.double()
+    tol = BF16_ULP if out_bf16 else 2e-5
+    if act:
+        assert util.rel_err(z[:, :Nout].double().cpu(), z_ref) <= tol
+        z_used = z[:, :Nout].double().cpu()  # the kernel applies GELU to the STORED pre-activation
+        y_ref = torch.nn.functional.gelu(z_used)
+    else:
+        y_ref = z_ref
+    assert util.rel_err(y[:, :Nout].double().cpu(), y_ref) <= tol, util.rel_err(y[:, :Nout].double().cpu(), y_ref)
+    # ---- dgrad (x gelu'(z_prev) when a pre-activation of the PREVIOUS layer is given; it has K columns)
+    ldgx = _pad8(K) if out_bf16 else K
+    gx = torch.zeros(M, ldgx, dtype=odt, device=DEV)
+    zp = (torch.randn(M, K, generator=g)).to(DEV).to(odt) if act else None
+    zp_pad = None
+    if zp is not None:
+        zp_pad = torch.zeros(M, ldgx, dtype=odt, device=DEV)
+        zp_pad[:, :K] = zp
+    L.call("isg_linear_bf16_dgrad", L.ptr(gyb), gyb.stride(0), L.ptr(wt), ldt, L.ptr(zp_pad), ldgx, L.ptr(gx), ldgx, 0, M,
+           Nout, K, code, L.stream())
+    gx_ref = gyr @ wr
+    if zp is not None:
+        gx_ref = gx_ref * _gelu_grad(zp.double().cpu())
+    assert util.rel_err(gx[:, :K].double().cpu(), gx_ref) <= tol, util.rel_err(gx[:, :K].double().cpu(), gx_ref)
+    if not out_bf16:  # accumulate (fp32 outputs only)
+        L.call("isg_linear_bf16_dgrad", L.ptr(gyb), gyb.stride(0), L.ptr(wt), ldt, L.ptr(zp_pad), ldgx, L.ptr(gx), ldgx, 1,
+               M, Nout, K, code, L.stream())
+        assert util.rel_err(gx[:, :K].double().cpu(), 2 * gx_ref) <= 2 * tol
+    # ---- wgrad (fp32, deterministic split over M)
+    gw = torch.empty(Nout, K, device=DEV)
+    nb = lib.isg_linear_bf16_wgrad_workspace_bytes(M, Nout, K)
+    ws = L.workspace(nb, DEV)
+    for _ in range(2):
+        L.call("isg_linear_bf16_wgrad", L.ptr(gyb), gyb.stride(0), L.ptr(xb), xb.stride(0), L.ptr(gw), M, Nout, K, L.ptr(ws),
+               nb, L.stream())
+        if _ == 0:
+            first = gw.clone()
+    assert torch.equal(first, gw)  # run-to-run identical
+    gw_ref = gyr.t() @ xr
+    assert util.rel_err(gw.double().cpu(), gw_ref) <= 2e-5, util.rel_err(gw.double().cpu(), gw_ref)
+
+
+def test_to_bf16_pads_with_zeros():
+    x = torch.randn(77, 300, device=DEV)
+    out = torch.full((77, 304), float("nan"), dtype=torch.bfloat16, device=DEV)
+    L.call("isg_to_bf16", L.ptr(x), 300, 77, 300, L.ptr(out), 304, L.stream())
+    assert torch.equal(out[:, :300], x.to(torch.bfloat16))
+    assert float(out[:, 300:].abs().sum()) == 0.0
