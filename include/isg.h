@@ -330,11 +330,12 @@ size_t isg_colsum_workspace_bytes(int64_t rows, int cols);
 int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, float* out,
                void* workspace, size_t workspace_bytes, void* stream);
 /* n (<= 12) independent column sums in two launches: out[i][c] = sum_r in[i][r, c].  Bit-identical to n isg_colsum
- * calls (same slabs, same fold order).  The arrays are host arrays.  Used by isg_mgat_layer_bwd for the bias /
+ * calls (same slabs, same fold order).  The arrays are host arrays; dtypes[i] = ISG_F32 / ISG_BF16 is the storage
+ * type of in[i] (NULL = all fp32; sums are always fp32).  Used by isg_mgat_layer_bwd for the bias /
  * GraphNorm-affine gradients of one layer (models/mgat_v2_conv.py:63-103 biases, models/mgat.py:79-89,163). */
 size_t isg_colsum_multi_workspace_bytes(int n, const int64_t* rows, const int* cols);
-int isg_colsum_multi(int n, const float* const* in, const int64_t* ld, const int64_t* rows, const int* cols,
-                     float* const* out, void* workspace, size_t workspace_bytes, void* stream);
+int isg_colsum_multi(int n, const void* const* in, const int* dtypes, const int64_t* ld, const int64_t* rows,
+                     const int* cols, float* const* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * SURVEY.md section 8 row f2 — scene-graph encoding layer in front of MGAT: torch_geometric MetaLayer(EdgeModel,

@@ -26,6 +26,8 @@
   X(D_ACC_EDGE_ATTR)   /* 1: g_edge_attr += (another layer already wrote it) */                                   \
   X(D_ACC_GLF)         /* 1: g_glf += */                                                                          \
   X(D_NEED_GEA)        /* 0: skip the edge_attr gradient */                                                       \
+  X(D_BF16)            /* 1: bf16 configuration — projections on kind::f16, bf16 storage of xlr / e_proj / out /   \
+                          y1 / z1 and of the gradients g_z1 / g_out / g_xlr / g_eproj (the P_*_BF slots are set) */ \
   X(D_WS_BYTES)
 #define ISG_LAYER_SCALARS(X) X(F_SLOPE) X(F_EPS) X(F_ALPHA) X(F_BETA) X(F_TAU_IN) X(F_TAU_TGT) X(F_GUMBEL_TAU)
 #define ISG_LAYER_PTRS(X)                                                                                      \
@@ -37,8 +39,11 @@
   /* parameters */                                                                                             \
   X(P_W_LR) X(P_B_LR) X(P_W_E) X(P_ATT) X(P_BIAS) X(P_WP0) X(P_BP0) X(P_WP2) X(P_BP2) X(P_BN_W) X(P_BN_B)       \
   X(P_BN_MS) X(P_WN) X(P_BNN) X(P_WQ) X(P_BQ) X(P_AIMLE_STATE)                                                   \
+  /* bf16 configuration: edge_attr [E, pad8(D)] and the weights as bf16 W [Nout, pad8(K)] / W^T [K, pad8(Nout)] */ \
+  X(P_EDGE_ATTR_BF) X(P_W_LR_BF) X(P_W_LR_T_BF) X(P_W_E_BF) X(P_W_E_T_BF) X(P_WP0_BF) X(P_WP0_T_BF) X(P_WP2_BF)   \
+  X(P_WP2_T_BF)                                                                                                \
   /* activations (written by the forward, read by the backward) */                                             \
-  X(P_XG) X(P_XLR) X(P_EPROJ) X(P_OUT) X(P_ALPHA) X(P_Z1) X(P_Y1) X(P_Z2) X(P_Y2) X(P_SA) X(P_MEAN) X(P_RSTD)    \
+  X(P_XG) X(P_XG_BF) X(P_XLR) X(P_EPROJ) X(P_OUT) X(P_ALPHA) X(P_Z1) X(P_Y1) X(P_Z2) X(P_Y2) X(P_SA) X(P_MEAN) X(P_RSTD)    \
   X(P_H_OUT) X(P_XN_PRE) X(P_XN) X(P_Q_PRE) X(P_Q) X(P_THETA) X(P_MASK) X(P_ZD) X(P_MARG) X(P_EMASK)              \
   /* backward: incoming gradients */                                                                           \
   X(P_G_H_OUT) X(P_G_MASK_EXT)                                                                                   \
@@ -66,13 +71,14 @@ const Slot kSlots[] = {ISG_LAYER_DIMS(X) ISG_LAYER_SCALARS(X) ISG_LAYER_PTRS(X)}
 #undef X
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int pad8(int x) { return (x + 7) & ~7; }
 inline size_t max2(size_t a, size_t b) { return a > b ? a : b; }
 
 enum { SAMP_IMLE = 1, SAMP_AIMLE = 2, SAMP_GUMBEL = 3, SAMP_SIMPLE = 4 };
 
 // Backward workspace layout (bytes), shared by the size query and the executor.
 struct BwdWs {
-  size_t g_y2, parts, g_z1, g_out, g_xlr, g_ep, g_em, g_xg, dy, g_theta, g_xn, g_q, scratch, colsum, colsum_bytes,
+  size_t g_y2, g_y2_bf, parts, g_z1, g_out, g_xlr, g_ep, g_em, g_xg, dy, g_theta, g_xn, g_q, scratch, colsum, colsum_bytes,
       wgrad, wgrad_bytes, edge, edge_bytes, aimle, aimle_bytes, total;
 };
 BwdWs bwd_ws(const int64_t* d) {
@@ -87,6 +93,7 @@ BwdWs bwd_ws(const int64_t* d) {
     return o;
   };
   w.g_y2 = take((size_t)N * D * 4);
+  w.g_y2_bf = take(d[D_BF16] ? (size_t)N * pad8(D) * 2 : 0);
   w.parts = take((size_t)3 * B * D * 4);
   w.g_z1 = take((size_t)N * HID * 4);
   w.g_out = take((size_t)N * HC * 4);
@@ -108,6 +115,10 @@ BwdWs bwd_ws(const int64_t* d) {
   w.wgrad_bytes = max2(max2(isg_linear_wgrad_workspace_bytes(E, HC, D), isg_linear_wgrad_workspace_bytes(N, 2 * HC, D)),
                        max2(max2(isg_linear_wgrad_workspace_bytes(N, HID, HC), isg_linear_wgrad_workspace_bytes(N, D, HID)),
                             max2(isg_linear_wgrad_workspace_bytes(N, D, D), isg_linear_wgrad_workspace_bytes(B, D, D))));
+  if (d[D_BF16])
+    w.wgrad_bytes = max2(w.wgrad_bytes,
+                         max2(max2(isg_linear_bf16_wgrad_workspace_bytes(E, HC, D), isg_linear_bf16_wgrad_workspace_bytes(N, 2 * HC, D)),
+                              max2(isg_linear_bf16_wgrad_workspace_bytes(N, HID, HC), isg_linear_bf16_wgrad_workspace_bytes(N, D, HID))));
   w.wgrad = take(w.wgrad_bytes);
   w.edge_bytes = isg_gat_edge_bwd_workspace_bytes(N, E, B, H, D);
   w.edge = take(w.edge_bytes);
@@ -205,6 +216,32 @@ extern "C" int isg_mgat_layer_fwd(const int64_t* d, const double* f, void* const
     }
   }
 
+  if (d[D_BF16]) {
+    // bf16 configuration: same sequence, projections on kind::f16 (bf16 operands, fp32 accumulation), bf16 storage
+    // of the big activations; the gate logits above and scatter-SDPA / GraphNorm below stay fp32
+    const int Dp = pad8(D);
+    if (HC % 8 || HID % 8) return ISG_EUNSUPPORTED;
+    CK(isg_to_bf16(xg, D, N, D, p[P_XG_BF], Dp, stream));
+    CK(isg_linear_bf16_fwd(p[P_XG_BF], Dp, p[P_W_LR_BF], Dp, ptr<const float>(p, P_B_LR), p[P_XLR], 2 * HC, nullptr, 0, N,
+                           2 * HC, D, ISG_ACT_NONE, ISG_BF16, stream));
+    if (E > 0)
+      CK(isg_linear_bf16_fwd(p[P_EDGE_ATTR_BF], Dp, p[P_W_E_BF], Dp, nullptr, p[P_EPROJ], HC, nullptr, 0, E, HC, D,
+                             ISG_ACT_NONE, ISG_BF16, stream));
+    const __nv_bfloat16* xlr16 = ptr<const __nv_bfloat16>(p, P_XLR);
+    CK(isg_gat_edge_fwd(xlr16, xlr16 + HC, 2 * HC, p[P_EPROJ], ptr<const float>(p, P_ATT), ptr<const float>(p, P_BIAS),
+                        emask, ptr<const int32_t>(p, P_DST_PTR), ptr<const int32_t>(p, P_DST_NBR),
+                        ptr<const int32_t>(p, P_DST_EID), ptr<const int32_t>(p, P_DST_ORDER), p[P_OUT], HC,
+                        ptr<float>(p, P_ALPHA), N, E, H, D, (float)f[F_SLOPE], ISG_BF16, stream));
+    CK(isg_linear_bf16_fwd(p[P_OUT], HC, p[P_WP0_BF], HC, ptr<const float>(p, P_BP0), p[P_Y1], HID, p[P_Z1], HID, N, HID,
+                           HC, ISG_ACT_GELU, ISG_BF16, stream));
+    CK(isg_linear_bf16_fwd(p[P_Y1], HID, p[P_WP2_BF], HID, ptr<const float>(p, P_BP2), p[P_Y2], D, p[P_Z2], D, N, D, HID,
+                           ISG_ACT_GELU, ISG_F32, stream));
+    CK(isg_sdpa_graphnorm_fwd(ptr<const float>(p, P_Y2), ins, x_in, ptr<const float>(p, P_BN_W),
+                              ptr<const float>(p, P_BN_B), ptr<const float>(p, P_BN_MS), gptr, B, D, nmax,
+                              (float)f[F_EPS], ptr<float>(p, P_H_OUT), ptr<float>(p, P_SA), ptr<float>(p, P_MEAN),
+                              ptr<float>(p, P_RSTD), stream));
+    return ISG_OK;
+  }
   float* xlr = ptr<float>(p, P_XLR);
   CK(isg_linear_fwd(xg, D, p[P_W_LR], nullptr, nullptr, ptr<const float>(p, P_B_LR), xlr, 2 * HC, nullptr, 0, N, 2 * HC,
                     D, ISG_ACT_NONE, mode, ISG_F32, stream));  // :177,181 (lin_l | lin_r, stacked weights)
@@ -258,19 +295,23 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
   const bool masked = d[D_MASKED] != 0;
   // bias / affine gradients are column sums of tensors this backward leaves in its workspace: they are collected
   // here and issued as one batched call (two launches) after the last producer
-  const float* cs_in[9];
+  const void* cs_in[9];
   float* cs_out[9];
   int64_t cs_ld[9], cs_rows[9];
-  int cs_cols[9], cs_n = 0;
-  auto colsum = [&](const float* t, int64_t rows, int cols, int slot) -> int {
+  int cs_cols[9], cs_dt[9], cs_n = 0;
+  auto colsum_t = [&](const void* t, int64_t rows, int cols, int slot, int dt) -> int {
     cs_in[cs_n] = t;
     cs_out[cs_n] = ptr<float>(p, slot);
     cs_ld[cs_n] = cols;
     cs_rows[cs_n] = rows;
     cs_cols[cs_n] = cols;
+    cs_dt[cs_n] = dt;
     ++cs_n;
     return ISG_OK;
   };
+  auto colsum = [&](const float* t, int64_t rows, int cols, int slot) -> int { return colsum_t(t, rows, cols, slot, ISG_F32); };
+  const bool bf = d[D_BF16] != 0;
+  const int Dp = pad8(D);
 
   // scatter-SDPA + GraphNorm + residual (mgat.py:168-172); the residual's share of g_h_in is added in the last step
   CK(isg_sdpa_graphnorm_bwd(g_h_out, ptr<const float>(p, P_Y2), ins, ptr<const float>(p, P_BN_W),
@@ -282,6 +323,16 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
   CK(colsum(parts + (size_t)2 * B * D, B, D, P_G_BN_MS));
   // x_proj[2]: y2 = gelu(z2), z2 = y1 Wp2^T + bp2
   CK(isg_gelu_bwd(g_y2, ptr<const float>(p, P_Z2), g_y2, N * (int64_t)D, stream_));
+  if (bf) {
+    void* gy2b = ws + w.g_y2_bf;
+    CK(isg_to_bf16(g_y2, D, N, D, gy2b, Dp, stream_));
+    CK(isg_linear_bf16_dgrad(gy2b, Dp, p[P_WP2_T_BF], Dp, p[P_Z1], HID, g_z1, HID, 0, N, D, HID, ISG_BF16, stream_));
+    CK(isg_linear_bf16_wgrad(gy2b, Dp, p[P_Y1], HID, ptr<float>(p, P_G_WP2), N, D, HID, wgw, w.wgrad_bytes, stream_));
+    CK(colsum(g_y2, N, D, P_G_BP2));
+    CK(isg_linear_bf16_dgrad(g_z1, HID, p[P_WP0_T_BF], HID, nullptr, 0, g_out, HC, 0, N, HID, HC, ISG_BF16, stream_));
+    CK(isg_linear_bf16_wgrad(g_z1, HID, p[P_OUT], HC, ptr<float>(p, P_G_WP0), N, HID, HC, wgw, w.wgrad_bytes, stream_));
+    CK(colsum_t(g_z1, N, HID, P_G_BP0, ISG_BF16));
+  } else {
   CK(isg_linear_dgrad(g_y2, D, p[P_WP2], nullptr, p[P_Z1], HID, g_z1, HID, 0, N, D, HID, mode, ISG_F32,
                       stream_));  // (g_z2 Wp2) * gelu'(z1): the first GELU's derivative in the epilogue
   CK(isg_linear_wgrad(g_y2, D, p[P_Y1], HID, ptr<float>(p, P_G_WP2), nullptr, N, D, HID, mode, ISG_F32, wgw,
@@ -292,19 +343,39 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
   CK(isg_linear_wgrad(g_z1, HID, p[P_OUT], HC, ptr<float>(p, P_G_WP0), nullptr, N, HID, HC, mode, ISG_F32, wgw,
                       w.wgrad_bytes, stream_));
   CK(colsum(g_z1, N, HID, P_G_BP0));
+  }
   // edge attention
-  const bool fused = d[D_EDGE_FUSED] && d[D_CLOSED];
+  const bool fused = d[D_EDGE_FUSED] && d[D_CLOSED] && !bf;
   const float* xlr = ptr<const float>(p, P_XLR);
-  CK(isg_gat_edge_bwd(g_out, HC, xlr, xlr + HC, 2 * HC, p[P_EPROJ], ptr<const float>(p, P_ATT),
+  const void* xr_ptr = bf ? (const void*)(ptr<const __nv_bfloat16>(p, P_XLR) + HC) : (const void*)(xlr + HC);
+  void* g_xr_ptr = bf ? (void*)((__nv_bfloat16*)g_xlr + HC) : (void*)(g_xlr + HC);
+  CK(isg_gat_edge_bwd(g_out, HC, xlr, xr_ptr, 2 * HC, p[P_EPROJ], ptr<const float>(p, P_ATT),
                       ptr<const float>(p, P_BIAS), masked ? ptr<const float>(p, P_EMASK) : nullptr,
                       ptr<const float>(p, P_ALPHA), p[P_OUT], HC, ptr<const int32_t>(p, P_DST_PTR),
                       ptr<const int32_t>(p, P_DST_NBR), ptr<const int32_t>(p, P_DST_EID),
                       ptr<const int32_t>(p, P_DST_ORDER), ptr<const int32_t>(p, P_SRC_PTR),
                       ptr<const int32_t>(p, P_SRC_NBR), ptr<const int32_t>(p, P_SRC_EID),
-                      ptr<const int32_t>(p, P_SRC_ORDER), g_xlr, g_xlr + HC, 2 * HC, g_ep, ptr<float>(p, P_G_ATT),
-                      masked ? g_em : nullptr, N, E, H, D, (float)f[F_SLOPE], ISG_F32, fused ? batch32 : nullptr,
+                      ptr<const int32_t>(p, P_SRC_ORDER), g_xlr, g_xr_ptr, 2 * HC, g_ep, ptr<float>(p, P_G_ATT),
+                      masked ? g_em : nullptr, N, E, H, D, (float)f[F_SLOPE], bf ? ISG_BF16 : ISG_F32,
+                      fused ? batch32 : nullptr,
                       fused ? gptr : nullptr, B, fused ? nmax : 0, ws + w.edge, w.edge_bytes, stream_));
-  CK(colsum(g_out, N, HC, P_G_BIAS));
+  CK(colsum_t(g_out, N, HC, P_G_BIAS, bf ? ISG_BF16 : ISG_F32));
+  if (bf) {
+    if (E > 0) {
+      if (d[D_NEED_GEA])
+        CK(isg_linear_bf16_dgrad(g_ep, HC, p[P_W_E_T_BF], HC, nullptr, 0, p[P_G_EDGE_ATTR], D, d[D_ACC_EDGE_ATTR] ? 1 : 0, E,
+                                 HC, D, ISG_F32, stream_));
+      CK(isg_linear_bf16_wgrad(g_ep, HC, p[P_EDGE_ATTR_BF], Dp, ptr<float>(p, P_G_W_E), E, HC, D, wgw, w.wgrad_bytes,
+                               stream_));
+    } else {
+      cudaError_t e = cudaMemsetAsync(p[P_G_W_E], 0, (size_t)HC * D * 4, stream);
+      if (e != cudaSuccess) return (int)e;
+    }
+    CK(isg_linear_bf16_dgrad(g_xlr, 2 * HC, p[P_W_LR_T_BF], 2 * HC, nullptr, 0, g_xg, D, 0, N, 2 * HC, D, ISG_F32, stream_));
+    CK(isg_linear_bf16_wgrad(g_xlr, 2 * HC, p[P_XG_BF], Dp, ptr<float>(p, P_G_W_LR), N, 2 * HC, D, wgw, w.wgrad_bytes,
+                             stream_));
+    CK(colsum_t(g_xlr, N, 2 * HC, P_G_B_LR, ISG_BF16));
+  } else {
   // lin_edge
   if (E > 0) {
     if (d[D_NEED_GEA])
@@ -321,6 +392,7 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
   CK(isg_linear_wgrad(g_xlr, 2 * HC, p[P_XG], D, ptr<float>(p, P_G_W_LR), nullptr, N, 2 * HC, D, mode, ISG_F32, wgw,
                       w.wgrad_bytes, stream_));
   CK(colsum(g_xlr, N, 2 * HC, P_G_B_LR));
+  }
   // node mask: NodeMaskToEdgeMask's custom backward, the sampler's perturbation gradient, the gate projections
   if (masked) {
     CK(isg_node_edge_mask_bwd(g_em, ptr<const int32_t>(p, P_DST_PTR), ptr<const int32_t>(p, P_DST_EID), N, dy, stream_));
@@ -364,7 +436,7 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
                         stream_));
     CK(colsum(g_q, B, D, P_G_BQ));
   }
-  CK(isg_colsum_multi(cs_n, cs_in, cs_ld, cs_rows, cs_cols, cs_out, cs, w.colsum_bytes, stream_));
+  CK(isg_colsum_multi(cs_n, cs_in, cs_dt, cs_ld, cs_rows, cs_cols, cs_out, cs, w.colsum_bytes, stream_));
   // gating + residual: g_x_in = g_xg * d gelu(x*ins)/dx + g_h_out;  g_ins += ...
   CK(isg_instr_gate_bwd(g_xg, ptr<const float>(p, P_X_IN), ins, gptr, B, D, g_h_out, 1, ptr<float>(p, P_G_X_IN),
                         ptr<float>(p, P_G_INS), stream_));

@@ -221,7 +221,9 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
       const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
       const int n0 = n_blk * BN;
-      const int n_lim = min(g.cols, n0 + BN);
+      // bf16 outputs are written in whole 8-column groups: a 300-wide output fills its pitch-304 row, pads = 0
+      const int c_lim = g.cols;
+      const int n_lim = min(OUT_BF16 ? ((g.cols + 7) & ~7) : g.cols, n0 + BN);
       const int ms = it & 1;
       const uint32_t mphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(mfull_bar(ms), mphase);
@@ -248,7 +250,7 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               if (g.bias) {
                 const float4 b0 = Vec4<float>::ld(g.bias + col);
                 w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
-                if (hi_ok) {
+                if (col + 4 < c_lim) {
                   const float4 b1 = Vec4<float>::ld(g.bias + col + 4);
                   w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
                 }
@@ -291,6 +293,11 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
             }
             if (OUT_BF16) {
+              if (col + 8 > c_lim) {  // pad columns of the last group: exact zeros whatever z_prev holds there
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (col + j >= c_lim) w[j] = 0.f;
+              }
               *reinterpret_cast<uint4*>((__nv_bfloat16*)g.C + row * g.ldc + col) =
                   make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
             } else {
@@ -555,8 +562,9 @@ extern "C" int isg_linear_bf16_fwd(const void* x, int64_t ldx, const void* w, in
   const bool ob = out_dtype == ISG_BF16;
   if (!ob && out_dtype != ISG_F32) return ISG_EUNSUPPORTED;
   const int q = ob ? 8 : 4;
-  if (Nout % q || ldy % q || (z_pre && ldz % q) || ((uintptr_t)y & 15) || ((uintptr_t)z_pre & 15) ||
-      (bias && ((uintptr_t)bias & 15)))
+  const int need_ld = ob ? ((Nout + 7) & ~7) : Nout;  // bf16 rows are written in whole 8-column groups
+  if (Nout % 4 || ldy % q || ldy < need_ld || (z_pre && (ldz % q || ldz < need_ld)) || ((uintptr_t)y & 15) ||
+      ((uintptr_t)z_pre & 15) || (bias && ((uintptr_t)bias & 15)))
     return ISG_EUNSUPPORTED;
   BfGemm t{};
   t.A = x; t.lda = ldx; t.B = w; t.ldb = ldw; t.C = y; t.ldc = ldy; t.rows = M; t.cols = Nout; t.R = K;
@@ -575,7 +583,9 @@ extern "C" int isg_linear_bf16_dgrad(const void* g_y, int64_t ldg, const void* w
   if (!ob && out_dtype != ISG_F32) return ISG_EUNSUPPORTED;
   if (ob && accumulate) return ISG_EUNSUPPORTED;
   const int q = ob ? 8 : 4;
-  if (K % q || ldgx % q || (z_prev && ldz % q) || ((uintptr_t)g_x & 15) || ((uintptr_t)z_prev & 15))
+  const int need_ld = ob ? ((K + 7) & ~7) : K;
+  if (K % 4 || ldgx % q || ldgx < need_ld || (z_prev && (ldz % q || ldz < need_ld)) || ((uintptr_t)g_x & 15) ||
+      ((uintptr_t)z_prev & 15))
     return ISG_EUNSUPPORTED;
   BfGemm t{};
   t.A = g_y; t.lda = ldg; t.B = w_t; t.ldb = ldwt; t.C = g_x; t.ldc = ldgx; t.rows = M; t.cols = K; t.R = Nout;

@@ -564,12 +564,12 @@ colsum_final_kernel(const float* __restrict__ part, int nparts, int cols, float*
 // the 5.3 ms c3 step).  Same slabs, same fold order as colsum_partial/final, so results are bit-identical.
 constexpr int CS_MAX_JOBS = 12;
 struct ColsumJob {
-  const float* in;
+  const void* in;  // fp32, or bf16 when `bf16` is set (4 columns = one 8-byte load)
   float* out;
   float* part;
   int64_t ld;
   int64_t rows;
-  int cols, parts, cblocks, block0, fblock0;
+  int cols, parts, cblocks, block0, fblock0, bf16;
 };
 struct ColsumBatch {
   ColsumJob job[CS_MAX_JOBS];
@@ -586,18 +586,30 @@ __global__ void __launch_bounds__(64) colsum_multi_partial_kernel(const __grid_c
   if (c >= J.cols) return;
   const int64_t r0 = (int64_t)slab * CS_ROWS;
   const int64_t r1 = min(J.rows, r0 + CS_ROWS);
-  const float* in = J.in;
   const int64_t ld = J.ld;
   float4 s = f4_zero();
   int64_t r = r0;
-  for (; r + 8 <= r1; r += 8) {
-    float4 v[8];
+  if (J.bf16) {
+    const __nv_bfloat16* in = (const __nv_bfloat16*)J.in;
+    for (; r + 8 <= r1; r += 8) {
+      float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = Vec4<float>::ld(in + (r + u) * ld + c);
+      for (int u = 0; u < 8; ++u) v[u] = Vec4<__nv_bfloat16>::ld(in + (r + u) * ld + c);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
+      for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
+    }
+    for (; r < r1; ++r) s = f4_add(s, Vec4<__nv_bfloat16>::ld(in + r * ld + c));
+  } else {
+    const float* in = (const float*)J.in;
+    for (; r + 8 <= r1; r += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = Vec4<float>::ld(in + (r + u) * ld + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
+    }
+    for (; r < r1; ++r) s = f4_add(s, Vec4<float>::ld(in + r * ld + c));
   }
-  for (; r < r1; ++r) s = f4_add(s, Vec4<float>::ld(in + r * ld + c));
   Vec4<float>::st(J.part + (int64_t)slab * J.cols + c, s);
 }
 
@@ -807,8 +819,8 @@ extern "C" size_t isg_colsum_multi_workspace_bytes(int n, const int64_t* rows, c
   return total;
 }
 
-extern "C" int isg_colsum_multi(int n, const float* const* in, const int64_t* ld, const int64_t* rows, const int* cols,
-                                float* const* out, void* workspace, size_t ws_bytes, void* stream_) {
+extern "C" int isg_colsum_multi(int n, const void* const* in, const int* dtypes, const int64_t* ld, const int64_t* rows,
+                                const int* cols, float* const* out, void* workspace, size_t ws_bytes, void* stream_) {
   if (n < 0 || n > CS_MAX_JOBS) return ISG_EINVAL;
   if (n == 0) return ISG_OK;
   if (!in || !ld || !rows || !cols || !out) return ISG_EINVAL;
@@ -826,8 +838,12 @@ extern "C" int isg_colsum_multi(int n, const float* const* in, const int64_t* ld
       continue;
     }
     if (!in[i]) return ISG_EINVAL;
-    if (cols[i] % 4 != 0 || ld[i] % 4 != 0 || ((uintptr_t)in[i] & 15) || ((uintptr_t)out[i] & 15)) return ISG_EUNSUPPORTED;
+    const int dt = dtypes ? dtypes[i] : ISG_F32;
+    if (dt != ISG_F32 && dt != ISG_BF16) return ISG_EUNSUPPORTED;
+    if (cols[i] % 4 != 0 || ld[i] % 4 != 0 || ((uintptr_t)in[i] & (dt == ISG_BF16 ? 7 : 15)) || ((uintptr_t)out[i] & 15))
+      return ISG_EUNSUPPORTED;
     ColsumJob& J = batch.job[batch.n++];
+    J.bf16 = dt == ISG_BF16 ? 1 : 0;
     J.in = in[i];
     J.out = out[i];
     J.part = (float*)ws;

@@ -97,10 +97,51 @@ def supported(model, explainer):
     return all(p.dtype == torch.float32 for p in model.parameters())
 
 
+BF16_MODE = 3  # ops.set_gemm_mode(3): the bf16 configuration (projections on kind::f16, bf16 activation storage)
+
+
+def pad8(n):
+    return (int(n) + 7) & ~7
+
+
+# the four big projection weights of a layer, as (slot stem, parameter getter)
+def _bf16_weights(model, i):
+    conv, xp = model.convs[i], model.x_proj[i]
+    wl, wr = conv.lin_l.weight, conv.lin_r.weight
+    w_lr = wl.data.new_empty(0).set_(wl.data.untyped_storage(), wl.data.storage_offset(),
+                                     (wl.shape[0] + wr.shape[0], wl.shape[1]))  # the stacked [W_l; W_r] (ensure_stacked)
+    return [("P_W_LR", w_lr), ("P_W_E", conv.lin_edge.weight.data), ("P_WP0", xp[0].weight.data),
+            ("P_WP2", xp[2].weight.data)]
+
+
+def convert_weights_bf16(model):
+    """bf16 copies W [Nout, pad8(K)] and W^T [K, pad8(Nout)] of the four projection weights of every layer, made by
+    ONE isg_weights_to_bf16 launch per forward (weights change every optimizer step).  Returns (buffer, {(layer,
+    slot): data_ptr})."""
+    jobs = [(i, stem, w) for i in range(len(model.convs)) for stem, w in _bf16_weights(model, i)]
+    total = sum(w.shape[0] * pad8(w.shape[1]) + w.shape[1] * pad8(w.shape[0]) + 16 for _i, _s, w in jobs)
+    buf = torch.empty(total, dtype=torch.bfloat16, device=jobs[0][2].device)
+    n = len(jobs)
+    base = buf.data_ptr()
+    ptrs, off = {}, 0
+    w_in, w_out, t_out = (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)()
+    rows, cols, ldw, ldt = ((ctypes.c_int * n)() for _ in range(4))
+    for j, (i, stem, w) in enumerate(jobs):
+        nout, k = w.shape
+        w_in[j], rows[j], cols[j], ldw[j], ldt[j] = w.data_ptr(), nout, k, pad8(k), pad8(nout)
+        w_out[j] = base + 2 * off
+        off += (nout * pad8(k) + 7) & ~7
+        t_out[j] = base + 2 * off
+        off += (k * pad8(nout) + 7) & ~7
+        ptrs[(i, stem + "_BF")], ptrs[(i, stem + "_T_BF")] = w_out[j], t_out[j]
+    L.call("isg_weights_to_bf16", n, w_in, rows, cols, w_out, ldw, t_out, ldt, L.stream())
+    return buf, ptrs
+
+
 class _Plan:
     """Per-(model, sizes) constants: arena offsets and the flat layout of the parameter gradients."""
 
-    def __init__(self, model, N, E, B, nmax):
+    def __init__(self, model, N, E, B, nmax, bf16=False):
         conv0 = model.convs[0]
         self.L = len(model.convs)
         self.D, self.H = conv0.out_channels, conv0.heads
@@ -109,11 +150,15 @@ class _Plan:
         D, H, HC, HID = self.D, self.H, self.HC, self.HID
         self.masked = [c.mask.masking_threshold != 1.0 for c in model.convs]
         off = 0
+        self.bf16 = bool(bf16)
+        half = {"P_XLR", "P_EPROJ", "P_OUT", "P_Z1", "P_Y1", "P_XG_BF"} if bf16 else set()  # stored as bf16
         self.act = []  # per layer: slot name -> byte offset in the arena
         for i in range(self.L):
             sizes = [("P_XG", N * D), ("P_XLR", N * 2 * HC), ("P_EPROJ", E * HC), ("P_OUT", N * HC), ("P_ALPHA", E * H),
                      ("P_Z1", N * HID), ("P_Y1", N * HID), ("P_Z2", N * D), ("P_Y2", N * D), ("P_SA", N),
                      ("P_MEAN", B * D), ("P_RSTD", B * D), ("P_H_OUT", N * D)]
+            if bf16:
+                sizes.append(("P_XG_BF", N * pad8(D)))
             if self.masked[i]:
                 k = int(model.convs[i].mask.sample_k)
                 sizes += [("P_XN_PRE", N * D), ("P_XN", N * D), ("P_Q_PRE", B * D), ("P_Q", B * D), ("P_THETA", N),
@@ -122,7 +167,7 @@ class _Plan:
             o = {}
             for name, n in sizes:
                 o[name] = off
-                off += _al(4 * max(n, 1))
+                off += _al((2 if name in half else 4) * max(n, 1))
             self.act.append(o)
         self.arena_bytes = off
         # parameter gradients: backward order (last layer first) so each layer is one contiguous slice
@@ -136,14 +181,14 @@ class _Plan:
         self.grad_numel = goff
 
 
-def _plan(model, N, E, B, nmax):
+def _plan(model, N, E, B, nmax, bf16=False):
     cache = model.__dict__.setdefault("_isg_plans", {})
-    key = (N, E, B, nmax)
+    key = (N, E, B, nmax, bool(bf16))
     pl = cache.get(key)
     if pl is None:
         if len(cache) > 64:
             cache.clear()
-        pl = cache[key] = _Plan(model, N, E, B, nmax)
+        pl = cache[key] = _Plan(model, N, E, B, nmax, bf16)
     return pl
 
 
@@ -157,9 +202,17 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, ins_ptr, glf, edge_attr, spec, arena_ptr, gemm_mode):
+def _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, ins_ptr, glf, edge_attr, spec, arena_ptr, gemm_mode, bf=None):
     s = slots()
     conv = model.convs[i]
+    if pl.bf16:
+        ea_bf, wptrs = bf
+        d[s.D_BF16] = 1
+        p[s.P_EDGE_ATTR_BF] = ea_bf.data_ptr()
+        for (layer, slot), ptr in wptrs.items():
+            if layer == i:
+                p[getattr(s, slot)] = ptr
+        gemm_mode = 1  # the small fp32 products that remain (gate projections' backward) run fp32-grade
     d[s.D_N], d[s.D_E], d[s.D_B], d[s.D_D], d[s.D_H], d[s.D_HID] = gi.N, gi.E, gi.B, pl.D, pl.H, pl.HID
     d[s.D_NMAX], d[s.D_MASKED] = gi.nmax, 1 if pl.masked[i] else 0
     d[s.D_GEMM_MODE], d[s.D_GATE_MODE] = gemm_mode, conv.mask.GATE_GEMM_MODE
@@ -191,7 +244,7 @@ def _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, ins_ptr, glf, edge_attr, s
         p[s.P_AIMLE_STATE] = spec["state"].data_ptr() if spec.get("state") is not None else 0
 
 
-def kernel_launches(spec, gi, backward):
+def kernel_launches(spec, gi, backward, bf16=False):
     """Kernels one isg_mgat_layer_fwd / _bwd call launches (memsets excluded) — mirrors csrc/executor.cu; used
     for bench.py's gpu_launches claim."""
     K = L.KERNELS_PER_CALL
@@ -204,13 +257,13 @@ def kernel_launches(spec, gi, backward):
                 n += K["isg_sampler_fused_fwd"]
             else:
                 n += K["isg_gate_theta_fwd"] + 1 + K["isg_node_edge_mask_fwd"]
-        return n
+        return n + (1 if bf16 else 0)  # + isg_to_bf16(xg)
     n = (K["isg_sdpa_graphnorm_bwd"] + K["isg_colsum_multi"] + K["isg_gelu_bwd"] + 4 * K["isg_linear_dgrad"] +
          4 * K["isg_linear_wgrad"] + K["isg_gat_edge_bwd"] + K["isg_instr_gate_bwd"])
     if masked:
         n += 1 + K["isg_node_edge_mask_bwd"] + (3 if spec["code"] == 2 else 1) + K["isg_gate_theta_bwd"] + \
             2 * (K["isg_gelu_bwd"] + K["isg_linear_dgrad"] + K["isg_linear_wgrad"])
-    return n
+    return n + (1 if bf16 else 0)  # + isg_to_bf16(g_y2)
 
 
 class MgatFunction(torch.autograd.Function):
@@ -220,18 +273,28 @@ class MgatFunction(torch.autograd.Function):
     def forward(ctx, model, gi, specs, gemm_mode, x, edge_attr, iv, glf, *params):
         ctx.set_materialize_grads(False)
         N, E, B = gi.N, gi.E, gi.B
-        pl = _plan(model, N, E, B, gi.nmax)
+        bf16 = gemm_mode == BF16_MODE
+        pl = _plan(model, N, E, B, gi.nmax, bf16)
         x, edge_attr, iv, glf = (t.contiguous() for t in (x, edge_attr, iv, glf))
         arena = torch.empty(pl.arena_bytes, dtype=torch.uint8, device=x.device)
         ap = arena.data_ptr()
         st = L.stream()
         s = slots()
+        bf = None
+        if bf16:  # per step: edge_attr once (shared by the 4 layers, forward and wgrad), all projection weights once
+            Dp = pad8(pl.D)
+            ea_bf = torch.empty(max(E, 1), Dp, dtype=torch.bfloat16, device=x.device)
+            L.call("isg_to_bf16", edge_attr.data_ptr(), pl.D, E, pl.D, ea_bf.data_ptr(), Dp, st)
+            wbuf, wptrs = convert_weights_bf16(model)
+            bf = (ea_bf, wptrs)
+            ctx.bf_keep = (ea_bf, wbuf)
+        ctx.bf = bf
         x_in_ptr = x.data_ptr()
         for i in range(pl.L):
             d, f, p = _arrays()
             _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, iv.data_ptr() + i * B * pl.D * 4, glf, edge_attr,
-                         specs[i], ap, gemm_mode)
-            L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, False))
+                         specs[i], ap, gemm_mode, bf)
+            L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, False, bf16))
             x_in_ptr = ap + pl.act[i]["P_H_OUT"]
         ctx.model, ctx.gi, ctx.specs, ctx.pl, ctx.gemm_mode, ctx.arena = model, gi, specs, pl, gemm_mode, arena
         ctx.save_for_backward(x, edge_attr, iv, glf, *params)
@@ -245,7 +308,7 @@ class MgatFunction(torch.autograd.Function):
                 n *= v
             return arena[off: off + 4 * n].view(torch.float32).view(shape)
 
-        cap = getattr(model, "capture_activations", None)
+        cap = getattr(model, "capture_activations", None) if not bf16 else None
         if cap is not None:  # test hook: the edge kernel's forward inputs of every layer (copies)
             HC = pl.HC
             for i in range(pl.L):
@@ -292,7 +355,7 @@ class MgatFunction(torch.autograd.Function):
             d, f, p = _arrays()
             x_in_ptr = x.data_ptr() if i == 0 else ap + pl.act[i - 1]["P_H_OUT"]
             _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, iv.data_ptr() + i * B * D * 4, glf, edge_attr, specs[i],
-                         ap, ctx.gemm_mode)
+                         ap, ctx.gemm_mode, ctx.bf)
             if ws is None:
                 ws_bytes = int(lib.isg_mgat_layer_bwd_workspace_bytes(_p(d)))
                 ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
@@ -317,7 +380,7 @@ class MgatFunction(torch.autograd.Function):
                     continue
                 slot = {"W_L": "P_G_W_LR", "B_L": "P_G_B_LR"}.get(name, "P_G_" + name)
                 p[getattr(s, slot)] = gp + 4 * pl.grad_off[(i, name)]
-            L.call("isg_mgat_layer_bwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, True))
+            L.call("isg_mgat_layer_bwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, True, pl.bf16))
             g_in_ptr = out.data_ptr()
             if hook is not None:
                 lo, hi = pl.layer_span[i]

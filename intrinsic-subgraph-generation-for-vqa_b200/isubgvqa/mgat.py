@@ -93,6 +93,9 @@ class MGAT(torch.nn.Module):
                 h, mask = executor.MgatFunction.apply(self, gi, specs, ops.gemm_mode(), x, edge_attr, instr_vectors,
                                                       global_language_feats, *executor.flat_params(self))
                 return h, mask, [], []
+        if ops.gemm_mode() == executor.BF16_MODE:
+            raise NotImplementedError("the bf16 configuration (gemm mode 3) runs through the layer executor only; this "
+                                      "model / call is outside what the executor covers (executor.supported)")
         h = x
         mask = None
         if self.use_global_mask:

@@ -71,7 +71,7 @@ SIGNATURES = {
     "isg_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
     "isg_colsum": (_I32, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
     "isg_colsum_multi_workspace_bytes": (_SZ, [_I32, _P, _P]),
-    "isg_colsum_multi": (_I32, [_I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "isg_colsum_multi": (_I32, [_I32, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "isg_gather_add_act_fwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "isg_segment_sum": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "isg_gather_rows": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),

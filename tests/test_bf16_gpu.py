@@ -111,3 +111,68 @@ def test_to_bf16_pads_with_zeros():
     L.call("isg_to_bf16", L.ptr(x), 300, 77, 300, L.ptr(out), 304, L.stream())
     assert torch.equal(out[:, :300], x.to(torch.bfloat16))
     assert float(out[:, 300:].abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# end to end: MGAT forward + backward in the bf16 configuration (gemm mode 3, layer executor) against the fp32
+# configuration of the same CUDA path (itself within 1e-4 of the oracle: tests/test_mgat_gpu.py) on the same inputs
+# and the same injected noise.  Stated tolerance: outputs and input gradients within 3e-2 of the tensor's scale,
+# parameter gradients within 5e-2 (bf16 has 8 significand bits: 2^-8 = 3.9e-3 per rounding, compounded over four
+# layers of projections and their backward).  The gate logits that feed the discrete sampler stay fp32, but they
+# are computed from bf16-perturbed activations, so a near-tie may flip: masks must agree on >= 95 % of the nodes
+# and the numeric bars apply when they agree everywhere.
+# ---------------------------------------------------------------------------------------------------------------
+def _run_mode(cfg, mode, steps=1):
+    from isg_b200 import ops
+
+    prev = ops.gemm_mode()
+    ops.set_gemm_mode(mode)
+    try:
+        return util.run_cuda_case(cfg, step_count=steps)
+    finally:
+        ops.set_gemm_mode(prev)
+
+
+@pytest.mark.parametrize("sampler,train,B", [("imle", True, 12), ("aimle", True, 64), ("gumbel", False, 16)])
+def test_mgat_bf16_configuration_tracks_fp32(sampler, train, B):
+    cfg = dict(sampler=sampler, train=train, channels=300, num_graphs=B, mean_nodes=14, mean_edges=90, k=2,
+               seed=77 + B, steps=1)
+    if sampler == "aimle":
+        cfg["aimle_beta0"] = 1.0
+    want = _run_mode(cfg, 1)[0]
+    got = _run_mode(cfg, 3)[0]
+    for key in ("h", "gx", "g_edge_attr", "g_instr", "g_glf"):
+        assert torch.isfinite(got[key]).all(), key
+    agree = float((got["mask"] == want["mask"]).float().mean()) if sampler != "gumbel" else 1.0
+    assert agree >= 0.95, agree
+    if sampler == "gumbel":
+        assert util.rel_err(got["mask"], want["mask"]) <= 5e-2
+    if agree == 1.0:
+        assert util.rel_err(got["h"], want["h"]) <= 3e-2, util.rel_err(got["h"], want["h"])
+        if train:
+            for key in ("gx", "g_edge_attr", "g_instr", "g_glf"):
+                assert util.rel_err(got[key], want[key]) <= 3e-2, (key, util.rel_err(got[key], want[key]))
+            worst = ("", 0.0)
+            for name, w in want["param_grads"].items():
+                g = got["param_grads"].get(name)
+                assert (g is None) == (w is None), name
+                if w is not None:
+                    e = util.rel_err(g, w)
+                    if e > worst[1]:
+                        worst = (name, e)
+            assert worst[1] <= 5e-2, worst
+
+
+def test_bf16_mode_refuses_the_per_operator_path():
+    from isg_b200 import ops
+    from isg_b200.isubgvqa import mgat as mgat_mod
+
+    cfg = dict(sampler="imle", train=True, channels=300, num_graphs=4, mean_nodes=8, mean_edges=30, k=2, seed=5, steps=1)
+    prev = ops.gemm_mode()
+    ops.set_gemm_mode(3)
+    try:
+        with pytest.raises(NotImplementedError):
+            util.run_cuda_case(cfg, executor=False)
+    finally:
+        ops.set_gemm_mode(prev)
+        mgat_mod.set_executor(True)

@@ -488,7 +488,7 @@ def test_colsum_multi_is_bit_identical_to_colsum():
     vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     nbytes = lib.isg_colsum_multi_workspace_bytes(n, vp(rows), vp(cols))
     ws = L.workspace(nbytes, DEV)
-    L.call("isg_colsum_multi", n, pin, vp(ld), vp(rows), vp(cols), pout, L.ptr(ws), nbytes, L.stream())
+    L.call("isg_colsum_multi", n, pin, None, vp(ld), vp(rows), vp(cols), pout, L.ptr(ws), nbytes, L.stream())
     for t, o in zip(ins, outs):
         r, c = t.shape
         want = torch.empty(c, device=DEV)
@@ -499,7 +499,18 @@ def test_colsum_multi_is_bit_identical_to_colsum():
         if r:
             assert util.rel_err(o.cpu(), t.double().sum(0).float().cpu()) <= 1e-5
     with pytest.raises(RuntimeError):  # too small a workspace is reported, not overrun
-        L.call("isg_colsum_multi", n, pin, vp(ld), vp(rows), vp(cols), pout, L.ptr(ws), 16, L.stream())
+        L.call("isg_colsum_multi", n, pin, None, vp(ld), vp(rows), vp(cols), pout, L.ptr(ws), 16, L.stream())
+    # bf16 storage (the bf16 configuration's g_out / g_xlr / g_z1): same sums of the rounded values
+    tb = [t.to(torch.bfloat16) for t in (ins[1], ins[4])]
+    ob = [torch.empty(t.shape[1], device=DEV) for t in tb]
+    dts = np.array([L.BF16, L.BF16], dtype=np.int32)
+    r2 = np.array([t.shape[0] for t in tb], dtype=np.int64)
+    c2 = np.array([t.shape[1] for t in tb], dtype=np.int32)
+    l2 = np.array([t.stride(0) for t in tb], dtype=np.int64)
+    L.call("isg_colsum_multi", 2, (ctypes.c_void_p * 2)(*[t.data_ptr() for t in tb]), vp(dts), vp(l2), vp(r2), vp(c2),
+           (ctypes.c_void_p * 2)(*[t.data_ptr() for t in ob]), L.ptr(ws), nbytes, L.stream())
+    for t, o in zip(tb, ob):
+        assert util.rel_err(o.cpu(), t.double().sum(0).float().cpu()) <= 1e-5
 
 
 def test_instr_gate_bwd_residual_and_accumulate_at_gqa_size():
