@@ -329,7 +329,11 @@ def main_isg(args, rank, world, local_rank):
 
     ops.set_gemm_mode(args.gemm_mode)
     gemm_desc = {0: "fp32 FFMA (mode 0)", 1: "tcgen05 3xTF32 split, fp32-grade (mode 1)",
-                 2: "tcgen05 single-pass TF32 (mode 2, NOT the parity configuration)"}[args.gemm_mode]
+                 2: "tcgen05 single-pass TF32 (mode 2, NOT the parity configuration)",
+                 3: "bf16 configuration (mode 3): tcgen05 kind::f16 projections, bf16 storage of x_l|x_r / e_proj / out "
+                    "and their gradients, fp32 accumulation, fp32 gate logits / SDPA / GraphNorm; NOT the parity "
+                    "configuration (tests/test_bf16_gpu.py states its tolerances)"}[args.gemm_mode]
+    bf16 = args.gemm_mode == 3
     desc, sampler, train, B = WORKLOADS[args.workload]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -566,13 +570,15 @@ def main_isg(args, rank, world, local_rank):
     # every kernel family is its own C-ABI call that lib.call can bracket with events on the launching stream
     # (the executor issues them from C).  Same kernels, same order, same step.
     kernel_names = ["isg_gat_edge_fwd", "isg_gat_edge_bwd", "isg_linear_fwd", "isg_linear_dgrad", "isg_linear_wgrad"]
-    mgat_mod.set_executor(False)
-    for _ in range(2):
-        step(resident, noise_d)
-    _, _, tsum = timed(lambda: step(resident, noise_d), args.steps,
-                       kernel_names if not args.breakdown else list(L.KERNELS_PER_CALL))
+    tsum = {}
+    if not bf16:  # (the bf16 configuration exists in the layer executor only: its edge kernels are timed alone below)
+        mgat_mod.set_executor(False)
+        for _ in range(2):
+            step(resident, noise_d)
+        _, _, tsum = timed(lambda: step(resident, noise_d), args.steps,
+                           kernel_names if not args.breakdown else list(L.KERNELS_PER_CALL))
+        mgat_mod.set_executor(True)
     tall = tsum
-    mgat_mod.set_executor(True)
     if layer_reducer is not None:  # e2e: the layer reducer again (eager, same hooks)
         from isg_b200.dp import LayerGradAllReduce
 
@@ -607,7 +613,21 @@ def main_isg(args, rank, world, local_rank):
     fwd_b_un, bwd_b_un = edge_bytes(N, E, False)
     fwd_b_m, bwd_b_m = edge_bytes(N, E, True)
     roof = None
-    if train and "isg_gat_edge_bwd" in tsum:
+    if bf16 and world == 1:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("bench_edge", os.path.join(ROOT, "scripts", "bench_edge.py"))
+        be = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(be)
+        t = be.run_point(B, 20, 150, False, 20, B, seed=seed, bf16=True)
+        key, kb = ("bwd_ms", "bwd_b") if train else ("fwd_ms", "fwd_b")
+        ach = t[kb] / (t[key] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "isg_gat_edge_%s, bf16 storage (register-load kernels, 8-byte loads), timed "
+                                          "alone on a batch of the workload's shape, L2 flushed" % ("bwd" if train else "fwd"),
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": t[kb], "ms_per_launch": t[key],
+                "launches_timed": 20}
+    elif train and "isg_gat_edge_bwd" in tsum:
         calls, tot = tsum["isg_gat_edge_bwd"]
         per_launch_ms = tot / calls
         alg = (3 * bwd_b_un + bwd_b_m) / 4.0  # 3 unmasked layers + 1 masked layer per step
@@ -680,7 +700,7 @@ def main_isg(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "graphs_per_gpu": B, "nodes": N, "edges": E, "nmax": nmax,
                    "channels": CHANNELS, "heads": HEADS, "layers": LAYERS, "sample_k": K_SAMPLE,
                    "step": "MGAT forward+backward" + (
@@ -744,7 +764,7 @@ def main():
     ap.add_argument("--dp-flat", action="store_true",
                     help="multi-GPU: the r1 reducer (flat 42 MB all-reduce with pack/unpack after each replay)")
     ap.add_argument("--no-edge-study", action="store_true", help="skip the batch-4096 edge-kernel roofline point")
-    ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2],
+    ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2, 3],
                     help="projection arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32 (default), 2 tcgen05 1xTF32")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
