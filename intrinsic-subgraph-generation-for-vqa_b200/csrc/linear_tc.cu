@@ -151,7 +151,13 @@ __device__ __forceinline__ float4 lo_part(float4 v) {
 // (measured by bisecting an instrumented build), so the hot instantiation carries none.
 // BLO: the lo plane of B comes pre-split from global memory (a second tensor map): the splitter warps then only
 // move A into tensor memory — no shared-memory stores and no generic->async proxy fence on the per-k-block chain.
-template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN, bool BLO>
+// P2 (mode 1, BN == 128; opt-in, see launch()): the CTAs run as cta_group::2 MMA PAIRS on adjacent M tiles of one N block.
+// The leader issues M = 256 instructions; each CTA stages its own A tile (and moves it to ITS tensor memory) and only
+// HALF of the B tile (64 of the 128 rows / columns), which the pair's MMA reads from both shared memories.  Per CTA
+// and 32-wide k-block the shared-memory traffic drops from 128 KB (TMA 32 + splitter 48 + MMA operand reads 48) to
+// 80 KB (24 + 32 + 24): at 128 B/clk that is 640 instead of 1024 cycles, below the 768-cycle MMA floor.  Measured
+// slower all the same (the added cross-SM synchronisation hops cost more than the traffic saves): see launch().
+template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN, bool BLO, bool P2 = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_blo, const TcArgs g) {
@@ -159,7 +165,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t CL = PAIR ? 2u : 1u;  // plain launch, or a cluster pair sharing the B tile
+  static_assert(!P2 || (SPLIT && MERGE && FULLBN && !PAIR && !BLO), "P2: mode 1, merged accumulator, BN = 128");
+  constexpr uint32_t CL = (PAIR || P2) ? 2u : 1u;  // plain launch, or a cluster pair sharing the B tile
   const uint32_t cta_rank = cluster_ctarank();
 
   const int S = SPLIT ? TS_STAGES : g.stages;  // mode 1: smem ring == TMEM A ring
@@ -187,22 +194,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 128);
-      mbar_init(empty_bar(s), CL);  // released by the MMA commits of every CTA of the cluster
+      mbar_init(conv_bar(s), P2 ? 8 : 128);  // P2: one arrival per splitter warp of BOTH CTAs, on the leader's barrier
+      mbar_init(empty_bar(s), P2 ? 1 : CL);  // released by the MMA commits of every CTA of the cluster (P2: the leader's)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(mfull_bar(s), 1);
-      mbar_init(mempty_bar(s), EPI_WARPS);
+      mbar_init(mempty_bar(s), P2 ? 2 * EPI_WARPS : EPI_WARPS);
       mbar_init(cfull_bar(s), 1);
       mbar_init(cempty_bar(s), EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (P2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive
@@ -239,7 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t fb = full_bar(stage);
-        mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + (BLO ? 2u : 1u) * b_tile_bytes);
+        mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + (P2 ? b_tile_bytes / 2 : (BLO ? 2u : 1u) * b_tile_bytes));
         const int r0 = (int)(r_beg + (int64_t)kb * BK);
         if (!A_MN) {
           tma_load_2d(sa, &map_a, fb, r0, m0);
@@ -247,7 +259,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &map_a, fb, m0 + 32 * c, r0);
         }
-        if (CL == 1) {
+        if (P2) {
+          // this CTA's half of the B tile, at the START of the B region (the pair's MMA reads N/2 from each CTA)
+          if (!B_MN) {
+            tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0 + (int)cta_rank * (MAX_BN / 2));
+          } else {
+#pragma unroll
+            for (int c = 0; c < MAX_BN / 64; ++c)
+              tma_load_2d(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + (int)cta_rank * (MAX_BN / 2) + 32 * c, r0);
+          }
+        } else if (CL == 1) {
           if (!B_MN) {
             tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0);
             if (BLO) tma_load_2d(sa + off_b_lo, &map_blo, fb, r0, n0);
@@ -275,10 +296,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
    }
   } else if (warp == 1) {
-   if (elect_one()) {
-    // ===================================================================== MMA issuer (one elected lane)
+   if ((!P2 || cta_rank == 0) && elect_one()) {
+    // ===================================================================== MMA issuer (one elected lane; P2: leader CTA)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                           ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                           ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)((P2 ? 2 * BM : BM) >> 4) << 24);
     // TS form: the splitters have already laid A out row-per-lane / k-per-column, i.e. K-major
     const uint32_t idesc_ts = idesc & ~(1u << 15);
     const uint32_t a_kstep = A_MN ? (1024u >> 4) : ((UMMA_K * 4u) >> 4);  // descriptor units of 16 B
@@ -300,12 +322,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int kb0 = 0; kb0 < num_kb; kb0 += DRAIN_KB, ++gchunk) {
         const int ms = gchunk & 1;
         const uint32_t mphase = (gchunk >> 1) & 1u;
-        mbar_wait(mempty_bar(ms), mphase ^ 1u);
+        if (P2) mbar_wait_cluster(mempty_bar(ms), mphase ^ 1u);
+        else mbar_wait(mempty_bar(ms), mphase ^ 1u);
         tc_fence_after();
         const uint32_t d_main = tmem_base + TM_MAIN + 128u * ms;
         const int kb1 = min(num_kb, kb0 + DRAIN_KB);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(SPLIT ? conv_bar(stage) : full_bar(stage), phase);
+          if (P2) mbar_wait_cluster(conv_bar(stage), phase);
+          else mbar_wait(SPLIT ? conv_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           // descriptors of stage s = those of stage 0 + s * stage_bytes/16 (the 14-bit address field cannot
           // carry: all operand addresses are below 227 KiB)
@@ -316,6 +340,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t bk = (uint64_t)(b_kstep * k);
+              if (P2) {
+                umma_tf32_ts_2cta(d_main, a_t + 8u * k, b_hi + bk, idesc_ts, (kb > kb0 || k > 0) ? 1u : 0u);
+                umma_tf32_ts_2cta(d_main, a_t + 8u * k, b_lo + bk, idesc_ts, 1u);
+                umma_tf32_ts_2cta(d_main, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_ts, 1u);
+                continue;
+              }
               umma_tf32_ts(d_main, a_t + 8u * k, b_hi + bk, idesc_ts, (kb > kb0 || k > 0) ? 1u : 0u);
               umma_tf32_ts(MERGE ? d_main : d_corr, a_t + 8u * k, b_lo + bk, idesc_ts,
                            (MERGE || kb > 0 || k > 0) ? 1u : 0u);
@@ -330,11 +360,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           // frees the smem stage (in every CTA of the cluster: the peer's multicast writes land here too)
-          if (CL > 1) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);
+          if (P2) umma_commit_2cta_mc(empty_bar(stage), (uint16_t)0x3);
+          else if (CL > 1) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);
           else umma_commit(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(mfull_bar(ms));  // chunk partial complete -> epilogue drains it
+        if (P2) umma_commit_2cta_mc(mfull_bar(ms), (uint16_t)0x3);  // both CTAs' epilogues drain their 128 rows
+        else umma_commit(mfull_bar(ms));  // chunk partial complete -> epilogue drains it
       }
       if (SPLIT && !MERGE) umma_commit(cfull_bar(0));
     }
@@ -384,15 +416,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (!BLO) {
 #pragma unroll
-            for (int u = 0; u < BK / 4; ++u) {  // b_tile_bytes / 16 / 128 float4 per thread at BN = 128
-              const int i = tid + 128 * u;
+            for (int u = 0; u < (P2 ? BK / 8 : BK / 4); ++u) {  // b_tile_bytes / 16 / 128 float4 per thread at BN = 128
+              const int i = tid + 128 * u;                      // (P2: this CTA's half of the tile)
               if (FULLBN || i < nb) sts_f4(sa + off_b_lo + (uint32_t)i * 16u, lo_part(lds_f4(sa + off_b_hi + (uint32_t)i * 16u)));
             }
           }
           tmem_st_wait();
           tc_fence_before();
           if (!BLO) fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-          mbar_arrive(conv_bar(stage));
+          if (P2) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(conv_bar(stage), 0);  // the leader's barrier: 4 + 4 warp arrivals
+          } else {
+            mbar_arrive(conv_bar(stage));
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
@@ -435,7 +472,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(mempty_bar(ms));  // this warp is done with the chunk's TMEM stage
+        if (lane == 0) {  // this warp is done with the chunk's TMEM stage (P2: tell the leader, whose MMAs write both)
+          if (P2) mbar_arrive_remote(mempty_bar(ms), 0);
+          else mbar_arrive(mempty_bar(ms));
+        }
       }
       if (SPLIT && !MERGE) {
         mbar_wait(cfull_bar(0), (uint32_t)(it & 1));
@@ -500,8 +540,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CL > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on it
   else __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
-                 : "memory");
+    if (P2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -590,7 +632,17 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   static const bool env_no_cluster = getenv("ISG_TC_NO_CLUSTER") != nullptr;
   const bool want_pair = p.split3 == 0 && !p.no_cluster && !env_no_cluster;
   const bool pair = want_pair && g.m_tiles >= 2 && (B_MN ? ((g.BN / 32) % 2 == 0) : true);
-  const int CLh = pair ? 2 : 1;
+  // mode 1 at BN == 128 (default build): cta_group::2 MMA pairs — see the kernel's header comment — are OPT-IN
+  // (ISG_TC_PAIR2=1).  Measured on B200 (r2, scripts/gemm_probe.py, profiles/r2_gemm_probe.txt): bit-identical
+  // results, but 1.5-1.7x SLOWER on every shape and product ([39809,300]x[300,1200] fwd 155 -> 245 us) although
+  // the pair halves the shared-memory traffic per k-block; 74 clusters are resident (cudaOccupancyMaxActiveClusters),
+  // so it is not a residency problem.  The mainloop is a latency loop (MMA commit -> free stage -> TMA -> splitter ->
+  // MMA) over only FOUR stages (the tensor-memory A ring), and the pair adds two cross-SM hops to it (multicast
+  // commit to the peer's barrier, the peer's remote arrive on the leader's); single CTAs stay the default.
+  static const bool env_pair2 = getenv("ISG_TC_PAIR2") != nullptr && atoi(getenv("ISG_TC_PAIR2")) != 0;
+  const bool pair2 = MERGE && p.split3 == 1 && g.BN == MAX_BN && p.B_lo == nullptr && g.m_tiles >= 2 && env_pair2 &&
+                     !p.no_cluster;
+  const int CLh = (pair || pair2) ? 2 : 1;
 
   CUtensorMap ma, mb;
   int rc;
@@ -613,7 +665,9 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   const bool fullbn = g.BN == MAX_BN;
   // (+ the pre-split-B variants of mode 1; wgrad's B is an activation and is always split in the kernel)
   constexpr bool CAN_BLO = !A_MN;
-  auto kern = p.split3 ? (blo && CAN_BLO ? (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, CAN_BLO>
+  constexpr bool CAN_P2 = MERGE;
+  auto kern = pair2   ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, false, CAN_P2>
+            : p.split3 ? (blo && CAN_BLO ? (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, CAN_BLO>
                                                    : tc_gemm_kernel<A_MN, B_MN, EPI, true, false, false, CAN_BLO>)
                                          : (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, false>
                                                    : tc_gemm_kernel<A_MN, B_MN, EPI, true, false, false, false>))
@@ -637,6 +691,12 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (CLh > 1 && getenv("ISG_TC_VERBOSE")) {
+    int nclusters = -1;
+    cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    fprintf(stderr, "[isg] tc_gemm cluster launch: grid %d, cluster %d, smem %d, max active clusters %d (pair2 %d)\n", grid,
+            CLh, smem, nclusters, (int)pair2);
+  }
   e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mblo, g);
   if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
