@@ -1293,6 +1293,546 @@ gat_edge_bwd_fused_ring_kernel(const float* __restrict__ gout, int64_t ld_g, con
 
 // Columns of the dst-major backward: K nodes per column, sized for ~6 waves of resident CTAs so that the
 // hardware block scheduler evens out the degree imbalance; K and the grid depend on (N, H) only.
+// ==========================================================================================
+// bf16 storage, ring kernels (r2): the bf16 configuration's edge kernels with 16-byte accesses.
+// A head row of bf16 is C*2 = 600 bytes — not a legal bulk-copy size and only 8-byte aligned for odd heads, which
+// is why the first bf16 kernels (above) used 8-byte register loads.  Here a warp owns a (node, HEAD PAIR): the rows
+// of heads (2p, 2p+1) are contiguous, 4C = 1200 bytes, 16-byte aligned — byte for byte the shape the fp32 ring
+// moves — so the same per-warp ring of cp.async.bulk copies applies.  Lane `lane` owns the 16-byte chunks
+// c = lane + 32k (k < VPL, c < C/4) of a pair row = 8 bf16 = two float4 groups; group (k, half) holds elements
+// 8c + 4*half .. +3 of the pair and belongs to the second head iff that offset is >= C (C % 4 == 0: no group
+// straddles the heads).  Every per-head scalar (logit, softmax state, alpha, t_e, gl) exists twice.
+// Arithmetic is fp32 throughout; only loads / stores convert.
+// ==========================================================================================
+__device__ __forceinline__ void bf8_to_f4(uint4 raw, float4& lo, float4& hi) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.z));
+  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.w));
+  lo = make_float4(a.x, a.y, b.x, b.y);
+  hi = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ uint4 f4_to_bf8(float4 lo, float4 hi) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(lo.x, lo.y), b = __floats2bfloat162_rn(lo.z, lo.w);
+  const __nv_bfloat162 c = __floats2bfloat162_rn(hi.x, hi.y), d = __floats2bfloat162_rn(hi.z, hi.w);
+  uint4 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&a);
+  r.y = *reinterpret_cast<const uint32_t*>(&b);
+  r.z = *reinterpret_cast<const uint32_t*>(&c);
+  r.w = *reinterpret_cast<const uint32_t*>(&d);
+  return r;
+}
+// acc_h += d for the head the group belongs to (selects, no dynamic register indexing)
+__device__ __forceinline__ void sel_add(float2& acc0, float2& acc1, bool second, float2 d) {
+  const float2 z = make_float2(0.f, 0.f);
+  acc0 = __fadd2_rn(acc0, second ? z : d);
+  acc1 = __fadd2_rn(acc1, second ? d : z);
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// smem per warp: RING slots of 2 pair rows (4C bytes each), then x_r pair row (4C bytes) and the pair's att (8C bytes)
+__host__ __device__ inline uint32_t pair_warp_bytes(int C, bool with_consts) {
+  return (uint32_t)(2 * RING) * (uint32_t)C * 4u + (with_consts ? (uint32_t)C * 12u : 0u);
+}
+inline size_t pair_smem_bytes(int C, bool with_consts, int extra_bars) {
+  return (size_t)EDGE_WARPS * (pair_warp_bytes(C, with_consts) + 8 * (RING + extra_bars));
+}
+
+// forward: one warp per (node, head pair)
+template <int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 5)
+gat_edge_fwd_pair_kernel(const __nv_bfloat16* __restrict__ xl, const __nv_bfloat16* __restrict__ xr, int64_t ld_x,
+                         const __nv_bfloat16* __restrict__ ep, const float* __restrict__ att,
+                         const float* __restrict__ bias, const float* __restrict__ emask,
+                         const int* __restrict__ rowptr, const int* __restrict__ nbr, const int* __restrict__ eid,
+                         const int* __restrict__ order, __nv_bfloat16* __restrict__ out, int64_t ld_out,
+                         float* __restrict__ alpha, int64_t NP, int H, int C, float slope) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = C >> 2, HP = H >> 1;  // 16-byte chunks per pair row; head pairs
+  const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
+  const int64_t HC = (int64_t)H * C;
+  const uint32_t wbytes = pair_warp_bytes(C, true);
+  WarpRing ring;
+  ring.init(smem_addr_u32(ring_smem) + warp * wbytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * (RING + 1), 2 * row_bytes, lane, 1);
+  const uint32_t xr_s = ring.data + 2 * RING * row_bytes, att_s = xr_s + row_bytes;
+  const uint32_t xbar = ring.extra_bar(0);
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const bool leader = warp_elect_one();
+  uint32_t xseq = 0;
+  int cur_pair = -1;
+  // per-lane group -> head selector: group (k, half) belongs to the pair's second head iff 8c + 4*half >= C
+  bool hb[2 * VPL], ok[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c = lane + 32 * k;
+    ok[k] = c < c4;
+    hb[2 * k] = 8 * c >= C;
+    hb[2 * k + 1] = 8 * c + 4 >= C;
+  }
+
+  for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NP; wid += (int64_t)gridDim.x * EDGE_WARPS) {
+    const int64_t slot = wid / HP;
+    const int pair = (int)(wid - slot * HP);
+    const int64_t node = order ? order[slot] : slot;
+    const int hoff = pair * 2 * C;
+    if (pair != cur_pair) {
+      for (int v = lane; v < 2 * c4; v += 32) sts_f4(att_s + 16u * v, Vec4<float>::ld(att + hoff + 4 * v));
+      cur_pair = pair;
+      __syncwarp();
+    }
+    if (leader) {
+      ring_expect(xbar, row_bytes);
+      ring_copy(xr_s, xr + node * ld_x + hoff, row_bytes, xbar, pol_keep);
+    }
+    float4 acc[2 * VPL];
+#pragma unroll
+    for (int g = 0; g < 2 * VPL; ++g) acc[g] = f4_zero();
+    const int beg = rowptr[node], end = rowptr[node + 1];
+    const bool single = end - beg <= 32;
+    float m_run0 = -INFINITY, m_run1 = -INFINITY, s_run0 = 0.f, s_run1 = 0.f;
+    bool xr_ready = false;
+    int keep_eid = 0;
+    float keep_logit0 = 0.f, keep_logit1 = 0.f;
+
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_src = 0, my_eid = 0;
+      float my_m = 1.f, my_logit0 = 0.f, my_logit1 = 0.f;
+      if (lane < cnt) {
+        my_src = nbr[base + lane];
+        my_eid = eid[base + lane];
+        if (MASKED) my_m = emask[my_eid];
+      }
+      const int npre = min(RING, cnt);
+      for (int t = 0; t < npre; ++t) {
+        const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (leader)
+          ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff, pol_stream,
+                      row_bytes);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t q = ring.seq + t;
+        const float m0 = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+        const int tn = t + RING < cnt ? t + RING : t;
+        const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
+        const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+        if (!xr_ready) {
+          ring_wait(xbar, xseq & 1u);
+          xr_ready = true;
+        }
+        ring.wait(q);
+        const uint32_t sx = ring.slot(q) + l16, sp = sx + row_bytes;
+        float2 part0 = make_float2(0.f, 0.f), part1 = make_float2(0.f, 0.f);
+        float4 xlv[2 * VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (ok[k]) {
+            float4 r0, r1, e0, e1;
+            bf8_to_f4(lds_u4(sx + 512u * k), xlv[2 * k], xlv[2 * k + 1]);
+            bf8_to_f4(lds_u4(sp + 512u * k), e0, e1);
+            bf8_to_f4(lds_u4(xr_s + l16 + 512u * k), r0, r1);
+            float4 s0 = p4_add(p4_add(r0, xlv[2 * k]), e0), s1 = p4_add(p4_add(r1, xlv[2 * k + 1]), e1);
+            if (MASKED) { s0 = p4_scale(s0, m0); s1 = p4_scale(s1, m0); }
+            float4 w0 = p4_leaky(s0, slope), w1 = p4_leaky(s1, slope);
+            if (MASKED) { w0 = p4_scale(w0, m0); w1 = p4_scale(w1, m0); }
+            const uint32_t as = att_s + 32u * (lane + 32 * k);
+            const float2 d0 = p4_dot_acc(w0, lds_f4(as), make_float2(0.f, 0.f));
+            const float2 d1 = p4_dot_acc(w1, lds_f4(as + 16u), make_float2(0.f, 0.f));
+            sel_add(part0, part1, hb[2 * k], d0);
+            sel_add(part0, part1, hb[2 * k + 1], d1);
+          } else {
+            xlv[2 * k] = f4_zero();
+            xlv[2 * k + 1] = f4_zero();
+          }
+        }
+        float pm0, pm1, sc0 = 1.f, sc1 = 1.f;
+        {
+          const float lg = warp_sum(p2_sum(part0));
+          if (lg > m_run0) {
+            sc0 = expf(m_run0 - lg);
+            s_run0 *= sc0;
+            m_run0 = lg;
+          }
+          const float pe = expf(lg - m_run0);
+          s_run0 += pe;
+          pm0 = MASKED ? pe * m0 : pe;
+          if (lane == t) my_logit0 = lg;
+        }
+        {
+          const float lg = warp_sum(p2_sum(part1));
+          if (lg > m_run1) {
+            sc1 = expf(m_run1 - lg);
+            s_run1 *= sc1;
+            m_run1 = lg;
+          }
+          const float pe = expf(lg - m_run1);
+          s_run1 += pe;
+          pm1 = MASKED ? pe * m0 : pe;
+          if (lane == t) my_logit1 = lg;
+        }
+        if (sc0 != 1.f || sc1 != 1.f) {  // warp-uniform
+#pragma unroll
+          for (int g = 0; g < 2 * VPL; ++g) acc[g] = p4_scale(acc[g], hb[g] ? sc1 : sc0);
+        }
+#pragma unroll
+        for (int g = 0; g < 2 * VPL; ++g) acc[g] = p4_fma_s(xlv[g], hb[g] ? pm1 : pm0, acc[g]);
+        __syncwarp();
+        if (leader && t + RING < cnt)
+          ring.issue2(q + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
+                      row_bytes);
+      }
+      ring.seq += cnt;
+      if (single) {
+        keep_eid = my_eid;
+        keep_logit0 = my_logit0;
+        keep_logit1 = my_logit1;
+      } else if (lane < cnt) {
+        alpha[(int64_t)my_eid * H + 2 * pair] = my_logit0;
+        alpha[(int64_t)my_eid * H + 2 * pair + 1] = my_logit1;
+      }
+    }
+    if (!xr_ready) ring_wait(xbar, xseq & 1u);
+    ++xseq;
+    __syncwarp();
+
+    const float inv0 = 1.f / (s_run0 + 1e-16f), inv1 = 1.f / (s_run1 + 1e-16f);
+    __nv_bfloat16* orow = out + node * ld_out + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (ok[k]) {
+        const int c = lane + 32 * k;
+        float4 o0 = f4_scale(acc[2 * k], hb[2 * k] ? inv1 : inv0), o1 = f4_scale(acc[2 * k + 1], hb[2 * k + 1] ? inv1 : inv0);
+        if (bias != nullptr) {
+          o0 = f4_add(o0, Vec4<float>::ld(bias + hoff + 8 * c));
+          o1 = f4_add(o1, Vec4<float>::ld(bias + hoff + 8 * c + 4));
+        }
+        *reinterpret_cast<uint4*>(orow + 8 * c) = f4_to_bf8(o0, o1);
+      }
+    }
+    if (single) {
+      if (lane < end - beg) {
+        alpha[(int64_t)keep_eid * H + 2 * pair] = expf(keep_logit0 - m_run0) * inv0;
+        alpha[(int64_t)keep_eid * H + 2 * pair + 1] = expf(keep_logit1 - m_run1) * inv1;
+      }
+    } else {
+      for (int base = beg; base < end; base += 32) {
+        if (base + lane < end) {
+          const int64_t idx = (int64_t)eid[base + lane] * H + 2 * pair;
+          alpha[idx] = expf(alpha[idx] - m_run0) * inv0;
+          alpha[idx + 1] = expf(alpha[idx + 1] - m_run1) * inv1;
+        }
+      }
+    }
+  }
+}
+
+// backward, src-major: g_xl[j, pair] = sum_{e: src = j} ( g_eproj[e, pair] + G[dst_e, pair] * alpha_h*m )
+template <int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 6)
+gat_edge_bwd_src_pair_kernel(const __nv_bfloat16* __restrict__ gout, int64_t ld_g, const __nv_bfloat16* __restrict__ g_ep,
+                             const float* __restrict__ emask, const float* __restrict__ alpha,
+                             const int* __restrict__ colptr, const int* __restrict__ nbr, const int* __restrict__ eid,
+                             const int* __restrict__ order, __nv_bfloat16* __restrict__ g_xl, int64_t ld_gx, int64_t NP,
+                             int H, int C) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = C >> 2, HP = H >> 1;
+  const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
+  const int64_t HC = (int64_t)H * C;
+  const uint32_t wbytes = pair_warp_bytes(C, false);
+  WarpRing ring;
+  ring.init(smem_addr_u32(ring_smem) + warp * wbytes, smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * RING,
+            2 * row_bytes, lane, 0);
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const bool leader = warp_elect_one();
+  bool hb[2 * VPL], ok[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c = lane + 32 * k;
+    ok[k] = c < c4;
+    hb[2 * k] = 8 * c >= C;
+    hb[2 * k + 1] = 8 * c + 4 >= C;
+  }
+  for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NP; wid += (int64_t)gridDim.x * EDGE_WARPS) {
+    const int64_t slot = wid / HP;
+    const int pair = (int)(wid - slot * HP);
+    const int64_t node = order ? order[slot] : slot;
+    const int hoff = pair * 2 * C;
+    float4 acc[2 * VPL];
+#pragma unroll
+    for (int g = 0; g < 2 * VPL; ++g) acc[g] = f4_zero();
+    const int beg = colptr[node], end = colptr[node + 1];
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      int my_dst = 0, my_eid = 0;
+      float my_am0 = 0.f, my_am1 = 0.f;
+      if (lane < cnt) {
+        my_dst = nbr[base + lane];
+        my_eid = eid[base + lane];
+        const float2 a2 = *reinterpret_cast<const float2*>(alpha + (int64_t)my_eid * H + 2 * pair);
+        const float m = MASKED ? emask[my_eid] : 1.f;
+        my_am0 = a2.x * m;
+        my_am1 = a2.y * m;
+      }
+      const int npre = min(RING, cnt);
+      for (int t = 0; t < npre; ++t) {
+        const int i = __shfl_sync(ISG_FULL_MASK, my_dst, t);
+        const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+        if (leader)
+          ring.issue2(ring.seq + t, g_ep + (int64_t)e * HC + hoff, pol_stream, gout + (int64_t)i * ld_g + hoff, pol_keep,
+                      row_bytes);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t s = ring.seq + t;
+        const float am0 = __shfl_sync(ISG_FULL_MASK, my_am0, t), am1 = __shfl_sync(ISG_FULL_MASK, my_am1, t);
+        const int tn = t + RING < cnt ? t + RING : t;
+        const int in_ = __shfl_sync(ISG_FULL_MASK, my_dst, tn);
+        const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+        ring.wait(s);
+        const uint32_t sg = ring.slot(s) + l16, sG = sg + row_bytes;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (ok[k]) {
+            float4 g0, g1, G0, G1;
+            bf8_to_f4(lds_u4(sg + 512u * k), g0, g1);
+            bf8_to_f4(lds_u4(sG + 512u * k), G0, G1);
+            acc[2 * k] = p4_add(acc[2 * k], p4_fma_s(G0, hb[2 * k] ? am1 : am0, g0));
+            acc[2 * k + 1] = p4_add(acc[2 * k + 1], p4_fma_s(G1, hb[2 * k + 1] ? am1 : am0, g1));
+          }
+        }
+        __syncwarp();
+        if (leader && t + RING < cnt)
+          ring.issue2(s + RING, g_ep + (int64_t)en * HC + hoff, pol_stream, gout + (int64_t)in_ * ld_g + hoff, pol_keep,
+                      row_bytes);
+      }
+      ring.seq += cnt;
+    }
+    __nv_bfloat16* grow = g_xl + node * ld_gx + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (ok[k]) *reinterpret_cast<uint4*>(grow + 8 * (lane + 32 * k)) = f4_to_bf8(acc[2 * k], acc[2 * k + 1]);
+  }
+}
+
+// backward, dst-major: one warp per (node, head pair); two sweeps per node as in gat_edge_bwd_dst_ring_kernel (sweep 1:
+// dot_h = sum_e a m t_h with t_h = <G_h, x_l[src]_h>; sweep 2: per-edge gradients from gl_h = a_h (m t_h - dot_h)).
+// The two-loop form only (sweep 2 recomputes the bit-identical t): g_att partial row (node*H + 2p) covers both heads.
+template <int VPL, bool MASKED>
+__global__ void __launch_bounds__(EDGE_WARPS * 32, 4)
+gat_edge_bwd_dst_pair_kernel(const __nv_bfloat16* __restrict__ gout, int64_t ld_g, const __nv_bfloat16* __restrict__ xl,
+                             const __nv_bfloat16* __restrict__ xr, int64_t ld_x, const __nv_bfloat16* __restrict__ ep,
+                             const float* __restrict__ att, const float* __restrict__ emask,
+                             const float* __restrict__ alpha, const int* __restrict__ rowptr,
+                             const int* __restrict__ nbr, const int* __restrict__ eid, const int* __restrict__ order,
+                             __nv_bfloat16* __restrict__ g_xr, int64_t ld_gx, __nv_bfloat16* __restrict__ g_ep,
+                             float* __restrict__ gatt_part, float* __restrict__ gm_h, int64_t N, int H, int C,
+                             float slope) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = C >> 2, HP = H >> 1;
+  const int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp;
+  const int64_t slot = wid / HP;
+  const int pair = (int)(wid - slot * HP);
+  if (slot >= N) return;  // (whole warps; no block-level synchronisation below)
+  const int64_t node = order ? order[slot] : slot;
+  const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
+  const int64_t HC = (int64_t)H * C;
+  const int hoff = pair * 2 * C;
+  const uint32_t wbytes = pair_warp_bytes(C, true);
+  WarpRing ring;
+  ring.init(smem_addr_u32(ring_smem) + warp * wbytes,
+            smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * (RING + 1), 2 * row_bytes, lane, 1);
+  const uint32_t xr_s = ring.data + 2 * RING * row_bytes, att_s = xr_s + row_bytes;
+  const uint32_t xbar = ring.extra_bar(0);
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  const bool leader = warp_elect_one();
+  bool hb[2 * VPL], ok[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c = lane + 32 * k;
+    ok[k] = c < c4;
+    hb[2 * k] = 8 * c >= C;
+    hb[2 * k + 1] = 8 * c + 4 >= C;
+  }
+  for (int v = lane; v < 2 * c4; v += 32) sts_f4(att_s + 16u * v, Vec4<float>::ld(att + hoff + 4 * v));
+  __syncwarp();
+  if (leader) {
+    ring_expect(xbar, row_bytes);
+    ring_copy(xr_s, xr + node * ld_x + hoff, row_bytes, xbar, pol_keep);
+  }
+  float4 G[2 * VPL], gxr[2 * VPL], gatt[2 * VPL];
+  {
+    const __nv_bfloat16* grow = gout + node * ld_g + hoff;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (ok[k]) bf8_to_f4(*reinterpret_cast<const uint4*>(grow + 8 * (lane + 32 * k)), G[2 * k], G[2 * k + 1]);
+      else G[2 * k] = G[2 * k + 1] = f4_zero();
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 2 * VPL; ++g) { gxr[g] = f4_zero(); gatt[g] = f4_zero(); }
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  bool xr_ready = false;
+
+  // t_h = <G_h, x_l row in the slot>, one fixed instruction sequence for both sweeps (bit-identical t)
+  auto row_dot = [&](uint32_t sx, float& t0, float& t1) {
+    float2 pp0 = make_float2(0.f, 0.f), pp1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (ok[k]) {
+        float4 x0, x1;
+        bf8_to_f4(lds_u4(sx + 512u * k), x0, x1);
+        const float2 d0 = p4_dot_acc(G[2 * k], x0, make_float2(0.f, 0.f));
+        const float2 d1 = p4_dot_acc(G[2 * k + 1], x1, make_float2(0.f, 0.f));
+        sel_add(pp0, pp1, hb[2 * k], d0);
+        sel_add(pp0, pp1, hb[2 * k + 1], d1);
+      }
+    }
+    t0 = warp_sum(p2_sum(pp0));
+    t1 = warp_sum(p2_sum(pp1));
+  };
+
+  // sweep 1
+  float dot0 = 0.f, dot1 = 0.f;
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    int my_src = 0;
+    float my_am0 = 0.f, my_am1 = 0.f;
+    if (lane < cnt) {
+      my_src = nbr[base + lane];
+      const int e = eid[base + lane];
+      const float2 a2 = *reinterpret_cast<const float2*>(alpha + (int64_t)e * H + 2 * pair);
+      const float m = MASKED ? emask[e] : 1.f;
+      my_am0 = a2.x * m;
+      my_am1 = a2.y * m;
+    }
+    const int npre = min(RING, cnt);
+    for (int t = 0; t < npre; ++t) {
+      const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+      if (leader) ring.issue1(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, row_bytes);
+    }
+    for (int t = 0; t < cnt; ++t) {
+      const uint32_t s = ring.seq + t;
+      const float am0 = __shfl_sync(ISG_FULL_MASK, my_am0, t), am1 = __shfl_sync(ISG_FULL_MASK, my_am1, t);
+      const int jn = __shfl_sync(ISG_FULL_MASK, my_src, t + RING < cnt ? t + RING : t);
+      ring.wait(s);
+      float t0, t1;
+      row_dot(ring.slot(s) + l16, t0, t1);  // warp_sum inside: every lane is past its slot reads
+      if (leader && t + RING < cnt) ring.issue1(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, row_bytes);
+      dot0 = fmaf(am0, t0, dot0);
+      dot1 = fmaf(am1, t1, dot1);
+    }
+    ring.seq += cnt;
+  }
+  // sweep 2
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    int my_src = 0, my_eid = 0;
+    float my_m = 1.f, my_a0 = 0.f, my_a1 = 0.f, my_gm0 = 0.f, my_gm1 = 0.f;
+    if (lane < cnt) {
+      my_src = nbr[base + lane];
+      my_eid = eid[base + lane];
+      if (MASKED) my_m = emask[my_eid];
+      const float2 a2 = *reinterpret_cast<const float2*>(alpha + (int64_t)my_eid * H + 2 * pair);
+      my_a0 = a2.x;
+      my_a1 = a2.y;
+    }
+    const int npre = min(RING, cnt);
+    for (int t = 0; t < npre; ++t) {
+      const int j = __shfl_sync(ISG_FULL_MASK, my_src, t);
+      const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+      if (leader)
+        ring.issue2(ring.seq + t, xl + (int64_t)j * ld_x + hoff, pol_keep, ep + (int64_t)e * HC + hoff, pol_stream,
+                    row_bytes);
+    }
+    for (int t = 0; t < cnt; ++t) {
+      const uint32_t s = ring.seq + t;
+      const int e = __shfl_sync(ISG_FULL_MASK, my_eid, t);
+      const float m = MASKED ? __shfl_sync(ISG_FULL_MASK, my_m, t) : 1.f;
+      const float a0 = __shfl_sync(ISG_FULL_MASK, my_a0, t), a1 = __shfl_sync(ISG_FULL_MASK, my_a1, t);
+      const int tn = t + RING < cnt ? t + RING : t;
+      const int jn = __shfl_sync(ISG_FULL_MASK, my_src, tn);
+      const int en = __shfl_sync(ISG_FULL_MASK, my_eid, tn);
+      ring.wait(s);
+      const uint32_t sx = ring.slot(s) + l16, sp = sx + row_bytes;
+      float t0, t1;
+      row_dot(sx, t0, t1);
+      if (!xr_ready) {
+        ring_wait(xbar, 0u);
+        xr_ready = true;
+      }
+      const float gl0 = a0 * (m * t0 - dot0), gl1 = a1 * (m * t1 - dot1);  // d loss / d logit[e, h]
+      const float glmm0 = MASKED ? gl0 * m * m : gl0, glmm1 = MASKED ? gl1 * m * m : gl1;
+      float2 av0 = make_float2(0.f, 0.f), av1 = make_float2(0.f, 0.f);
+      __nv_bfloat16* gerow = g_ep + (int64_t)e * HC + hoff;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (ok[k]) {
+          float4 x0, x1, e0, e1, r0, r1;
+          bf8_to_f4(lds_u4(sx + 512u * k), x0, x1);
+          bf8_to_f4(lds_u4(sp + 512u * k), e0, e1);
+          bf8_to_f4(lds_u4(xr_s + l16 + 512u * k), r0, r1);
+          const uint32_t as = att_s + 32u * (lane + 32 * k);
+          float4 gs[2];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int g = 2 * k + hf;
+            const bool h1 = hb[g];
+            const float4 sv = p4_add(p4_add(hf ? r1 : r0, hf ? x1 : x0), hf ? e1 : e0);
+            const float4 u = MASKED ? p4_scale(sv, m) : sv;
+            const float4 v = p4_leaky(u, slope);
+            const float4 at = lds_f4(as + 16u * hf);
+            gatt[g] = p4_fma_s(MASKED ? p4_scale(v, m) : v, h1 ? gl1 : gl0, gatt[g]);
+            const float4 lk = make_float4(u.x > 0.f ? 1.f : slope, u.y > 0.f ? 1.f : slope, u.z > 0.f ? 1.f : slope,
+                                          u.w > 0.f ? 1.f : slope);
+            gs[hf] = p4_scale(p4_mul(at, lk), h1 ? glmm1 : glmm0);
+            gxr[g] = p4_add(gxr[g], gs[hf]);
+            if (MASKED) sel_add(av0, av1, h1, p4_dot_acc(at, v, make_float2(0.f, 0.f)));
+          }
+          const uint4 packed = f4_to_bf8(gs[0], gs[1]);
+          asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(gerow + 8 * (lane + 32 * k)),
+                       "r"(packed.x), "r"(packed.y), "r"(packed.z), "r"(packed.w)
+                       : "memory");
+        }
+      }
+      if (MASKED) {
+        const float gm0 = warp_sum(2.f * gl0 * p2_sum(av0)) + t0 * a0;
+        const float gm1 = warp_sum(2.f * gl1 * p2_sum(av1)) + t1 * a1;
+        if (lane == t) { my_gm0 = gm0; my_gm1 = gm1; }
+      }
+      __syncwarp();
+      if (leader && t + RING < cnt)
+        ring.issue2(s + RING, xl + (int64_t)jn * ld_x + hoff, pol_keep, ep + (int64_t)en * HC + hoff, pol_stream,
+                    row_bytes);
+    }
+    ring.seq += cnt;
+    if (MASKED && lane < cnt) {
+      gm_h[(int64_t)my_eid * H + 2 * pair] = my_gm0;
+      gm_h[(int64_t)my_eid * H + 2 * pair + 1] = my_gm1;
+    }
+  }
+  if (!xr_ready) ring_wait(xbar, 0u);
+  __syncwarp();
+  __nv_bfloat16* grow = g_xr + node * ld_gx + hoff;
+  float* prow = gatt_part + (node * H + 2 * pair) * C;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    if (ok[k]) {
+      const int c = lane + 32 * k;
+      *reinterpret_cast<uint4*>(grow + 8 * c) = f4_to_bf8(gxr[2 * k], gxr[2 * k + 1]);
+      Vec4<float>::st(prow + 8 * c, gatt[2 * k]);
+      Vec4<float>::st(prow + 8 * c + 4, gatt[2 * k + 1]);
+    }
+  }
+}
+
+
 struct BwdRingPlan {
   int K;
   int64_t cols, blocks, warps, parts2;
@@ -1510,6 +2050,68 @@ int launch_bwd(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r
   return ISG_OK;
 }
 
+
+template <int VPL, bool MASKED>
+int launch_fwd_pair(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj, const float* att, const float* bias,
+                    const float* emask, const int* dst_ptr, const int* dst_nbr, const int* dst_eid, const int* dst_order,
+                    void* out, int64_t ld_out, float* alpha, int64_t N, int H, int C, float slope, cudaStream_t stream) {
+  const int64_t NP = N * (H / 2);
+  const size_t smem = pair_smem_bytes(C, true, 1);
+  auto kern = gat_edge_fwd_pair_kernel<VPL, MASKED>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<(unsigned)ceil_div(NP, (int64_t)EDGE_WARPS), EDGE_WARPS * 32, smem, stream>>>(
+      (const __nv_bfloat16*)x_l, (const __nv_bfloat16*)x_r, ld_x, (const __nv_bfloat16*)e_proj, att, bias, emask, dst_ptr,
+      dst_nbr, dst_eid, dst_order, (__nv_bfloat16*)out, ld_out, alpha, NP, H, C, slope);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+template <int VPL, bool MASKED>
+int launch_bwd_pair(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj,
+                    const float* att, const float* emask, const float* alpha, const int* dst_ptr, const int* dst_nbr,
+                    const int* dst_eid, const int* dst_order, const int* src_ptr, const int* src_nbr, const int* src_eid,
+                    const int* src_order, void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att,
+                    float* g_emask, int64_t N, int64_t E, int H, int C, float slope, float* gatt_part, float* gatt_part2,
+                    float* gm_h, cudaStream_t stream) {
+  const size_t smem_d = pair_smem_bytes(C, true, 1), smem_s = pair_smem_bytes(C, false, 0);
+  auto kd = gat_edge_bwd_dst_pair_kernel<VPL, MASKED>;
+  auto ks = gat_edge_bwd_src_pair_kernel<VPL, MASKED>;
+  cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t NP = N * (H / 2);
+  const unsigned blocks = (unsigned)ceil_div(NP, (int64_t)EDGE_WARPS);
+  kd<<<blocks, EDGE_WARPS * 32, smem_d, stream>>>(
+      (const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)x_l, (const __nv_bfloat16*)x_r, ld_x,
+      (const __nv_bfloat16*)e_proj, att, emask, alpha, dst_ptr, dst_nbr, dst_eid, dst_order, (__nv_bfloat16*)g_xr, ld_gx,
+      (__nv_bfloat16*)g_eproj, gatt_part, gm_h, N, H, C, slope);
+  ISG_CHECK_LAUNCH();
+  const int HC = H * C;
+  const int64_t parts2 = (N + GR_ROWS - 1) / GR_ROWS;  // gatt_part viewed as [N rows, H*C], keyed by the node
+  gat_att_reduce1_kernel<<<dim3(ceil_div(HC / 4, 64), (unsigned)parts2), 64, 0, stream>>>(gatt_part, N, HC, gatt_part2);
+  ISG_CHECK_LAUNCH();
+  gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)parts2, HC, g_att);
+  ISG_CHECK_LAUNCH();
+  ks<<<blocks, EDGE_WARPS * 32, smem_s, stream>>>((const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)g_eproj, emask,
+                                                  alpha, src_ptr, src_nbr, src_eid, src_order, (__nv_bfloat16*)g_xl, ld_gx,
+                                                  NP, H, C);
+  ISG_CHECK_LAUNCH();
+  if (MASKED && E > 0) {
+    gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
+    ISG_CHECK_LAUNCH();
+  }
+  return ISG_OK;
+}
+
+// the pair kernels need an even head count and 16-byte aligned pair rows (ISG_EDGE_BF16_PAIR=0: the 8-byte kernels)
+inline bool pair_ok(int H, int C, int64_t ld0, int64_t ld1, int64_t ld2, const void* a, const void* b, const void* c,
+                    const void* d, const void* e) {
+  static const bool off = getenv("ISG_EDGE_BF16_PAIR") != nullptr && atoi(getenv("ISG_EDGE_BF16_PAIR")) == 0;
+  if (off || H % 2 || C % 4 || ld0 % 8 || ld1 % 8 || ld2 % 8) return false;
+  return !(((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & 15);
+}
+
 inline int vpl_for(int C) { return (C / 4 + 31) / 32; }
 
 }  // namespace
@@ -1545,6 +2147,20 @@ extern "C" int isg_gat_edge_fwd(const void* x_l, const void* x_r, int64_t ld_x, 
     }
 #undef ISG_FWD_RING
   } else if (dtype == ISG_BF16) {
+    if (pair_ok(H, C, ld_x, ld_out, 8, x_l, x_r, e_proj, out, nullptr)) {  // 16-byte ring kernels, one warp per head pair
+#define ISG_FWD_PAIR(V)                                                                                        \
+  return edge_mask ? launch_fwd_pair<V, true>(x_l, x_r, ld_x, e_proj, att, bias, edge_mask, dst_ptr, dst_nbr, dst_eid, \
+                                              dst_order, out, ld_out, alpha, N, H, C, slope, stream)               \
+                   : launch_fwd_pair<V, false>(x_l, x_r, ld_x, e_proj, att, bias, edge_mask, dst_ptr, dst_nbr,     \
+                                               dst_eid, dst_order, out, ld_out, alpha, N, H, C, slope, stream)
+      switch (vpl) {
+        case 1: ISG_FWD_PAIR(1);
+        case 2: ISG_FWD_PAIR(2);
+        case 3: ISG_FWD_PAIR(3);
+        case 4: ISG_FWD_PAIR(4);
+      }
+#undef ISG_FWD_PAIR
+    }
     switch (vpl) {
       case 1: ISG_FWD_CASE(__nv_bfloat16, 1);
       case 2: ISG_FWD_CASE(__nv_bfloat16, 2);
@@ -1662,6 +2278,29 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
     }
 #undef ISG_BWD_RING
   } else if (dtype == ISG_BF16) {
+    if (pair_ok(H, C, ld_x, ld_g, ld_gx, x_l, x_r, e_proj, g_out, g_eproj) && !(((uintptr_t)g_xl | (uintptr_t)g_xr) & 15)) {
+      float* pp_part = (float*)workspace;
+      float* pp_part2 = (float*)((char*)workspace + align256((size_t)(N + EDGE_WARPS) * (size_t)H * (size_t)C * sizeof(float)));
+      float* pp_gmh = (float*)((char*)pp_part2 +
+                               align256((size_t)((N + GR_ROWS - 1) / GR_ROWS) * (size_t)H * (size_t)C * sizeof(float)) +
+                               align256((size_t)(1 + B) * sizeof(int)));
+#define ISG_BWD_PAIR(V)                                                                                          \
+  return edge_mask ? launch_bwd_pair<V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha, dst_ptr,   \
+                                              dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, src_order,  \
+                                              g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,   \
+                                              pp_part, pp_part2, pp_gmh, stream)                                 \
+                   : launch_bwd_pair<V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha, dst_ptr,  \
+                                               dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, src_order, \
+                                               g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,  \
+                                               pp_part, pp_part2, pp_gmh, stream)
+      switch (vpl) {
+        case 1: ISG_BWD_PAIR(1);
+        case 2: ISG_BWD_PAIR(2);
+        case 3: ISG_BWD_PAIR(3);
+        case 4: ISG_BWD_PAIR(4);
+      }
+#undef ISG_BWD_PAIR
+    }
     switch (vpl) {
       case 1: ISG_BWD_CASE(__nv_bfloat16, 1);
       case 2: ISG_BWD_CASE(__nv_bfloat16, 2);

@@ -251,15 +251,17 @@ def test_edge_fused_pitch_and_isolated_nodes():
 
 
 @pytest.mark.parametrize("masked", [False, True])
-def test_edge_bf16_storage(masked):
+@pytest.mark.parametrize("B,mn,me,H,C", [(12, 14, 90, 4, 300), (3, 40, 900, 4, 300), (5, 9, 40, 2, 64), (4, 10, 50, 3, 300)],
+                         ids=["gqa", "deg>32", "H2C64", "H3-8byte-kernels"])
+def test_edge_bf16_storage(masked, B, mn, me, H, C):
     """bf16 STORAGE of the edge-kernel tensors (x_l|x_r, e_proj, out and their gradients), fp32 accumulation
     inside the kernel — the configuration BASELINE states separately.  Reference = the oracle in fp64 on the
-    bf16-rounded inputs; bound = bf16 output rounding (2^-8 relative) with margin."""
+    bf16-rounded inputs; bound = bf16 output rounding (2^-8 relative) with margin.  Even head counts run the ring
+    kernels (one warp per head pair, 16-byte accesses); H = 3 exercises the older 8-byte register-load kernels."""
     import isg_oracle as O
     from isg_b200 import ops
 
-    H, C = 4, 300
-    d = _edge_case(12, 14, 90, C, H, masked, seed=21)
+    d = _edge_case(B, mn, me, C, H, masked, seed=21)
     for k in ("x_l", "x_r", "e_proj", "g_out"):
         d[k] = d[k].to(torch.bfloat16).float()  # inputs exactly representable in bf16
     want = _run_edge_oracle(d, H, C)
