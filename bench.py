@@ -242,7 +242,8 @@ def run_cpu_reference(sampler, train, B, steps, warmup, seed=3407):
         return None
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    with rl.scratch_cwd():
+    # the reference prints "using aimle as sample method" from its constructors: keep stdout for the ONE JSON line
+    with rl.scratch_cwd(), contextlib.redirect_stdout(sys.stderr):
         rl.load()
         from ISubGVQA.models.mgat import MGAT as RefMGAT
 
