@@ -360,13 +360,20 @@ def main_isg(args, rank, world, local_rank):
     # graph (isg_b200.dp.OverlappedGradAllReduce; the process group must then exist before the capture).  Measured
     # on 2 GPUs (r1i): 5.47-5.48 vs 5.43 ms/step — the bucket collectives compete with the persistent GEMM CTAs for
     # SMs and nothing is gained at this scale, so it stays opt-in (8 GPUs not measured).
-    # Default since r2: isg_b200.dp.LayerGradAllReduce — .grad tensors are views of the executor's flat gradient
-    # buffer (no pack / unpack), each layer's slice is all-reduced on a communication stream as soon as that layer's
-    # backward has been issued, and the collectives are captured into the step's CUDA graph.  --dp-flat keeps the r1
-    # path (one flat all-reduce with pack / unpack after each replay), --overlap the r1 hook-based bucketing.
+    # Reducers (isg_b200.dp), measured on 2 and 8 B200 in r2 (profiles/r2_bench_8gpu*.json):
+    #   flat (default)   GradAllReduce: pack -> one 42 MB NCCL AVG all-reduce -> unpack, issued after each replay
+    #                    8 GPUs 5.35 ms/step, 2 GPUs 5.24
+    #   --dp-layer       LayerGradAllReduce: .grad tensors ARE views of the executor's flat gradient buffer (no pack /
+    #                    unpack), one collective after the backward pass, captured in the step graph: 5.42 / 5.33
+    #   --dp-layer --dp-overlap   the same bucket, one slice per layer issued on a communication stream as soon as that
+    #                    layer's backward has been issued: 5.36 / 5.29 (eager e2e suffers: the collectives queue behind
+    #                    the persistent GEMM CTAs and couple the ranks' timing)
+    #   --overlap        r1's hook-based bucketing (OverlappedGradAllReduce)
+    # All within 1.5 %: the collective itself is 0.10 ms at 2 GPUs (scripts/allreduce_probe.py) and the rest of the
+    # 1 -> 8 GPU gap is the max over ranks of differently sized batches, which no reducer removes.
     dp_mode = "none"
     if world > 1 and train:
-        dp_mode = "hooks" if (args.overlap and not args.no_graph) else ("flat" if args.dp_flat else "layer")
+        dp_mode = "hooks" if (args.overlap and not args.no_graph) else ("layer" if (args.dp_layer or args.dp_overlap) else "flat")
     overlap = dp_mode in ("hooks", "layer")  # the reduction is part of step_core (and of the captured graph)
     reducer = None
     if overlap:
@@ -762,8 +769,9 @@ def main():
                          "in the step graph, instead of one flat all-reduce after the step")
     ap.add_argument("--dp-overlap", action="store_true",
                     help="multi-GPU: issue each layer's all-reduce during the backward pass (communication stream)")
-    ap.add_argument("--dp-flat", action="store_true",
-                    help="multi-GPU: the r1 reducer (flat 42 MB all-reduce with pack/unpack after each replay)")
+    ap.add_argument("--dp-layer", action="store_true",
+                    help="multi-GPU: the in-place reducer on the executor's flat gradient buffer (LayerGradAllReduce)")
+    ap.add_argument("--dp-flat", action="store_true", help="(default) flat 42 MB all-reduce with pack/unpack after each replay")
     ap.add_argument("--no-edge-study", action="store_true", help="skip the batch-4096 edge-kernel roofline point")
     ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2, 3],
                     help="projection arithmetic: 0 fp32 FFMA, 1 tcgen05 3xTF32 (default), 2 tcgen05 1xTF32")

@@ -301,76 +301,127 @@ extern "C" int isg_graph_ptr(const int64_t* batch, int64_t N, int64_t B, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Task order for the edge kernels: nodes by decreasing segment length (longest-processing-time-first).  The edge
-// kernels run one warp per (node, head) and the hardware dispatches CTAs in index order; in the natural node order
-// a 40-edge node that happens to sit near the end of the batch finishes ~15 us after everything else at the c3 size
-// (4.7 waves of CTAs: a simulated makespan 1.47x the balanced one, which is also the measured gap between the c3
-// launch and the batch-4096 launches).  Counting sort over min(deg, 255); ties land in arbitrary order (atomic
-// cursors) — the order only decides WHEN a task runs, never what it computes or where it writes.
+// Task order for the edge kernels: HEAVY NODES FIRST, everything else in its natural order.  The edge kernels run one
+// warp per (node, head) and the hardware dispatches CTAs in index order; in the natural node order a 40-edge node
+// that happens to sit near the end of the batch finishes ~15 us after everything else at the c3 size (4.7 waves of
+// CTAs: a simulated makespan 1.47x the balanced one).  A full sort by degree fixes the tail but scatters the
+// gathers: the natural order walks a graph's nodes together and re-uses their x_l rows in L1 / L2, and at batch 4096
+// (x_l|x_r = 390 MB, beyond L2) the fully sorted schedule cost the forward kernel 22 % (0.78 -> 0.61 of the HBM peak).
+// So only the nodes whose segment is at least twice the mean length (~7 % of them) are moved to the front — a STABLE
+// partition, deterministic — which bounds the tail by a mean-sized task and keeps the locality of the other 93 %.
+// The order only decides WHEN a task runs, never what it computes or where it writes.
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
-constexpr int ORD_BINS = 256;
-__global__ void order_hist_kernel(const int* __restrict__ ptr_a, const int* __restrict__ ptr_b, int64_t N,
-                                  int* __restrict__ hist /* [2][ORD_BINS] */) {
-  __shared__ int h[2][ORD_BINS];
-  for (int i = threadIdx.x; i < 2 * ORD_BINS; i += blockDim.x) (&h[0][0])[i] = 0;
+constexpr int ORD_THREADS = 256;
+// heavy(n) = deg(n) >= thr, thr = max(2, 2 * E / N) computed by the host from sizes it already knows
+__global__ void __launch_bounds__(ORD_THREADS)
+order_count_kernel(const int* __restrict__ ptr_a, const int* __restrict__ ptr_b, int64_t N, int thr,
+                   int* __restrict__ blk /* [2][nblocks] */, int nblocks) {
+  __shared__ int ca, cb;
+  if (threadIdx.x == 0) ca = cb = 0;
   __syncthreads();
-  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
-    atomicAdd(&h[0][min(ptr_a[n + 1] - ptr_a[n], ORD_BINS - 1)], 1);
-    atomicAdd(&h[1][min(ptr_b[n + 1] - ptr_b[n], ORD_BINS - 1)], 1);
+  const int64_t n = blockIdx.x * (int64_t)ORD_THREADS + threadIdx.x;
+  const bool ha = n < N && ptr_a[n + 1] - ptr_a[n] >= thr, hb = n < N && ptr_b[n + 1] - ptr_b[n] >= thr;
+  const unsigned ma = __ballot_sync(ISG_FULL_MASK, ha), mb = __ballot_sync(ISG_FULL_MASK, hb);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&ca, __popc(ma));  // integer counts: the order of the adds does not matter
+    atomicAdd(&cb, __popc(mb));
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * ORD_BINS; i += blockDim.x) {
-    const int v = (&h[0][0])[i];
-    if (v) atomicAdd(hist + i, v);
+  if (threadIdx.x == 0) {
+    blk[blockIdx.x] = ca;
+    blk[nblocks + blockIdx.x] = cb;
   }
 }
-// hist -> start offset of each bin in DESCENDING bin order (in place); one block of 2 warps, one per ordering
-__global__ void order_scan_kernel(int* __restrict__ hist) {
-  int* h = hist + (threadIdx.x >> 5) * ORD_BINS;
-  const int lane = threadIdx.x & 31;
-  int carry = 0;
-  for (int base = ORD_BINS - 32; base >= 0; base -= 32) {
-    const int bin = base + 31 - lane;  // lane 0 owns the largest bin of the chunk
-    const int v = h[bin];
+// exclusive scan of the per-block heavy counts (one block per ordering); blk[which][nblocks] receives the total
+__global__ void __launch_bounds__(1024) order_scan_kernel(int* __restrict__ blk, int nblocks) {
+  int* b = blk + (int64_t)blockIdx.x * (nblocks + 1);
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? b[i] : 0;
     int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(ISG_FULL_MASK, incl, o);
       if (lane >= o) incl += t;
     }
-    h[bin] = carry + incl - v;
-    carry += __shfl_sync(ISG_FULL_MASK, incl, 31);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(ISG_FULL_MASK, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_tot[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int before = carry + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+    if (i < nblocks) b[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) b[nblocks] = carry;
+}
+__global__ void __launch_bounds__(ORD_THREADS)
+order_place_kernel(const int* __restrict__ ptr_a, const int* __restrict__ ptr_b, int64_t N, int thr,
+                   const int* __restrict__ blk, int nblocks, int* __restrict__ order_a, int* __restrict__ order_b) {
+  __shared__ int wcount[2][ORD_THREADS / 32];
+  const int64_t n = blockIdx.x * (int64_t)ORD_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool ha = n < N && ptr_a[n + 1] - ptr_a[n] >= thr, hb = n < N && ptr_b[n + 1] - ptr_b[n] >= thr;
+  const unsigned ma = __ballot_sync(ISG_FULL_MASK, ha), mb = __ballot_sync(ISG_FULL_MASK, hb);
+  if (lane == 0) {
+    wcount[0][warp] = __popc(ma);
+    wcount[1][warp] = __popc(mb);
+  }
+  __syncthreads();
+  if (n >= N) return;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const unsigned m = which ? mb : ma;
+    const bool heavy = which ? hb : ha;
+    int before = __popc(m & lt);  // heavy nodes of this block that precede n
+    for (int w = 0; w < warp; ++w) before += wcount[which][w];
+    const int* b = blk + (int64_t)which * (nblocks + 1);
+    const int heavy_before = b[blockIdx.x] + before, total_heavy = b[nblocks];
+    const int64_t pos = heavy ? heavy_before : total_heavy + (n - heavy_before);
+    (which ? order_b : order_a)[pos] = (int)n;
   }
 }
-__global__ void order_place_kernel(const int* __restrict__ ptr_a, const int* __restrict__ ptr_b, int64_t N,
-                                   int* __restrict__ cursor, int* __restrict__ order_a, int* __restrict__ order_b) {
-  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  order_a[atomicAdd(cursor + min(ptr_a[n + 1] - ptr_a[n], ORD_BINS - 1), 1)] = (int)n;
-  order_b[atomicAdd(cursor + ORD_BINS + min(ptr_b[n + 1] - ptr_b[n], ORD_BINS - 1), 1)] = (int)n;
-}
-
 }  // namespace
 
-extern "C" size_t isg_degree_order_workspace_bytes(void) { return 2 * ORD_BINS * sizeof(int); }
+extern "C" size_t isg_degree_order_workspace_bytes(int64_t N) {
+  const int64_t nblocks = ((N > 0 ? N : 1) + ORD_THREADS - 1) / ORD_THREADS;
+  return (size_t)2 * (size_t)(nblocks + 1) * sizeof(int);
+}
 
-extern "C" int isg_degree_order(const int32_t* dst_ptr, const int32_t* src_ptr, int64_t N, int32_t* dst_order,
+extern "C" int isg_degree_order(const int32_t* dst_ptr, const int32_t* src_ptr, int64_t N, int64_t E, int32_t* dst_order,
                                 int32_t* src_order, void* workspace, size_t ws_bytes, void* stream_) {
-  if (N < 0 || N >= (int64_t)INT32_MAX) return ISG_EINVAL;
+  if (N < 0 || E < 0 || N >= (int64_t)INT32_MAX) return ISG_EINVAL;
   if (N == 0) return ISG_OK;
   if (!dst_ptr || !src_ptr || !dst_order || !src_order) return ISG_EINVAL;
-  if (ws_bytes < isg_degree_order_workspace_bytes() || !workspace) return ISG_EWORKSPACE;
+  if (ws_bytes < isg_degree_order_workspace_bytes(N) || !workspace) return ISG_EWORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
-  cudaError_t err = cudaMemsetAsync(workspace, 0, isg_degree_order_workspace_bytes(), stream);
-  if (err != cudaSuccess) return (int)err;
-  const int blocks = (int)min((int64_t)ISG_NUM_SMS * 4, (int64_t)isg::ceil_div(N, 256));
-  order_hist_kernel<<<blocks, 256, 0, stream>>>(dst_ptr, src_ptr, N, (int*)workspace);
+  const int nblocks = (int)((N + ORD_THREADS - 1) / ORD_THREADS);
+  int thr = (int)((2 * E + N - 1) / N);
+  if (thr < 2) thr = 2;
+  // layout: [heavy counts of dst ordering: nblocks + 1][of src ordering: nblocks + 1] — the count kernel writes
+  // with stride nblocks, so it gets a compact staging view and the scan kernel the padded one
+  int* blk = (int*)workspace;
+  order_count_kernel<<<nblocks, ORD_THREADS, 0, stream>>>(dst_ptr, src_ptr, N, thr, blk, nblocks + 1);
   ISG_CHECK_LAUNCH();
-  order_scan_kernel<<<1, 64, 0, stream>>>((int*)workspace);
+  order_scan_kernel<<<2, 1024, 0, stream>>>(blk, nblocks);
   ISG_CHECK_LAUNCH();
-  order_place_kernel<<<isg::ceil_div(N, 256), 256, 0, stream>>>(dst_ptr, src_ptr, N, (int*)workspace, dst_order,
-                                                                src_order);
+  order_place_kernel<<<nblocks, ORD_THREADS, 0, stream>>>(dst_ptr, src_ptr, N, thr, blk, nblocks, dst_order, src_order);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

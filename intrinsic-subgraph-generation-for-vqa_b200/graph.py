@@ -9,6 +9,10 @@ import os
 from . import lib as L
 
 _EDGE_ORDER = os.environ.get("ISG_EDGE_ORDER", "1") != "0"  # A/B switch: "0" keeps the natural node order
+# The heavy-first schedule pays where a launch is a handful of CTA waves (c3: 4.7 waves, backward 0.373 -> 0.408 and
+# forward 0.518 -> 0.563 of the HBM peak in-step); at batch 4096 (92 waves) the tail is already negligible and the
+# moved nodes only cost locality (forward 0.779 -> 0.751), so larger batches keep the natural order.
+EDGE_ORDER_MAX_NODES = int(os.environ.get("ISG_EDGE_ORDER_MAX_NODES", "32768"))
 
 
 class GraphIndex:
@@ -44,11 +48,11 @@ class GraphIndex:
                                   L.ptr(self.src_eid), L.ptr(self.status), L.ptr(ws), ws_bytes, st)
         # task order of the edge kernels: longest segments first (csrc/csr.cu, isg_degree_order)
         self.dst_order = self.src_order = None
-        if _EDGE_ORDER:
+        if _EDGE_ORDER and N <= EDGE_ORDER_MAX_NODES:
             self.dst_order = torch.empty(max(N, 1), **i32)
             self.src_order = torch.empty(max(N, 1), **i32)
-            ows = L.workspace(lib.isg_degree_order_workspace_bytes(), dev)
-            L.call("isg_degree_order", L.ptr(self.dst_ptr), L.ptr(self.src_ptr), N, L.ptr(self.dst_order),
+            ows = L.workspace(lib.isg_degree_order_workspace_bytes(N), dev)
+            L.call("isg_degree_order", L.ptr(self.dst_ptr), L.ptr(self.src_ptr), N, E, L.ptr(self.dst_order),
                    L.ptr(self.src_order), L.ptr(ows), ows.numel(), st)
         self.graph_ptr = torch.empty(B + 1, **i32)
         self.batch32 = torch.empty(max(N, 1), **i32)
@@ -61,6 +65,28 @@ class GraphIndex:
         self._closed = None
         self._key = None
         self._keepalive = None
+
+    @classmethod
+    def from_host(cls, edge_index, batch, host_index):
+        """GraphIndex from the CSR a data loader built on the host (isg_b200.collate.collate_scene_graphs: per-image
+        cached CSR, concatenated at collate time) — uploads the int32 arrays instead of running the device build.
+        edge_index / batch are the batch's DEVICE tensors; a per-image cache guarantees that no edge leaves its graph."""
+        L.require_cuda(edge_index, batch)
+        self = cls.__new__(cls)
+        dev = edge_index.device
+        self.edge_index, self.batch = edge_index.contiguous(), batch.contiguous()
+        self.N, self.E, self.B = int(batch.numel()), int(edge_index.size(1)), int(host_index["num_graphs"])
+        for name in ("dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr", "src_eid", "graph_ptr", "batch32",
+                     "dst_order", "src_order"):
+            t = host_index[name]
+            setattr(self, name, t.to(dev, non_blocking=True) if not t.is_cuda else t)
+        if not _EDGE_ORDER or self.N > EDGE_ORDER_MAX_NODES:
+            self.dst_order = self.src_order = None
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._nmax_dev = None
+        self._nmax, self._closed = int(host_index["nmax"]), True
+        self._key = self._keepalive = None
+        return self
 
     @property
     def nmax(self):
@@ -114,6 +140,18 @@ def get_graph_index(edge_index, batch, num_graphs):
             return gi
     gi = GraphIndex(edge_index, batch, num_graphs)
     gi._key = key
+    gi._keepalive = (edge_index, batch)
+    _cache.insert(0, gi)
+    del _cache[_CACHE_SIZE:]
+    return gi
+
+
+def register_graph_index(gi):
+    """Puts a GraphIndex built elsewhere (GraphIndex.from_host) into the cache, so that MGAT.forward — which looks
+    the index up by the identity of the edge_index / batch tensors it is given — finds it."""
+    edge_index, batch = gi.edge_index, gi.batch
+    gi._key = (edge_index.data_ptr(), edge_index.storage_offset(), edge_index._version, tuple(edge_index.shape),
+               batch.data_ptr(), batch.storage_offset(), batch._version, int(batch.numel()), int(gi.B), edge_index.device)
     gi._keepalive = (edge_index, batch)
     _cache.insert(0, gi)
     del _cache[_CACHE_SIZE:]

@@ -26,8 +26,8 @@ SIGNATURES = {
     "isg_graph_ptr": (_I32, [_P, _I64, _I64, _P, _P, _P, _P]),
     "isg_gat_edge_fwd": (_I32, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I32, _I32,
                                 _F, _I32, _P]),
-    "isg_degree_order_workspace_bytes": (_SZ, []),
-    "isg_degree_order": (_I32, [_P, _P, _I64, _P, _P, _P, _SZ, _P]),
+    "isg_degree_order_workspace_bytes": (_SZ, [_I64]),
+    "isg_degree_order": (_I32, [_P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "isg_graph_closure": (_I32, [_P, _I64, _P, _I64, _P, _P]),
     "isg_gat_edge_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32, _I32]),
     "isg_gat_edge_bwd": (_I32, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P,

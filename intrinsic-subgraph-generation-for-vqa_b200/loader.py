@@ -6,7 +6,7 @@ stream while batch i is being computed, and the number of nodes of the largest g
 time — is handed to the GraphIndex so no device -> host read is needed."""
 import torch
 
-from .graph import get_graph_index
+from .graph import GraphIndex, get_graph_index, register_graph_index
 
 _KEYS = ("x", "edge_index", "instr_vectors", "global_language_feats", "edge_attr", "batch")
 
@@ -26,7 +26,10 @@ class DevicePrefetcher:
             dev = {k: host_batch[k].to(self.device, non_blocking=True) for k in _KEYS if k in host_batch}
             ext = {k: v.to(self.device, non_blocking=True) for k, v in (extra or {}).items()}
             gi = None
-            if build_index:
+            if build_index and host_batch.get("host_index") is not None:
+                # CSR built at collate time from the per-image cache (isg_b200.collate): upload, no device build
+                gi = register_graph_index(GraphIndex.from_host(dev["edge_index"], dev["batch"], host_batch["host_index"]))
+            elif build_index:
                 gi = get_graph_index(dev["edge_index"], dev["batch"], int(dev["instr_vectors"].shape[1]))
                 if nmax is not None:
                     gi.set_nmax(nmax)
@@ -42,7 +45,8 @@ class DevicePrefetcher:
         tensors = list(dev.values()) + list(ext.values())
         if gi is not None:
             tensors += [t for t in (getattr(gi, n) for n in ("dst_ptr", "dst_nbr", "dst_eid", "src_ptr", "src_nbr", "src_eid",
-                                                 "dst_order", "src_order", "status", "graph_ptr", "batch32", "_nmax_dev")) if t is not None]
+                                                 "dst_order", "src_order", "status", "graph_ptr", "batch32", "_nmax_dev"))
+                        if t is not None]
         for t in tensors:
             t.record_stream(main)  # allocated on the copy stream, consumed on the compute stream
         return dev, ext
