@@ -640,7 +640,8 @@ def main_isg(args, rank, world, local_rank):
         per_launch_ms = tot / calls
         alg = (3 * bwd_b_un + bwd_b_m) / 4.0  # 3 unmasked layers + 1 masked layer per step
         ach = alg / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst_ring + gat_att_reduce1/2 + gat_edge_bwd_src_ring)",
+        roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst_ring + gat_att_reduce1/2 + gat_edge_bwd_src_ring; "
+                                          "heavy-first task schedule)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": measured_traffic("isg_gat_edge_bwd", args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
@@ -693,7 +694,8 @@ def main_isg(args, rank, world, local_rank):
         samp = {"kernel": "sampler_fused_fwd_kernel (gate dot + dropout + tau*noise + top-k + node mask + edge mask, "
                           "one launch)", "ms_per_launch": t_ms, "algorithmic_bytes_per_launch": sb,
                 "achieved_GBps": sb / (t_ms * 1e-3) / 1e9, "frac": sb / (t_ms * 1e-3) / 1e9 / peak,
-                "note": "latency-bound at this size (SURVEY.md section 8d): one warp per graph, ~20 nodes each"}
+                "note": "latency-bound at this size (SURVEY.md section 8d: ~20 B per node): one CTA per graph, one warp "
+                        "per node row for the gate dot products; 6.8 MB per launch"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r, kind, what = run_cpu_arm(sampler, train, B, 2, 1)
