@@ -151,12 +151,11 @@ __device__ __forceinline__ float4 lo_part(float4 v) {
 // (measured by bisecting an instrumented build), so the hot instantiation carries none.
 // BLO: the lo plane of B comes pre-split from global memory (a second tensor map): the splitter warps then only
 // move A into tensor memory — no shared-memory stores and no generic->async proxy fence on the per-k-block chain.
-// P2 (mode 1, BN == 128; opt-in, see launch()): the CTAs run as cta_group::2 MMA PAIRS on adjacent M tiles of one N block.
+// P2 (mode 1, BN == 128; selected by launch()): the CTAs run as cta_group::2 MMA PAIRS on adjacent M tiles of one N block.
 // The leader issues M = 256 instructions; each CTA stages its own A tile (and moves it to ITS tensor memory) and only
 // HALF of the B tile (64 of the 128 rows / columns), which the pair's MMA reads from both shared memories.  Per CTA
 // and 32-wide k-block the shared-memory traffic drops from 128 KB (TMA 32 + splitter 48 + MMA operand reads 48) to
-// 80 KB (24 + 32 + 24): at 128 B/clk that is 640 instead of 1024 cycles, below the 768-cycle MMA floor.  Measured
-// slower all the same (the added cross-SM synchronisation hops cost more than the traffic saves): see launch().
+// 80 KB (24 + 32 + 24) and the L2 -> SM operand traffic from 32 to 24 KB: 5-9 % faster on the E-sized products.
 template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN, bool BLO, bool P2 = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -632,16 +631,17 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   static const bool env_no_cluster = getenv("ISG_TC_NO_CLUSTER") != nullptr;
   const bool want_pair = p.split3 == 0 && !p.no_cluster && !env_no_cluster;
   const bool pair = want_pair && g.m_tiles >= 2 && (B_MN ? ((g.BN / 32) % 2 == 0) : true);
-  // mode 1 at BN == 128 (default build): cta_group::2 MMA pairs — see the kernel's header comment — are OPT-IN
-  // (ISG_TC_PAIR2=1).  Measured on B200 (r2, scripts/gemm_probe.py, profiles/r2_gemm_probe.txt): bit-identical
-  // results, but 1.5-1.7x SLOWER on every shape and product ([39809,300]x[300,1200] fwd 155 -> 245 us) although
-  // the pair halves the shared-memory traffic per k-block; 74 clusters are resident (cudaOccupancyMaxActiveClusters),
-  // so it is not a residency problem.  The mainloop is a latency loop (MMA commit -> free stage -> TMA -> splitter ->
-  // MMA) over only FOUR stages (the tensor-memory A ring), and the pair adds two cross-SM hops to it (multicast
-  // commit to the peer's barrier, the peer's remote arrive on the leader's); single CTAs stay the default.
-  static const bool env_pair2 = getenv("ISG_TC_PAIR2") != nullptr && atoi(getenv("ISG_TC_PAIR2")) != 0;
-  const bool pair2 = MERGE && p.split3 == 1 && g.BN == MAX_BN && p.B_lo == nullptr && g.m_tiles >= 2 && env_pair2 &&
-                     !p.no_cluster;
+  // mode 1 at BN == 128 (default build): cta_group::2 MMA pairs — see the kernel's header comment.  Measured on B200
+  // (r2, scripts/gemm_probe.py, profiles/r2_gemm_probe.txt), bit-identical results: [39809,300]x[300,1200] fwd 145 ->
+  // 133 us, dgrad 154 -> 142, wgrad 161 -> 153; node-sized fwd / dgrad 2-5 % faster, node-sized wgrad 20 % SLOWER (the
+  // reduction split leaves the 74 pairs one short wave), so wgrad pairs only from 16 K reduction rows.  ISG_TC_PAIR2=0
+  // keeps single CTAs everywhere.  (The first version waited / arrived on the cross-CTA barriers with
+  // .acquire.cluster / .release.cluster and was 1.5-1.7x SLOWER than single CTAs: a cluster-scope acquire on every
+  // per-k-block wait of the MMA thread.  The default-scope forms — what CUTLASS's cluster barriers use — are enough:
+  // the tensor-memory and async-proxy hand-offs are ordered by the tcgen05 / proxy fences next to them.)
+  static const bool env_no_pair2 = getenv("ISG_TC_PAIR2") != nullptr && atoi(getenv("ISG_TC_PAIR2")) == 0;
+  const bool pair2 = MERGE && p.split3 == 1 && g.BN == MAX_BN && p.B_lo == nullptr && g.m_tiles >= 2 && !env_no_pair2 &&
+                     !p.no_cluster && (!A_MN || p.R >= 16384);
   const int CLh = (pair || pair2) ? 2 : 1;
 
   CUtensorMap ma, mb;
