@@ -381,6 +381,243 @@ sdpa_graphnorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__
   }
 }
 
+// ---- D % 4 == 0 variants: float4 columns x SG_LANES row lanes ------------------------------------------------
+// The kernels above give every thread one channel and walk the graph's nodes serially in each of their per-channel
+// passes (three in the forward, two in the backward): chains of ~20-40 dependent L2 round trips, 20 us per launch
+// at the c3 size for 12 MB.  Here thread (cx, ly) owns the float4 column cx and the rows ly, ly + SG_LANES, ...;
+// per-lane partial sums are folded through shared memory in a fixed order (deterministic).
+constexpr int SG_COLS = 80, SG_LANES = 4;  // 320 threads; D <= 320 per column pass (looped beyond)
+
+__device__ __forceinline__ float4 sg_fold(float4 (*red)[SG_COLS], int cx, int ly, float4 v) {
+  __syncthreads();  // protect `red` from the previous use
+  red[ly][cx] = v;
+  __syncthreads();
+  float4 t = red[0][cx];
+#pragma unroll
+  for (int y = 1; y < SG_LANES; ++y) t = f4_add(t, red[y][cx]);
+  return t;
+}
+
+__global__ void __launch_bounds__(SG_COLS * SG_LANES)
+sdpa_graphnorm_fwd_v4_kernel(const float* __restrict__ v, const float* __restrict__ ins, const float* __restrict__ h_in,
+                             const float* __restrict__ weight, const float* __restrict__ bias,
+                             const float* __restrict__ mean_scale, const int* __restrict__ gptr, int D, float eps,
+                             float* __restrict__ h_out, float* __restrict__ a_out, float* __restrict__ mean_out,
+                             float* __restrict__ rstd_out) {
+  extern __shared__ float sm[];  // [nmax] attention weights
+  __shared__ float red1[32];
+  __shared__ float4 red[SG_LANES][SG_COLS];
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], n1 = gptr[b + 1], cnt = n1 - n0;
+  const int d4 = D >> 2;
+  if (cnt <= 0) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      mean_out[(int64_t)b * D + c] = 0.f;
+      rstd_out[(int64_t)b * D + c] = 0.f;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* ib = ins + (int64_t)b * D;
+  const float rs = 1.0f / sqrtf((float)D);
+  for (int i = warp; i < cnt; i += nw) {  // logits: warp per node, same arithmetic order as the scalar kernel
+    const float* vr = v + (int64_t)(n0 + i) * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s = fmaf(ib[c], vr[c], s);
+    s = warp_sum(s);
+    if (lane == 0) sm[i] = s * rs;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) mx = fmaxf(mx, sm[i]);
+  mx = block_max(mx, red1);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float e = expf(sm[i] - mx);
+    sm[i] = e;
+    se += e;
+  }
+  se = block_sum(se, red1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float a = sm[i] / se;  // torch_scatter.scatter_softmax: no epsilon
+    sm[i] = a;
+    a_out[n0 + i] = a;
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / (float)cnt;
+  const int cx = threadIdx.x % SG_COLS, ly = threadIdx.x / SG_COLS;
+  for (int c0 = 0; c0 < d4; c0 += SG_COLS) {
+    const int c4 = c0 + cx;
+    const bool on = c4 < d4;
+    const int64_t cb = 4 * (int64_t)c4;
+    float4 s1 = f4_zero();
+    if (on)
+      for (int i = ly; i < cnt; i += SG_LANES) s1 = f4_fma(Vec4<float>::ld(v + (int64_t)(n0 + i) * D + cb), sm[i], s1);
+    s1 = sg_fold(red, cx, ly, s1);
+    float4 mean = f4_zero(), shift = f4_zero(), s2 = f4_zero();
+    if (on) {
+      mean = f4_scale(s1, inv_cnt);
+      const float4 ms = Vec4<float>::ld(mean_scale + cb);
+      shift = make_float4(mean.x * ms.x, mean.y * ms.y, mean.z * ms.z, mean.w * ms.w);
+      for (int i = ly; i < cnt; i += SG_LANES) {
+        const float4 vv = Vec4<float>::ld(v + (int64_t)(n0 + i) * D + cb);
+        const float a = sm[i];
+        const float4 o = make_float4(a * vv.x - shift.x, a * vv.y - shift.y, a * vv.z - shift.z, a * vv.w - shift.w);
+        s2 = make_float4(fmaf(o.x, o.x, s2.x), fmaf(o.y, o.y, s2.y), fmaf(o.z, o.z, s2.z), fmaf(o.w, o.w, s2.w));
+      }
+    }
+    s2 = sg_fold(red, cx, ly, s2);
+    if (on) {
+      const float4 rstd = make_float4(1.0f / sqrtf(s2.x * inv_cnt + eps), 1.0f / sqrtf(s2.y * inv_cnt + eps),
+                                      1.0f / sqrtf(s2.z * inv_cnt + eps), 1.0f / sqrtf(s2.w * inv_cnt + eps));
+      if (ly == 0) {
+        Vec4<float>::st(mean_out + (int64_t)b * D + cb, mean);
+        Vec4<float>::st(rstd_out + (int64_t)b * D + cb, rstd);
+      }
+      const float4 wv = Vec4<float>::ld(weight + cb), bb = Vec4<float>::ld(bias + cb);
+      const float4 w = make_float4(wv.x * rstd.x, wv.y * rstd.y, wv.z * rstd.z, wv.w * rstd.w);
+      for (int i = ly; i < cnt; i += SG_LANES) {
+        const int64_t o_ = (int64_t)(n0 + i) * D + cb;
+        const float4 vv = Vec4<float>::ld(v + o_), hi = Vec4<float>::ld(h_in + o_);
+        const float a = sm[i];
+        Vec4<float>::st(h_out + o_, make_float4(fmaf(w.x, a * vv.x - shift.x, bb.x) + hi.x, fmaf(w.y, a * vv.y - shift.y, bb.y) + hi.y,
+                                                fmaf(w.z, a * vv.z - shift.z, bb.z) + hi.z, fmaf(w.w, a * vv.w - shift.w, bb.w) + hi.w));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SG_COLS * SG_LANES)
+sdpa_graphnorm_bwd_v4_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ ins,
+                             const float* __restrict__ weight, const float* __restrict__ mean_scale,
+                             const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ rstd,
+                             const int* __restrict__ gptr, int D, float* __restrict__ g_v, float* __restrict__ g_ins,
+                             float* __restrict__ gw_part, float* __restrict__ gb_part, float* __restrict__ gms_part) {
+  // dynamic smem: coefA[D], coefB[D], coefC[D], shift[D], sa[cnt], sga[cnt]
+  extern __shared__ __align__(16) float sm4[];
+  __shared__ float red1[32];
+  __shared__ float4 red[SG_LANES][SG_COLS];
+  float* cA = sm4;
+  float* cB = cA + D;
+  float* cC = cB + D;
+  float* sh = cC + D;
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], n1 = gptr[b + 1], cnt = n1 - n0;
+  const int d4 = D >> 2;
+  float* sa = sh + D;
+  float* sga = sa + max(cnt, 0);
+  if (cnt <= 0) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      const int64_t o = (int64_t)b * D + c;
+      g_ins[o] = 0.f;
+      gw_part[o] = 0.f;
+      gb_part[o] = 0.f;
+      gms_part[o] = 0.f;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float inv_cnt = 1.0f / (float)cnt;
+  const float rs = 1.0f / sqrtf((float)D);
+  const int cx = threadIdx.x % SG_COLS, ly = threadIdx.x / SG_COLS;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) sa[i] = a[n0 + i];
+  __syncthreads();
+  // P1: per-channel sums -> coefficients of g_y = A*G + B*o + C
+  for (int c0 = 0; c0 < d4; c0 += SG_COLS) {
+    const int c4 = c0 + cx;
+    const bool on = c4 < d4;
+    const int64_t cb = 4 * (int64_t)c4, bc = (int64_t)b * D + cb;
+    float4 mu = f4_zero(), r = f4_zero(), ms = f4_zero(), w = f4_zero(), shift = f4_zero(), s1 = f4_zero(), s2 = f4_zero();
+    if (on) {
+      mu = Vec4<float>::ld(mean + bc);
+      r = Vec4<float>::ld(rstd + bc);
+      ms = Vec4<float>::ld(mean_scale + cb);
+      w = Vec4<float>::ld(weight + cb);
+      shift = make_float4(mu.x * ms.x, mu.y * ms.y, mu.z * ms.z, mu.w * ms.w);
+      for (int i = ly; i < cnt; i += SG_LANES) {
+        const int64_t o_ = (int64_t)(n0 + i) * D + cb;
+        const float4 G = Vec4<float>::ld(g + o_), vv = Vec4<float>::ld(v + o_);
+        const float ai = sa[i];
+        s1 = f4_add(s1, G);
+        s2 = make_float4(fmaf(G.x, ai * vv.x - shift.x, s2.x), fmaf(G.y, ai * vv.y - shift.y, s2.y),
+                         fmaf(G.z, ai * vv.z - shift.z, s2.z), fmaf(G.w, ai * vv.w - shift.w, s2.w));
+      }
+    }
+    s1 = sg_fold(red, cx, ly, s1);
+    s2 = sg_fold(red, cx, ly, s2);
+    if (on && ly == 0) {
+      const float s1v[4] = {s1.x, s1.y, s1.z, s1.w}, s2v[4] = {s2.x, s2.y, s2.z, s2.w};
+      const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rv[4] = {r.x, r.y, r.z, r.w}, msv[4] = {ms.x, ms.y, ms.z, ms.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w}, shv[4] = {shift.x, shift.y, shift.z, shift.w};
+      float gbv[4], gwv[4], gmsv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        gbv[j] = s1v[j];
+        gwv[j] = s2v[j] * rv[j];
+        const float g_var = -0.5f * (wv[j] * s2v[j]) * rv[j] * rv[j] * rv[j];
+        // sum_n g_o = w r S1 + g_var*(2/cnt)*sum_n o ;  sum_n o = cnt*mean*(1-ms)
+        const float sum_go = wv[j] * rv[j] * s1v[j] + g_var * 2.0f * muv[j] * (1.0f - msv[j]);
+        gmsv[j] = -muv[j] * sum_go;
+        const int c = 4 * c4 + j;
+        cA[c] = wv[j] * rv[j];
+        cB[c] = g_var * 2.0f * inv_cnt;
+        cC[c] = -msv[j] * sum_go * inv_cnt;
+        sh[c] = shv[j];
+      }
+      Vec4<float>::st(gb_part + bc, make_float4(gbv[0], gbv[1], gbv[2], gbv[3]));
+      Vec4<float>::st(gw_part + bc, make_float4(gwv[0], gwv[1], gwv[2], gwv[3]));
+      Vec4<float>::st(gms_part + bc, make_float4(gmsv[0], gmsv[1], gmsv[2], gmsv[3]));
+    }
+  }
+  __syncthreads();
+  // P2: g_a[n] = sum_c g_y[n,c] * v[n,c]   (warp per node)
+  for (int i = warp; i < cnt; i += nw) {
+    const int64_t ro = (int64_t)(n0 + i) * D;
+    const float ai = sa[i];
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float vv = v[ro + c];
+      const float gy = fmaf(cA[c], g[ro + c], fmaf(cB[c], ai * vv - sh[c], cC[c]));
+      s = fmaf(gy, vv, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) sga[i] = s;
+  }
+  __syncthreads();
+  // P3: softmax backward  g_logit = a * (g_a - sum a*g_a)
+  float dp = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) dp = fmaf(sa[i], sga[i], dp);
+  dp = block_sum(dp, red1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) sga[i] = sa[i] * (sga[i] - dp) * rs;  // includes 1/sqrt(D)
+  __syncthreads();
+  // P4: g_v and g_ins
+  for (int c0 = 0; c0 < d4; c0 += SG_COLS) {
+    const int c4 = c0 + cx;
+    const bool on = c4 < d4;
+    const int64_t cb = 4 * (int64_t)c4;
+    float4 gi = f4_zero();
+    if (on) {
+      const float4 ic = Vec4<float>::ld(ins + (int64_t)b * D + cb);
+      const float4 A = *reinterpret_cast<const float4*>(cA + cb), Bc = *reinterpret_cast<const float4*>(cB + cb);
+      const float4 Cc = *reinterpret_cast<const float4*>(cC + cb), S = *reinterpret_cast<const float4*>(sh + cb);
+      for (int i = ly; i < cnt; i += SG_LANES) {
+        const int64_t o_ = (int64_t)(n0 + i) * D + cb;
+        const float4 vv = Vec4<float>::ld(v + o_), G = Vec4<float>::ld(g + o_);
+        const float ai = sa[i], gl = sga[i];
+        const float4 gy = make_float4(fmaf(A.x, G.x, fmaf(Bc.x, ai * vv.x - S.x, Cc.x)), fmaf(A.y, G.y, fmaf(Bc.y, ai * vv.y - S.y, Cc.y)),
+                                      fmaf(A.z, G.z, fmaf(Bc.z, ai * vv.z - S.z, Cc.z)), fmaf(A.w, G.w, fmaf(Bc.w, ai * vv.w - S.w, Cc.w)));
+        Vec4<float>::st(g_v + o_, make_float4(fmaf(gy.x, ai, gl * ic.x), fmaf(gy.y, ai, gl * ic.y), fmaf(gy.z, ai, gl * ic.z),
+                                              fmaf(gy.w, ai, gl * ic.w)));
+        gi = f4_fma(vv, gl, gi);
+      }
+    }
+    gi = sg_fold(red, cx, ly, gi);
+    if (on && ly == 0) Vec4<float>::st(g_ins + (int64_t)b * D + cb, gi);
+  }
+}
+
 // ---------------------------------------------------------------- misc
 
 // ---------------------------------------------------------------- masked attention pooling (§8 f1)
@@ -713,6 +950,18 @@ extern "C" int isg_sdpa_graphnorm_fwd(const float* v, const float* ins, const fl
     cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
+  const bool v4 = D % 4 == 0 && !(((uintptr_t)v | (uintptr_t)ins | (uintptr_t)h_in | (uintptr_t)weight | (uintptr_t)bias |
+                                   (uintptr_t)mean_scale | (uintptr_t)h_out | (uintptr_t)mean | (uintptr_t)rstd) & 15);
+  if (v4) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    sdpa_graphnorm_fwd_v4_kernel<<<(unsigned)B, SG_COLS * SG_LANES, smem, (cudaStream_t)stream_>>>(
+        v, ins, h_in, weight, bias, mean_scale, gptr, D, eps, h_out, a, mean, rstd);
+    ISG_CHECK_LAUNCH();
+    return ISG_OK;
+  }
   sdpa_graphnorm_fwd_kernel<<<(unsigned)B, SG_THREADS, smem, (cudaStream_t)stream_>>>(
       v, ins, h_in, weight, bias, mean_scale, gptr, D, eps, h_out, a, mean, rstd);
   ISG_CHECK_LAUNCH();
@@ -734,6 +983,19 @@ extern "C" int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const 
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+  }
+  const bool v4 = D % 4 == 0 && !(((uintptr_t)g_out | (uintptr_t)v | (uintptr_t)ins | (uintptr_t)weight | (uintptr_t)mean_scale |
+                                   (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)g_v | (uintptr_t)g_ins | (uintptr_t)gw_part |
+                                   (uintptr_t)gb_part | (uintptr_t)gms_part) & 15);
+  if (v4) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_bwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    sdpa_graphnorm_bwd_v4_kernel<<<(unsigned)B, SG_COLS * SG_LANES, smem, (cudaStream_t)stream_>>>(
+        g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part);
+    ISG_CHECK_LAUNCH();
+    return ISG_OK;
   }
   sdpa_graphnorm_bwd_kernel<<<(unsigned)B, SG_THREADS, smem, (cudaStream_t)stream_>>>(
       g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part);
