@@ -28,6 +28,7 @@
   X(D_NEED_GEA)        /* 0: skip the edge_attr gradient */                                                       \
   X(D_BF16)            /* 1: bf16 configuration — projections on kind::f16, bf16 storage of xlr / e_proj / out /   \
                           y1 / z1 and of the gradients g_z1 / g_out / g_xlr / g_eproj (the P_*_BF slots are set) */ \
+  X(D_SIDE_WGRAD)      /* 1: the weight-gradient products run on P_SIDE_STREAM, forked / joined with P_EV_FORK / P_EV_JOIN */ \
   X(D_WS_BYTES)
 #define ISG_LAYER_SCALARS(X) X(F_SLOPE) X(F_EPS) X(F_ALPHA) X(F_BETA) X(F_TAU_IN) X(F_TAU_TGT) X(F_GUMBEL_TAU)
 #define ISG_LAYER_PTRS(X)                                                                                      \
@@ -51,6 +52,7 @@
   X(P_G_X_IN) X(P_G_INS) X(P_G_GLF) X(P_G_EDGE_ATTR)                                                             \
   X(P_G_W_LR) X(P_G_B_LR) X(P_G_W_E) X(P_G_ATT) X(P_G_BIAS) X(P_G_WP0) X(P_G_BP0) X(P_G_WP2) X(P_G_BP2)          \
   X(P_G_BN_W) X(P_G_BN_B) X(P_G_BN_MS) X(P_G_WN) X(P_G_BNN) X(P_G_WQ) X(P_G_BQ)                                   \
+  X(P_SIDE_STREAM) X(P_EV_FORK) X(P_EV_JOIN)                                                                    \
   X(P_WS)
 // clang-format on
 
@@ -312,6 +314,20 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
   auto colsum = [&](const float* t, int64_t rows, int cols, int slot) -> int { return colsum_t(t, rows, cols, slot, ISG_F32); };
   const bool bf = d[D_BF16] != 0;
   const int Dp = pad8(D);
+  // Weight gradients on a side stream.  Nothing downstream in this layer's backward reads a weight gradient, and the
+  // projections are persistent kernels whose tile counts rarely fill whole waves of 148 CTAs (lin_l|lin_r: 5.007
+  // waves): issued on a second stream, a wgrad's CTAs start on the SMs the main stream's kernel leaves idle in its tail
+  // (and next to the memory-bound edge kernels).  fork(): the side stream waits for everything issued so far on the
+  // main stream; the join at the end of the layer makes the main stream wait for the side stream (the next layer
+  // re-uses this workspace).  Capturable: the event edges become graph dependencies.
+  const bool side_on = d[D_SIDE_WGRAD] && p[P_SIDE_STREAM] && p[P_EV_FORK] && p[P_EV_JOIN];
+  void* wstream = side_on ? p[P_SIDE_STREAM] : stream_;
+  auto fork = [&]() -> int {
+    if (!side_on) return ISG_OK;
+    cudaError_t e = cudaEventRecord((cudaEvent_t)p[P_EV_FORK], stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)p[P_SIDE_STREAM], (cudaEvent_t)p[P_EV_FORK], 0);
+    return e == cudaSuccess ? ISG_OK : (int)e;
+  };
 
   // scatter-SDPA + GraphNorm + residual (mgat.py:168-172); the residual's share of g_h_in is added in the last step
   CK(isg_sdpa_graphnorm_bwd(g_h_out, ptr<const float>(p, P_Y2), ins, ptr<const float>(p, P_BN_W),
@@ -327,21 +343,25 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
     void* gy2b = ws + w.g_y2_bf;
     CK(isg_to_bf16(g_y2, D, N, D, gy2b, Dp, stream_));
     CK(isg_linear_bf16_dgrad(gy2b, Dp, p[P_WP2_T_BF], Dp, p[P_Z1], HID, g_z1, HID, 0, N, D, HID, ISG_BF16, stream_));
-    CK(isg_linear_bf16_wgrad(gy2b, Dp, p[P_Y1], HID, ptr<float>(p, P_G_WP2), N, D, HID, wgw, w.wgrad_bytes, stream_));
+    CK(fork());
+  CK(isg_linear_bf16_wgrad(gy2b, Dp, p[P_Y1], HID, ptr<float>(p, P_G_WP2), N, D, HID, wgw, w.wgrad_bytes, wstream));
     CK(colsum(g_y2, N, D, P_G_BP2));
     CK(isg_linear_bf16_dgrad(g_z1, HID, p[P_WP0_T_BF], HID, nullptr, 0, g_out, HC, 0, N, HID, HC, ISG_BF16, stream_));
-    CK(isg_linear_bf16_wgrad(g_z1, HID, p[P_OUT], HC, ptr<float>(p, P_G_WP0), N, HID, HC, wgw, w.wgrad_bytes, stream_));
+    CK(fork());
+  CK(isg_linear_bf16_wgrad(g_z1, HID, p[P_OUT], HC, ptr<float>(p, P_G_WP0), N, HID, HC, wgw, w.wgrad_bytes, wstream));
     CK(colsum_t(g_z1, N, HID, P_G_BP0, ISG_BF16));
   } else {
   CK(isg_linear_dgrad(g_y2, D, p[P_WP2], nullptr, p[P_Z1], HID, g_z1, HID, 0, N, D, HID, mode, ISG_F32,
                       stream_));  // (g_z2 Wp2) * gelu'(z1): the first GELU's derivative in the epilogue
+  CK(fork());
   CK(isg_linear_wgrad(g_y2, D, p[P_Y1], HID, ptr<float>(p, P_G_WP2), nullptr, N, D, HID, mode, ISG_F32, wgw,
-                      w.wgrad_bytes, stream_));
+                      w.wgrad_bytes, wstream));
   CK(colsum(g_y2, N, D, P_G_BP2));
   // x_proj[0]
   CK(isg_linear_dgrad(g_z1, HID, p[P_WP0], nullptr, nullptr, 0, g_out, HC, 0, N, HID, HC, mode, ISG_F32, stream_));
+  CK(fork());
   CK(isg_linear_wgrad(g_z1, HID, p[P_OUT], HC, ptr<float>(p, P_G_WP0), nullptr, N, HID, HC, mode, ISG_F32, wgw,
-                      w.wgrad_bytes, stream_));
+                      w.wgrad_bytes, wstream));
   CK(colsum(g_z1, N, HID, P_G_BP0));
   }
   // edge attention
@@ -365,15 +385,17 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
       if (d[D_NEED_GEA])
         CK(isg_linear_bf16_dgrad(g_ep, HC, p[P_W_E_T_BF], HC, nullptr, 0, p[P_G_EDGE_ATTR], D, d[D_ACC_EDGE_ATTR] ? 1 : 0, E,
                                  HC, D, ISG_F32, stream_));
-      CK(isg_linear_bf16_wgrad(g_ep, HC, p[P_EDGE_ATTR_BF], Dp, ptr<float>(p, P_G_W_E), E, HC, D, wgw, w.wgrad_bytes,
-                               stream_));
+      CK(fork());
+    CK(isg_linear_bf16_wgrad(g_ep, HC, p[P_EDGE_ATTR_BF], Dp, ptr<float>(p, P_G_W_E), E, HC, D, wgw, w.wgrad_bytes,
+                               wstream));
     } else {
       cudaError_t e = cudaMemsetAsync(p[P_G_W_E], 0, (size_t)HC * D * 4, stream);
       if (e != cudaSuccess) return (int)e;
     }
     CK(isg_linear_bf16_dgrad(g_xlr, 2 * HC, p[P_W_LR_T_BF], 2 * HC, nullptr, 0, g_xg, D, 0, N, 2 * HC, D, ISG_F32, stream_));
-    CK(isg_linear_bf16_wgrad(g_xlr, 2 * HC, p[P_XG_BF], Dp, ptr<float>(p, P_G_W_LR), N, 2 * HC, D, wgw, w.wgrad_bytes,
-                             stream_));
+    CK(fork());
+  CK(isg_linear_bf16_wgrad(g_xlr, 2 * HC, p[P_XG_BF], Dp, ptr<float>(p, P_G_W_LR), N, 2 * HC, D, wgw, w.wgrad_bytes,
+                             wstream));
     CK(colsum_t(g_xlr, N, 2 * HC, P_G_B_LR, ISG_BF16));
   } else {
   // lin_edge
@@ -381,16 +403,18 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
     if (d[D_NEED_GEA])
       CK(isg_linear_dgrad(g_ep, HC, p[P_W_E], nullptr, nullptr, 0, p[P_G_EDGE_ATTR], D, d[D_ACC_EDGE_ATTR] ? 1 : 0, E, HC,
                           D, mode, ISG_F32, stream_));
-    CK(isg_linear_wgrad(g_ep, HC, p[P_EDGE_ATTR], D, ptr<float>(p, P_G_W_E), nullptr, E, HC, D, mode, ISG_F32, wgw,
-                        w.wgrad_bytes, stream_));
+    CK(fork());
+  CK(isg_linear_wgrad(g_ep, HC, p[P_EDGE_ATTR], D, ptr<float>(p, P_G_W_E), nullptr, E, HC, D, mode, ISG_F32, wgw,
+                        w.wgrad_bytes, wstream));
   } else {
     cudaError_t e = cudaMemsetAsync(p[P_G_W_E], 0, (size_t)HC * D * 4, stream);
     if (e != cudaSuccess) return (int)e;
   }
   // lin_l | lin_r
   CK(isg_linear_dgrad(g_xlr, 2 * HC, p[P_W_LR], nullptr, nullptr, 0, g_xg, D, 0, N, 2 * HC, D, mode, ISG_F32, stream_));
+  CK(fork());
   CK(isg_linear_wgrad(g_xlr, 2 * HC, p[P_XG], D, ptr<float>(p, P_G_W_LR), nullptr, N, 2 * HC, D, mode, ISG_F32, wgw,
-                      w.wgrad_bytes, stream_));
+                      w.wgrad_bytes, wstream));
   CK(colsum(g_xlr, N, 2 * HC, P_G_B_LR));
   }
   // node mask: NodeMaskToEdgeMask's custom backward, the sampler's perturbation gradient, the gate projections
@@ -425,16 +449,23 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
     // node_nn: xn = gelu(xg Wn^T + bn)
     CK(isg_gelu_bwd(g_xn, ptr<const float>(p, P_XN_PRE), g_xn, N * (int64_t)D, stream_));
     CK(isg_linear_dgrad(g_xn, D, p[P_WN], nullptr, nullptr, 0, g_xg, D, 1, N, D, D, mode, ISG_F32, stream_));
-    CK(isg_linear_wgrad(g_xn, D, p[P_XG], D, ptr<float>(p, P_G_WN), nullptr, N, D, D, mode, ISG_F32, wgw, w.wgrad_bytes,
-                        stream_));
+    CK(fork());
+  CK(isg_linear_wgrad(g_xn, D, p[P_XG], D, ptr<float>(p, P_G_WN), nullptr, N, D, D, mode, ISG_F32, wgw, w.wgrad_bytes,
+                        wstream));
     CK(colsum(g_xn, N, D, P_G_BNN));
     // ques_nn: q = gelu(glf Wq^T + bq)
     CK(isg_gelu_bwd(g_q, ptr<const float>(p, P_Q_PRE), g_q, B * (int64_t)D, stream_));
     CK(isg_linear_dgrad(g_q, D, p[P_WQ], nullptr, nullptr, 0, p[P_G_GLF], D, d[D_ACC_GLF] ? 1 : 0, B, D, D, mode, ISG_F32,
                         stream_));
-    CK(isg_linear_wgrad(g_q, D, p[P_GLF], D, ptr<float>(p, P_G_WQ), nullptr, B, D, D, mode, ISG_F32, wgw, w.wgrad_bytes,
-                        stream_));
+    CK(fork());
+  CK(isg_linear_wgrad(g_q, D, p[P_GLF], D, ptr<float>(p, P_G_WQ), nullptr, B, D, D, mode, ISG_F32, wgw, w.wgrad_bytes,
+                        wstream));
     CK(colsum(g_q, B, D, P_G_BQ));
+  }
+  if (side_on) {  // join: the next layer's backward re-uses this workspace
+    cudaError_t e = cudaEventRecord((cudaEvent_t)p[P_EV_JOIN], (cudaStream_t)p[P_SIDE_STREAM]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, (cudaEvent_t)p[P_EV_JOIN], 0);
+    if (e != cudaSuccess) return (int)e;
   }
   CK(isg_colsum_multi(cs_n, cs_in, cs_dt, cs_ld, cs_rows, cs_cols, cs_out, cs, w.colsum_bytes, stream_));
   // gating + residual: g_x_in = g_xg * d gelu(x*ins)/dx + g_h_out;  g_ins += ...

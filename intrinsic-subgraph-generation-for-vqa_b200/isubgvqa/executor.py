@@ -12,6 +12,7 @@ data-parallel reducer can (a) supply that buffer (`model._isg_grad_bucket`), so 
 what .grad points at, and (b) be notified after each layer's backward (`model._isg_after_layer_backward`) to start
 that layer's all-reduce while the earlier layers are still computing (isg_b200.dp.LayerOverlappedAllReduce)."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -41,6 +42,25 @@ def slots():
     if _slots is None:
         _slots = _Slots()
     return _slots
+
+
+# Weight gradients on a side stream (csrc/executor.cu: fork / join inside isg_mgat_layer_bwd): one stream and two
+# events per device, created on first use.  ISG_SIDE_WGRAD=0 keeps everything on the caller's stream.
+_SIDE_WGRAD = os.environ.get("ISG_SIDE_WGRAD", "1") != "0"
+_side = {}
+
+
+def _side_handles(device):
+    h = _side.get(device)
+    if h is None:
+        st = torch.cuda.Stream(device=device)
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        if torch.cuda.is_current_stream_capturing():
+            return None  # the events must exist before a capture starts (first use happens in the warm-up steps)
+        for ev in evs:
+            ev.record()  # materialises the cudaEvent_t
+        h = _side[device] = (st, evs)
+    return h
 
 
 def _al(nbytes):
@@ -349,6 +369,7 @@ class MgatFunction(torch.autograd.Function):
         ap = arena.data_ptr()
         ws, ws_bytes = None, 0
         hook = getattr(model, "_isg_after_layer_backward", None)
+        side = _side_handles(dev) if _SIDE_WGRAD else None
         g_in_ptr = g_h.data_ptr()
         first_ea, first_glf = True, True
         for i in reversed(range(pl.L)):
@@ -368,6 +389,10 @@ class MgatFunction(torch.autograd.Function):
                 first_glf = False
                 p[s.P_G_GLF] = g_glf.data_ptr()
             p[s.P_WS] = ws.data_ptr()
+            if side is not None:
+                d[s.D_SIDE_WGRAD] = 1
+                p[s.P_SIDE_STREAM], p[s.P_EV_FORK], p[s.P_EV_JOIN] = side[0].cuda_stream, side[1][0].cuda_event, \
+                    side[1][1].cuda_event
             p[s.P_G_H_OUT] = g_in_ptr
             p[s.P_G_MASK_EXT] = g_mask.data_ptr() if (g_mask is not None and i == pl.L - 1 and pl.masked[i]) else 0
             out = g_x if i == 0 else pong[i % 2]
