@@ -447,6 +447,11 @@ inline size_t ring_smem_bytes(int C, int extra_rows, int extra_bars) {
   return (size_t)EDGE_WARPS * (ring_warp_bytes(C, extra_rows) + 8 * (RING + extra_bars));
 }
 
+__device__ __forceinline__ void st_f4_policy(float* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void sts_f4(uint32_t addr, float4 a) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
 }
@@ -631,7 +636,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
                              const int* __restrict__ nbr, const int* __restrict__ eid,
                              const int* __restrict__ order, float* __restrict__ g_xr, int64_t ld_gx,
                              float* __restrict__ g_ep, float* __restrict__ gatt_part, float* __restrict__ gm_h,
-                             int64_t N, int H_, int C_, float slope, int K) {
+                             int64_t N, int H_, int C_, float slope, int K, int ep_keep) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -708,7 +713,8 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
           const float4 gs = p4_scale(p4_mul(at, lk), glmm);
           gxr[k] = p4_add(gxr[k], gs);
           if (MASKED) av2 = p4_dot_acc(at, v, av2);
-          Vec4<float>::st_stream(gerow + 128 * k, gs);
+          if (ep_keep) st_f4_policy(gerow + 128 * k, gs, pol_keep);  // g_eproj is re-read by the src pass
+          else Vec4<float>::st_stream(gerow + 128 * k, gs);
         }
       }
       // d/dm of logit = sum_c att*(dw/dm): w = leaky(s*m)*m  =>  gw*v + gu*s = 2*gl*att*v per channel
@@ -1914,6 +1920,14 @@ int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* 
   return ISG_OK;
 }
 
+// g_eproj stores of the dst pass carry an L2 evict_last hint: the src pass and the two lin_edge backward products
+// re-read them (191 MB at c3, more than L2 keeps, so this only raises the share that survives).  Measured in-step at
+// c3: backward 0.189 -> 0.186 ms.  ISG_EDGE_EP_KEEP=0 restores the plain streaming stores.
+inline int ep_keep_mode() {
+  static const int v = getenv("ISG_EDGE_EP_KEEP") ? atoi(getenv("ISG_EDGE_EP_KEEP")) : 1;
+  return v;
+}
+
 template <int VPL, bool MASKED>
 int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r, int64_t ld_x,
                     const void* e_proj, const float* att, const float* emask, const float* alpha,
@@ -1934,7 +1948,7 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
   kd<<<(unsigned)plan.blocks, EDGE_WARPS * 32, smem_d, stream>>>(
       (const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, emask, alpha,
       dst_ptr, dst_nbr, dst_eid, dst_order, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H, C, slope,
-      plan.K);
+      plan.K, ep_keep_mode());
   ISG_CHECK_LAUNCH();
   const int HC = H * C;
   const int64_t rows = plan.warps / H;
