@@ -229,6 +229,14 @@ int isg_instr_gate_bwd(const float* g_y, const float* x, const float* ins,
  * called directly with a per-node u).  keep [N] or NULL: the dropout keep-mask of models/masking.py:159
  * (0 or 1/(1-p)), multiplied into theta (and into g_theta in the backward).
  * bwd: g_xn [N,D], g_q (same shape as q). */
+/* concat_instr variant (models/mgat_v2_conv.py:153-154, `--concat_instr 1`, off by default): y[n] = [x[n],
+ * instruction[batch[n]]] [N,2D]; the conv's lin_l / lin_r and the mask's node_nn then take 2D inputs.
+ * bwd: g_x = g_y[:, :D] (+ g_residual), g_ins[b] (+)= sum of g_y[n, D:] over the graph's nodes. */
+int isg_concat_instr_fwd(const float* x, const float* instruction, const int32_t* batch32, int64_t num_nodes, int dim,
+                         float* y /* [N,2D] */, void* stream);
+int isg_concat_instr_bwd(const float* g_y /* [N,2D] */, const int32_t* graph_ptr, int64_t num_graphs, int dim,
+                         const float* g_residual /* [N,D] or NULL */, int accumulate_ins, float* g_x, float* g_ins,
+                         void* stream);
 int isg_gate_theta_fwd(const float* xn, const float* q, const int32_t* batch32,
                        int64_t num_nodes, int dim, int double_gather, const float* keep, float* theta,
                        void* stream);

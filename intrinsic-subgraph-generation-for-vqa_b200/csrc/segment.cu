@@ -110,6 +110,35 @@ instr_gate_bwd_v4_kernel(const float* __restrict__ gy, const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------- concat_instr variant of the gating
+// y[n] = [x[n], ins[batch[n]]]  (mgat_v2_conv.py:153-154, `--concat_instr 1`; the conv then has in_channels = 2C)
+__global__ void concat_instr_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ins,
+                                        const int* __restrict__ batch, int64_t N, int D, float* __restrict__ y) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N * 2 * D) return;
+  const int64_t n = i / (2 * D);
+  const int c = (int)(i - n * 2 * D);
+  y[i] = c < D ? x[n * D + c] : ins[(int64_t)batch[n] * D + (c - D)];
+}
+// gx[n] = gy[n, :D] (+ residual gradient);  gins[b] (+)= sum over the graph's nodes of gy[n, D:]  (fixed order)
+__global__ void concat_instr_bwd_kernel(const float* __restrict__ gy, const int* __restrict__ gptr, int D,
+                                        const float* __restrict__ gres, int acc_ins, float* __restrict__ gx,
+                                        float* __restrict__ gins) {
+  const int b = blockIdx.x;
+  const int n0 = gptr[b], n1 = gptr[b + 1];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int n = n0; n < n1; ++n) {
+      const float* row = gy + (int64_t)n * 2 * D;
+      const int64_t o = (int64_t)n * D + c;
+      gx[o] = gres ? __fadd_rn(row[c], gres[o]) : row[c];
+      acc += row[D + c];
+    }
+    const int64_t oi = (int64_t)b * D + c;
+    gins[oi] = acc_ins ? gins[oi] + acc : acc;
+  }
+}
+
 // ---------------------------------------------------------------- gate logits theta
 // warp per node
 __global__ void gate_theta_fwd_kernel(const float* __restrict__ xn, const float* __restrict__ q,
@@ -908,6 +937,27 @@ extern "C" int isg_instr_gate_bwd(const float* g_y, const float* x, const float*
   else
     instr_gate_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, x, ins, gptr, D, g_residual,
                                                                           accumulate_ins, g_x, g_ins);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_concat_instr_fwd(const float* x, const float* instruction, const int32_t* batch32, int64_t N, int D,
+                                    float* y, void* stream_) {
+  if (N < 0 || D <= 0) return ISG_EINVAL;
+  if (N == 0) return ISG_OK;
+  if (!x || !instruction || !batch32 || !y) return ISG_EINVAL;
+  concat_instr_fwd_kernel<<<(unsigned)isg::ceil_div(N * 2 * D, 256), 256, 0, (cudaStream_t)stream_>>>(x, instruction, batch32,
+                                                                                                  N, D, y);
+  ISG_CHECK_LAUNCH();
+  return ISG_OK;
+}
+
+extern "C" int isg_concat_instr_bwd(const float* g_y, const int32_t* gptr, int64_t B, int D, const float* g_residual,
+                                    int accumulate_ins, float* g_x, float* g_ins, void* stream_) {
+  if (B < 0 || D <= 0) return ISG_EINVAL;
+  if (B == 0) return ISG_OK;
+  if (!g_y || !gptr || !g_x || !g_ins) return ISG_EINVAL;
+  concat_instr_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, gptr, D, g_residual, accumulate_ins, g_x, g_ins);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

@@ -46,9 +46,9 @@ class MaskingGATv2Conv(torch.nn.Module):
         super().__init__()
         if add_self_loops:
             raise NotImplementedError("MGAT builds the conv with add_self_loops=False (mgat.py:63)")
-        if not concat or dropout != 0.0 or concat_instr or use_all_instrs or not isinstance(in_channels, int):
-            raise NotImplementedError("only concat=True, dropout=0, concat_instr=False, use_all_instrs=False and an "
-                                      "int in_channels are on the ISubGVQA path")
+        if not concat or dropout != 0.0 or use_all_instrs or not isinstance(in_channels, int):
+            raise NotImplementedError("only concat=True, dropout=0, use_all_instrs=False and an int in_channels are on "
+                                      "the ISubGVQA path")
         if edge_dim is None:
             raise NotImplementedError("MGAT always passes edge_dim (mgat.py:61)")
         self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
@@ -84,7 +84,9 @@ class MaskingGATv2Conv(torch.nn.Module):
         if gi is None:
             num_graphs = instruction.shape[0] if instruction is not None else int(batch[-1].item()) + 1
             gi = get_graph_index(edge_index, batch, num_graphs)
-        if self.use_instr:
+        if self.use_instr and self.concat_instr:
+            x = ops.ConcatInstr.apply(x, instruction, gi)  # :153-154
+        elif self.use_instr:
             x = ops.InstrGate.apply(x, instruction, gi)  # :156-157
         mask, edge_mask = None, None
         if self.mask.masking_threshold != 1.0:  # :161

@@ -48,6 +48,8 @@ SIGNATURES = {
     "isg_simple_marginals_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "isg_instr_gate_fwd": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
     "isg_instr_gate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _P, _I32, _P, _P, _P]),
+    "isg_concat_instr_fwd": (_I32, [_P, _P, _P, _I64, _I32, _P, _P]),
+    "isg_concat_instr_bwd": (_I32, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P]),
     "isg_gate_theta_fwd": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "isg_gate_theta_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "isg_sdpa_graphnorm_fwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
@@ -113,7 +115,7 @@ KERNELS_PER_CALL = {
     "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_graph_closure": 1, "isg_degree_order": 3, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 4,
     "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_sampler_fused_fwd": 1, "isg_imle_bwd": 1,
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
-    "isg_instr_gate_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
+    "isg_instr_gate_bwd": 1, "isg_concat_instr_fwd": 1, "isg_concat_instr_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
     "isg_sdpa_graphnorm_bwd": 1, "isg_attn_pool_fwd": 1, "isg_attn_pool_bwd": 1, "isg_split_lo": 1, "isg_transpose_split": 1, "isg_linear_fwd": 1, "isg_linear_dgrad": 1, "isg_linear_wgrad": 2,
     "isg_to_bf16": 1, "isg_weights_to_bf16": 1, "isg_linear_bf16_fwd": 1, "isg_linear_bf16_dgrad": 1,
     "isg_linear_bf16_wgrad": 2, "isg_gelu_bwd": 1, "isg_colsum": 2, "isg_colsum_multi": 2, "isg_gather_add_act_fwd": 1, "isg_segment_sum": 1, "isg_gather_rows": 1,

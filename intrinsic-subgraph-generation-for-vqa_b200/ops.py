@@ -283,6 +283,29 @@ class InstrGate(torch.autograd.Function):
         return gx, gins, None
 
 
+class ConcatInstr(torch.autograd.Function):
+    """x = cat(x, instruction[batch])  (models/mgat_v2_conv.py:153-154, the `concat_instr` variant)."""
+
+    @staticmethod
+    def forward(ctx, x, ins, gi):
+        L.require_cuda(x, ins)
+        x, ins = _c(x), _c(ins)
+        N, D = x.shape
+        y = torch.empty(N, 2 * D, dtype=x.dtype, device=x.device)
+        L.call("isg_concat_instr_fwd", L.ptr(x), L.ptr(ins), L.ptr(gi.batch32), N, D, L.ptr(y), L.stream())
+        ctx.gi, ctx.D, ctx.ins_shape = gi, D, ins.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gi, D = ctx.gi, ctx.D
+        gy = _c(gy)
+        gx = torch.empty(gy.shape[0], D, dtype=gy.dtype, device=gy.device)
+        gins = torch.empty(ctx.ins_shape, dtype=gy.dtype, device=gy.device)
+        L.call("isg_concat_instr_bwd", L.ptr(gy), L.ptr(gi.graph_ptr), gi.B, D, None, 0, L.ptr(gx), L.ptr(gins), L.stream())
+        return gx, gins, None
+
+
 class GateTheta(torch.autograd.Function):
     """theta = gelu(<xn, q[batch[batch]]> / sqrt(D)) [* keep]  (models/masking.py:151-155, double gather via
     models/mgat_v2_conv.py:166-168; keep [N,1] = the dropout keep-mask of masking.py:159, 0 or 1/(1-p), folded

@@ -95,21 +95,22 @@ def gumbel_noise(num_graphs, nmax, scale=0.3, seed=3407, nb_samples=1):
     return -scale * torch.log(-torch.log(u))
 
 
-def mgat_param_shapes(channels=300, heads=4, num_ins=4):
+def mgat_param_shapes(channels=300, heads=4, num_ins=4, concat_instr=False):
     """state_dict layout of the reference MGAT (enumerated from models/mgat.py:55-102,
     mgat_v2_conv.py:63-128, masking.py:77-90)."""
     D, H = channels, heads
+    Din = 2 * D if concat_instr else D  # mgat.py:41-44: the conv sees [x, instruction[batch]]
     shapes = {}
     for i in range(num_ins):
         p = f"convs.{i}."
         shapes.update({
             p + "att": (1, H, D), p + "bias": (H * D,),
-            p + "lin_l.weight": (H * D, D), p + "lin_l.bias": (H * D,),
-            p + "lin_r.weight": (H * D, D), p + "lin_r.bias": (H * D,),
+            p + "lin_l.weight": (H * D, Din), p + "lin_l.bias": (H * D,),
+            p + "lin_r.weight": (H * D, Din), p + "lin_r.bias": (H * D,),
             p + "lin_edge.weight": (H * D, D),
             p + "mask.gate_nn.0.weight": (D, D), p + "mask.gate_nn.0.bias": (D,),
             p + "mask.gate_nn.2.weight": (1, D), p + "mask.gate_nn.2.bias": (1,),
-            p + "mask.node_nn.0.weight": (D, D), p + "mask.node_nn.0.bias": (D,),
+            p + "mask.node_nn.0.weight": (D, Din), p + "mask.node_nn.0.bias": (D,),
             p + "mask.ques_nn.0.weight": (D, D), p + "mask.ques_nn.0.bias": (D,),
             p + "mask.gate_top.select.weight": (1, D),
         })
@@ -125,13 +126,13 @@ def mgat_param_shapes(channels=300, heads=4, num_ins=4):
     return shapes
 
 
-def make_state_dict(channels=300, heads=4, num_ins=4, seed=3407):
+def make_state_dict(channels=300, heads=4, num_ins=4, seed=3407, concat_instr=False):
     """Deterministic random-init weights in the reference MGAT layout, independent of module
     construction order (so goldens need not store 42 MB of weights).  Matrices ~ U(+-sqrt(6/(in+out))),
     vectors ~ small noise around their neutral value so every parameter is exercised."""
     g = torch.Generator().manual_seed(seed + 1)
     sd = {}
-    for k, s in mgat_param_shapes(channels, heads, num_ins).items():
+    for k, s in mgat_param_shapes(channels, heads, num_ins, concat_instr).items():
         if len(s) >= 2:
             a = (6.0 / (s[-1] + s[-2])) ** 0.5
             t = (torch.rand(s, generator=g) * 2 - 1) * a

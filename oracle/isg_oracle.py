@@ -537,8 +537,9 @@ class OracleMGAT(torch.nn.Module):
 
     def __init__(self, channels=300, num_ins=4, heads=4, masking_thresholds=(1.0, 1.0, 1.0, 0.1),
                  sampler_type="imle", sample_k=2, nb_samples=1, alpha=1.0, beta=10.0, tau=1.0,
-                 interpretable_mode=False, use_global_mask=False):
+                 interpretable_mode=False, use_global_mask=False, concat_instr=False):
         super().__init__()
+        self.concat_instr = bool(concat_instr)  # mgat.py:41-44, mgat_v2_conv.py:153-154
         self.C, self.H, self.L = channels, heads, num_ins
         self.thr = [int(t) if t > 1 else t for t in masking_thresholds]
         self.sampler_type, self.k, self.S = sampler_type, sample_k, nb_samples
@@ -551,17 +552,18 @@ class OracleMGAT(torch.nn.Module):
         self.replay = None  # set to a recorded dict to force those discrete decisions (fp64 arbiter)
         self.aimle_state = [AimleState(alpha, 0.0) for _ in range(num_ins)]
         D, H = channels, heads
+        Din = 2 * D if concat_instr else D
         shapes = {}
         for i in range(num_ins):
             p = f"convs.{i}."
             shapes.update({
                 p + "att": (1, H, D), p + "bias": (H * D,),
-                p + "lin_l.weight": (H * D, D), p + "lin_l.bias": (H * D,),
-                p + "lin_r.weight": (H * D, D), p + "lin_r.bias": (H * D,),
+                p + "lin_l.weight": (H * D, Din), p + "lin_l.bias": (H * D,),
+                p + "lin_r.weight": (H * D, Din), p + "lin_r.bias": (H * D,),
                 p + "lin_edge.weight": (H * D, D),
                 p + "mask.gate_nn.0.weight": (D, D), p + "mask.gate_nn.0.bias": (D,),
                 p + "mask.gate_nn.2.weight": (1, D), p + "mask.gate_nn.2.bias": (1,),
-                p + "mask.node_nn.0.weight": (D, D), p + "mask.node_nn.0.bias": (D,),
+                p + "mask.node_nn.0.weight": (D, Din), p + "mask.node_nn.0.bias": (D,),
                 p + "mask.ques_nn.0.weight": (D, D), p + "mask.ques_nn.0.bias": (D,),
                 p + "mask.gate_top.select.weight": (1, D),
             })
@@ -636,7 +638,7 @@ class OracleMGAT(torch.nn.Module):
         """MaskingGATv2Conv.forward (mgat_v2_conv.py:138-241)."""
         H, C = self.H, self.C
         pre = f"convs.{i}."
-        x = instr_gate(x, ins, batch)
+        x = torch.cat((x, ins[batch]), dim=1) if self.concat_instr else instr_gate(x, ins, batch)  # :153-157
         mask, em, theta = None, None, None
         if self.thr[i] != 1.0:  # :161
             mask, theta = self._mask(i, x, imle_att[batch], batch, noise, drop_mask, num_graphs)

@@ -66,15 +66,15 @@ def case_dropout(N, train, seed):
     return (torch.rand(N, 1, generator=g) > 0.2).float() / 0.8
 
 
-def run_reference(sampler, train, C, B, mn, me, k, seed, aimle_steps=1):
+def run_reference(sampler, train, C, B, mn, me, k, seed, aimle_steps=1, concat_instr=False):
     from ISubGVQA.models.mgat import MGAT
 
     b = synth.make_batch(B, channels=C, mean_nodes=mn, mean_edges=me, seed=seed)
     with rl.scratch_cwd():
         ref = MGAT(channels=C, num_ins=4, heads=4, use_instr=True, masking_thresholds=[1.0, 1.0, 1.0, 0.1],
                    use_topk=True, interpretable_mode=False, sampler_type=sampler, sample_k=k, nb_samples=1,
-                   alpha=1.0, beta=10.0, tau=1.0)
-    ref.load_state_dict(synth.make_state_dict(C, 4, 4, seed))
+                   alpha=1.0, beta=10.0, tau=1.0, concat_instr=concat_instr)
+    ref.load_state_dict(synth.make_state_dict(C, 4, 4, seed, concat_instr=concat_instr))
     ref.train(train)
     if sampler == "aimle":
         # The reference starts AIMLE at beta = 0 (masking.py:258) and moves it by 1e-4 per step, so its

@@ -173,3 +173,17 @@ def test_dropin_surface():
     assert em.shape == (b["edge_index"].shape[1], 1) and em.dtype == torch.float32
     with pytest.raises(RuntimeError):
         m.cpu()(b["x"], b["edge_index"], b["instr_vectors"], b["global_language_feats"], b["edge_attr"], b["batch"])
+
+
+@pytest.mark.parametrize("sampler,train", [("imle", True), ("imle", False), ("aimle", True)])
+def test_concat_instr_variant_matches_oracle(sampler, train):
+    """`--concat_instr 1` (models/mgat_v2_conv.py:153-154, mgat.py:41-44; off by default, utils/arg_parser.py:102): the
+    conv input is [x, instruction[batch]] (isg_concat_instr_fwd / _bwd), lin_l / lin_r / mask.node_nn take 2C inputs.
+    Runs the per-operator path (the layer executor covers the default configuration only)."""
+    cfg = dict(sampler=sampler, train=train, channels=300, num_graphs=9, mean_nodes=12, mean_edges=70, k=2, seed=611,
+               steps=1, concat_instr=True)
+    if sampler == "aimle":
+        cfg["aimle_beta0"] = 1.0
+    want = util.run_oracle_case(cfg)[0]
+    got = util.run_cuda_case(cfg)[0]
+    util.compare_step(got, want, sampler)

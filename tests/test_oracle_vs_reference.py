@@ -40,6 +40,19 @@ def test_oracle_matches_live_reference(golden_mod, sampler, train, C, B, k, seed
         util.compare_step(g, w, sampler, rtol=util.RTOL if (sampler == "gumbel" and train) else 2e-5)
 
 
+@pytest.mark.parametrize("sampler,train,seed", [("imle", True, 4200), ("gumbel", False, 4201)])
+def test_oracle_matches_live_reference_concat_instr(golden_mod, sampler, train, seed):
+    """The `--concat_instr 1` variant (models/mgat_v2_conv.py:153-154, mgat.py:41-44): the conv sees
+    [x, instruction[batch]] and its lin_l / lin_r / mask.node_nn take 2C inputs."""
+    C, B, k = 16, 5, 2
+    torch.manual_seed(seed)
+    ref = golden_mod.run_reference(sampler, train, C, B, 9, 40, k, seed, 1, concat_instr=True)
+    cfg = dict(sampler=sampler, train=train, channels=C, num_graphs=B, mean_nodes=9, mean_edges=40, k=k, seed=seed,
+               steps=1, concat_instr=True)
+    got = util.run_oracle_case(cfg)
+    util.compare_step(got[0], ref[0], sampler, rtol=2e-5)
+
+
 def test_simple_circuit_restatement_matches_live_layer(golden_mod):
     """Layer.log_pr (simple.py:214-244) vs oracle.simple_marginals on logits with exact zeros (the -1000 dummy
     pad regime), incl. the gradient that the reference obtains by differentiating through both passes."""

@@ -139,8 +139,9 @@ def run_oracle_case(cfg, step_count=None, dtype=torch.float32, replay=None, reco
 
     C, B, seed, sampler, train = cfg["channels"], cfg["num_graphs"], cfg["seed"], cfg["sampler"], cfg["train"]
     b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
-    model = O.OracleMGAT(channels=C, sampler_type=sampler, sample_k=cfg["k"]).to(dtype)
-    model.load_state_dict({k: v.to(dtype) for k, v in synth.make_state_dict(C, 4, 4, seed).items()})
+    cat = bool(cfg.get("concat_instr"))
+    model = O.OracleMGAT(channels=C, sampler_type=sampler, sample_k=cfg["k"], concat_instr=cat).to(dtype)
+    model.load_state_dict({k: v.to(dtype) for k, v in synth.make_state_dict(C, 4, 4, seed, concat_instr=cat).items()})
     model.train(train)
     if cfg.get("aimle_beta0") is not None:
         for st in model.aimle_state:
@@ -199,8 +200,8 @@ def _run_cuda_case(cfg, step_count, device, capture, executor, MGAT):
     b = synth.make_batch(B, channels=C, mean_nodes=cfg["mean_nodes"], mean_edges=cfg["mean_edges"], seed=seed)
     model = MGAT(channels=C, num_ins=4, heads=4, use_instr=True, masking_thresholds=[1.0, 1.0, 1.0, 0.1],
                  use_topk=True, interpretable_mode=False, sampler_type=sampler, sample_k=cfg["k"], nb_samples=1,
-                 alpha=1.0, beta=10.0, tau=1.0)
-    model.load_state_dict(synth.make_state_dict(C, 4, 4, seed))
+                 alpha=1.0, beta=10.0, tau=1.0, concat_instr=bool(cfg.get("concat_instr")))
+    model.load_state_dict(synth.make_state_dict(C, 4, 4, seed, concat_instr=bool(cfg.get("concat_instr"))))
     model.to(device)
     model.train(train)
     if cfg.get("aimle_beta0") is not None:
