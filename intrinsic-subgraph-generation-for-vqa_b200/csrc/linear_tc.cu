@@ -156,7 +156,11 @@ __device__ __forceinline__ float4 lo_part(float4 v) {
 // HALF of the B tile (64 of the 128 rows / columns), which the pair's MMA reads from both shared memories.  Per CTA
 // and 32-wide k-block the shared-memory traffic drops from 128 KB (TMA 32 + splitter 48 + MMA operand reads 48) to
 // 80 KB (24 + 32 + 24) and the L2 -> SM operand traffic from 32 to 24 KB: 5-9 % faster on the E-sized products.
-template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN, bool BLO, bool P2 = false>
+// DEEP (with P2): the shared-memory ring is decoupled from the four-slot A ring in tensor memory.  A pair's stage is
+// only 32 KiB (A 16 + B_hi half 8 + B_lo half 8), so SIX stages fit where four 48 KiB ones did: the TMA producer runs
+// up to six k-blocks ahead of the MMAs (its loop: commit -> free stage -> TMA latency -> full), the splitter up to four
+// (its loop: commit -> free TMEM slot -> convert -> MMA).  Two commits per k-block instead of one.
+template <bool A_MN, bool B_MN, int EPI, bool SPLIT, bool PAIR, bool FULLBN, bool BLO, bool P2 = false, bool DEEP = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_blo, const TcArgs g) {
@@ -165,17 +169,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   static_assert(!P2 || (SPLIT && MERGE && FULLBN && !PAIR && !BLO), "P2: mode 1, merged accumulator, BN = 128");
+  static_assert(!DEEP || P2, "DEEP needs the half-sized B tiles of a pair");
+  constexpr int TSLOTS = TS_STAGES;  // A-ring slots in tensor memory
   constexpr uint32_t CL = (PAIR || P2) ? 2u : 1u;  // plain launch, or a cluster pair sharing the B tile
   const uint32_t cta_rank = cluster_ctarank();
 
-  const int S = SPLIT ? TS_STAGES : g.stages;  // mode 1: smem ring == TMEM A ring
+  const int S = DEEP ? 6 : (SPLIT ? TS_STAGES : g.stages);  // mode 1: smem ring == TMEM A ring (DEEP: six smem stages)
   const int BN = FULLBN ? MAX_BN : g.BN;
   const uint32_t b_tile_bytes = (uint32_t)BN * (BK * 4);
   // stage layout: mode 1 [A raw 8K][B BN*64][B_lo BN*64] (A goes on to TMEM); mode 2 [A 8K][B BN*64]
   const uint32_t off_b_hi = A_TILE_BYTES;
-  const uint32_t off_b_lo = off_b_hi + b_tile_bytes;
+  const uint32_t off_b_lo = DEEP ? off_b_hi + b_tile_bytes / 2 : off_b_hi + b_tile_bytes;
   // stage size: a compile-time constant in the hot instantiation (A 8 KiB + B 8 KiB + B_lo 8 KiB)
-  const uint32_t stage_bytes = (SPLIT && FULLBN) ? (uint32_t)(A_TILE_BYTES + 2 * MAX_BN * BK * 4) : (uint32_t)g.stage_bytes;
+  const uint32_t stage_bytes = DEEP ? (uint32_t)(A_TILE_BYTES + MAX_BN * BK * 4)
+                             : (SPLIT && FULLBN) ? (uint32_t)(A_TILE_BYTES + 2 * MAX_BN * BK * 4) : (uint32_t)g.stage_bytes;
   const uint32_t epi_base = smem_base + (uint32_t)S * stage_bytes;
   const uint32_t bar_base = epi_base + EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -186,6 +193,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto cfull_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 4 + s); };
   auto cempty_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 6 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 8);
+  auto tfree_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + 10 + s); };  // DEEP: TMEM A slot s is free
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (threadIdx.x == 0) {
@@ -196,6 +204,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(conv_bar(s), P2 ? 8 : 128);  // P2: one arrival per splitter warp of BOTH CTAs, on the leader's barrier
       mbar_init(empty_bar(s), P2 ? 1 : CL);  // released by the MMA commits of every CTA of the cluster (P2: the leader's)
     }
+    if (DEEP)
+      for (int s = 0; s < TSLOTS; ++s) mbar_init(tfree_bar(s), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(mfull_bar(s), 1);
       mbar_init(mempty_bar(s), P2 ? 2 * EPI_WARPS : EPI_WARPS);
@@ -307,6 +317,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint64_t a_hi0 = make_desc(smem_base, A_MN), b_hi0 = make_desc(smem_base + off_b_hi, B_MN);
     int stage = 0;
     uint32_t phase = 0;
+    int ts = 0;  // TMEM A slot (== stage unless DEEP)
     uint32_t gchunk = 0;
     int it = 0;
     for (int t = work0; t < total_tiles; t += work_stride, ++it) {
@@ -333,9 +344,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // descriptors of stage s = those of stage 0 + s * stage_bytes/16 (the 14-bit address field cannot
           // carry: all operand addresses are below 227 KiB)
           const uint32_t sdelta = (uint32_t)stage * (stage_bytes >> 4);
-          const uint64_t b_hi = b_hi0 + sdelta, b_lo = b_hi + (b_tile_bytes >> 4);
+          const uint64_t b_hi = b_hi0 + sdelta, b_lo = b_hi + ((off_b_lo - off_b_hi) >> 4);
           if (SPLIT) {
-            const uint32_t a_t = tmem_base + TM_A + (uint32_t)(2 * BK) * (uint32_t)stage;  // hi at +0, lo at +BK
+            const uint32_t a_t = tmem_base + TM_A + (uint32_t)(2 * BK) * (uint32_t)(DEEP ? ts : stage);  // hi at +0, lo at +BK
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t bk = (uint64_t)(b_kstep * k);
@@ -362,6 +373,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (P2) umma_commit_2cta_mc(empty_bar(stage), (uint16_t)0x3);
           else if (CL > 1) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);
           else umma_commit(empty_bar(stage));
+          if (DEEP) {
+            umma_commit_2cta_mc(tfree_bar(ts), (uint16_t)0x3);
+            if (++ts == TSLOTS) ts = 0;
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         if (P2) umma_commit_2cta_mc(mfull_bar(ms), (uint16_t)0x3);  // both CTAs' epilogues drain their 128 rows
@@ -379,13 +394,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int nb = (int)(b_tile_bytes / 16);  // <= 32*BK float4
       int stage = 0;
       uint32_t phase = 0;
+      int ts = 0;
+      uint32_t tphase = 0;
       for (int t = work0; t < total_tiles; t += work_stride) {
         const int num_kb = tile_kb(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (DEEP) {  // the MMAs that read TMEM slot ts four k-blocks ago have completed
+            mbar_wait(tfree_bar(ts), tphase ^ 1u);
+            tc_fence_after();
+          }
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           // ---- A: row `tid` of the tile -> BK k-values -> TMEM (hi = raw, lo = exact remainder), 16 at a time
-          const uint32_t a_t = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + TM_A + (uint32_t)(2 * BK) * (uint32_t)stage;
+          const uint32_t a_t = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + TM_A +
+                               (uint32_t)(2 * BK) * (uint32_t)(DEEP ? ts : stage);
 #pragma unroll
           for (int hh = 0; hh < BK / 16; ++hh) {
             float av[16];
@@ -429,6 +451,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             mbar_arrive(conv_bar(stage));
           }
+          if (DEEP && ++ts == TSLOTS) { ts = 0; tphase ^= 1u; }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
@@ -666,7 +689,9 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   // (+ the pre-split-B variants of mode 1; wgrad's B is an activation and is always split in the kernel)
   constexpr bool CAN_BLO = !A_MN;
   constexpr bool CAN_P2 = MERGE;
-  auto kern = pair2   ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, false, CAN_P2>
+  static const bool env_no_deep = getenv("ISG_TC_P2_DEEP") != nullptr && atoi(getenv("ISG_TC_P2_DEEP")) == 0;
+  auto kern = (pair2 && !env_no_deep) ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, false, CAN_P2, CAN_P2>
+            : pair2   ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, false, CAN_P2>
             : p.split3 ? (blo && CAN_BLO ? (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, CAN_BLO>
                                                    : tc_gemm_kernel<A_MN, B_MN, EPI, true, false, false, CAN_BLO>)
                                          : (fullbn ? tc_gemm_kernel<A_MN, B_MN, EPI, true, false, true, false>
