@@ -72,6 +72,11 @@ constexpr int BM = 128;      // UMMA M (cta_group::1)
 #define ISG_TC_BK 16
 #endif
 constexpr bool MERGE = ISG_TC_MERGE != 0;
+// Diagnostics only (WRONG RESULTS): -DISG_TC_DIAG=<bits> removes parts of the splitter's per-k-block work to see what the
+// mainloop waits for.  1: no B_lo split (and no proxy fence), 2: no A_lo tensor-memory stores, 4: no A_hi stores either.
+#ifndef ISG_TC_DIAG
+#define ISG_TC_DIAG 0
+#endif
 constexpr int BK = ISG_TC_BK;  // fp32 elements per k-block: 16 (64-byte K-major rows, SWIZZLE_64B) or 32 (128-byte, SWIZZLE_128B)
 static_assert(BK == 16 || BK == 32, "BK must be 16 or 32");
 constexpr int UMMA_K = 8;    // kind::tf32
@@ -429,13 +434,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < 16; ++k) av[k] = lds_f1(ca + (uint32_t)k * 128u + (((ml >> 3) ^ ((uint32_t)k & 3u)) << 5));
             }
-            tmem_st16(a_t + 16u * hh, av);
+            if (!(ISG_TC_DIAG & 4)) tmem_st16(a_t + 16u * hh, av);
             float al[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) al[k] = lo1(av[k]);
-            tmem_st16(a_t + (uint32_t)BK + 16u * hh, al);
+            if (!(ISG_TC_DIAG & 2)) tmem_st16(a_t + (uint32_t)BK + 16u * hh, al);
           }
-          if (!BLO) {
+          if (!BLO && !(ISG_TC_DIAG & 1)) {
 #pragma unroll
             for (int u = 0; u < (P2 ? BK / 8 : BK / 4); ++u) {  // b_tile_bytes / 16 / 128 float4 per thread at BN = 128
               const int i = tid + 128 * u;                      // (P2: this CTA's half of the tile)
@@ -444,7 +449,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           tmem_st_wait();
           tc_fence_before();
-          if (!BLO) fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          if (!BLO && !(ISG_TC_DIAG & 1)) fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
           if (P2) {
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(conv_bar(stage), 0);  // the leader's barrier: 4 + 4 warp arrivals
