@@ -79,21 +79,20 @@ def collate_scene_graphs(graphs, cache=None, pin=False):
     out = {
         "x": torch.cat([g["x"] for g in graphs], dim=0),
         "edge_attr": torch.cat([g["edge_attr"] for g in graphs], dim=0),
-        "edge_index": torch.cat([g["edge_index"] + int(n_off[i]) for i, g in enumerate(graphs)], dim=1),
+        "edge_index": torch.cat([g["edge_index"] for g in graphs], dim=1) + torch.from_numpy(np.repeat(n_off[:-1], es)),
         "batch": torch.repeat_interleave(torch.arange(B, dtype=torch.int64), torch.from_numpy(ns)),
     }
     idx = {}
+    node_rep = np.repeat(n_off[:-1], es).astype(np.int32)  # node offset of the graph each edge belongs to
+    edge_rep_e = np.repeat(e_off[:-1], es).astype(np.int32)  # edge offset, per edge
+    edge_rep_n = np.repeat(e_off[:-1], ns).astype(np.int32)  # edge offset, per node
     for side in ("dst", "src"):
-        ptr = np.empty(N + 1, dtype=np.int32)
-        ptr[0] = 0
-        nbr = np.empty(E, dtype=np.int32)
-        eid = np.empty(E, dtype=np.int32)
-        for i, c in enumerate(csrs):
-            n0, e0 = int(n_off[i]), int(e_off[i])
-            ptr[n0 + 1: n0 + c.n + 1] = getattr(c, side + "_ptr")[1:] + e0
-            nbr[e0: e0 + c.e] = getattr(c, side + "_nbr") + n0
-            eid[e0: e0 + c.e] = getattr(c, side + "_eid") + e0
-        idx[side + "_ptr"], idx[side + "_nbr"], idx[side + "_eid"] = ptr, nbr, eid
+        ptr = np.zeros(N + 1, dtype=np.int32)
+        if N:
+            ptr[1:] = np.concatenate([getattr(c, side + "_ptr")[1:] for c in csrs]) + edge_rep_n
+        nbr = (np.concatenate([getattr(c, side + "_nbr") for c in csrs]) + node_rep) if E else np.zeros(0, dtype=np.int32)
+        eid = (np.concatenate([getattr(c, side + "_eid") for c in csrs]) + edge_rep_e) if E else np.zeros(0, dtype=np.int32)
+        idx[side + "_ptr"], idx[side + "_nbr"], idx[side + "_eid"] = ptr, nbr.astype(np.int32), eid.astype(np.int32)
         heavy = np.diff(ptr) >= max(2, -(-2 * E // max(N, 1)))  # isg_degree_order's rule: >= twice the mean degree
         idx[side + "_order"] = np.concatenate([np.flatnonzero(heavy), np.flatnonzero(~heavy)]).astype(np.int32)
     idx["graph_ptr"] = n_off.astype(np.int32)
