@@ -189,6 +189,22 @@ def make_inputs(B, seed):
     return b
 
 
+def make_inputs_dp(B, world, rank, seed):
+    """Data-parallel runs: ONE global batch of B x world graphs (same seed as the single-GPU batch), whole graphs
+    dealt to the ranks by isg_b200.dp.balanced_shards (equal counts, near-equal node + edge totals) — a size-aware
+    sampler in place of the reference's random DistributedSampler, so that no rank is the step's straggler."""
+    from isg_b200 import synth
+    from isg_b200.dp import balanced_shards
+
+    topo = synth.make_topology(B * world, seed=seed)
+    # per-graph cost ~ 17 ns per edge + 86 ns per node and layer (E-sized projections and edge kernels; node-sized
+    # projections and the per-node kernels): weight a node as five edges
+    sizes = (topo["num_edges"] + 5 * topo["num_nodes"]).tolist()
+    ids = balanced_shards(sizes, world)[rank]
+    return synth.make_batch_from_topology(synth.subset_topology(topo, ids), channels=CHANNELS, num_ins=LAYERS,
+                                          seed=seed + rank)
+
+
 # --------------------------------------------------------------------------------------------- CPU arm
 def run_cpu_port(sampler, train, B, steps, warmup, seed=3407):
     """oracle/isg_oracle.py::OracleMGAT (CPU restatement of the reference) on all host threads."""
@@ -346,7 +362,7 @@ def main_isg(args, rank, world, local_rank):
         out_stream = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
     seed = 3407 + rank
-    b = make_inputs(B, seed)
+    b = make_inputs(B, seed) if world == 1 else make_inputs_dp(B, world, rank, 3407)
     N, E, nmax = int(b["x"].shape[0]), int(b["edge_index"].shape[1]), b["nmax"]
     model = MGAT(channels=CHANNELS, num_ins=LAYERS, heads=HEADS, use_instr=True,
                  masking_thresholds=[1.0, 1.0, 1.0, 0.1], use_topk=True, interpretable_mode=False,
@@ -545,9 +561,11 @@ def main_isg(args, rank, world, local_rank):
         if train:
             reducer = GradAllReduce(model)
 
+    no_reduce = os.environ.get("ISG_BENCH_NO_REDUCE") == "1"  # diagnostics: what the gradient exchange costs
+
     def graphed_step():
         graph.replay()
-        if reducer is not None and not overlap:
+        if reducer is not None and not overlap and not no_reduce:
             reducer.all_reduce_mean()
 
     from isg_b200.isubgvqa import mgat as mgat_mod

@@ -86,6 +86,35 @@ def make_batch(num_graphs, channels=300, num_ins=4, mean_nodes=20, mean_edges=15
     return out
 
 
+def subset_topology(topo, graph_ids):
+    """The sub-batch made of the given graphs (ascending ids) of a make_topology() batch, nodes renumbered the way
+    Batch.from_data_list would number them."""
+    ids = torch.as_tensor(sorted(int(g) for g in graph_ids), dtype=torch.int64)
+    B = int(topo["num_nodes"].numel())
+    new_gid = torch.full((B,), -1, dtype=torch.int64)
+    new_gid[ids] = torch.arange(ids.numel())
+    keep_n = new_gid[topo["batch"]] >= 0
+    remap = torch.full((topo["batch"].numel(),), -1, dtype=torch.int64)
+    remap[keep_n] = torch.arange(int(keep_n.sum()))
+    ei = topo["edge_index"]
+    keep_e = keep_n[ei[0]]
+    return dict(edge_index=remap[ei[:, keep_e]], batch=new_gid[topo["batch"][keep_n]],
+                num_nodes=topo["num_nodes"][ids], num_edges=topo["num_edges"][ids])
+
+
+def make_batch_from_topology(topo, channels=300, num_ins=4, seed=3407, dtype=torch.float32):
+    """make_batch() on a given topology (features from the seeded CPU generator)."""
+    g = torch.Generator().manual_seed(seed)
+    N, E, B = topo["batch"].numel(), topo["edge_index"].size(1), int(topo["num_nodes"].numel())
+    out = dict(topo)
+    out["x"] = torch.randn(N, channels, generator=g).to(dtype)
+    out["edge_attr"] = torch.randn(E, channels, generator=g).to(dtype)
+    out["instr_vectors"] = torch.randn(num_ins, B, channels, generator=g).to(dtype)
+    out["global_language_feats"] = torch.randn(B, channels, generator=g).to(dtype)
+    out["nmax"] = int(topo["num_nodes"].max())
+    return out
+
+
 def gumbel_noise(num_graphs, nmax, scale=0.3, seed=3407, nb_samples=1):
     """Gumbel(0, scale) noise [B, S, Nmax, 1] from the CPU generator — the tensor that is injected
     into both the reference sampler and the CUDA sampler for bit-exact mask parity

@@ -256,3 +256,23 @@ def test_layer_grad_allreduce_in_place_and_accumulation():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker_layer, args=(2, port, ret), nprocs=2, join=True)
     assert ret["ok_0"] and ret["ok_1"], dict(ret)
+
+
+def test_balanced_shards_equal_counts_and_near_equal_sizes():
+    from isg_b200 import synth
+    from isg_b200.dp import balanced_shards
+
+    topo = synth.make_topology(64 * 4, seed=5)
+    sizes = (topo["num_edges"] + 5 * topo["num_nodes"]).tolist()
+    shards = balanced_shards(sizes, 4)
+    assert sorted(g for s in shards for g in s) == list(range(256)) and all(len(s) == 64 for s in shards)
+    tot = [sum(sizes[g] for g in s) for s in shards]
+    assert (max(tot) - min(tot)) / (sum(tot) / 4) < 0.01  # random dealing of these graphs is off by several percent
+    sub = synth.subset_topology(topo, shards[1])
+    assert int(sub["batch"].max()) == 63 and sub["batch"].numel() == int(topo["num_nodes"][shards[1]].sum())
+    assert sub["edge_index"].shape[1] == int(topo["num_edges"][shards[1]].sum())
+    assert int(sub["edge_index"].min()) >= 0 and int(sub["edge_index"].max()) < sub["batch"].numel()
+    b = sub["batch"]
+    assert bool((b[sub["edge_index"][0]] == b[sub["edge_index"][1]]).all())  # edges stay inside their graphs
+    with pytest.raises(ValueError):
+        balanced_shards(sizes[:-1], 4)
