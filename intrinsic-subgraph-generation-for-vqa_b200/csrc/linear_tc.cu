@@ -275,12 +275,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (P2) {
           // this CTA's half of the B tile, at the START of the B region (the pair's MMA reads N/2 from each CTA)
+          // (a ragged last N tile is multiplied at its own width, see n_eff in the MMA issuer: the halves split there)
+          const int half = min(MAX_BN, ((g.cols - n0) + 15) & ~15) / 2;
           if (!B_MN) {
-            tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0 + (int)cta_rank * (MAX_BN / 2));
+            tma_load_2d(sa + off_b_hi, &map_b, fb, r0, n0 + (int)cta_rank * half);
           } else {
 #pragma unroll
             for (int c = 0; c < MAX_BN / 64; ++c)
-              tma_load_2d(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + (int)cta_rank * (MAX_BN / 2) + 32 * c, r0);
+              tma_load_2d(sa + off_b_hi + c * (BK * 128), &map_b, fb, n0 + (int)cta_rank * half + 32 * c, r0);
           }
         } else if (CL == 1) {
           if (!B_MN) {
@@ -329,6 +331,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int num_kb = tile_kb(t);
       const int tp = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      // A ragged last N tile (1200 = 9 x 128 + 48; 300 = 2 x 128 + 44) is multiplied at ITS width, rounded up to 16,
+      // instead of the full 128: the tensor pipe's time per instruction is proportional to N (the shared-memory tile
+      // and the accumulator keep their size; the epilogue ignores the columns past the edge anyway).
+      const int n0_t = ((t % tiles_mn) % g.n_tiles) * BN;
+      const int n_eff = (SPLIT && FULLBN) ? min(BN, ((g.cols - n0_t) + 15) & ~15) : BN;
+      const uint32_t idesc_t = (idesc_ts & ~(0x3fu << 17)) | ((uint32_t)(n_eff >> 3) << 17);
       const uint32_t d_corr = tmem_base + TM_CORR;  // single stage: drained once per tile by the epilogue
       if (SPLIT && !MERGE) {
         mbar_wait(cempty_bar(0), (uint32_t)(it & 1) ^ 1u);
@@ -356,15 +364,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t bk = (uint64_t)(b_kstep * k);
               if (P2) {
-                umma_tf32_ts_2cta(d_main, a_t + 8u * k, b_hi + bk, idesc_ts, (kb > kb0 || k > 0) ? 1u : 0u);
-                umma_tf32_ts_2cta(d_main, a_t + 8u * k, b_lo + bk, idesc_ts, 1u);
-                umma_tf32_ts_2cta(d_main, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_ts, 1u);
+                umma_tf32_ts_2cta(d_main, a_t + 8u * k, b_hi + bk, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
+                umma_tf32_ts_2cta(d_main, a_t + 8u * k, b_lo + bk, idesc_t, 1u);
+                umma_tf32_ts_2cta(d_main, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_t, 1u);
                 continue;
               }
-              umma_tf32_ts(d_main, a_t + 8u * k, b_hi + bk, idesc_ts, (kb > kb0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(MERGE ? d_main : d_corr, a_t + 8u * k, b_lo + bk, idesc_ts,
+              umma_tf32_ts(d_main, a_t + 8u * k, b_hi + bk, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(MERGE ? d_main : d_corr, a_t + 8u * k, b_lo + bk, idesc_t,
                            (MERGE || kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(MERGE ? d_main : d_corr, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_ts, 1u);
+              umma_tf32_ts(MERGE ? d_main : d_corr, a_t + (uint32_t)BK + 8u * k, b_hi + bk, idesc_t, 1u);
             }
           } else {
             const uint64_t a_hi = a_hi0 + sdelta;
