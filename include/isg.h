@@ -250,7 +250,9 @@ int isg_gate_theta_bwd(const float* g_theta, const float* xn, const float* q,
  *   a = softmax_graph(<ins[b], v_n>/sqrt(D)); y = a*v; o = y - mean*mean_scale;
  *   h_out = weight*o*rsqrt(mean(o^2)+eps) + bias + h_in.
  * saves a [N], mean [B,D], rstd [B,D].  bwd returns g_v [N,D], g_ins [B,D] and per-graph
- * partials gw_part/gb_part/gms_part [B,D] (column-summed by isg_colsum). g_h_in == g_out. */
+ * partials gw_part/gb_part/gms_part [B,D] (column-summed by isg_colsum). g_h_in == g_out.
+ * z_gelu [N,D] or NULL: when v = gelu(z) closes the projection that produced it (x_proj[2], models/mgat.py:156), the
+ * backward of that GELU is fused: g_v is returned already multiplied by gelu'(z_gelu). */
 int isg_sdpa_graphnorm_fwd(const float* v, const float* ins, const float* h_in,
                            const float* weight, const float* bias, const float* mean_scale,
                            const int32_t* graph_ptr, int64_t num_graphs, int dim, int nmax, float eps,
@@ -260,7 +262,7 @@ int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const float* ins,
                            const float* a, const float* mean, const float* rstd,
                            const int32_t* graph_ptr, int64_t num_graphs, int dim, int nmax,
                            float* g_v, float* g_ins, float* gw_part, float* gb_part, float* gms_part,
-                           void* stream);
+                           const float* z_gelu /* or NULL */, void* stream);
 
 /* masked attention pooling — SURVEY.md section 8 row f1, GlobalAttention.forward
  * (models/att_pooling.py:57-77; called from models/isubgvqa.py:280-287) after its node_nn / ques_nn MLPs:

@@ -333,12 +333,11 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
   CK(isg_sdpa_graphnorm_bwd(g_h_out, ptr<const float>(p, P_Y2), ins, ptr<const float>(p, P_BN_W),
                             ptr<const float>(p, P_BN_MS), ptr<const float>(p, P_SA), ptr<const float>(p, P_MEAN),
                             ptr<const float>(p, P_RSTD), gptr, B, D, nmax, g_y2, ptr<float>(p, P_G_INS), parts,
-                            parts + (size_t)B * D, parts + (size_t)2 * B * D, stream_));
+                            parts + (size_t)B * D, parts + (size_t)2 * B * D, ptr<const float>(p, P_Z2), stream_));
   CK(colsum(parts, B, D, P_G_BN_W));
   CK(colsum(parts + (size_t)B * D, B, D, P_G_BN_B));
   CK(colsum(parts + (size_t)2 * B * D, B, D, P_G_BN_MS));
-  // x_proj[2]: y2 = gelu(z2), z2 = y1 Wp2^T + bp2
-  CK(isg_gelu_bwd(g_y2, ptr<const float>(p, P_Z2), g_y2, N * (int64_t)D, stream_));
+  // x_proj[2]: y2 = gelu(z2), z2 = y1 Wp2^T + bp2 — the GELU's backward is fused into the kernel above (z_gelu)
   if (bf) {
     void* gy2b = ws + w.g_y2_bf;
     CK(isg_to_bf16(g_y2, D, N, D, gy2b, Dp, stream_));

@@ -322,7 +322,8 @@ sdpa_graphnorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__
                           const float* __restrict__ mean, const float* __restrict__ rstd,
                           const int* __restrict__ gptr, int D, float* __restrict__ g_v,
                           float* __restrict__ g_ins, float* __restrict__ gw_part,
-                          float* __restrict__ gb_part, float* __restrict__ gms_part) {
+                          float* __restrict__ gb_part, float* __restrict__ gms_part,
+                          const float* __restrict__ zg) {
   // dynamic smem: coefA[D], coefB[D], coefC[D], shift[D], sa[nmax], sga[nmax]
   extern __shared__ float sm[];
   __shared__ float red[32];
@@ -403,7 +404,8 @@ sdpa_graphnorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__
       const int64_t o_ = (int64_t)(n0 + i) * D + c;
       const float vv = v[o_];
       const float gy = fmaf(cA[c], g[o_], fmaf(cB[c], sa[i] * vv - sh[c], cC[c]));
-      g_v[o_] = fmaf(gy, sa[i], sga[i] * ic);
+      const float gvv = fmaf(gy, sa[i], sga[i] * ic);
+      g_v[o_] = zg ? gvv * gelu_grad_f(zg[o_]) : gvv;  // (zg: the closing GELU of the producer of v, fused)
       gi = fmaf(sga[i], vv, gi);
     }
     g_ins[(int64_t)b * D + c] = gi;
@@ -522,7 +524,8 @@ sdpa_graphnorm_bwd_v4_kernel(const float* __restrict__ g, const float* __restric
                              const float* __restrict__ weight, const float* __restrict__ mean_scale,
                              const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ rstd,
                              const int* __restrict__ gptr, int D, float* __restrict__ g_v, float* __restrict__ g_ins,
-                             float* __restrict__ gw_part, float* __restrict__ gb_part, float* __restrict__ gms_part) {
+                             float* __restrict__ gw_part, float* __restrict__ gb_part, float* __restrict__ gms_part,
+                             const float* __restrict__ zg) {
   // dynamic smem: coefA[D], coefB[D], coefC[D], shift[D], sa[cnt], sga[cnt]
   extern __shared__ __align__(16) float sm4[];
   __shared__ float red1[32];
@@ -637,8 +640,13 @@ sdpa_graphnorm_bwd_v4_kernel(const float* __restrict__ g, const float* __restric
         const float ai = sa[i], gl = sga[i];
         const float4 gy = make_float4(fmaf(A.x, G.x, fmaf(Bc.x, ai * vv.x - S.x, Cc.x)), fmaf(A.y, G.y, fmaf(Bc.y, ai * vv.y - S.y, Cc.y)),
                                       fmaf(A.z, G.z, fmaf(Bc.z, ai * vv.z - S.z, Cc.z)), fmaf(A.w, G.w, fmaf(Bc.w, ai * vv.w - S.w, Cc.w)));
-        Vec4<float>::st(g_v + o_, make_float4(fmaf(gy.x, ai, gl * ic.x), fmaf(gy.y, ai, gl * ic.y), fmaf(gy.z, ai, gl * ic.z),
-                                              fmaf(gy.w, ai, gl * ic.w)));
+        float4 gvv = make_float4(fmaf(gy.x, ai, gl * ic.x), fmaf(gy.y, ai, gl * ic.y), fmaf(gy.z, ai, gl * ic.z),
+                                 fmaf(gy.w, ai, gl * ic.w));
+        if (zg) {  // the closing GELU of the projection that produced v (x_proj[2]), fused: g_z = g_v * gelu'(z)
+          const float4 z = Vec4<float>::ld(zg + o_);
+          gvv = make_float4(gvv.x * gelu_grad_f(z.x), gvv.y * gelu_grad_f(z.y), gvv.z * gelu_grad_f(z.z), gvv.w * gelu_grad_f(z.w));
+        }
+        Vec4<float>::st(g_v + o_, gvv);
         gi = f4_fma(vv, gl, gi);
       }
     }
@@ -1022,7 +1030,7 @@ extern "C" int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const 
                                       const float* mean_scale, const float* a, const float* mean,
                                       const float* rstd, const int32_t* gptr, int64_t B, int D, int nmax,
                                       float* g_v, float* g_ins, float* gw_part, float* gb_part, float* gms_part,
-                                      void* stream_) {
+                                      const float* z_gelu, void* stream_) {
   if (B < 0 || D <= 0 || nmax < 0) return ISG_EINVAL;
   if (B == 0) return ISG_OK;
   if (!g_out || !v || !ins || !weight || !mean_scale || !a || !mean || !rstd || !gptr || !g_v || !g_ins ||
@@ -1036,19 +1044,19 @@ extern "C" int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const 
   }
   const bool v4 = D % 4 == 0 && !(((uintptr_t)g_out | (uintptr_t)v | (uintptr_t)ins | (uintptr_t)weight | (uintptr_t)mean_scale |
                                    (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)g_v | (uintptr_t)g_ins | (uintptr_t)gw_part |
-                                   (uintptr_t)gb_part | (uintptr_t)gms_part) & 15);
+                                   (uintptr_t)gb_part | (uintptr_t)gms_part | (uintptr_t)z_gelu) & 15);
   if (v4) {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_bwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
     sdpa_graphnorm_bwd_v4_kernel<<<(unsigned)B, SG_COLS * SG_LANES, smem, (cudaStream_t)stream_>>>(
-        g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part);
+        g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part, z_gelu);
     ISG_CHECK_LAUNCH();
     return ISG_OK;
   }
   sdpa_graphnorm_bwd_kernel<<<(unsigned)B, SG_THREADS, smem, (cudaStream_t)stream_>>>(
-      g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part);
+      g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part, z_gelu);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

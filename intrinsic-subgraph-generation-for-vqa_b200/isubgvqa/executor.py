@@ -278,7 +278,7 @@ def kernel_launches(spec, gi, backward, bf16=False):
             else:
                 n += K["isg_gate_theta_fwd"] + 1 + K["isg_node_edge_mask_fwd"]
         return n + (1 if bf16 else 0)  # + isg_to_bf16(xg)
-    n = (K["isg_sdpa_graphnorm_bwd"] + K["isg_colsum_multi"] + K["isg_gelu_bwd"] + 4 * K["isg_linear_dgrad"] +
+    n = (K["isg_sdpa_graphnorm_bwd"] + K["isg_colsum_multi"] + 4 * K["isg_linear_dgrad"] +
          4 * K["isg_linear_wgrad"] + K["isg_gat_edge_bwd"] + K["isg_instr_gate_bwd"])
     if masked:
         n += 1 + K["isg_node_edge_mask_bwd"] + (3 if spec["code"] == 2 else 1) + K["isg_gate_theta_bwd"] + \

@@ -54,7 +54,7 @@ SIGNATURES = {
     "isg_gate_theta_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "isg_sdpa_graphnorm_fwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "isg_sdpa_graphnorm_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P,
-                                      _P]),
+                                      _P, _P]),
     "isg_attn_pool_fwd": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "isg_attn_pool_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "isg_split_lo": (_I32, [_P, _I64, _P, _P]),

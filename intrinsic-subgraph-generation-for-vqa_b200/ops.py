@@ -373,7 +373,7 @@ class SdpaGraphNormResidual(torch.autograd.Function):
         L.call("isg_sdpa_graphnorm_bwd", L.ptr(g), L.ptr(v), L.ptr(ins), L.ptr(weight), L.ptr(mean_scale),
                                                 L.ptr(a), L.ptr(mean), L.ptr(rstd), L.ptr(gi.graph_ptr), gi.B, D,
                                                 gi.nmax, L.ptr(gv), L.ptr(gins), L.ptr(parts[0]), L.ptr(parts[1]),
-                                                L.ptr(parts[2]), L.stream())
+                                                L.ptr(parts[2]), None, L.stream())
         gw, gb, gms = colsum(parts[0]), colsum(parts[1]), colsum(parts[2])
         return gv, gins, g, gw, gb, gms, None, None
 
