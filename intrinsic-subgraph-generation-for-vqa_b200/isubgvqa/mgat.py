@@ -81,7 +81,7 @@ class MGAT(torch.nn.Module):
             params = self.__dict__["_param_list"] = list(self.parameters())
         ops.allow_side_stream(all(p.grad is None for p in params))
         gi = get_graph_index(edge_index, batch, instr_vectors.shape[1])
-        if _USE_EXECUTOR and executor.supported(self, explainer):
+        if _USE_EXECUTOR and executor.supported(self, explainer, params):
             masked = [c for c in self.convs if c.mask.masking_threshold != 1.0]
             if masked and gi.B > x.shape[0]:  # batch[batch[n]] (quirk Q1): the reference raises here too
                 raise IndexError(f"double gather needs num_graphs <= num_nodes, got B={gi.B}, N={x.shape[0]}")
