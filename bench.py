@@ -658,7 +658,7 @@ def main_isg(args, rank, world, local_rank):
         per_launch_ms = tot / calls
         alg = (3 * bwd_b_un + bwd_b_m) / 4.0  # 3 unmasked layers + 1 masked layer per step
         ach = alg / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst_ring + gat_att_reduce1/2 + gat_edge_bwd_src_ring; "
+        roof = {"bound": "hbm", "kernel": "isg_gat_edge_bwd (gat_edge_bwd_dst_ring + gat_edge_bwd_src_ring with the g_att fold as block roles; "
                                           "heavy-first task schedule)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": measured_traffic("isg_gat_edge_bwd", args.workload),

@@ -636,10 +636,14 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
                              const int* __restrict__ nbr, const int* __restrict__ eid,
                              const int* __restrict__ order, float* __restrict__ g_xr, int64_t ld_gx,
                              float* __restrict__ g_ep, float* __restrict__ gatt_part, float* __restrict__ gm_h,
-                             int64_t N, int H_, int C_, float slope, int K, int ep_keep) {
+                             int64_t N, int H_, int C_, float slope, int K, int ep_keep, int* __restrict__ red_cnt,
+                             int red_n) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // arrival counters of the g_att fold that rides in the src kernel (launched after this one completes)
+  if (blockIdx.x == 0)
+    for (int v = threadIdx.x; v < red_n; v += blockDim.x) red_cnt[v] = 0;
   const int64_t wid0 = (int64_t)blockIdx.x * EDGE_WARPS + warp;  // gridDim.x*EDGE_WARPS is a multiple of H
   const int head = (int)(wid0 % H);
   int64_t col = wid0 / H;
@@ -858,20 +862,28 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
 // g_att = column sums of gatt_part viewed as [rows, H*C] (row = column index of the dst kernel), two
 // fixed-order stages: slabs of GR_ROWS rows -> part2 [parts2, H*C], then part2 -> g_att with GR2_LANES
 // row lanes per column and a fixed-order shared-memory fold.
-constexpr int GR_ROWS = 16;
+constexpr int GR_ROWS = 64;   // rows per slab (64 keeps the second stage's serial chain short: N/64/16 steps)
+constexpr int GR_BATCH = 16;  // loads in flight per thread
 constexpr int GR2_LANES = 16;
+// rows [r0, r1) of column group c summed in ascending row order, starting from row r0's value
+__device__ __forceinline__ float4 slab_fold(const float* __restrict__ part, int64_t r0, int64_t r1, int cols, int c) {
+  float4 s = f4_zero();
+  for (int64_t b = r0; b < r1; b += GR_BATCH) {
+    float4 v[GR_BATCH];
+#pragma unroll
+    for (int u = 0; u < GR_BATCH; ++u) v[u] = (b + u < r1) ? Vec4<float>::ld(part + (b + u) * cols + c) : f4_zero();
+#pragma unroll
+    for (int u = 0; u < GR_BATCH; ++u)
+      if (b + u < r1) s = (b + u == r0) ? v[u] : f4_add(s, v[u]);
+  }
+  return s;
+}
 __global__ void __launch_bounds__(64)
 gat_att_reduce1_kernel(const float* __restrict__ part, int64_t rows, int cols, float* __restrict__ part2) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= cols) return;
   const int64_t r0 = (int64_t)blockIdx.y * GR_ROWS, r1 = min(rows, r0 + GR_ROWS);
-  float4 v[GR_ROWS];
-#pragma unroll
-  for (int u = 0; u < GR_ROWS; ++u) v[u] = (r0 + u < r1) ? Vec4<float>::ld(part + (r0 + u) * cols + c) : f4_zero();
-  float4 s = v[0];
-#pragma unroll
-  for (int u = 1; u < GR_ROWS; ++u) s = f4_add(s, v[u]);
-  Vec4<float>::st(part2 + (int64_t)blockIdx.y * cols + c, s);
+  Vec4<float>::st(part2 + (int64_t)blockIdx.y * cols + c, slab_fold(part, r0, r1, cols, c));
 }
 __global__ void __launch_bounds__(64 * GR2_LANES)
 gat_att_reduce2_kernel(const float* __restrict__ part2, int nparts, int cols, float* __restrict__ g_att) {
@@ -899,6 +911,68 @@ gat_att_reduce2_kernel(const float* __restrict__ part2, int nparts, int cols, fl
   }
 }
 
+// The same two-stage fold as block roles of the src kernel (fp32 ring path).  Block b < red_blocks folds slab
+// b / cb of column block b % cb exactly as gat_att_reduce1_kernel does, then bumps the column block's arrival
+// counter; the block that arrives last folds part2 over the slabs in gat_att_reduce2_kernel's order (row p goes to
+// lane sum p % GR2_LANES, ascending p; lane sums folded 0..15), so g_att is bit-identical to the two-kernel fold and
+// independent of which block arrives last.  Counters are zeroed by the dst kernel.
+struct AttFold {
+  const float* part;   // [rows, H*C] g_att partials of the dst pass
+  float* part2;        // [parts2, H*C]
+  float* g_att;        // [H*C]
+  int* cnt;            // [cb] arrival counters
+  const float* gm_h;   // [E, H] per-head edge-mask gradients (masked only)
+  float* g_emask;      // [E]
+  int64_t rows, E;
+  int parts2, red_blocks, gm_blocks;
+};
+constexpr int FOLD_THREADS = EDGE_WARPS * 32;
+__device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __noinline__ void att_fold_role(const AttFold& f, int cols) {
+  __shared__ int s_last;
+  const int cb = (cols / 4 + FOLD_THREADS - 1) / FOLD_THREADS;
+  const int y = (int)blockIdx.x / cb, x = (int)blockIdx.x - y * cb;
+  const int c = (x * FOLD_THREADS + (int)threadIdx.x) * 4;
+  if (c < cols) {
+    const int64_t r0 = (int64_t)y * GR_ROWS, r1 = min(f.rows, r0 + GR_ROWS);
+    Vec4<float>::st(f.part2 + (int64_t)y * cols + c, slab_fold(f.part, r0, r1, cols, c));
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(f.cnt + x, 1) == f.parts2 - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (c >= cols) return;
+  float4 s[GR2_LANES];
+#pragma unroll
+  for (int u = 0; u < GR2_LANES; ++u) s[u] = f4_zero();
+  for (int p0 = 0; p0 < f.parts2; p0 += GR2_LANES) {
+    float4 v[GR2_LANES];
+#pragma unroll
+    for (int u = 0; u < GR2_LANES; ++u)
+      v[u] = p0 + u < f.parts2 ? ldcg_f4(f.part2 + (int64_t)(p0 + u) * cols + c) : f4_zero();
+#pragma unroll
+    for (int u = 0; u < GR2_LANES; ++u)
+      if (p0 + u < f.parts2) s[u] = f4_add(s[u], v[u]);
+  }
+  float4 t = s[0];
+#pragma unroll
+  for (int u = 1; u < GR2_LANES; ++u) t = f4_add(t, s[u]);
+  Vec4<float>::st(f.g_att + c, t);
+}
+
+// g_edge_mask[e] = sum_h gm_h[e, h] (gm_head_sum_kernel's arithmetic), grid-strided over the gm blocks
+__device__ __forceinline__ void gm_fold_role(const AttFold& f, int H) {
+  const int64_t stride = (int64_t)f.gm_blocks * FOLD_THREADS;
+  for (int64_t e = (int64_t)((int)blockIdx.x - f.red_blocks) * FOLD_THREADS + threadIdx.x; e < f.E; e += stride) {
+    float s = 0.f;
+    for (int h = 0; h < H; ++h) s += f.gm_h[e * H + h];
+    f.g_emask[e] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // backward, pass 2 (src-major): g_xl[j] = sum_{e: src = j} ( g_eproj[e] + G[dst_e] * alpha*m ).
 // ------------------------------------------------------------------------------------------
@@ -908,13 +982,22 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
                              const float* __restrict__ emask, const float* __restrict__ alpha,
                              const int* __restrict__ colptr, const int* __restrict__ nbr,
                              const int* __restrict__ eid, const int* __restrict__ order, float* __restrict__ g_xl,
-                             int64_t ld_gx, int64_t NH, int H_, int C_) {
+                             int64_t ld_gx, int64_t NH, int H_, int C_, AttFold fold) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2;
   const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
   const int64_t HC = (int64_t)H * C;
+  // the leading blocks of the grid fold the dst pass's g_att partials (and the per-head edge-mask gradients) while
+  // the remaining blocks stream g_eproj: three launches fewer, and the fold is hidden under the src pass
+  if ((int)blockIdx.x < fold.red_blocks + fold.gm_blocks) {
+    if ((int)blockIdx.x < fold.red_blocks) att_fold_role(fold, (int)HC);
+    else if (MASKED) gm_fold_role(fold, H);
+    return;
+  }
+  const int64_t first = (int64_t)(blockIdx.x - fold.red_blocks - fold.gm_blocks);
+  const int64_t nblk = (int64_t)(gridDim.x - fold.red_blocks - fold.gm_blocks);
   const uint32_t wbytes = ring_warp_bytes(C, 0);
   WarpRing ring;
   ring.init(smem_addr_u32(ring_smem) + warp * wbytes, smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * RING,
@@ -922,7 +1005,7 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   const bool leader = warp_elect_one();
 
-  for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NH; wid += (int64_t)gridDim.x * EDGE_WARPS) {
+  for (int64_t wid = first * EDGE_WARPS + warp; wid < NH; wid += nblk * EDGE_WARPS) {
     const int64_t slot = wid / H;
     const int head = (int)(wid - slot * H);
     const int64_t node = order ? order[slot] : slot;  // longest segments first (isg_degree_order)
@@ -1558,12 +1641,20 @@ gat_edge_bwd_src_pair_kernel(const __nv_bfloat16* __restrict__ gout, int64_t ld_
                              const float* __restrict__ emask, const float* __restrict__ alpha,
                              const int* __restrict__ colptr, const int* __restrict__ nbr, const int* __restrict__ eid,
                              const int* __restrict__ order, __nv_bfloat16* __restrict__ g_xl, int64_t ld_gx, int64_t NP,
-                             int H, int C) {
+                             int H, int C, AttFold fold) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2, HP = H >> 1;
   const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
   const int64_t HC = (int64_t)H * C;
+  // leading blocks: the g_att / edge-mask folds (see att_fold_role)
+  if ((int)blockIdx.x < fold.red_blocks + fold.gm_blocks) {
+    if ((int)blockIdx.x < fold.red_blocks) att_fold_role(fold, (int)HC);
+    else if (MASKED) gm_fold_role(fold, H);
+    return;
+  }
+  const int64_t first = (int64_t)(blockIdx.x - fold.red_blocks - fold.gm_blocks);
+  const int64_t nblk = (int64_t)(gridDim.x - fold.red_blocks - fold.gm_blocks);
   const uint32_t wbytes = pair_warp_bytes(C, false);
   WarpRing ring;
   ring.init(smem_addr_u32(ring_smem) + warp * wbytes, smem_addr_u32(ring_smem) + EDGE_WARPS * wbytes + warp * 8 * RING,
@@ -1578,7 +1669,7 @@ gat_edge_bwd_src_pair_kernel(const __nv_bfloat16* __restrict__ gout, int64_t ld_
     hb[2 * k] = 8 * c >= C;
     hb[2 * k + 1] = 8 * c + 4 >= C;
   }
-  for (int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp; wid < NP; wid += (int64_t)gridDim.x * EDGE_WARPS) {
+  for (int64_t wid = first * EDGE_WARPS + warp; wid < NP; wid += nblk * EDGE_WARPS) {
     const int64_t slot = wid / HP;
     const int pair = (int)(wid - slot * HP);
     const int64_t node = order ? order[slot] : slot;
@@ -1651,10 +1742,12 @@ gat_edge_bwd_dst_pair_kernel(const __nv_bfloat16* __restrict__ gout, int64_t ld_
                              const int* __restrict__ nbr, const int* __restrict__ eid, const int* __restrict__ order,
                              __nv_bfloat16* __restrict__ g_xr, int64_t ld_gx, __nv_bfloat16* __restrict__ g_ep,
                              float* __restrict__ gatt_part, float* __restrict__ gm_h, int64_t N, int H, int C,
-                             float slope) {
+                             float slope, int* __restrict__ red_cnt, int red_n) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2, HP = H >> 1;
+  if (blockIdx.x == 0)  // arrival counters of the fold roles in the src kernel
+    for (int v = threadIdx.x; v < red_n; v += blockDim.x) red_cnt[v] = 0;
   const int64_t wid = (int64_t)blockIdx.x * EDGE_WARPS + warp;
   const int64_t slot = wid / HP;
   const int pair = (int)(wid - slot * HP);
@@ -1910,6 +2003,7 @@ inline int bwd_grid_blocks(int64_t N, int H) {
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int fold_col_blocks(int H, int C) { return (H * C / 4 + FOLD_THREADS - 1) / FOLD_THREADS; }
 
 template <int VPL, bool MASKED>
 int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* e_proj, const float* att,
@@ -1941,15 +2035,22 @@ inline int ep_keep_mode() {
   return v;
 }
 
+// ISG_EDGE_FOLD=0: g_att / edge-mask folds as separate launches instead of block roles of the src kernel
+inline int fold_mode() {
+  static const int v = getenv("ISG_EDGE_FOLD") ? atoi(getenv("ISG_EDGE_FOLD")) : 1;
+  return v;
+}
+
 template <int VPL, bool MASKED>
 int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r, int64_t ld_x,
                     const void* e_proj, const float* att, const float* emask, const float* alpha,
                     const int* dst_ptr, const int* dst_nbr, const int* dst_eid, const int* dst_order,
                     const int* src_ptr, const int* src_nbr, const int* src_eid, const int* src_order, void* g_xl,
                     void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att, float* g_emask, int64_t N, int64_t E,
-                    int H, int C, float slope, float* gatt_part, float* gatt_part2, float* gm_h,
+                    int H, int C, float slope, float* gatt_part, float* gatt_part2, float* gm_h, int* red_cnt,
                     const BwdRingPlan& plan, cudaStream_t stream) {
   const size_t smem_d = ring_smem_bytes(C, 2, 1), smem_s = ring_smem_bytes(C, 0, 0);
+  const int fold_cb = fold_col_blocks(H, C);
   const bool ref_shape = VPL == 3 && C == 300 && H == 4;
   auto kd = ref_shape ? gat_edge_bwd_dst_ring_kernel<VPL, MASKED, VPL == 3 ? 300 : 0, VPL == 3 ? 4 : 0>
                       : gat_edge_bwd_dst_ring_kernel<VPL, MASKED, 0, 0>;
@@ -1961,22 +2062,37 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
   kd<<<(unsigned)plan.blocks, EDGE_WARPS * 32, smem_d, stream>>>(
       (const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, emask, alpha,
       dst_ptr, dst_nbr, dst_eid, dst_order, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H, C, slope,
-      plan.K, ep_keep_mode());
-  ISG_CHECK_LAUNCH();
-  const int HC = H * C;
-  const int64_t rows = plan.warps / H;
-  gat_att_reduce1_kernel<<<dim3(ceil_div(HC / 4, 64), (unsigned)plan.parts2), 64, 0, stream>>>(gatt_part, rows, HC,
-                                                                                           gatt_part2);
-  ISG_CHECK_LAUNCH();
-  gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)plan.parts2, HC,
-                                                                                   g_att);
+      plan.K, ep_keep_mode(), red_cnt, fold_cb);
   ISG_CHECK_LAUNCH();
   const int64_t NH = N * H;
-  ks<<<(unsigned)ceil_div(NH, (int64_t)EDGE_WARPS), EDGE_WARPS * 32, smem_s, stream>>>(
-      (const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, src_order,
-      (float*)g_xl, ld_gx, NH, H, C);
+  AttFold fold;
+  fold.part = gatt_part;
+  fold.part2 = gatt_part2;
+  fold.g_att = g_att;
+  fold.cnt = red_cnt;
+  fold.gm_h = gm_h;
+  fold.g_emask = g_emask;
+  fold.rows = plan.warps / H;
+  fold.E = E;
+  fold.parts2 = (int)plan.parts2;
+  fold.red_blocks = (int)plan.parts2 * fold_cb;
+  fold.gm_blocks = (MASKED && E > 0) ? (int)std::min<int64_t>(ceil_div(E, (int64_t)FOLD_THREADS), 2 * ISG_NUM_SMS) : 0;
+  const bool folded = fold_mode() != 0;
+  if (!folded) {  // ISG_EDGE_FOLD=0: the fold as launches of its own, ahead of the src pass
+    fold.red_blocks = fold.gm_blocks = 0;
+    const int HC = H * C;
+    gat_att_reduce1_kernel<<<dim3(ceil_div(HC / 4, 64), (unsigned)plan.parts2), 64, 0, stream>>>(gatt_part, fold.rows, HC,
+                                                                                             gatt_part2);
+    ISG_CHECK_LAUNCH();
+    gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)plan.parts2, HC,
+                                                                                     g_att);
+    ISG_CHECK_LAUNCH();
+  }
+  ks<<<(unsigned)(fold.red_blocks + fold.gm_blocks + ceil_div(NH, (int64_t)EDGE_WARPS)), EDGE_WARPS * 32, smem_s,
+       stream>>>((const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, src_order,
+                 (float*)g_xl, ld_gx, NH, H, C, fold);
   ISG_CHECK_LAUNCH();
-  if (MASKED && E > 0) {
+  if (!folded && MASKED && E > 0) {
     gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
     ISG_CHECK_LAUNCH();
   }
@@ -2100,8 +2216,9 @@ int launch_bwd_pair(const void* g_out, int64_t ld_g, const void* x_l, const void
                     const int* dst_eid, const int* dst_order, const int* src_ptr, const int* src_nbr, const int* src_eid,
                     const int* src_order, void* g_xl, void* g_xr, int64_t ld_gx, void* g_eproj, float* g_att,
                     float* g_emask, int64_t N, int64_t E, int H, int C, float slope, float* gatt_part, float* gatt_part2,
-                    float* gm_h, cudaStream_t stream) {
+                    float* gm_h, int* red_cnt, cudaStream_t stream) {
   const size_t smem_d = pair_smem_bytes(C, true, 1), smem_s = pair_smem_bytes(C, false, 0);
+  const int fold_cb = fold_col_blocks(H, C);
   auto kd = gat_edge_bwd_dst_pair_kernel<VPL, MASKED>;
   auto ks = gat_edge_bwd_src_pair_kernel<VPL, MASKED>;
   cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
@@ -2112,19 +2229,35 @@ int launch_bwd_pair(const void* g_out, int64_t ld_g, const void* x_l, const void
   kd<<<blocks, EDGE_WARPS * 32, smem_d, stream>>>(
       (const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)x_l, (const __nv_bfloat16*)x_r, ld_x,
       (const __nv_bfloat16*)e_proj, att, emask, alpha, dst_ptr, dst_nbr, dst_eid, dst_order, (__nv_bfloat16*)g_xr, ld_gx,
-      (__nv_bfloat16*)g_eproj, gatt_part, gm_h, N, H, C, slope);
+      (__nv_bfloat16*)g_eproj, gatt_part, gm_h, N, H, C, slope, red_cnt, fold_cb);
   ISG_CHECK_LAUNCH();
   const int HC = H * C;
   const int64_t parts2 = (N + GR_ROWS - 1) / GR_ROWS;  // gatt_part viewed as [N rows, H*C], keyed by the node
-  gat_att_reduce1_kernel<<<dim3(ceil_div(HC / 4, 64), (unsigned)parts2), 64, 0, stream>>>(gatt_part, N, HC, gatt_part2);
+  AttFold fold;
+  fold.part = gatt_part;
+  fold.part2 = gatt_part2;
+  fold.g_att = g_att;
+  fold.cnt = red_cnt;
+  fold.gm_h = gm_h;
+  fold.g_emask = g_emask;
+  fold.rows = N;
+  fold.E = E;
+  fold.parts2 = (int)parts2;
+  fold.red_blocks = (int)parts2 * fold_cb;
+  fold.gm_blocks = (MASKED && E > 0) ? (int)std::min<int64_t>(ceil_div(E, (int64_t)FOLD_THREADS), 2 * ISG_NUM_SMS) : 0;
+  const bool folded = fold_mode() != 0;
+  if (!folded) {
+    fold.red_blocks = fold.gm_blocks = 0;
+    gat_att_reduce1_kernel<<<dim3(ceil_div(HC / 4, 64), (unsigned)parts2), 64, 0, stream>>>(gatt_part, N, HC, gatt_part2);
+    ISG_CHECK_LAUNCH();
+    gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)parts2, HC, g_att);
+    ISG_CHECK_LAUNCH();
+  }
+  ks<<<blocks + (unsigned)(fold.red_blocks + fold.gm_blocks), EDGE_WARPS * 32, smem_s, stream>>>(
+      (const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, src_order,
+      (__nv_bfloat16*)g_xl, ld_gx, NP, H, C, fold);
   ISG_CHECK_LAUNCH();
-  gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)parts2, HC, g_att);
-  ISG_CHECK_LAUNCH();
-  ks<<<blocks, EDGE_WARPS * 32, smem_s, stream>>>((const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)g_eproj, emask,
-                                                  alpha, src_ptr, src_nbr, src_eid, src_order, (__nv_bfloat16*)g_xl, ld_gx,
-                                                  NP, H, C);
-  ISG_CHECK_LAUNCH();
-  if (MASKED && E > 0) {
+  if (!folded && MASKED && E > 0) {
     gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
     ISG_CHECK_LAUNCH();
   }
@@ -2215,7 +2348,7 @@ extern "C" size_t isg_gat_edge_bwd_workspace_bytes(int64_t N, int64_t E, int64_t
                    align256((size_t)(1 + B) * sizeof(int));
   size_t m = a > b ? a : b;
   m = m > c ? m : c;
-  return m + align256((size_t)E * (size_t)h * sizeof(float));
+  return m + align256((size_t)E * (size_t)h * sizeof(float)) + align256((size_t)fold_col_blocks(h, C) * sizeof(int));
 }
 
 extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l, const void* x_r,
@@ -2263,11 +2396,11 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
   return edge_mask ? launch_bwd_ring<V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,     \
                                               dst_ptr, dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, \
                                               src_order, g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, \
-                                              H, C, slope, rp_part, rp_part2, rp_gmh, rplan, stream)          \
+                                              H, C, slope, rp_part, rp_part2, rp_gmh, rp_cnt, rplan, stream)          \
                    : launch_bwd_ring<V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha,    \
                                                dst_ptr, dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, \
                                                src_order, g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, \
-                                               H, C, slope, rp_part, rp_part2, rp_gmh, rplan, stream)
+                                               H, C, slope, rp_part, rp_part2, rp_gmh, rp_cnt, rplan, stream)
     if (((uintptr_t)x_l & 15) || ((uintptr_t)g_out & 15) || ((uintptr_t)e_proj & 15) || ((uintptr_t)g_eproj & 15))
       return ISG_EUNSUPPORTED;
     if (batch32 && graph_ptr && nmax > 0 && B > 0) {
@@ -2297,6 +2430,7 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
     float* rp_part = (float*)workspace;
     float* rp_part2 = (float*)((char*)workspace + align256((size_t)rplan.warps * (size_t)C * sizeof(float)));
     float* rp_gmh = (float*)((char*)rp_part2 + align256((size_t)rplan.parts2 * (size_t)H * (size_t)C * sizeof(float)));
+    int* rp_cnt = (int*)((char*)rp_gmh + align256((size_t)E * (size_t)H * sizeof(float)));
     switch (vpl) {
       case 1: ISG_BWD_RING(1);
       case 2: ISG_BWD_RING(2);
@@ -2311,15 +2445,16 @@ extern "C" int isg_gat_edge_bwd(const void* g_out, int64_t ld_g, const void* x_l
       float* pp_gmh = (float*)((char*)pp_part2 +
                                align256((size_t)((N + GR_ROWS - 1) / GR_ROWS) * (size_t)H * (size_t)C * sizeof(float)) +
                                align256((size_t)(1 + B) * sizeof(int)));
+      int* pp_cnt = (int*)((char*)pp_gmh + align256((size_t)E * (size_t)H * sizeof(float)));
 #define ISG_BWD_PAIR(V)                                                                                          \
   return edge_mask ? launch_bwd_pair<V, true>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha, dst_ptr,   \
                                               dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, src_order,  \
                                               g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,   \
-                                              pp_part, pp_part2, pp_gmh, stream)                                 \
+                                              pp_part, pp_part2, pp_gmh, pp_cnt, stream)                                 \
                    : launch_bwd_pair<V, false>(g_out, ld_g, x_l, x_r, ld_x, e_proj, att, edge_mask, alpha, dst_ptr,  \
                                                dst_nbr, dst_eid, dst_order, src_ptr, src_nbr, src_eid, src_order, \
                                                g_xl, g_xr, ld_gx, g_eproj, g_att, g_edge_mask, N, E, H, C, slope,  \
-                                               pp_part, pp_part2, pp_gmh, stream)
+                                               pp_part, pp_part2, pp_gmh, pp_cnt, stream)
       switch (vpl) {
         case 1: ISG_BWD_PAIR(1);
         case 2: ISG_BWD_PAIR(2);

@@ -296,7 +296,7 @@ def kernel_launches(spec, gi, backward, bf16=False):
     n = (K["isg_sdpa_graphnorm_bwd"] + K["isg_colsum_multi"] + 4 * K["isg_linear_dgrad"] +
          4 * K["isg_linear_wgrad"] + K["isg_gat_edge_bwd"] + K["isg_instr_gate_bwd"])
     if masked:
-        n += 1 + K["isg_node_edge_mask_bwd"] + (3 if spec["code"] == 2 else 1) + K["isg_gate_theta_bwd"] + \
+        n += K["isg_node_edge_mask_bwd"] + (3 if spec["code"] == 2 else 1) + K["isg_gate_theta_bwd"] + \
             2 * (K["isg_gelu_bwd"] + K["isg_linear_dgrad"] + K["isg_linear_wgrad"])
     return n + (1 if bf16 else 0)  # + isg_to_bf16(g_y2)
 

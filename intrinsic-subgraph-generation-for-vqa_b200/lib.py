@@ -112,7 +112,7 @@ def load():
 
 # kernels launched per C-ABI call (memsets excluded); used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
-    "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_graph_closure": 1, "isg_degree_order": 3, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 4,
+    "isg_csr_build": 5, "isg_graph_ptr": 2, "isg_graph_closure": 1, "isg_degree_order": 3, "isg_gat_edge_fwd": 1, "isg_gat_edge_bwd": 2,
     "isg_node_edge_mask_fwd": 1, "isg_node_edge_mask_bwd": 1, "isg_topk_mask_fwd": 1, "isg_sampler_fused_fwd": 1, "isg_imle_bwd": 1,
     "isg_aimle_bwd": 3, "isg_gumbel_topk_fwd": 1, "isg_gumbel_topk_bwd": 1, "isg_simple_marginals_fwd": 1, "isg_simple_marginals_bwd": 1, "isg_instr_gate_fwd": 1,
     "isg_instr_gate_bwd": 1, "isg_concat_instr_fwd": 1, "isg_concat_instr_bwd": 1, "isg_gate_theta_fwd": 1, "isg_gate_theta_bwd": 2, "isg_sdpa_graphnorm_fwd": 1,
