@@ -94,7 +94,10 @@ def collate_scene_graphs(graphs, cache=None, pin=False):
         eid = (np.concatenate([getattr(c, side + "_eid") for c in csrs]) + edge_rep_e) if E else np.zeros(0, dtype=np.int32)
         idx[side + "_ptr"], idx[side + "_nbr"], idx[side + "_eid"] = ptr, nbr.astype(np.int32), eid.astype(np.int32)
         heavy = np.diff(ptr) >= max(2, -(-2 * E // max(N, 1)))  # isg_degree_order's rule: >= twice the mean degree
-        idx[side + "_order"] = np.concatenate([np.flatnonzero(heavy), np.flatnonzero(~heavy)]).astype(np.int32)
+        light = np.flatnonzero(~heavy)
+        if side == "src":  # the src pass walks the light nodes backwards (csrc/csr.cu order_place_kernel)
+            light = light[::-1]
+        idx[side + "_order"] = np.concatenate([np.flatnonzero(heavy), light]).astype(np.int32)
     idx["graph_ptr"] = n_off.astype(np.int32)
     idx["batch32"] = np.repeat(np.arange(B, dtype=np.int32), ns) if N else np.zeros(1, dtype=np.int32)
     host = {k: torch.from_numpy(v) for k, v in idx.items()}

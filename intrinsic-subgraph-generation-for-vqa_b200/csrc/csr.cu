@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(1024) order_scan_kernel(int* __restrict__ blk,
 }
 __global__ void __launch_bounds__(ORD_THREADS)
 order_place_kernel(const int* __restrict__ ptr_a, const int* __restrict__ ptr_b, int64_t N, int thr,
-                   const int* __restrict__ blk, int nblocks, int* __restrict__ order_a, int* __restrict__ order_b) {
+                   const int* __restrict__ blk, int nblocks, int* __restrict__ order_a, int* __restrict__ order_b,
+                   int reverse_b) {
   __shared__ int wcount[2][ORD_THREADS / 32];
   const int64_t n = blockIdx.x * (int64_t)ORD_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -393,7 +394,10 @@ order_place_kernel(const int* __restrict__ ptr_a, const int* __restrict__ ptr_b,
     for (int w = 0; w < warp; ++w) before += wcount[which][w];
     const int* b = blk + (int64_t)which * (nblocks + 1);
     const int heavy_before = b[blockIdx.x] + before, total_heavy = b[nblocks];
-    const int64_t pos = heavy ? heavy_before : total_heavy + (n - heavy_before);
+    int64_t pos = heavy ? heavy_before : total_heavy + (n - heavy_before);
+    // ordering b (the src pass of the edge backward) walks the light nodes in DESCENDING order: it starts with the
+    // nodes whose g_eproj rows the dst pass wrote last, which are the ones still in L2
+    if (which && reverse_b && !heavy) pos = total_heavy + (N - 1 - pos);
     (which ? order_b : order_a)[pos] = (int)n;
   }
 }
@@ -421,7 +425,9 @@ extern "C" int isg_degree_order(const int32_t* dst_ptr, const int32_t* src_ptr, 
   ISG_CHECK_LAUNCH();
   order_scan_kernel<<<2, 1024, 0, stream>>>(blk, nblocks);
   ISG_CHECK_LAUNCH();
-  order_place_kernel<<<nblocks, ORD_THREADS, 0, stream>>>(dst_ptr, src_ptr, N, thr, blk, nblocks, dst_order, src_order);
+  static const int reverse_src = getenv("ISG_SRC_ORDER_REV") ? atoi(getenv("ISG_SRC_ORDER_REV")) : 1;
+  order_place_kernel<<<nblocks, ORD_THREADS, 0, stream>>>(dst_ptr, src_ptr, N, thr, blk, nblocks, dst_order, src_order,
+                                                          reverse_src);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }

@@ -39,7 +39,7 @@ def test_collate_matches_from_data_list_layout_and_oracle_csr():
                                                           torch.bincount(b["batch"], minlength=7).cumsum(0)]))
     N, E = b["x"].shape[0], b["edge_index"].shape[1]
     for side in ("dst", "src"):
-        assert torch.equal(hi[side + "_order"].long(), util.heavy_first_order(hi[side + "_ptr"], N, E))
+        assert torch.equal(hi[side + "_order"].long(), util.heavy_first_order(hi[side + "_ptr"], N, E, side))
     # second epoch: every image comes out of the cache; a shuffled batch of the same images is consistent
     assert cache.misses == 7 and cache.hits == 0
     perm = [4, 0, 6, 2]

@@ -193,15 +193,15 @@ def test_edge_bwd_single_launch_is_bit_identical_to_two_pass(B, mn, me, masked):
 
 @pytest.mark.parametrize("B,mn,me,masked", [(64, 20, 150, True), (256, 20, 150, False), (3, 300, 20000, False)])
 def test_edge_task_order_longest_first_changes_no_bit(B, mn, me, masked):
-    """isg_degree_order: the nodes with at least twice the mean degree first, then the rest, each group in node order
-    (a stable partition); the edge kernels scheduled in that order give bit-identical results to the natural order."""
+    """isg_degree_order: the nodes with at least twice the mean degree first in node order, then the rest (ascending for
+    the dst ordering, descending for the src ordering); the edge kernels scheduled in that order give bit-identical results to the natural order."""
     from isg_b200 import graph, ops
 
     d = _edge_case(B, mn, me, 300, 4, masked, seed=11 + B)
     gi = _gi(d["edge_index"], d["batch"], B)
     N = gi.N
-    for order, ptr in ((gi.dst_order, gi.dst_ptr), (gi.src_order, gi.src_ptr)):
-        assert torch.equal(order.cpu().long(), util.heavy_first_order(ptr.cpu(), N, gi.E))
+    for side, order, ptr in (("dst", gi.dst_order, gi.dst_ptr), ("src", gi.src_order, gi.src_ptr)):
+        assert torch.equal(order.cpu().long(), util.heavy_first_order(ptr.cpu(), N, gi.E, side))
     keys = ("out", "alpha", "g_x_l", "g_x_r", "g_e_proj", "g_att", "g_bias") + (("g_mask",) if masked else ())
     prev = ops._EDGE_BWD_FUSED
     try:

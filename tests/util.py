@@ -262,10 +262,11 @@ def compare_step(got, want, sampler, rtol=RTOL, exact=None):
             check_param_grad(name, got["param_grads"].get(name), exact["param_grads"][name], rtol)
 
 
-def heavy_first_order(ptr, N, E):
-    """The task schedule isg_degree_order / isg_b200.collate produce: nodes with degree >= max(2, ceil(2E/N)) first,
-    then the others, both in increasing node id."""
+def heavy_first_order(ptr, N, E, side="dst"):
+    """The task schedule isg_degree_order / isg_b200.collate produce: nodes with degree >= max(2, ceil(2E/N)) first in
+    increasing node id, then the others — increasing for the dst ordering, decreasing for the src ordering."""
     deg = (ptr[1:N + 1] - ptr[:N]).long()
     thr = max(2, -(-2 * E // max(N, 1)))
     ids = torch.arange(N)
-    return torch.cat([ids[deg >= thr], ids[deg < thr]])
+    light = ids[deg < thr]
+    return torch.cat([ids[deg >= thr], light.flip(0) if side == "src" else light])
