@@ -59,6 +59,7 @@ struct BfArgs {
   int BN;
   int stages;
   int stage_bytes;
+  int res_kb;  // > 0 (K-major, no split): the CTA keeps its column block's B tile (res_kb k-blocks) in shared memory
   int m_tiles, n_tiles, splits;
   int64_t r_chunk;
   int64_t c_split_stride;
@@ -117,13 +118,20 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int BN = g.BN;
   const uint32_t stage_bytes = (uint32_t)g.stage_bytes;
   const uint32_t b_tile_bytes = stage_bytes - A_TILE_BYTES;
-  const uint32_t epi_base = smem_base + (uint32_t)S * stage_bytes;
+  // B-resident form (short reductions: K <= 5 k-blocks): [B tile, res_kb k-blocks][A-only ring of S stages]; the CTA
+  // works on ONE column block and walks the row blocks, so the weight tile is read from L2 once per CTA instead of
+  // once per output tile (the [39809,304]x[304,1200] product pulled 350 MB through L2 for 24 + 96 MB of HBM traffic)
+  const int res_kb = MN ? 0 : g.res_kb;
+  const uint32_t ring_base = smem_base + (uint32_t)res_kb * b_tile_bytes;
+  const uint32_t ring_stride = res_kb ? (uint32_t)A_TILE_BYTES : stage_bytes;
+  const uint32_t epi_base = ring_base + (uint32_t)S * ring_stride;
   const uint32_t bar_base = epi_base + EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto mfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
   auto mempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t bres_bar = bar_base + 8u * (2 * MAX_STAGES + 5);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (threadIdx.x == 0) {
@@ -137,6 +145,7 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(mfull_bar(s), 1);
       mbar_init(mempty_bar(s), EPI_WARPS);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -151,6 +160,14 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int tiles_mn = g.m_tiles * g.n_tiles;
   const int total_tiles = tiles_mn * g.splits;
+  // tile walk: round-robin over all tiles, or (B-resident) the row blocks of this CTA's column block
+  int t_first = blockIdx.x, t_step = gridDim.x;
+  if (res_kb) {
+    const int n_blk = (int)blockIdx.x % g.n_tiles, j = (int)blockIdx.x / g.n_tiles;
+    const int group = ((int)gridDim.x - n_blk + g.n_tiles - 1) / g.n_tiles;  // CTAs that share this column block
+    t_first = j * g.n_tiles + n_blk;
+    t_step = group * g.n_tiles;
+  }
   auto tile_kb = [&](int t) {
     const int split = t / tiles_mn;
     const int64_t r_beg = (int64_t)split * g.r_chunk;
@@ -164,7 +181,12 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const int b_chunks = (BN + 63) / 64;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (res_kb && t_first < total_tiles) {
+        const int n0 = (t_first % g.n_tiles) * BN;
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)res_kb * b_tile_bytes);
+        for (int kb = 0; kb < res_kb; ++kb) tma_load_2d(smem_base + (uint32_t)kb * b_tile_bytes, &map_b, bres_bar, kb * BK, n0);
+      }
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int split = t / tiles_mn, rem = t - split * tiles_mn;
         const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
         const int m0 = m_blk * BM, n0 = n_blk * BN;
@@ -172,13 +194,13 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int num_kb = tile_kb(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t sa = ring_base + (uint32_t)stage * ring_stride;
           const uint32_t fb = full_bar(stage);
-          mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + b_tile_bytes);
+          mbar_arrive_expect_tx(fb, (uint32_t)A_TILE_BYTES + (res_kb ? 0u : b_tile_bytes));
           const int r0 = (int)(r_beg + (int64_t)kb * BK);
           if (!MN) {
             tma_load_2d(sa, &map_a, fb, r0, m0);
-            tma_load_2d(sa + A_TILE_BYTES, &map_b, fb, r0, n0);
+            if (!res_kb) tma_load_2d(sa + A_TILE_BYTES, &map_b, fb, r0, n0);
           } else {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * CHUNK_BYTES, &map_a, fb, m0 + 64 * c, r0);
@@ -196,11 +218,12 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((MN ? 1u : 0u) << 15) | ((MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t kstep = MN ? ((UMMA_K * 128u) >> 4) : ((UMMA_K * 2u) >> 4);  // 16-byte units per K = 16
-      const uint64_t a0 = make_desc16(smem_base, MN), b0 = make_desc16(smem_base + A_TILE_BYTES, MN);
+      const uint64_t a0 = make_desc16(ring_base, MN), b0 = make_desc16(res_kb ? smem_base : smem_base + A_TILE_BYTES, MN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      if (res_kb && t_first < total_tiles) mbar_wait(bres_bar, 0u);
+      for (int t = t_first; t < total_tiles; t += t_step, ++it) {
         const int num_kb = tile_kb(t);
         const int ms = it & 1;
         const uint32_t mphase = (uint32_t)(it >> 1) & 1u;
@@ -210,8 +233,8 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sdelta = (uint32_t)stage * (stage_bytes >> 4);
-          const uint64_t a = a0 + sdelta, b = b0 + sdelta;
+          const uint32_t sdelta = (uint32_t)stage * (ring_stride >> 4);
+          const uint64_t a = a0 + sdelta, b = b0 + (res_kb ? (uint32_t)kb * (b_tile_bytes >> 4) : sdelta);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_bf16(d, a + (uint64_t)(kstep * k), b + (uint64_t)(kstep * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -235,7 +258,7 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t stg = epi_base + (uint32_t)(warp - 4) * EPI_STG_BYTES;
     const int n_pass = (BN + PASS_COLS - 1) / PASS_COLS;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = t_first; t < total_tiles; t += t_step, ++it) {
       const int split = t / tiles_mn, rem = t - split * tiles_mn;
       const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
       const int64_t row0 = (int64_t)m_blk * BM + q * 32;
@@ -267,25 +290,33 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
         const int piece = lane & 7;
         const int col = col0 + piece * PIECE;
-        if (col < n_lim) {
+        // all eight shared-memory reads first, then the stores: with one register quad re-used per row the LDS of row
+        // i + 1 waited for the STG of row i (ncu: those two instructions held 53 % of the epilogue warps' samples)
+        uint4 o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = 4 * i + (lane >> 3);
-            const int64_t r = row0 + rl;
-            if (r < g.rows) {
-              uint4 o = lds_u4(stg + rl * EPI_ROW_BYTES + piece * 16);
-              if (OUT_BF16) {
-                *reinterpret_cast<uint4*>((__nv_bfloat16*)base + r * ld + col) = o;
-              } else {
-                float* dst = (float*)base + extra + r * ld + col;
-                if (accumulate) {
-                  const float4 c = Vec4<float>::ld(dst);
-                  o = make_uint4(__float_as_uint(__uint_as_float(o.x) + c.x), __float_as_uint(__uint_as_float(o.y) + c.y),
-                                 __float_as_uint(__uint_as_float(o.z) + c.z), __float_as_uint(__uint_as_float(o.w) + c.w));
-                }
-                *reinterpret_cast<uint4*>(dst) = o;
-              }
+        for (int i = 0; i < 8; ++i) o[i] = lds_u4(stg + (4 * i + (lane >> 3)) * EPI_ROW_BYTES + piece * 16);
+        if (col < n_lim) {
+          const int64_t r_first = row0 + (lane >> 3);
+          if (OUT_BF16) {
+            __nv_bfloat16* dst = (__nv_bfloat16*)base + r_first * ld + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (r_first + 4 * i < g.rows) *reinterpret_cast<uint4*>(dst + (int64_t)(4 * i) * ld) = o[i];
+          } else {
+            float* dst = (float*)base + extra + r_first * ld + col;
+            if (accumulate) {
+              float4 c[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                c[i] = (r_first + 4 * i < g.rows) ? Vec4<float>::ld(dst + (int64_t)(4 * i) * ld) : f4_zero();
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                o[i] = make_uint4(__float_as_uint(__uint_as_float(o[i].x) + c[i].x), __float_as_uint(__uint_as_float(o[i].y) + c[i].y),
+                                  __float_as_uint(__uint_as_float(o[i].z) + c[i].z), __float_as_uint(__uint_as_float(o[i].w) + c[i].w));
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (r_first + 4 * i < g.rows) *reinterpret_cast<uint4*>(dst + (int64_t)(4 * i) * ld) = o[i];
           }
         }
       };
@@ -294,16 +325,15 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (col0 >= n_lim) break;  // warp-uniform
         float v[PASS_COLS];
         {
-          uint32_t r[32];
+          uint32_t r[32], r2[32];
           tmem_ld32_nowait(tmem_base + lane_sel + 256u * ms + (uint32_t)(PASS_COLS * c), r);
-          tmem_ld_wait();
+          if (OUT_BF16) tmem_ld32_nowait(tmem_base + lane_sel + 256u * ms + (uint32_t)(PASS_COLS * c) + 32u, r2);
+          tmem_ld_wait();  // both loads in flight
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (OUT_BF16) {
-            tmem_ld32_nowait(tmem_base + lane_sel + 256u * ms + (uint32_t)(PASS_COLS * c) + 32u, r);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[(OUT_BF16 ? 32 : 0) + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[(OUT_BF16 ? 32 : 0) + j] = __uint_as_float(r2[j]);
           }
         }
         if (EPI == EPI_FWD) {
@@ -410,6 +440,15 @@ int make_map16(CUtensorMap* m, const void* base, int64_t dim0, int64_t dim1, int
   return r == CUDA_SUCCESS ? ISG_OK : ISG_EINVAL;
 }
 
+constexpr int RES_MAX_KB = 5;
+// ISG_BF16_BRES=0: never keep the B tile resident; n >= 2: resident form with at least n A stages (default 4).
+// Measured on [39809,304]x[304,1200] (ncu): 43.9 -> 40.0 us, L2 sectors 13.9 M -> 10.2 M; the product stays bound by its
+// epilogue warps (84 % busy) and the shared-memory pipe, so the gain is small.
+inline int bres_mode() {
+  static const int v = getenv("ISG_BF16_BRES") ? atoi(getenv("ISG_BF16_BRES")) : 1;
+  return v;
+}
+
 int pick_bn16(int cols) {
   const int parts = (cols + MAX_BN - 1) / MAX_BN;
   int bn = (cols + parts - 1) / parts;
@@ -438,13 +477,40 @@ int launch16(const BfGemm& p, cudaStream_t stream) {
   BfArgs g{};
   g.C = p.C; g.ldc = p.ldc; g.rows = p.rows; g.cols = p.cols; g.R = p.R;
   g.BN = pick_bn16(p.cols);
-  const int b_bytes = MN ? ((g.BN + 63) / 64) * CHUNK_BYTES : g.BN * BK * 2;
+  int b_bytes = MN ? ((g.BN + 63) / 64) * CHUNK_BYTES : g.BN * BK * 2;
   g.stage_bytes = A_TILE_BYTES + b_bytes;
   g.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_BYTES) / g.stage_bytes;
   if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
   if (g.stages < 2) return ISG_EUNSUPPORTED;
   g.m_tiles = ceil_div(p.rows, BM);
   g.n_tiles = ceil_div(p.cols, g.BN);
+  g.res_kb = 0;
+  if (!MN && p.splits == 1 && bres_mode() != 0) {
+    // B-resident form: the reduction fits in RES_MAX_KB k-blocks, at least `min_stages` A stages remain beside the
+    // resident tile, and every CTA gets at least two row blocks of its column block (otherwise nothing is re-used)
+    const int kbs = (int)ceil_div(p.R, (int64_t)BK);
+    const int min_stages = bres_mode() > 1 ? bres_mode() : 4;
+    if (kbs <= RES_MAX_KB) {
+      for (int parts = (p.cols + MAX_BN - 1) / MAX_BN; parts <= 16; ++parts) {
+        int bn = (p.cols + parts - 1) / parts;
+        bn = ((bn + 15) / 16) * 16;
+        const int bb = bn * BK * 2;
+        int st = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_BYTES - kbs * bb) / A_TILE_BYTES;
+        if (st < min_stages) continue;
+        if (st > MAX_STAGES) st = MAX_STAGES;
+        const int nt = ceil_div(p.cols, bn);
+        if (nt <= ISG_NUM_SMS && (int64_t)g.m_tiles * nt >= 2ll * ISG_NUM_SMS) {
+          g.BN = bn;
+          b_bytes = bb;
+          g.stage_bytes = A_TILE_BYTES + bb;
+          g.stages = st;
+          g.n_tiles = nt;
+          g.res_kb = kbs;
+        }
+        break;
+      }
+    }
+  }
   g.splits = p.splits; g.r_chunk = p.r_chunk; g.c_split_stride = p.c_split_stride;
   g.bias = p.bias; g.Z = p.Z; g.ldz = p.ldz; g.Zprev = p.Zprev; g.act = p.act; g.accumulate = p.accumulate;
   if (p.rows >= (1ll << 31) || p.R >= (1ll << 31)) return ISG_EUNSUPPORTED;
@@ -457,7 +523,8 @@ int launch16(const BfGemm& p, cudaStream_t stream) {
     if ((rc = make_map16(&ma, p.A, p.rows, p.R, p.lda, 64, BK)) != ISG_OK) return rc;
     if ((rc = make_map16(&mb, p.B, p.cols, p.R, p.ldb, 64, BK)) != ISG_OK) return rc;
   }
-  const int smem = 1024 + g.stages * g.stage_bytes + EPI_BYTES + BAR_BYTES;
+  const int smem = 1024 + (g.res_kb ? g.res_kb * b_bytes + g.stages * A_TILE_BYTES : g.stages * g.stage_bytes) + EPI_BYTES +
+                   BAR_BYTES;
   auto kern = bf16_gemm_kernel<MN, EPI, OUT_BF16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;

@@ -545,11 +545,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                acc[32 * cc + 4 * j + 3]));
         }
         __syncwarp();
+        // all shared-memory reads of the pass first: with one register quad per row the read of row i + 1 would wait
+        // for the store of row i
+        float4 vs[EPI_ROWS / 4];
+#pragma unroll
+        for (int i = 0; i < EPI_ROWS / 4; ++i)
+          vs[i] = lds_f4(stg + (i * 4 + (lane >> 3)) * EPI_ROW_BYTES + (lane & 7) * 16);
 #pragma unroll
         for (int i = 0; i < EPI_ROWS / 4; ++i) {
           const int rl = i * 4 + (lane >> 3);
           const int64_t row = m0 + rh * EPI_ROWS + rl;
-          float4 v = lds_f4(stg + rl * EPI_ROW_BYTES + (lane & 7) * 16);
+          float4 v = vs[i];
           if (row < g.rows && col < n_lim) {
             if (EPI == EPI_FWD) {
               if (g.bias) v = f4_add(v, Vec4<float>::ld(g.bias + col));

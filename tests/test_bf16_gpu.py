@@ -35,6 +35,9 @@ def _gelu_grad(z):
 @pytest.mark.parametrize("M,K,Nout,act,out_bf16", [
     (1, 300, 1200, 0, True), (37, 300, 2400, 0, True), (4910, 300, 1200, 0, True), (515, 1200, 600, 1, True),
     (4910, 600, 300, 1, False), (129, 300, 300, 0, False), (3000, 64, 48, 1, True), (40000, 300, 1200, 0, True),
+    # resident-weight-tile form (reduction <= 320, >= 2 row blocks per CTA): forward with a ragged last column block,
+    # dgrad through Nout = 300, fp32 output with GELU
+    (4910, 300, 2400, 0, True), (20000, 1200, 300, 1, True), (9000, 300, 2400, 1, False),
 ])
 def test_linear_bf16_fwd_dgrad_wgrad(M, K, Nout, act, out_bf16):
     lib = L.load()
