@@ -32,6 +32,9 @@ namespace {
 using namespace isg;
 using namespace isg_tc;
 
+#ifndef ISG_BF16_DIAG
+#define ISG_BF16_DIAG 0  // scripts/gemm_diag.sh: 1 = epilogue without its global stores, 2 = without the staging round trip too
+#endif
 constexpr int BM = 128;
 constexpr int BK = 64;       // bf16 elements per k-block: 128-byte rows, SWIZZLE_128B
 constexpr int UMMA_K = 16;   // kind::f16
@@ -273,6 +276,7 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       // stage `v` (this thread's row, PASS_COLS columns from col0) and write it to `base` (row pitch ld) coalesced
       auto store_pass = [&](void* base, int64_t ld, int64_t extra, const float* v, int col0, bool accumulate) {
+        if (ISG_BF16_DIAG & 2) return;
         __syncwarp();
         if (OUT_BF16) {
 #pragma unroll
@@ -295,6 +299,7 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint4 o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = lds_u4(stg + (4 * i + (lane >> 3)) * EPI_ROW_BYTES + piece * 16);
+        if (ISG_BF16_DIAG & 1) return;  // diagnostic build: no global stores (wrong results)
         if (col < n_lim) {
           const int64_t r_first = row0 + (lane >> 3);
           if (OUT_BF16) {

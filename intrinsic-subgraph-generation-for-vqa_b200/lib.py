@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisg.so")
+# ISG_LIB_PATH: a diagnostic build of the same library (scripts/gemm_diag.sh); the default is the in-tree libisg.so
+LIB_PATH = os.environ.get("ISG_LIB_PATH") or os.path.join(_HERE, "libisg.so")
 _lib = None
 
 F32, BF16 = 0, 1
