@@ -183,7 +183,7 @@ __global__ void gate_theta_bwd_xn_kernel(const float* __restrict__ gth, const fl
 // g_q[r] = sum over nodes n with batch[batch[n]] == r of gpre[n]*xn[n].  Nodes of graph g all use
 // row batch[g]; the graphs g with batch[g] == r are g in [gptr[r], gptr[r+1]) ∩ [0,B) — a
 // contiguous range of graphs, hence a contiguous range of nodes.  One CTA per row r.
-constexpr int GQ_COLS = 80, GQ_LANES = 4;  // 320 threads: 80 float4 column groups (D <= 320) x 4 row lanes
+constexpr int GQ_COLS = 80, GQ_LANES = 12;  // 960 threads: 80 float4 column groups (D <= 320) x 12 row lanes
 __global__ void __launch_bounds__(GQ_COLS * GQ_LANES)
 gate_theta_bwd_q_kernel(const float* __restrict__ gpre, const float* __restrict__ xn, const int* __restrict__ gptr,
                         int B, int D, int dbl, float* __restrict__ gq) {
@@ -989,7 +989,7 @@ extern "C" int isg_gate_theta_bwd(const float* g_theta, const float* xn, const f
   cudaStream_t stream = (cudaStream_t)stream_;
   gate_theta_bwd_xn_kernel<<<isg::ceil_div(N * 32, 128), 128, 0, stream>>>(g_theta, xn, q, batch32, N, D, double_gather, keep, g_xn, scratch);
   ISG_CHECK_LAUNCH();
-  gate_theta_bwd_q_kernel<<<(unsigned)(double_gather ? B : N), 320, 0, stream>>>(scratch, xn, gptr, (int)B, D, double_gather, g_q);
+  gate_theta_bwd_q_kernel<<<(unsigned)(double_gather ? B : N), GQ_COLS * GQ_LANES, 0, stream>>>(scratch, xn, gptr, (int)B, D, double_gather, g_q);
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
