@@ -54,7 +54,7 @@ __global__ void instr_gate_bwd_kernel(const float* __restrict__ gy, const float*
 // D % 4 == 0: float4 columns x IG_LANES row lanes (the serial walk above is a chain of ~20-40 dependent DRAM
 // round trips per thread: 32 us at the c3 size for 24 MB); per-lane partial sums of g_ins are folded in a fixed
 // order, so the result is deterministic.
-constexpr int IG_COLS = 80, IG_LANES = 4;
+constexpr int IG_COLS = 80, IG_LANES = 8;  // 640 threads (4 lanes: 15.2 us per launch at c3, 8 lanes: 11.1)
 __global__ void __launch_bounds__(IG_COLS * IG_LANES)
 instr_gate_bwd_v4_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ ins,
                          const int* __restrict__ gptr, int D, const float* __restrict__ gres, int acc_ins,
@@ -417,7 +417,7 @@ sdpa_graphnorm_bwd_kernel(const float* __restrict__ g, const float* __restrict__
 // passes (three in the forward, two in the backward): chains of ~20-40 dependent L2 round trips, 20 us per launch
 // at the c3 size for 12 MB.  Here thread (cx, ly) owns the float4 column cx and the rows ly, ly + SG_LANES, ...;
 // per-lane partial sums are folded through shared memory in a fixed order (deterministic).
-constexpr int SG_COLS = 80, SG_LANES = 4;  // 320 threads; D <= 320 per column pass (looped beyond)
+constexpr int SG_COLS = 80, SG_LANES = 4;  // 320 threads (8 lanes measured slower: fwd 15.4 -> 19.9 us, bwd 20.9 -> 24.5); D <= 320 per column pass (looped beyond)
 
 __device__ __forceinline__ float4 sg_fold(float4 (*red)[SG_COLS], int cx, int ly, float4 v) {
   __syncthreads();  // protect `red` from the previous use
