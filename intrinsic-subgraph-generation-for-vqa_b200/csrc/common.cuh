@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/isg.h"
 
@@ -16,6 +17,45 @@
   } while (0)
 
 namespace isg {
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched through launch_pdl() may become resident while
+// the previous kernel of its stream is still draining; it must call pdl_enter() BEFORE its first global-memory access
+// (the wait returns once every prerequisite grid has completed and its writes are visible, so the data flow is the
+// plain stream order), and only on-chip set-up (barrier init, tensor-memory allocation, descriptor prefetch) may
+// precede it.  What overlaps is the next grid's launch latency and prologue with this grid's tail.  Both
+// instructions are no-ops in a kernel launched without the attribute.  ISG_PDL=0 drops the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ISG_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+inline void pdl_attribute(cudaLaunchAttribute* a) {
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = 1;
+}
+// kern<<<grid, block, smem, stream>>>(args...) with the programmatic-serialization attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  pdl_attribute(&attr[0]);
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

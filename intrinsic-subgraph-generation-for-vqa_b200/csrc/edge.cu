@@ -477,6 +477,7 @@ gat_edge_fwd_ring_kernel(const float* __restrict__ xl, const float* __restrict__
                          const int* __restrict__ eid, const int* __restrict__ order, float* __restrict__ out,
                          int64_t ld_out, float* __restrict__ alpha, int64_t NH, int H_, int C_, float slope) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  pdl_enter();  // first global access below (no-op unless launched through launch_pdl)
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2;
@@ -639,6 +640,7 @@ gat_edge_bwd_dst_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
                              int64_t N, int H_, int C_, float slope, int K, int ep_keep, int* __restrict__ red_cnt,
                              int red_n) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  pdl_enter();  // first global access below (no-op unless launched through launch_pdl)
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // arrival counters of the g_att fold that rides in the src kernel (launched after this one completes)
@@ -984,6 +986,7 @@ gat_edge_bwd_src_ring_kernel(const float* __restrict__ gout, int64_t ld_g, const
                              const int* __restrict__ eid, const int* __restrict__ order, float* __restrict__ g_xl,
                              int64_t ld_gx, int64_t NH, int H_, int C_, AttFold fold) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  pdl_enter();  // first global access below (no-op unless launched through launch_pdl)
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2;
@@ -1101,6 +1104,7 @@ gat_edge_bwd_fused_ring_kernel(const float* __restrict__ gout, int64_t ld_g, con
                                float* __restrict__ gatt_part, float* __restrict__ gm_h, int* __restrict__ sync,
                                int64_t NH, int64_t nblocks_role, int lag_blocks, int H_, int C_, float slope) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  pdl_enter();  // first global access below (no-op unless launched through launch_pdl)
   __shared__ int s_ticket;
   const int C = CT > 0 ? CT : C_, H = HT > 0 ? HT : H_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1446,6 +1450,7 @@ gat_edge_fwd_pair_kernel(const __nv_bfloat16* __restrict__ xl, const __nv_bfloat
                          const int* __restrict__ order, __nv_bfloat16* __restrict__ out, int64_t ld_out,
                          float* __restrict__ alpha, int64_t NP, int H, int C, float slope) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  pdl_enter();  // first global access below (no-op unless launched through launch_pdl)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2, HP = H >> 1;  // 16-byte chunks per pair row; head pairs
   const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
@@ -1643,6 +1648,7 @@ gat_edge_bwd_src_pair_kernel(const __nv_bfloat16* __restrict__ gout, int64_t ld_
                              const int* __restrict__ order, __nv_bfloat16* __restrict__ g_xl, int64_t ld_gx, int64_t NP,
                              int H, int C, AttFold fold) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  pdl_enter();  // first global access below (no-op unless launched through launch_pdl)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2, HP = H >> 1;
   const uint32_t row_bytes = (uint32_t)C * 4u, l16 = 16u * lane;
@@ -1744,6 +1750,7 @@ gat_edge_bwd_dst_pair_kernel(const __nv_bfloat16* __restrict__ gout, int64_t ld_
                              float* __restrict__ gatt_part, float* __restrict__ gm_h, int64_t N, int H, int C,
                              float slope, int* __restrict__ red_cnt, int red_n) {
   extern __shared__ __align__(128) uint8_t ring_smem[];
+  pdl_enter();  // first global access below (no-op unless launched through launch_pdl)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c4 = C >> 2, HP = H >> 1;
   if (blockIdx.x == 0)  // arrival counters of the fold roles in the src kernel
@@ -2020,9 +2027,10 @@ int launch_fwd_ring(const void* x_l, const void* x_r, int64_t ld_x, const void* 
   if (e != cudaSuccess) return (int)e;
   // one CTA per EDGE_WARPS (node, head) tasks: the block scheduler balances the degree spread
   const int64_t blocks = ceil_div(NH, (int64_t)EDGE_WARPS);
-  kern<<<(unsigned)blocks, EDGE_WARPS * 32, smem, stream>>>(
-      (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, bias, emask, dst_ptr, dst_nbr,
-      dst_eid, dst_order, (float*)out, ld_out, alpha, NH, H, C, slope);
+  e = launch_pdl(kern, dim3((unsigned)blocks), dim3(EDGE_WARPS * 32), smem, stream, (const float*)x_l,
+                 (const float*)x_r, ld_x, (const float*)e_proj, att, bias, emask, dst_ptr, dst_nbr, dst_eid, dst_order,
+                 (float*)out, ld_out, alpha, NH, H, C, slope);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -2059,10 +2067,11 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
   cudaError_t e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
   if (e != cudaSuccess) return (int)e;
-  kd<<<(unsigned)plan.blocks, EDGE_WARPS * 32, smem_d, stream>>>(
-      (const float*)g_out, ld_g, (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, emask, alpha,
-      dst_ptr, dst_nbr, dst_eid, dst_order, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H, C, slope,
-      plan.K, ep_keep_mode(), red_cnt, fold_cb);
+  e = launch_pdl(kd, dim3((unsigned)plan.blocks), dim3(EDGE_WARPS * 32), smem_d, stream, (const float*)g_out, ld_g,
+                 (const float*)x_l, (const float*)x_r, ld_x, (const float*)e_proj, att, emask, alpha, dst_ptr, dst_nbr,
+                 dst_eid, dst_order, (float*)g_xr, ld_gx, (float*)g_eproj, gatt_part, gm_h, N, H, C, slope, plan.K,
+                 ep_keep_mode(), red_cnt, fold_cb);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   const int64_t NH = N * H;
   AttFold fold;
@@ -2088,9 +2097,10 @@ int launch_bwd_ring(const void* g_out, int64_t ld_g, const void* x_l, const void
                                                                                      g_att);
     ISG_CHECK_LAUNCH();
   }
-  ks<<<(unsigned)(fold.red_blocks + fold.gm_blocks + ceil_div(NH, (int64_t)EDGE_WARPS)), EDGE_WARPS * 32, smem_s,
-       stream>>>((const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, src_order,
-                 (float*)g_xl, ld_gx, NH, H, C, fold);
+  e = launch_pdl(ks, dim3((unsigned)(fold.red_blocks + fold.gm_blocks + ceil_div(NH, (int64_t)EDGE_WARPS))),
+                 dim3(EDGE_WARPS * 32), smem_s, stream, (const float*)g_out, ld_g, (const float*)g_eproj, emask, alpha,
+                 src_ptr, src_nbr, src_eid, src_order, (float*)g_xl, ld_gx, NH, H, C, fold);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   if (!folded && MASKED && E > 0) {
     gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);
@@ -2203,9 +2213,10 @@ int launch_fwd_pair(const void* x_l, const void* x_r, int64_t ld_x, const void* 
   auto kern = gat_edge_fwd_pair_kernel<VPL, MASKED>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<(unsigned)ceil_div(NP, (int64_t)EDGE_WARPS), EDGE_WARPS * 32, smem, stream>>>(
-      (const __nv_bfloat16*)x_l, (const __nv_bfloat16*)x_r, ld_x, (const __nv_bfloat16*)e_proj, att, bias, emask, dst_ptr,
-      dst_nbr, dst_eid, dst_order, (__nv_bfloat16*)out, ld_out, alpha, NP, H, C, slope);
+  e = launch_pdl(kern, dim3((unsigned)ceil_div(NP, (int64_t)EDGE_WARPS)), dim3(EDGE_WARPS * 32), smem, stream,
+                 (const __nv_bfloat16*)x_l, (const __nv_bfloat16*)x_r, ld_x, (const __nv_bfloat16*)e_proj, att, bias, emask,
+                 dst_ptr, dst_nbr, dst_eid, dst_order, (__nv_bfloat16*)out, ld_out, alpha, NP, H, C, slope);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -2226,10 +2237,11 @@ int launch_bwd_pair(const void* g_out, int64_t ld_g, const void* x_l, const void
   if (e != cudaSuccess) return (int)e;
   const int64_t NP = N * (H / 2);
   const unsigned blocks = (unsigned)ceil_div(NP, (int64_t)EDGE_WARPS);
-  kd<<<blocks, EDGE_WARPS * 32, smem_d, stream>>>(
-      (const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)x_l, (const __nv_bfloat16*)x_r, ld_x,
-      (const __nv_bfloat16*)e_proj, att, emask, alpha, dst_ptr, dst_nbr, dst_eid, dst_order, (__nv_bfloat16*)g_xr, ld_gx,
-      (__nv_bfloat16*)g_eproj, gatt_part, gm_h, N, H, C, slope, red_cnt, fold_cb);
+  e = launch_pdl(kd, dim3(blocks), dim3(EDGE_WARPS * 32), smem_d, stream, (const __nv_bfloat16*)g_out, ld_g,
+                 (const __nv_bfloat16*)x_l, (const __nv_bfloat16*)x_r, ld_x, (const __nv_bfloat16*)e_proj, att, emask, alpha,
+                 dst_ptr, dst_nbr, dst_eid, dst_order, (__nv_bfloat16*)g_xr, ld_gx, (__nv_bfloat16*)g_eproj, gatt_part, gm_h,
+                 N, H, C, slope, red_cnt, fold_cb);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   const int HC = H * C;
   const int64_t parts2 = (N + GR_ROWS - 1) / GR_ROWS;  // gatt_part viewed as [N rows, H*C], keyed by the node
@@ -2253,9 +2265,10 @@ int launch_bwd_pair(const void* g_out, int64_t ld_g, const void* x_l, const void
     gat_att_reduce2_kernel<<<ceil_div(HC / 4, 64), dim3(64, GR2_LANES), 0, stream>>>(gatt_part2, (int)parts2, HC, g_att);
     ISG_CHECK_LAUNCH();
   }
-  ks<<<blocks + (unsigned)(fold.red_blocks + fold.gm_blocks), EDGE_WARPS * 32, smem_s, stream>>>(
-      (const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid, src_order,
-      (__nv_bfloat16*)g_xl, ld_gx, NP, H, C, fold);
+  e = launch_pdl(ks, dim3(blocks + (unsigned)(fold.red_blocks + fold.gm_blocks)), dim3(EDGE_WARPS * 32), smem_s, stream,
+                 (const __nv_bfloat16*)g_out, ld_g, (const __nv_bfloat16*)g_eproj, emask, alpha, src_ptr, src_nbr, src_eid,
+                 src_order, (__nv_bfloat16*)g_xl, ld_gx, NP, H, C, fold);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   if (!folded && MASKED && E > 0) {
     gm_head_sum_kernel<<<ceil_div(E, 256), 256, 0, stream>>>(gm_h, E, H, g_emask);

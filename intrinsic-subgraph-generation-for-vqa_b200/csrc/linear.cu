@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(GemmArgs g) {
 // out[i] = sum_s part[s*stride + i]   (fixed order)
 __global__ void split_reduce_kernel(const float* __restrict__ part, int splits, int64_t stride, int64_t n,
                                     float* __restrict__ out) {
+  pdl_enter();
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 s = f4_zero();
@@ -325,7 +326,9 @@ extern "C" int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int
     if (rc != ISG_OK) return rc;
     if (ts > 1) {
       const int64_t n = (int64_t)Nout * K;
-      split_reduce_kernel<<<isg::ceil_div(n / 4, 256), 256, 0, stream>>>((const float*)workspace, ts, n, n, g_w);
+      cudaError_t le = isg::launch_pdl(split_reduce_kernel, dim3((unsigned)isg::ceil_div(n / 4, 256)), dim3(256), 0, stream,
+                                       (const float*)workspace, ts, n, n, g_w);
+      if (le != cudaSuccess) return (int)le;
       ISG_CHECK_LAUNCH();
     }
     return ISG_OK;
@@ -347,7 +350,9 @@ extern "C" int isg_linear_wgrad(const void* g_y, int64_t ldg, const void* x, int
   ISG_CHECK_LAUNCH();
   if (splits > 1) {
     const int64_t n = (int64_t)Nout * K;
-    split_reduce_kernel<<<isg::ceil_div(n / 4, 256), 256, 0, stream>>>((const float*)workspace, splits, n, n, g_w);
+    cudaError_t le = isg::launch_pdl(split_reduce_kernel, dim3((unsigned)isg::ceil_div(n / 4, 256)), dim3(256), 0, stream,
+                                     (const float*)workspace, splits, n, n, g_w);
+    if (le != cudaSuccess) return (int)le;
     ISG_CHECK_LAUNCH();
   }
   (void)g_b;  // bias gradient: the caller runs isg_colsum(g_y) (keeps this entry point a pure GEMM)

@@ -159,6 +159,7 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();  // on-chip set-up above overlaps the previous kernel's tail; operands are read from here on
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int tiles_mn = g.m_tiles * g.n_tiles;
@@ -535,7 +536,8 @@ int launch16(const BfGemm& p, cudaStream_t stream) {
   if (e != cudaSuccess) return (int)e;
   const int total = g.m_tiles * g.n_tiles * g.splits;
   const int grid = total < ISG_NUM_SMS ? total : ISG_NUM_SMS;
-  kern<<<grid, NTHREADS, smem, stream>>>(ma, mb, g);
+  e = launch_pdl(kern, dim3((unsigned)grid), dim3(NTHREADS), (size_t)smem, stream, ma, mb, g);
+  if (e != cudaSuccess) return (int)e;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -567,6 +569,7 @@ int wgrad_splits16(int64_t M, int Nout, int K, int64_t* r_chunk) {
 
 __global__ void split_reduce16_kernel(const float* __restrict__ part, int splits, int64_t stride, int64_t n,
                                       float* __restrict__ out) {
+  pdl_enter();
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 s = f4_zero();
@@ -737,7 +740,9 @@ extern "C" int isg_linear_bf16_wgrad(const void* g_y, int64_t ldg, const void* x
   if (rc != ISG_OK) return rc;
   if (ts > 1) {
     const int64_t n = (int64_t)Nout * K;
-    split_reduce16_kernel<<<isg::ceil_div(n / 4, 256), 256, 0, stream>>>((const float*)workspace, ts, n, n, g_w);
+    cudaError_t le = isg::launch_pdl(split_reduce16_kernel, dim3((unsigned)isg::ceil_div(n / 4, 256)), dim3(256), 0, stream,
+                                     (const float*)workspace, ts, n, n, g_w);
+    if (le != cudaSuccess) return (int)le;
     ISG_CHECK_LAUNCH();
   }
   return ISG_OK;

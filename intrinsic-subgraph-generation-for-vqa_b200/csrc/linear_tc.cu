@@ -234,6 +234,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CL > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive
   else __syncthreads();
   tc_fence_after();
+  // everything above is on-chip set-up and overlaps the previous kernel's tail; the operands are read from here on
+  pdl_enter();
   const uint32_t tmem_base = *tmem_slot_gen;
 
   // Work items are (split, M-tile group of CL adjacent tiles, N block); CTA `cta_rank` of the cluster takes
@@ -728,13 +730,14 @@ int launch(const isg::TcGemm& p, cudaStream_t stream) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)CLh;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  pdl_attribute(&attr[1]);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (CLh > 1 && getenv("ISG_TC_VERBOSE")) {
     int nclusters = -1;
     cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);

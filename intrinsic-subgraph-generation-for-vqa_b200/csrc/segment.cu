@@ -15,6 +15,7 @@ using namespace isg;
 __global__ void instr_gate_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ins,
                                       const int* __restrict__ batch, int64_t N, int D4,
                                       float* __restrict__ y) {
+  pdl_enter();
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // over N * D4 float4s
   if (idx >= N * D4) return;
   const int64_t n = idx / D4;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(IG_COLS * IG_LANES)
 instr_gate_bwd_v4_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ ins,
                          const int* __restrict__ gptr, int D, const float* __restrict__ gres, int acc_ins,
                          float* __restrict__ gx, float* __restrict__ gins) {
+  pdl_enter();
   __shared__ float4 red[IG_LANES][IG_COLS];
   const int b = blockIdx.x;
   const int n0 = gptr[b], n1 = gptr[b + 1];
@@ -435,6 +437,7 @@ sdpa_graphnorm_fwd_v4_kernel(const float* __restrict__ v, const float* __restric
                              const float* __restrict__ mean_scale, const int* __restrict__ gptr, int D, float eps,
                              float* __restrict__ h_out, float* __restrict__ a_out, float* __restrict__ mean_out,
                              float* __restrict__ rstd_out) {
+  pdl_enter();
   extern __shared__ float sm[];  // [nmax] attention weights
   __shared__ float red1[32];
   __shared__ float4 red[SG_LANES][SG_COLS];
@@ -526,6 +529,7 @@ sdpa_graphnorm_bwd_v4_kernel(const float* __restrict__ g, const float* __restric
                              const int* __restrict__ gptr, int D, float* __restrict__ g_v, float* __restrict__ g_ins,
                              float* __restrict__ gw_part, float* __restrict__ gb_part, float* __restrict__ gms_part,
                              const float* __restrict__ zg) {
+  pdl_enter();
   // dynamic smem: coefA[D], coefB[D], coefC[D], shift[D], sa[cnt], sga[cnt]
   extern __shared__ __align__(16) float sm4[];
   __shared__ float red1[32];
@@ -777,6 +781,7 @@ attn_pool_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ 
 
 // gz may alias gy (the layer executor runs it in place): no __restrict__ on those two
 __global__ void gelu_bwd_kernel(const float* gy, const float* __restrict__ z, float* gz, int64_t n) {
+  pdl_enter();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) gz[i] = gy[i] * gelu_grad_f(z[i]);
 }
@@ -786,6 +791,7 @@ constexpr int CS_ROWS = 64;  // rows per partial
 // CS_ROWS independent loads per thread, grid = (cols/4/128) x (rows/CS_ROWS) CTAs.
 __global__ void colsum_partial_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
                                       float* __restrict__ part) {
+  pdl_enter();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= cols) return;
   const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
@@ -809,6 +815,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ in, int64_t ld, 
 constexpr int CS_LANES = 16;
 __global__ void __launch_bounds__(64 * CS_LANES)
 colsum_final_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float4 red[CS_LANES][64];
   const int c = (blockIdx.x * 64 + threadIdx.x) * 4;
   float4 s = f4_zero();
@@ -851,6 +858,7 @@ struct ColsumBatch {
 };
 
 __global__ void __launch_bounds__(64) colsum_multi_partial_kernel(const __grid_constant__ ColsumBatch batch) {
+  pdl_enter();
   int j = 0;
   while (j + 1 < batch.n && (int)blockIdx.x >= batch.job[j + 1].block0) ++j;
   const ColsumJob& J = batch.job[j];
@@ -888,6 +896,7 @@ __global__ void __launch_bounds__(64) colsum_multi_partial_kernel(const __grid_c
 }
 
 __global__ void __launch_bounds__(64 * CS_LANES) colsum_multi_final_kernel(const __grid_constant__ ColsumBatch batch) {
+  pdl_enter();
   __shared__ float4 red[CS_LANES][64];
   int j = 0;
   while (j + 1 < batch.n && (int)blockIdx.x >= batch.job[j + 1].fblock0) ++j;
@@ -926,7 +935,9 @@ extern "C" int isg_instr_gate_fwd(const float* x, const float* ins, const int32_
   if (N == 0) return ISG_OK;
   if (!x || !ins || !batch32 || !y) return ISG_EINVAL;
   const int64_t total = N * (D / 4);
-  instr_gate_fwd_kernel<<<isg::ceil_div(total, 256), 256, 0, (cudaStream_t)stream_>>>(x, ins, batch32, N, D / 4, y);
+  cudaError_t le = isg::launch_pdl(instr_gate_fwd_kernel, dim3((unsigned)isg::ceil_div(total, 256)), dim3(256), 0,
+                                   (cudaStream_t)stream_, x, ins, batch32, N, D / 4, y);
+  if (le != cudaSuccess) return (int)le;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -939,10 +950,11 @@ extern "C" int isg_instr_gate_bwd(const float* g_y, const float* x, const float*
   if (!g_y || !x || !ins || !gptr || !g_x || !g_ins) return ISG_EINVAL;
   const bool v4 = D % 4 == 0 && !(((uintptr_t)g_y | (uintptr_t)x | (uintptr_t)ins | (uintptr_t)g_x | (uintptr_t)g_ins |
                                    (uintptr_t)g_residual) & 15);
-  if (v4)
-    instr_gate_bwd_v4_kernel<<<(unsigned)B, IG_COLS * IG_LANES, 0, (cudaStream_t)stream_>>>(
-        g_y, x, ins, gptr, D, g_residual, accumulate_ins, g_x, g_ins);
-  else
+  if (v4) {
+    cudaError_t le = isg::launch_pdl(instr_gate_bwd_v4_kernel, dim3((unsigned)B), dim3(IG_COLS * IG_LANES), 0,
+                                     (cudaStream_t)stream_, g_y, x, ins, gptr, D, g_residual, accumulate_ins, g_x, g_ins);
+    if (le != cudaSuccess) return (int)le;
+  } else
     instr_gate_bwd_kernel<<<(unsigned)B, 320, 0, (cudaStream_t)stream_>>>(g_y, x, ins, gptr, D, g_residual,
                                                                           accumulate_ins, g_x, g_ins);
   ISG_CHECK_LAUNCH();
@@ -1015,8 +1027,10 @@ extern "C" int isg_sdpa_graphnorm_fwd(const float* v, const float* ins, const fl
       cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_fwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    sdpa_graphnorm_fwd_v4_kernel<<<(unsigned)B, SG_COLS * SG_LANES, smem, (cudaStream_t)stream_>>>(
-        v, ins, h_in, weight, bias, mean_scale, gptr, D, eps, h_out, a, mean, rstd);
+    cudaError_t le = isg::launch_pdl(sdpa_graphnorm_fwd_v4_kernel, dim3((unsigned)B), dim3(SG_COLS * SG_LANES), smem,
+                                     (cudaStream_t)stream_, v, ins, h_in, weight, bias, mean_scale, gptr, D, eps, h_out, a,
+                                     mean, rstd);
+    if (le != cudaSuccess) return (int)le;
     ISG_CHECK_LAUNCH();
     return ISG_OK;
   }
@@ -1050,8 +1064,10 @@ extern "C" int isg_sdpa_graphnorm_bwd(const float* g_out, const float* v, const 
       cudaError_t e = cudaFuncSetAttribute(sdpa_graphnorm_bwd_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    sdpa_graphnorm_bwd_v4_kernel<<<(unsigned)B, SG_COLS * SG_LANES, smem, (cudaStream_t)stream_>>>(
-        g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v, g_ins, gw_part, gb_part, gms_part, z_gelu);
+    cudaError_t le = isg::launch_pdl(sdpa_graphnorm_bwd_v4_kernel, dim3((unsigned)B), dim3(SG_COLS * SG_LANES), smem,
+                                     (cudaStream_t)stream_, g_out, v, ins, weight, mean_scale, a, mean, rstd, gptr, D, g_v,
+                                     g_ins, gw_part, gb_part, gms_part, z_gelu);
+    if (le != cudaSuccess) return (int)le;
     ISG_CHECK_LAUNCH();
     return ISG_OK;
   }
@@ -1102,7 +1118,9 @@ extern "C" int isg_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_
   if (n < 0) return ISG_EINVAL;
   if (n == 0) return ISG_OK;
   if (!g_y || !z || !g_z) return ISG_EINVAL;
-  gelu_bwd_kernel<<<isg::ceil_div(n, 256), 256, 0, (cudaStream_t)stream_>>>(g_y, z, g_z, n);
+  cudaError_t le = isg::launch_pdl(gelu_bwd_kernel, dim3((unsigned)isg::ceil_div(n, 256)), dim3(256), 0,
+                                   (cudaStream_t)stream_, g_y, z, g_z, n);
+  if (le != cudaSuccess) return (int)le;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -1124,10 +1142,13 @@ extern "C" int isg_colsum(const float* in, int64_t ld, int64_t rows, int cols, f
   if (cols % 4 != 0 || ld % 4 != 0 || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return ISG_EUNSUPPORTED;
   if (ws_bytes < isg_colsum_workspace_bytes(rows, cols) || !workspace) return ISG_EWORKSPACE;
   const int parts = (int)((rows + CS_ROWS - 1) / CS_ROWS);
-  colsum_partial_kernel<<<dim3(isg::ceil_div(cols / 4, 64), parts), 64, 0, stream>>>(in, ld, rows, cols, (float*)workspace);
+  cudaError_t le = isg::launch_pdl(colsum_partial_kernel, dim3(isg::ceil_div(cols / 4, 64), parts), dim3(64), 0, stream, in,
+                                   ld, rows, cols, (float*)workspace);
+  if (le != cudaSuccess) return (int)le;
   ISG_CHECK_LAUNCH();
-  colsum_final_kernel<<<isg::ceil_div(cols / 4, 64), dim3(64, CS_LANES), 0, stream>>>((const float*)workspace, parts,
-                                                                                      cols, out);
+  le = isg::launch_pdl(colsum_final_kernel, dim3(isg::ceil_div(cols / 4, 64)), dim3(64, CS_LANES), 0, stream,
+                       (const float*)workspace, parts, cols, out);
+  if (le != cudaSuccess) return (int)le;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
@@ -1179,9 +1200,11 @@ extern "C" int isg_colsum_multi(int n, const void* const* in, const int* dtypes,
     fblocks += J.cblocks;
   }
   if (batch.n == 0) return ISG_OK;
-  colsum_multi_partial_kernel<<<blocks, 64, 0, stream>>>(batch);
+  cudaError_t le = isg::launch_pdl(colsum_multi_partial_kernel, dim3(blocks), dim3(64), 0, stream, batch);
+  if (le != cudaSuccess) return (int)le;
   ISG_CHECK_LAUNCH();
-  colsum_multi_final_kernel<<<fblocks, dim3(64, CS_LANES), 0, stream>>>(batch);
+  le = isg::launch_pdl(colsum_multi_final_kernel, dim3(fblocks), dim3(64, CS_LANES), 0, stream, batch);
+  if (le != cudaSuccess) return (int)le;
   ISG_CHECK_LAUNCH();
   return ISG_OK;
 }
