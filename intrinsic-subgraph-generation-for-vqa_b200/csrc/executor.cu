@@ -29,6 +29,8 @@
   X(D_BF16)            /* 1: bf16 configuration — projections on kind::f16, bf16 storage of xlr / e_proj / out /   \
                           y1 / z1 and of the gradients g_z1 / g_out / g_xlr / g_eproj (the P_*_BF slots are set) */ \
   X(D_SIDE_WGRAD)      /* 1: the weight-gradient products run on P_SIDE_STREAM, forked / joined with P_EV_FORK / P_EV_JOIN */ \
+  X(D_EPROJ_READY)     /* 1 (forward): P_EPROJ is being written by a lin_edge product the host issued on another    \
+                          stream (edge_attr does not depend on the layer); the edge kernel waits for P_EV_EPROJ */  \
   X(D_WS_BYTES)
 #define ISG_LAYER_SCALARS(X) X(F_SLOPE) X(F_EPS) X(F_ALPHA) X(F_BETA) X(F_TAU_IN) X(F_TAU_TGT) X(F_GUMBEL_TAU)
 #define ISG_LAYER_PTRS(X)                                                                                      \
@@ -52,7 +54,7 @@
   X(P_G_X_IN) X(P_G_INS) X(P_G_GLF) X(P_G_EDGE_ATTR)                                                             \
   X(P_G_W_LR) X(P_G_B_LR) X(P_G_W_E) X(P_G_ATT) X(P_G_BIAS) X(P_G_WP0) X(P_G_BP0) X(P_G_WP2) X(P_G_BP2)          \
   X(P_G_BN_W) X(P_G_BN_B) X(P_G_BN_MS) X(P_G_WN) X(P_G_BNN) X(P_G_WQ) X(P_G_BQ)                                   \
-  X(P_SIDE_STREAM) X(P_EV_FORK) X(P_EV_JOIN)                                                                    \
+  X(P_SIDE_STREAM) X(P_EV_FORK) X(P_EV_JOIN) X(P_EV_EPROJ)                                                       \
   X(P_WS)
 // clang-format on
 
@@ -247,9 +249,13 @@ extern "C" int isg_mgat_layer_fwd(const int64_t* d, const double* f, void* const
   float* xlr = ptr<float>(p, P_XLR);
   CK(isg_linear_fwd(xg, D, p[P_W_LR], nullptr, nullptr, ptr<const float>(p, P_B_LR), xlr, 2 * HC, nullptr, 0, N, 2 * HC,
                     D, ISG_ACT_NONE, mode, ISG_F32, stream));  // :177,181 (lin_l | lin_r, stacked weights)
-  if (E > 0)
+  if (E > 0 && !d[D_EPROJ_READY])
     CK(isg_linear_fwd(p[P_EDGE_ATTR], D, p[P_W_E], nullptr, nullptr, nullptr, p[P_EPROJ], HC, nullptr, 0, E, HC, D,
                       ISG_ACT_NONE, mode, ISG_F32, stream));  // :259
+  if (d[D_EPROJ_READY] && p[P_EV_EPROJ]) {
+    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)p[P_EV_EPROJ], 0);
+    if (e != cudaSuccess) return (int)e;
+  }
   CK(isg_gat_edge_fwd(xlr, xlr + HC, 2 * HC, p[P_EPROJ], ptr<const float>(p, P_ATT), ptr<const float>(p, P_BIAS), emask,
                       ptr<const int32_t>(p, P_DST_PTR), ptr<const int32_t>(p, P_DST_NBR),
                       ptr<const int32_t>(p, P_DST_EID), ptr<const int32_t>(p, P_DST_ORDER), p[P_OUT], HC,

@@ -54,13 +54,27 @@ def _side_handles(device):
     h = _side.get(device)
     if h is None:
         st = torch.cuda.Stream(device=device)
-        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        evs = [torch.cuda.Event() for _ in range(2 + _MAX_EPROJ_EVENTS)]
         if torch.cuda.is_current_stream_capturing():
             return None  # the events must exist before a capture starts (first use happens in the warm-up steps)
         for ev in evs:
             ev.record()  # materialises the cudaEvent_t
-        h = _side[device] = (st, evs)
+        h = _side[device] = (st, evs[:2], evs[2:])
     return h
+
+
+# Forward: the lin_edge products of ALL layers depend on edge_attr only, so they are issued on the side stream at the
+# start of the forward pass and run beside the main stream's chain — gating, the gate projections and the sampler of
+# a masked layer, lin_l|lin_r, the x_proj pair, scatter-SDPA + GraphNorm — most of which are launches that fill a
+# fraction of the 148 SMs (one CTA per graph, or a last wave of a few tiles).  Layer i's edge kernel waits for event i.
+# ISG_SIDE_EPROJ=0 keeps the products inside the layer call on the caller's stream.
+_SIDE_EPROJ = os.environ.get("ISG_SIDE_EPROJ", "1") != "0"
+_MAX_EPROJ_EVENTS = 8
+
+
+def set_side_eproj(on):
+    global _SIDE_EPROJ
+    _SIDE_EPROJ = bool(on)
 
 
 def _al(nbytes):
@@ -325,11 +339,27 @@ class MgatFunction(torch.autograd.Function):
             ctx.bf_keep = (ea_bf, wbuf)
         ctx.bf = bf
         x_in_ptr = x.data_ptr()
+        side = _side_handles(x.device) if (_SIDE_EPROJ and not bf16 and E > 0 and pl.L <= _MAX_EPROJ_EVENTS) else None
+        if side is not None:
+            side_st, (ev_fork, _ev_join), ev_eproj = side
+            cur = torch.cuda.current_stream(x.device)
+            ev_fork.record(cur)  # edge_attr, the weights and the arena are ready in the caller's stream order
+            side_st.wait_event(ev_fork)
+            sst = side_st.cuda_stream
+            for i in range(pl.L):
+                w_e = model.convs[i].lin_edge.weight
+                L.call("isg_linear_fwd", edge_attr.data_ptr(), pl.D, w_e.data_ptr(), None, None, None,
+                       ap + pl.act[i]["P_EPROJ"], pl.HC, None, 0, E, pl.HC, pl.D, L.ACT_NONE, gemm_mode, L.F32, sst)
+                ev_eproj[i].record(side_st)
         for i in range(pl.L):
             d, f, p = _arrays()
             _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, iv.data_ptr() + i * B * pl.D * 4, glf, edge_attr,
                          specs[i], ap, gemm_mode, bf)
-            L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, False, bf16))
+            n_launch = kernel_launches(specs[i], gi, False, bf16)
+            if side is not None:
+                d[s.D_EPROJ_READY], p[s.P_EV_EPROJ] = 1, ev_eproj[i].cuda_event
+                n_launch -= L.KERNELS_PER_CALL["isg_linear_fwd"]  # counted with the side-stream call above
+            L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=n_launch)
             x_in_ptr = ap + pl.act[i]["P_H_OUT"]
         ctx.model, ctx.gi, ctx.specs, ctx.pl, ctx.gemm_mode, ctx.arena = model, gi, specs, pl, gemm_mode, arena
         ctx.save_for_backward(x, edge_attr, iv, glf, *params)

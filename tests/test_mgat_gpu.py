@@ -95,6 +95,31 @@ def test_layer_executor_matches_per_operator_path(sampler, train, k):
                 assert util.rel_err(a["param_grads"][name], g) <= 1e-5, name
 
 
+@pytest.mark.parametrize("sampler,train", [("aimle", True), ("gumbel", False)])
+def test_side_stream_edge_projections_change_no_bit(sampler, train):
+    """The forward issues the lin_edge products of all layers on the side stream at the start of the pass
+    (executor.py, ISG_SIDE_EPROJ); the same kernels on the same operands, so every output and gradient is
+    bit-identical to the in-order issue, also over two consecutive steps (arena and events re-used)."""
+    from isg_b200.isubgvqa import executor
+
+    cfg = dict(sampler=sampler, train=train, channels=300, num_graphs=24, mean_nodes=16, mean_edges=110, k=2,
+               seed=909, steps=2, aimle_beta0=2.0 if sampler == "aimle" else None)
+    res = {}
+    for on in (True, False):
+        executor.set_side_eproj(on)
+        try:
+            res[on] = util.run_cuda_case(cfg, executor=True)
+        finally:
+            executor.set_side_eproj(True)
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a["h"], b["h"]) and torch.equal(a["mask"], b["mask"])
+        if train:
+            for key in ("gx", "g_edge_attr", "g_instr", "g_glf"):
+                assert torch.equal(a[key], b[key]), key
+            for name, g in b["param_grads"].items():
+                assert (g is None and a["param_grads"][name] is None) or torch.equal(a["param_grads"][name], g), name
+
+
 def test_layer_executor_accumulates_into_existing_grads_and_external_mask_gradient():
     """Two backward passes without zero_grad add up (the flat gradient buffer is fresh per backward), and a
     gradient that reaches the returned node mask from OUTSIDE MGAT (the pooling layer multiplies by it,
