@@ -500,6 +500,8 @@ def main_isg(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_step_log = []  # per-step times of every timed() pass, in call order (ISG_BENCH_PER_STEP=1 prints them)
+
     def timed(fn, steps, timing_names=None):
         evs = []
         barrier()
@@ -516,6 +518,7 @@ def main_isg(args, rank, world, local_rank):
         barrier()
         t = L.disable_timing() if timing_names else None
         ms = sum(a.elapsed_time(e) for a, e in evs)
+        per_step_log.append([round(a.elapsed_time(e), 4) for a, e in evs])
         if world > 1:
             tt = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -769,6 +772,8 @@ def main_isg(args, rank, world, local_rank):
     if args.breakdown:
         line["breakdown_ms_per_step"] = {k: round(v[1] / args.steps, 4)
                                          for k, v in sorted(tall.items(), key=lambda kv: -kv[1][1])}
+    if os.environ.get("ISG_BENCH_PER_STEP") == "1":  # diagnostics: [eager pass, replay pass, per-operator pass]
+        line["per_step_ms"] = per_step_log
     out_stream.write(json.dumps(line) + "\n")
     out_stream.flush()
     teardown()

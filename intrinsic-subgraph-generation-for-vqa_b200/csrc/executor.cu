@@ -29,6 +29,10 @@
   X(D_BF16)            /* 1: bf16 configuration — projections on kind::f16, bf16 storage of xlr / e_proj / out /   \
                           y1 / z1 and of the gradients g_z1 / g_out / g_xlr / g_eproj (the P_*_BF slots are set) */ \
   X(D_SIDE_WGRAD)      /* 1: the weight-gradient products run on P_SIDE_STREAM, forked / joined with P_EV_FORK / P_EV_JOIN */ \
+  X(D_DEFER_JOIN)      /* 1 (backward, with D_SIDE_WGRAD): the main stream does not wait for this layer's weight         \
+                          gradients at the end of the call — P_EV_JOIN is only recorded on the side stream; the host     \
+                          alternates two workspaces, passes the event of the layer that used this one last as           \
+                          P_EV_WS_FREE (waited for before the first kernel) and joins after the last layer */            \
   X(D_EPROJ_READY)     /* 1 (forward): P_EPROJ is being written by a lin_edge product the host issued on another    \
                           stream (edge_attr does not depend on the layer); the edge kernel waits for P_EV_EPROJ */  \
   X(D_WS_BYTES)
@@ -54,7 +58,7 @@
   X(P_G_X_IN) X(P_G_INS) X(P_G_GLF) X(P_G_EDGE_ATTR)                                                             \
   X(P_G_W_LR) X(P_G_B_LR) X(P_G_W_E) X(P_G_ATT) X(P_G_BIAS) X(P_G_WP0) X(P_G_BP0) X(P_G_WP2) X(P_G_BP2)          \
   X(P_G_BN_W) X(P_G_BN_B) X(P_G_BN_MS) X(P_G_WN) X(P_G_BNN) X(P_G_WQ) X(P_G_BQ)                                   \
-  X(P_SIDE_STREAM) X(P_EV_FORK) X(P_EV_JOIN) X(P_EV_EPROJ)                                                       \
+  X(P_SIDE_STREAM) X(P_EV_FORK) X(P_EV_JOIN) X(P_EV_EPROJ) X(P_EV_WS_FREE)                                                      \
   X(P_WS)
 // clang-format on
 
@@ -228,9 +232,13 @@ extern "C" int isg_mgat_layer_fwd(const int64_t* d, const double* f, void* const
     CK(isg_to_bf16(xg, D, N, D, p[P_XG_BF], Dp, stream));
     CK(isg_linear_bf16_fwd(p[P_XG_BF], Dp, p[P_W_LR_BF], Dp, ptr<const float>(p, P_B_LR), p[P_XLR], 2 * HC, nullptr, 0, N,
                            2 * HC, D, ISG_ACT_NONE, ISG_BF16, stream));
-    if (E > 0)
+    if (E > 0 && !d[D_EPROJ_READY])
       CK(isg_linear_bf16_fwd(p[P_EDGE_ATTR_BF], Dp, p[P_W_E_BF], Dp, nullptr, p[P_EPROJ], HC, nullptr, 0, E, HC, D,
                              ISG_ACT_NONE, ISG_BF16, stream));
+    if (d[D_EPROJ_READY] && p[P_EV_EPROJ]) {
+      cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)p[P_EV_EPROJ], 0);
+      if (e != cudaSuccess) return (int)e;
+    }
     const __nv_bfloat16* xlr16 = ptr<const __nv_bfloat16>(p, P_XLR);
     CK(isg_gat_edge_fwd(xlr16, xlr16 + HC, 2 * HC, p[P_EPROJ], ptr<const float>(p, P_ATT), ptr<const float>(p, P_BIAS),
                         emask, ptr<const int32_t>(p, P_DST_PTR), ptr<const int32_t>(p, P_DST_NBR),
@@ -335,6 +343,10 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
     return e == cudaSuccess ? ISG_OK : (int)e;
   };
 
+  if (p[P_EV_WS_FREE]) {  // deferred join: the weight gradients of the layer that used this workspace last
+    cudaError_t e = cudaStreamWaitEvent(stream, (cudaEvent_t)p[P_EV_WS_FREE], 0);
+    if (e != cudaSuccess) return (int)e;
+  }
   // scatter-SDPA + GraphNorm + residual (mgat.py:168-172); the residual's share of g_h_in is added in the last step
   CK(isg_sdpa_graphnorm_bwd(g_h_out, ptr<const float>(p, P_Y2), ins, ptr<const float>(p, P_BN_W),
                             ptr<const float>(p, P_BN_MS), ptr<const float>(p, P_SA), ptr<const float>(p, P_MEAN),
@@ -467,9 +479,9 @@ extern "C" int isg_mgat_layer_bwd(const int64_t* d, const double* f, void* const
                         wstream));
     CK(colsum(g_q, B, D, P_G_BQ));
   }
-  if (side_on) {  // join: the next layer's backward re-uses this workspace
+  if (side_on) {  // join: the next layer's backward re-uses this workspace (D_DEFER_JOIN: the host alternates two)
     cudaError_t e = cudaEventRecord((cudaEvent_t)p[P_EV_JOIN], (cudaStream_t)p[P_SIDE_STREAM]);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, (cudaEvent_t)p[P_EV_JOIN], 0);
+    if (e == cudaSuccess && !d[D_DEFER_JOIN]) e = cudaStreamWaitEvent(stream, (cudaEvent_t)p[P_EV_JOIN], 0);
     if (e != cudaSuccess) return (int)e;
   }
   CK(isg_colsum_multi(cs_n, cs_in, cs_dt, cs_ld, cs_rows, cs_cols, cs_out, cs, w.colsum_bytes, stream_));

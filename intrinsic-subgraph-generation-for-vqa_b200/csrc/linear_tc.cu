@@ -331,6 +331,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int it = 0;
     for (int t = work0; t < total_tiles; t += work_stride, ++it) {
       const int num_kb = tile_kb(t);
+      // k-steps of the LAST k-block that hold reduction elements (TMA zero-fills the rest: K = 300 leaves 12 of 32,
+      // i.e. two of four k-steps; products with an all-zero operand add +0 and are not issued)
+      const int last_ksteps = [&] {
+        const int split = t / tiles_mn;
+        const int64_t r_beg = (int64_t)split * g.r_chunk;
+        const int64_t r_len = min(g.R, r_beg + g.r_chunk) - r_beg;
+        const int rem = (int)(r_len - (int64_t)(num_kb - 1) * BK);
+        return (rem + UMMA_K - 1) / UMMA_K;
+      }();
       const int tp = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       // A ragged last N tile (1200 = 9 x 128 + 48; 300 = 2 x 128 + 44) is multiplied at ITS width, rounded up to 16,
@@ -360,10 +369,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // carry: all operand addresses are below 227 KiB)
           const uint32_t sdelta = (uint32_t)stage * (stage_bytes >> 4);
           const uint64_t b_hi = b_hi0 + sdelta, b_lo = b_hi + ((off_b_lo - off_b_hi) >> 4);
+          const int ksteps = kb == num_kb - 1 ? last_ksteps : BK / UMMA_K;
           if (SPLIT) {
             const uint32_t a_t = tmem_base + TM_A + (uint32_t)(2 * BK) * (uint32_t)(DEEP ? ts : stage);  // hi at +0, lo at +BK
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k >= ksteps) break;
               const uint64_t bk = (uint64_t)(b_kstep * k);
               if (P2) {
                 umma_tf32_ts_2cta(d_main, a_t + 8u * k, b_hi + bk, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
@@ -380,6 +391,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t a_hi = a_hi0 + sdelta;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k >= ksteps) break;
               const uint64_t ak = (uint64_t)(a_kstep * k), bk = (uint64_t)(b_kstep * k);
               umma_tf32(d_main, a_hi + ak, b_hi + bk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }

@@ -54,12 +54,12 @@ def _side_handles(device):
     h = _side.get(device)
     if h is None:
         st = torch.cuda.Stream(device=device)
-        evs = [torch.cuda.Event() for _ in range(2 + _MAX_EPROJ_EVENTS)]
+        evs = [torch.cuda.Event() for _ in range(4 + _MAX_EPROJ_EVENTS)]
         if torch.cuda.is_current_stream_capturing():
             return None  # the events must exist before a capture starts (first use happens in the warm-up steps)
         for ev in evs:
             ev.record()  # materialises the cudaEvent_t
-        h = _side[device] = (st, evs[:2], evs[2:])
+        h = _side[device] = (st, evs[:2], evs[4:], evs[2:4])
     return h
 
 
@@ -75,6 +75,19 @@ _MAX_EPROJ_EVENTS = 8
 def set_side_eproj(on):
     global _SIDE_EPROJ
     _SIDE_EPROJ = bool(on)
+
+
+# Backward: the join with the side stream at the end of every layer made the main stream wait for the two products
+# forked last (the E-sized lin_edge weight gradient among them), which then ran beside nothing.  With two alternating
+# workspaces layer i's weight gradients may still run while layer i-1's chain is under way; layer i-2 waits for them
+# (it re-uses the workspace) and the main stream joins once after the last layer.  Off when a per-layer hook reads the
+# gradients during the backward pass (dp.LayerGradAllReduce).  ISG_DEFER_JOIN=0 restores the per-layer join.
+_DEFER_JOIN = os.environ.get("ISG_DEFER_JOIN", "1") != "0"
+
+
+def set_defer_join(on):
+    global _DEFER_JOIN
+    _DEFER_JOIN = bool(on)
 
 
 def _al(nbytes):
@@ -339,17 +352,21 @@ class MgatFunction(torch.autograd.Function):
             ctx.bf_keep = (ea_bf, wbuf)
         ctx.bf = bf
         x_in_ptr = x.data_ptr()
-        side = _side_handles(x.device) if (_SIDE_EPROJ and not bf16 and E > 0 and pl.L <= _MAX_EPROJ_EVENTS) else None
+        side = _side_handles(x.device) if (_SIDE_EPROJ and E > 0 and pl.L <= _MAX_EPROJ_EVENTS) else None
         if side is not None:
-            side_st, (ev_fork, _ev_join), ev_eproj = side
+            side_st, (ev_fork, _ev_join), ev_eproj = side[:3]
             cur = torch.cuda.current_stream(x.device)
             ev_fork.record(cur)  # edge_attr, the weights and the arena are ready in the caller's stream order
             side_st.wait_event(ev_fork)
             sst = side_st.cuda_stream
             for i in range(pl.L):
-                w_e = model.convs[i].lin_edge.weight
-                L.call("isg_linear_fwd", edge_attr.data_ptr(), pl.D, w_e.data_ptr(), None, None, None,
-                       ap + pl.act[i]["P_EPROJ"], pl.HC, None, 0, E, pl.HC, pl.D, L.ACT_NONE, gemm_mode, L.F32, sst)
+                if bf16:  # (the conversions of edge_attr and of the weights above are ordered before the fork)
+                    L.call("isg_linear_bf16_fwd", bf[0].data_ptr(), Dp, bf[1][(i, "P_W_E_BF")], Dp, None,
+                           ap + pl.act[i]["P_EPROJ"], pl.HC, None, 0, E, pl.HC, pl.D, L.ACT_NONE, L.BF16, sst)
+                else:
+                    w_e = model.convs[i].lin_edge.weight
+                    L.call("isg_linear_fwd", edge_attr.data_ptr(), pl.D, w_e.data_ptr(), None, None, None,
+                           ap + pl.act[i]["P_EPROJ"], pl.HC, None, 0, E, pl.HC, pl.D, L.ACT_NONE, gemm_mode, L.F32, sst)
                 ev_eproj[i].record(side_st)
         for i in range(pl.L):
             d, f, p = _arrays()
@@ -358,7 +375,7 @@ class MgatFunction(torch.autograd.Function):
             n_launch = kernel_launches(specs[i], gi, False, bf16)
             if side is not None:
                 d[s.D_EPROJ_READY], p[s.P_EV_EPROJ] = 1, ev_eproj[i].cuda_event
-                n_launch -= L.KERNELS_PER_CALL["isg_linear_fwd"]  # counted with the side-stream call above
+                n_launch -= L.KERNELS_PER_CALL["isg_linear_bf16_fwd" if bf16 else "isg_linear_fwd"]  # counted above
             L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=n_launch)
             x_in_ptr = ap + pl.act[i]["P_H_OUT"]
         ctx.model, ctx.gi, ctx.specs, ctx.pl, ctx.gemm_mode, ctx.arena = model, gi, specs, pl, gemm_mode, arena
@@ -415,9 +432,11 @@ class MgatFunction(torch.autograd.Function):
         ws, ws_bytes = None, 0
         hook = getattr(model, "_isg_after_layer_backward", None)
         side = _side_handles(dev) if _SIDE_WGRAD else None
+        defer = side is not None and hook is None and _DEFER_JOIN and pl.L > 1
+        ws_pair = [None, None]
         g_in_ptr = g_h.data_ptr()
         first_ea, first_glf = True, True
-        for i in reversed(range(pl.L)):
+        for idx, i in enumerate(reversed(range(pl.L))):
             d, f, p = _arrays()
             x_in_ptr = x.data_ptr() if i == 0 else ap + pl.act[i - 1]["P_H_OUT"]
             _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, iv.data_ptr() + i * B * D * 4, glf, edge_attr, specs[i],
@@ -425,6 +444,7 @@ class MgatFunction(torch.autograd.Function):
             if ws is None:
                 ws_bytes = int(lib.isg_mgat_layer_bwd_workspace_bytes(_p(d)))
                 ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+                ws_pair = [ws, torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev) if defer else ws]
             d[s.D_WS_BYTES] = ws_bytes
             d[s.D_NEED_GEA] = 1 if need_gea else 0
             d[s.D_ACC_EDGE_ATTR] = 0 if first_ea else 1
@@ -433,11 +453,15 @@ class MgatFunction(torch.autograd.Function):
                 d[s.D_ACC_GLF] = 0 if first_glf else 1
                 first_glf = False
                 p[s.P_G_GLF] = g_glf.data_ptr()
-            p[s.P_WS] = ws.data_ptr()
+            p[s.P_WS] = ws_pair[idx % 2].data_ptr()
             if side is not None:
                 d[s.D_SIDE_WGRAD] = 1
                 p[s.P_SIDE_STREAM], p[s.P_EV_FORK], p[s.P_EV_JOIN] = side[0].cuda_stream, side[1][0].cuda_event, \
                     side[1][1].cuda_event
+                if defer:
+                    d[s.D_DEFER_JOIN] = 1
+                    p[s.P_EV_JOIN] = side[3][idx % 2].cuda_event
+                    p[s.P_EV_WS_FREE] = side[3][idx % 2].cuda_event if idx >= 2 else 0
             p[s.P_G_H_OUT] = g_in_ptr
             p[s.P_G_MASK_EXT] = g_mask.data_ptr() if (g_mask is not None and i == pl.L - 1 and pl.masked[i]) else 0
             out = g_x if i == 0 else pong[i % 2]
@@ -455,6 +479,10 @@ class MgatFunction(torch.autograd.Function):
             if hook is not None:
                 lo, hi = pl.layer_span[i]
                 hook(i, gflat, lo, hi)
+        if defer:  # the side stream is serial: the event of the last layer covers every weight gradient
+            cur = torch.cuda.current_stream(dev)
+            for k in range(min(2, pl.L)):
+                cur.wait_event(side[3][(pl.L - 1 - k) % 2])
         grads = []
         for i in range(pl.L):
             for name, t in layer_params(model, i):

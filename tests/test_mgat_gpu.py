@@ -120,6 +120,30 @@ def test_side_stream_edge_projections_change_no_bit(sampler, train):
                 assert (g is None and a["param_grads"][name] is None) or torch.equal(a["param_grads"][name], g), name
 
 
+@pytest.mark.parametrize("sampler", ["aimle", "imle"])
+def test_deferred_side_stream_join_changes_no_bit(sampler):
+    """Backward: with two alternating workspaces the main stream joins the weight-gradient stream once after the
+    last layer instead of after every layer (executor.py, ISG_DEFER_JOIN); same kernels, same operands — every
+    gradient is bit-identical to the per-layer join, over three consecutive steps."""
+    from isg_b200.isubgvqa import executor
+
+    cfg = dict(sampler=sampler, train=True, channels=300, num_graphs=24, mean_nodes=16, mean_edges=110, k=2,
+               seed=1311, steps=3, aimle_beta0=2.0 if sampler == "aimle" else None)
+    res = {}
+    for on in (True, False):
+        executor.set_defer_join(on)
+        try:
+            res[on] = util.run_cuda_case(cfg, executor=True)
+        finally:
+            executor.set_defer_join(True)
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a["h"], b["h"]) and torch.equal(a["mask"], b["mask"])
+        for key in ("gx", "g_edge_attr", "g_instr", "g_glf"):
+            assert torch.equal(a[key], b[key]), key
+        for name, g in b["param_grads"].items():
+            assert (g is None and a["param_grads"][name] is None) or torch.equal(a["param_grads"][name], g), name
+
+
 def test_layer_executor_accumulates_into_existing_grads_and_external_mask_gradient():
     """Two backward passes without zero_grad add up (the flat gradient buffer is fresh per backward), and a
     gradient that reaches the returned node mask from OUTSIDE MGAT (the pooling layer multiplies by it,
