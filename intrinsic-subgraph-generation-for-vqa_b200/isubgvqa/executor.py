@@ -368,16 +368,21 @@ class MgatFunction(torch.autograd.Function):
                     L.call("isg_linear_fwd", edge_attr.data_ptr(), pl.D, w_e.data_ptr(), None, None, None,
                            ap + pl.act[i]["P_EPROJ"], pl.HC, None, 0, E, pl.HC, pl.D, L.ACT_NONE, gemm_mode, L.F32, sst)
                 ev_eproj[i].record(side_st)
-        for i in range(pl.L):
-            d, f, p = _arrays()
-            _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, iv.data_ptr() + i * B * pl.D * 4, glf, edge_attr,
-                         specs[i], ap, gemm_mode, bf)
-            n_launch = kernel_launches(specs[i], gi, False, bf16)
-            if side is not None:
-                d[s.D_EPROJ_READY], p[s.P_EV_EPROJ] = 1, ev_eproj[i].cuda_event
-                n_launch -= L.KERNELS_PER_CALL["isg_linear_bf16_fwd" if bf16 else "isg_linear_fwd"]  # counted above
-            L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=n_launch)
-            x_in_ptr = ap + pl.act[i]["P_H_OUT"]
+        try:
+            for i in range(pl.L):
+                d, f, p = _arrays()
+                _fill_common(model, pl, gi, i, d, f, p, x_in_ptr, iv.data_ptr() + i * B * pl.D * 4, glf, edge_attr,
+                             specs[i], ap, gemm_mode, bf)
+                n_launch = kernel_launches(specs[i], gi, False, bf16)
+                if side is not None:
+                    d[s.D_EPROJ_READY], p[s.P_EV_EPROJ] = 1, ev_eproj[i].cuda_event
+                    n_launch -= L.KERNELS_PER_CALL["isg_linear_bf16_fwd" if bf16 else "isg_linear_fwd"]  # counted above
+                L.call("isg_mgat_layer_fwd", _p(d), _p(f), _p(p), st, launches=n_launch)
+                x_in_ptr = ap + pl.act[i]["P_H_OUT"]
+        except BaseException:
+            if side is not None:  # the arena goes back to the allocator: order its re-use after the side stream's writes
+                torch.cuda.current_stream(x.device).wait_stream(side[0])
+            raise
         ctx.model, ctx.gi, ctx.specs, ctx.pl, ctx.gemm_mode, ctx.arena = model, gi, specs, pl, gemm_mode, arena
         ctx.save_for_backward(x, edge_attr, iv, glf, *params)
         D = pl.D
@@ -474,7 +479,13 @@ class MgatFunction(torch.autograd.Function):
                     continue
                 slot = {"W_L": "P_G_W_LR", "B_L": "P_G_B_LR"}.get(name, "P_G_" + name)
                 p[getattr(s, slot)] = gp + 4 * pl.grad_off[(i, name)]
-            L.call("isg_mgat_layer_bwd", _p(d), _p(f), _p(p), st, launches=kernel_launches(specs[i], gi, True, pl.bf16))
+            try:
+                L.call("isg_mgat_layer_bwd", _p(d), _p(f), _p(p), st,
+                       launches=kernel_launches(specs[i], gi, True, pl.bf16))
+            except BaseException:
+                if defer:  # the workspaces go back to the allocator: order their re-use after the pending products
+                    torch.cuda.current_stream(dev).wait_stream(side[0])
+                raise
             g_in_ptr = out.data_ptr()
             if hook is not None:
                 lo, hi = pl.layer_span[i]
