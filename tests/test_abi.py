@@ -63,3 +63,20 @@ def test_argument_validation_without_gpu():
                                 301, 0.2, 0, None) == -2  # C % 4 != 0 -> ISG_EUNSUPPORTED
     assert lib.isg_linear_fwd(None, 0, None, None, None, None, None, 0, None, 0, -1, 4, 4, 0, 0, 0, None) == -1
     assert lib.isg_csr_build(None, -1, 4, None, None, None, None, None, None, None, None, 0, None) == -1
+
+
+def test_executor_slots_used_by_the_host_exist():
+    """isubgvqa/executor.py addresses the layer executor's flat arrays by slot NAME (isg_layer_slot); every name the
+    host side uses — including the launch-overlap slots (side-stream lin_edge, deferred join) — resolves, and the three
+    tables have the sizes the library reports."""
+    dll = ctypes.CDLL(L.LIB_PATH)
+    dll.isg_layer_slot.restype = ctypes.c_int
+    dll.isg_layer_slot.argtypes = [ctypes.c_char_p]
+    src = open(os.path.join(ROOT, "intrinsic-subgraph-generation-for-vqa_b200", "isubgvqa", "executor.py")).read()
+    names = set(re.findall(r"\bs\.((?:D|F|P)_[A-Z0-9_]+)\b", src)) | set(re.findall(r"\"(P_[A-Z0-9_]*[A-Z0-9])\"", src))
+    assert {"D_EPROJ_READY", "P_EV_EPROJ", "D_DEFER_JOIN", "P_EV_WS_FREE", "D_SIDE_WGRAD", "P_SIDE_STREAM"} <= names
+    missing = [n for n in sorted(names) if dll.isg_layer_slot(n.encode()) < 0]
+    assert not missing, f"slots used by executor.py but unknown to libisg.so: {missing}"
+    assert dll.isg_layer_slot(b"P_NO_SUCH_SLOT") < 0
+    for which in (0, 1, 2):
+        assert dll.isg_layer_slot_count(which) > 0
