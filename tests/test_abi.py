@@ -80,3 +80,21 @@ def test_executor_slots_used_by_the_host_exist():
     assert dll.isg_layer_slot(b"P_NO_SUCH_SLOT") < 0
     for which in (0, 1, 2):
         assert dll.isg_layer_slot_count(which) > 0
+
+
+def test_header_is_c99_and_links_from_c(tmp_path):
+    """include/isg.h is a C header (strict C99, no C++ / torch types) and libisg.so is callable from a plain-C
+    program: tests/abi_c/abi_check.c is compiled with gcc -std=c99 -pedantic -Werror, linked against the library and
+    run (version, error strings, host-side argument validation — no device needed)."""
+    import __graft_entry__ as ge
+
+    ge.build()
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.dirname(L.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "abi_c", "abi_check.c"), "-o", exe, "-L", libdir, "-lisg",
+                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "abi_check ok" in run.stdout
