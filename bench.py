@@ -297,7 +297,8 @@ def run_cpu_reference(sampler, train, B, steps, warmup, seed=3407):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     return {"value": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
-            "N": int(b["x"].shape[0]), "E": int(b["edge_index"].shape[1]), "root": rl.REFERENCE_ROOT}
+            "N": int(b["x"].shape[0]), "E": int(b["edge_index"].shape[1]), "nmax": int(b["nmax"]),
+            "root": rl.REFERENCE_ROOT}
 
 
 def run_cpu_arm(sampler, train, B, steps, warmup):
@@ -319,7 +320,8 @@ def main_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "graphs_per_gpu": B, "nodes": r["N"], "edges": r["E"],
-                   "channels": CHANNELS, "heads": HEADS, "layers": LAYERS, "sample_k": K_SAMPLE,
+                   "nmax": r.get("nmax"), "channels": CHANNELS, "heads": HEADS, "layers": LAYERS, "sample_k": K_SAMPLE,
+                   "step": "MGAT forward+backward" if train else "MGAT forward (no_grad)",
                    "sample": f"the full {B}-graph batch of the workload per step, CPU only"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind,
                          "sample": f"{what}; {B}-graph batches (N={r['N']}, E={r['E']}) of the same workload, "
