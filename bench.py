@@ -578,7 +578,11 @@ def main_isg(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    # (1) eager step through the layer executor (what a caller of the nn.Module gets with resident inputs)
+    # (1) eager step through the layer executor (what a caller of the nn.Module gets with resident inputs).  The
+    # warm-up ran on the capture stream, so the FIRST eager step on the current stream pays a one-off ~30 ms
+    # (autograd re-binds its AccumulateGrad streams, the allocator grows this stream's pool —
+    # profiles/r2c_per_step_power_cap.json): one untimed step takes it out of the quoted eager time.
+    step(resident, noise_d)
     ms_eager, launches, _ = timed(lambda: step(resident, noise_d), args.steps)
     # (2) value: the same step replayed from the captured graph
     if graph is not None:
