@@ -657,7 +657,7 @@ def main_isg(args, rank, world, local_rank):
         t = be.run_point(B, 20, 150, False, 20, B, seed=seed, bf16=True)
         key, kb = ("bwd_ms", "bwd_b") if train else ("fwd_ms", "fwd_b")
         ach = t[kb] / (t[key] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "isg_gat_edge_%s, bf16 storage (register-load kernels, 8-byte loads), timed "
+        roof = {"bound": "hbm", "kernel": "isg_gat_edge_%s, bf16 storage (head-pair ring kernels, 16-byte accesses), timed "
                                           "alone on a batch of the workload's shape, L2 flushed" % ("bwd" if train else "fwd"),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": t[kb], "ms_per_launch": t[key],
