@@ -93,7 +93,7 @@ def test_header_is_c99_and_links_from_c(tmp_path):
     libdir = os.path.dirname(L.LIB_PATH)
     cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                          os.path.join(ROOT, "tests", "abi_c", "abi_check.c"), "-o", exe, "-L", libdir, "-lisg",
-                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
+                         "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
     assert cc.returncode == 0, cc.stderr
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 0, run.stdout + run.stderr
