@@ -40,6 +40,45 @@ def test_oracle_matches_live_reference(golden_mod, sampler, train, C, B, k, seed
         util.compare_step(g, w, sampler, rtol=util.RTOL if (sampler == "gumbel" and train) else 2e-5)
 
 
+@pytest.mark.parametrize("sampler,train,B,k,mn,me,seed", [
+    ("imle", True, 1, 2, 9, 40, 5000),    # a single graph
+    ("imle", True, 4, 3, 2, 3, 5001),     # k = Nmax: every node of the largest graph is selected
+    ("aimle", True, 4, 3, 2, 3, 5002),    # k > Nmax (local_k = min(k, Nmax), imle_scheme.py)
+    ("gumbel", True, 4, 3, 2, 3, 5003),   # k > Nmax through the relaxed top-k
+    ("imle", True, 3, 5, 3, 6, 5007),     # k far above every graph size
+    ("simple", False, 1, 2, 2, 2, 5005),  # one 3-node graph, padded to 4 leaves
+    ("gumbel", False, 1, 2, 9, 40, 5006)])
+def test_oracle_matches_live_reference_on_degenerate_batches(golden_mod, sampler, train, B, k, mn, me, seed):
+    """Edge cases the reference handles implicitly: one graph, graphs smaller than k, k above Nmax.  Tolerance is the
+    1e-4 bar itself: on 6-10 node batches two fp32 evaluations of the same sums differ by up to ~3e-5."""
+    steps = 2 if sampler == "aimle" else 1
+    torch.manual_seed(seed)
+    ref = golden_mod.run_reference(sampler, train, 16, B, mn, me, k, seed, steps)
+    cfg = dict(sampler=sampler, train=train, channels=16, num_graphs=B, mean_nodes=mn, mean_edges=me, k=k, seed=seed,
+               steps=steps, aimle_beta0=golden_mod.AIMLE_BETA0 if sampler == "aimle" else None)
+    got = util.run_oracle_case(cfg)
+    assert len(got) == len(ref)
+    for g, w in zip(got, ref):
+        assert bool(torch.isfinite(w["h"]).all()) and bool(torch.isfinite(w["mask"]).all())
+        util.compare_step(g, w, sampler, rtol=util.RTOL)
+
+
+def test_simple_with_graphs_smaller_than_k_is_nan_in_the_reference_and_in_the_oracle(golden_mod):
+    """SIMPLE in training mode on a batch whose smallest graphs have fewer than k nodes: the reference's exact-k circuit
+    (simple.py:214-244) has no assignment with k ones among the real leaves, its marginals come out NaN for those graphs
+    — the restatement reproduces the NaNs in the same positions and the finite values elsewhere (the drop-in therefore
+    owes nothing for this input; GQA scene graphs have >= 2 = k objects)."""
+    seed, B, k = 5004, 4, 3
+    torch.manual_seed(seed)
+    ref = golden_mod.run_reference("simple", True, 16, B, 2, 3, k, seed, 1)[0]
+    cfg = dict(sampler="simple", train=True, channels=16, num_graphs=B, mean_nodes=2, mean_edges=3, k=k, seed=seed, steps=1)
+    got = util.run_oracle_case(cfg)[0]
+    nan_ref, nan_got = torch.isnan(ref["mask"]), torch.isnan(got["mask"])
+    assert bool(nan_ref.any()), "expected the reference to produce NaN marginals here"
+    assert torch.equal(nan_ref, nan_got)
+    assert torch.allclose(ref["mask"][~nan_ref], got["mask"][~nan_got], rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("sampler,train,seed", [("imle", True, 4200), ("gumbel", False, 4201)])
 def test_oracle_matches_live_reference_concat_instr(golden_mod, sampler, train, seed):
     """The `--concat_instr 1` variant (models/mgat_v2_conv.py:153-154, mgat.py:41-44): the conv sees
