@@ -63,6 +63,36 @@ def test_oracle_matches_live_reference_on_degenerate_batches(golden_mod, sampler
         util.compare_step(g, w, sampler, rtol=util.RTOL)
 
 
+@pytest.mark.parametrize("sampler", ["imle", "aimle", "gumbel", "simple"])
+def test_oracle_matches_live_reference_on_unselected_seeds(golden_mod, sampler):
+    """Ten CONSECUTIVE seeds per sampler (6000-6009), training and evaluation mode — no scan, no selection (the
+    committed fixtures' seeds were picked away from leaky-ReLU kinks, oracle/make_golden.py:30-34; this sweep is not).
+    Bound: the 1e-4 bar, except the Gumbel tau = 0.1 relaxation in training mode, whose gradient is ill-conditioned
+    in fp32 (log(1 - onehot) with onehot -> 1, gumbel_scheme.py:76-80): at seed 6003 the two fp32 evaluations differ
+    by 2.8e-4 on every gradient while the oracle in fp64 is within 1.1e-5 of the reference's fp32 — same function,
+    different rounding of theta by one ulp; at seed 6009 it is the reference's fp32 that sits 1.6e-4 from the fp64
+    value — so in that one mode both fp32 evaluations are held to 1e-3 of each other and of the oracle's fp64 replay
+    (the arbiter), and `h` to the 1e-4 bar."""
+    for seed in range(6000, 6010):
+        for train in ((True,) if sampler == "aimle" else (True, False)):
+            steps = 2 if sampler == "aimle" else 1
+            torch.manual_seed(seed)
+            ref = golden_mod.run_reference(sampler, train, 16, 5, 9, 40, 2, seed, steps)
+            cfg = dict(sampler=sampler, train=train, channels=16, num_graphs=5, mean_nodes=9, mean_edges=40, k=2,
+                       seed=seed, steps=steps, aimle_beta0=golden_mod.AIMLE_BETA0 if sampler == "aimle" else None)
+            if sampler == "gumbel" and train:
+                got, exact = util.run_oracle_fp64_arbiter(cfg)
+                util.compare_step(got[0], ref[0], sampler, rtol=1e-3)
+                assert util.rel_err(got[0]["h"], ref[0]["h"]) <= util.RTOL
+                for key in ("h", "gx", "g_edge_attr", "g_instr", "g_glf"):
+                    assert util.rel_err(ref[0][key], exact[0][key]) <= 1e-3, (seed, key)
+                    assert util.rel_err(got[0][key], exact[0][key]) <= 1e-3, (seed, key)
+                continue
+            got = util.run_oracle_case(cfg)
+            for g, w in zip(got, ref):
+                util.compare_step(g, w, sampler, rtol=util.RTOL)
+
+
 def test_simple_with_graphs_smaller_than_k_is_nan_in_the_reference_and_in_the_oracle(golden_mod):
     """SIMPLE in training mode on a batch whose smallest graphs have fewer than k nodes: the reference's exact-k circuit
     (simple.py:214-244) has no assignment with k ones among the real leaves, its marginals come out NaN for those graphs
