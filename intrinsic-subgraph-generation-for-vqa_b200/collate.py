@@ -58,8 +58,9 @@ def collate_scene_graphs(graphs, cache=None, pin=False):
     """Batch.from_data_list for scene graphs + the batch CSR from the per-image caches.
 
     graphs: sequence of dicts with `x` [n,D], `edge_index` [2,e] int64, `edge_attr` [e,De] and optionally `image_id`
-    (cache key) or a ready `csr` (GraphCsr).  Returns a dict: x, edge_index, edge_attr, batch (as PyG lays them out)
-    and `host_index` = dict of int32 tensors (dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, graph_ptr, batch32,
+    (cache key) or a ready `csr` (GraphCsr), `x_bbox` [n,4], `added_sym_edge` [m] (scene_graph_data.SceneGraphStore).
+    Returns a dict: x, edge_index, edge_attr, batch (as PyG lays them out), x_bbox / added_sym_edge when given, and
+    `host_index` = dict of int32 tensors (dst_ptr, dst_nbr, dst_eid, src_ptr, src_nbr, src_eid, graph_ptr, batch32,
     dst_order, src_order) + nmax, for GraphIndex.from_host."""
     B = len(graphs)
     ns = np.array([int(g["x"].shape[0]) for g in graphs], dtype=np.int64)
@@ -82,6 +83,14 @@ def collate_scene_graphs(graphs, cache=None, pin=False):
         "edge_index": torch.cat([g["edge_index"] for g in graphs], dim=1) + torch.from_numpy(np.repeat(n_off[:-1], es)),
         "batch": torch.repeat_interleave(torch.arange(B, dtype=torch.int64), torch.from_numpy(ns)),
     }
+    if B and all(g.get("x_bbox") is not None for g in graphs):
+        out["x_bbox"] = torch.cat([g["x_bbox"] for g in graphs], dim=0)
+    if B and all(g.get("added_sym_edge") is not None for g in graphs):
+        # PyG concatenates this attribute WITHOUT adding edge offsets (Data.__inc__ only shifts keys containing "index"),
+        # and models/scene_graph_encoder.py:80 applies it to the batch's edge rows as is; `added_sym_edge_global` holds
+        # the positions in the batch's edge numbering for callers that want what the name says
+        out["added_sym_edge"] = torch.cat([g["added_sym_edge"] for g in graphs], dim=0)
+        out["added_sym_edge_global"] = torch.cat([g["added_sym_edge"] + int(e_off[i]) for i, g in enumerate(graphs)], dim=0)
     idx = {}
     node_rep = np.repeat(n_off[:-1], es).astype(np.int32)  # node offset of the graph each edge belongs to
     edge_rep_e = np.repeat(e_off[:-1], es).astype(np.int32)  # edge offset, per edge

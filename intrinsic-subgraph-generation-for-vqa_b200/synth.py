@@ -9,8 +9,10 @@ import numpy as np
 import torch
 
 
-def _one_graph(rng, n, target_edges):
-    """Returns (src, dst) int64 arrays for one graph with n nodes in reference order."""
+def _one_graph(rng, n, target_edges, relations=None):
+    """Returns (src, dst) int64 arrays for one graph with n nodes in reference order.  `relations`: a list that
+    receives the drawn (source, target) relation arrays (tests/test_scene_graph_data.py feeds them through the
+    reference-pinned record conversion and expects these very edges)."""
     n_rel = 0
     if n >= 2 and target_edges > n:
         # E = n + 2R - R*p with p ~= P[(t,v) is itself a relation] ~= R / (n(n-1)); two fixed-point steps
@@ -21,10 +23,14 @@ def _one_graph(rng, n, target_edges):
         n_rel = max(0, int(round(r)))
     if n_rel == 0:
         v = np.arange(n, dtype=np.int64)
+        if relations is not None:
+            relations.append((v[:0], v[:0]))
         return v, v.copy()
     rs = np.sort(rng.integers(0, n, size=n_rel), kind="stable").astype(np.int64)
     rt = rng.integers(0, n - 1, size=n_rel).astype(np.int64)
     rt = rt + (rt >= rs)  # uniform over targets != source
+    if relations is not None:
+        relations.append((rs, rt))
     key = rs * n + rt
     has_rev = np.isin(rt * n + rs, key)
     emit = 2 - has_rev.astype(np.int64)  # relation + optional reverse
