@@ -48,3 +48,40 @@ def test_quoted_entry_point_count_is_the_headers():
     for doc in ("README.md", "DESIGN.md"):
         counts = re.findall(r"(\d+) entry points", open(os.path.join(ROOT, doc)).read())
         assert counts and all(int(c) == n for c in counts), (doc, counts, n)
+
+
+def test_reference_citations_point_at_existing_lines():
+    """Every `path.py:line[-line]` citation of the reference — in include/isg.h, the documents, the package, the oracle,
+    the tests and bench.py — names a file of the reference tree and a line range inside it (skipped where the tree is
+    absent)."""
+    import pytest
+
+    ref = os.environ.get("ISG_REFERENCE_SRC", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "ISubGVQA", "models")):
+        pytest.skip("the reference tree is not present on this machine")
+    lengths = {}
+    for p in glob.glob(os.path.join(ref, "**", "*.py"), recursive=True):
+        with open(p, errors="ignore") as f:
+            lengths[os.path.relpath(p, ref)] = sum(1 for _ in f)
+    own = {os.path.relpath(p, ROOT) for p in glob.glob(os.path.join(ROOT, "**", "*.py"), recursive=True)}
+    files = [os.path.join(ROOT, n) for n in ("include/isg.h", "DESIGN.md", "INTEGRATION.md", "README.md", "bench.py")]
+    for pattern in ("intrinsic-subgraph-generation-for-vqa_b200/**/*.py", "intrinsic-subgraph-generation-for-vqa_b200/csrc/*",
+                    "oracle/*.py", "tests/*.py"):
+        files += glob.glob(os.path.join(ROOT, pattern), recursive=True)
+    cite = re.compile(r"((?:[A-Za-z_]+/)*[A-Za-z_0-9]+\.py):(\d+)(?:-(\d+))?")
+    checked, bad = 0, []
+    for f in files:
+        if os.sep + "build" + os.sep in f or not os.path.isfile(f):
+            continue
+        for m in cite.finditer(open(f, errors="ignore").read()):
+            path, a, b = m.group(1), int(m.group(2)), int(m.group(3) or m.group(2))
+            cands = [r for r in lengths if r == path or r.endswith("/" + path)]
+            if not cands:
+                if path in own or any(o.endswith("/" + path) for o in own):
+                    continue  # a citation of this repository's own file
+                bad.append((os.path.relpath(f, ROOT), m.group(0), "no such file in the reference"))
+                continue
+            checked += 1
+            if not any(a <= b <= lengths[r] for r in cands):
+                bad.append((os.path.relpath(f, ROOT), m.group(0), [(r, lengths[r]) for r in cands]))
+    assert checked >= 300 and not bad, bad[:20]
