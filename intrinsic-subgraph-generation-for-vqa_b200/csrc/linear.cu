@@ -291,6 +291,7 @@ extern "C" int isg_linear_dgrad(const void* g_y, int64_t ldg, const void* w, con
 
 extern "C" size_t isg_linear_wgrad_workspace_bytes(int64_t M, int Nout, int K) {
   // mode-agnostic: large enough for the FFMA split and for the tensor-core split
+  if (M <= 0 || Nout <= 0 || K <= 0) return 0;  // (the tile heuristics below divide by sizes derived from Nout and K)
   int64_t chunk = 0;
   const int s0 = wgrad_splits(M, Nout, K);
   const int s1 = isg::tc_wgrad_splits(M > 0 ? M : 1, Nout, K, &chunk);

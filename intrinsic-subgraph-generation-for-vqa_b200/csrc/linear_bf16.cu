@@ -713,6 +713,7 @@ extern "C" int isg_linear_bf16_dgrad(const void* g_y, int64_t ldg, const void* w
 }
 
 extern "C" size_t isg_linear_bf16_wgrad_workspace_bytes(int64_t M, int Nout, int K) {
+  if (M <= 0 || Nout <= 0 || K <= 0) return 0;
   int64_t chunk = 0;
   const int s = wgrad_splits16(M > 0 ? M : 1, Nout, K, &chunk);
   return s > 1 ? (size_t)s * (size_t)Nout * (size_t)K * sizeof(float) : 0;

@@ -154,7 +154,8 @@ extern "C" int isg_opt_max_tensors(void) { return ISG_OPT_MAX_TENSORS; }
 
 extern "C" int64_t isg_opt_blocks(const int64_t* numel, int count) {
   int64_t b = 0;
-  for (int i = 0; i < count; ++i) b += (numel[i] + OPT_CHUNK - 1) / OPT_CHUNK;
+  if (!numel) return 0;
+  for (int i = 0; i < count; ++i) b += numel[i] > 0 ? (numel[i] + OPT_CHUNK - 1) / OPT_CHUNK : 0;
   return b;
 }
 

@@ -5,6 +5,8 @@ import os
 import re
 import subprocess
 
+import pytest
+
 import isg_b200
 from isg_b200 import lib as L
 
@@ -98,3 +100,51 @@ def test_header_is_c99_and_links_from_c(tmp_path):
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "abi_check ok" in run.stdout
+
+
+_SWEEP = r"""
+import ctypes, sys
+sys.path.insert(0, sys.argv[1])
+FILL = int(sys.argv[2])
+from isg_b200 import lib as L
+lib = L.load()
+for name in sorted(L.SIGNATURES):
+    res, args = L.SIGNATURES[name]
+    vals = []
+    for a in args:
+        if a in (ctypes.c_float, ctypes.c_double):
+            vals.append(0.0)
+        elif a in (ctypes.c_size_t, ctypes.c_uint64):
+            vals.append(max(FILL, 0))
+        elif a in (ctypes.c_int, ctypes.c_int64, ctypes.c_int32):
+            vals.append(FILL)
+        else:
+            vals.append(None)  # every pointer (and by-value struct slot) null
+    print("CALL", name, flush=True)
+    r = getattr(lib, name)(*vals)
+    print("RET", name, r if not isinstance(r, bytes) else r.decode(), flush=True)
+"""
+
+
+@pytest.mark.parametrize("fill", [0, -1, 8, 300])
+def test_every_entry_point_survives_null_pointers(tmp_path, fill):
+    """"Nothing throws, nothing exits" (include/isg.h): each of the entry points is called in a child process with null
+    pointers and every integer argument set to `fill` (an empty problem, negative sizes, plausible sizes) — it must
+    return (ISG_OK for an empty problem, a negative ISG_E* code for a rejected one, a byte count for the sizing
+    helpers), never crash, and never reach the device (a positive return is a cudaError_t)."""
+    script = tmp_path / "sweep.py"
+    script.write_text(_SWEEP)
+    run = subprocess.run([os.sys.executable, str(script), ROOT, str(fill)], capture_output=True, text=True, timeout=300)
+    calls = re.findall(r"^CALL (\S+)$", run.stdout, flags=re.M)
+    rets = dict(re.findall(r"^RET (\S+) (.*)$", run.stdout, flags=re.M))
+    crashed = [c for c in calls if c not in rets]
+    assert run.returncode == 0 and not crashed, f"crashed in {crashed} (exit code {run.returncode}): {run.stderr[-400:]}"
+    assert sorted(rets) == sorted(L.SIGNATURES)
+    sizing = {n for n in rets if n.endswith(("_bytes", "_count", "_npad", "_blocks", "_tensors")) or n in ("isg_version",)}
+    for name, r in rets.items():
+        if name == "isg_error_string":
+            assert r
+        elif name in sizing:  # (isg_layer_slot_count answers -1 for a table that does not exist)
+            assert int(r) >= 0 or (name == "isg_layer_slot_count" and int(r) == -1), (name, r)
+        else:
+            assert int(r) in (0, -1, -2, -3), (name, r)
