@@ -1965,7 +1965,12 @@ inline BwdRingPlan bwd_ring_plan(int64_t N, int H) {
   if (p.K < 1) p.K = 1;
   p.cols = (N + p.K - 1) / p.K;
   p.blocks = (p.cols * H + EDGE_WARPS - 1) / EDGE_WARPS;
-  while ((p.blocks * EDGE_WARPS) % H != 0) ++p.blocks;
+  {  // next block count whose warps divide by H (closed form, see bwd_grid_blocks)
+    int64_t g = H, r = EDGE_WARPS;
+    while (r) { const int64_t t = g % r; g = r; r = t; }
+    const int64_t step = H / g;
+    p.blocks = (p.blocks + step - 1) / step * step;
+  }
   p.warps = p.blocks * EDGE_WARPS;
   p.parts2 = (p.warps / H + GR_ROWS - 1) / GR_ROWS;
   return p;
@@ -2005,7 +2010,12 @@ inline int bwd_grid_blocks(int64_t N, int H) {
   int64_t cap = (int64_t)ISG_NUM_SMS * 4;  // 4 CTAs of 128 threads per SM at ~100 regs
   int64_t blocks = want < cap ? want : cap;
   if (blocks < 1) blocks = 1;
-  while ((blocks * EDGE_WARPS) % H != 0) ++blocks;
+  // round up to the next count whose warps divide by H: a multiple of H / gcd(H, EDGE_WARPS) (closed form — the
+  // sizing helper must not spin on an absurd H)
+  int64_t g = H, r = EDGE_WARPS;
+  while (r) { const int64_t t = g % r; g = r; r = t; }
+  const int64_t step = H / g;
+  blocks = (blocks + step - 1) / step * step;
   return (int)blocks;
 }
 

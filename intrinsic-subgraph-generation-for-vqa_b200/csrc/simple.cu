@@ -317,6 +317,7 @@ __global__ void simple_bwd_kernel(const float* __restrict__ dy, const float* __r
 }
 
 int pad_pow2(int nmax) {
+  if (nmax > (1 << 30)) return 0;  // no power of two fits an int (and the doubling below would never terminate)
   int n = 1;
   while (n < nmax) n <<= 1;
   return n;

@@ -126,10 +126,10 @@ for name in sorted(L.SIGNATURES):
 """
 
 
-@pytest.mark.parametrize("fill", [0, -1, 8, 300])
+@pytest.mark.parametrize("fill", [0, -1, 8, 300, 2147483647])
 def test_every_entry_point_survives_null_pointers(tmp_path, fill):
     """"Nothing throws, nothing exits" (include/isg.h): each of the entry points is called in a child process with null
-    pointers and every integer argument set to `fill` (an empty problem, negative sizes, plausible sizes) — it must
+    pointers and every integer argument set to `fill` (an empty problem, negative sizes, plausible sizes, INT_MAX) — it must
     return (ISG_OK for an empty problem, a negative ISG_E* code for a rejected one, a byte count for the sizing
     helpers), never crash, and never reach the device (a positive return is a cudaError_t)."""
     script = tmp_path / "sweep.py"
