@@ -167,6 +167,8 @@ extern "C" int isg_layer_slot_count(int which) {
 
 extern "C" size_t isg_mgat_layer_bwd_workspace_bytes(const int64_t* dims) {
   if (!dims) return 0;
+  if (dims[D_N] < 0 || dims[D_E] < 0 || dims[D_B] < 0 || dims[D_D] <= 0 || dims[D_H] <= 0 || dims[D_HID] <= 0)
+    return 0;  // the layer calls reject these with ISG_EINVAL; no size wraps around here
   return bwd_ws(dims).total;
 }
 

@@ -148,3 +148,51 @@ def test_every_entry_point_survives_null_pointers(tmp_path, fill):
             assert int(r) >= 0 or (name == "isg_layer_slot_count" and int(r) == -1), (name, r)
         else:
             assert int(r) in (0, -1, -2, -3), (name, r)
+
+
+_HOST_ARRAYS = r"""
+import ctypes, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+from isg_b200 import lib as L
+lib = L.load()
+nd, nf, npt = (lib.isg_layer_slot_count(i) for i in range(3))
+P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+slot = lambda n: lib.isg_layer_slot(n.encode())
+base = dict(D_N=100, D_E=500, D_B=4, D_D=300, D_H=4, D_HID=600, D_NMAX=30)
+for label, setup in [("zeros", {}), ("null_ptrs", base), ("masked_null_ptrs", dict(base, D_MASKED=1, D_SAMPLER=1, D_K=2)),
+                     ("negative", dict(base, D_N=-5, D_E=-1, D_B=-1)), ("bf16_odd", dict(D_N=10, D_E=20, D_B=1, D_D=7, D_H=3, D_HID=9, D_BF16=1))]:
+    d, f, p = np.zeros(nd, dtype=np.int64), np.zeros(nf, dtype=np.float64), np.zeros(npt, dtype=np.uint64)
+    for k, v in setup.items():
+        d[slot(k)] = v
+    print("CALL", label, flush=True)
+    print("RET", label, lib.isg_mgat_layer_bwd_workspace_bytes(P(d)), lib.isg_mgat_layer_fwd(P(d), P(f), P(p), None),
+          lib.isg_mgat_layer_bwd(P(d), P(f), P(p), None), flush=True)
+n = 3
+vp, ints, i64 = (ctypes.c_void_p * n)(), (ctypes.c_int * n)(*[8] * n), (ctypes.c_int64 * n)(*[8] * n)
+for label, fn in [("weights_to_bf16", lambda: lib.isg_weights_to_bf16(n, vp, ints, ints, vp, ints, vp, ints, None)),
+                  ("weights_to_bf16_too_many", lambda: lib.isg_weights_to_bf16(100, vp, ints, ints, vp, ints, vp, ints, None)),
+                  ("colsum_multi", lambda: lib.isg_colsum_multi(n, vp, ints, i64, i64, ints, vp, None, 0, None)),
+                  ("grad_sq_partials", lambda: lib.isg_grad_sq_partials(vp, i64, n, None, None, 0, None, None)),
+                  ("adam_update", lambda: lib.isg_adam_update(vp, vp, vp, vp, i64, n, None, None, None, 1e-3, 0.9, 0.999, 1e-8, None)),
+                  ("adam_update_too_many", lambda: lib.isg_adam_update(vp, vp, vp, vp, i64, 1000, None, None, None, 1e-3, 0.9, 0.999, 1e-8, None))]:
+    print("CALL", label, flush=True)
+    print("RET", label, 0, fn(), 0, flush=True)
+"""
+
+
+def test_host_array_entry_points_reject_null_device_pointers(tmp_path):
+    """The entry points that take HOST arrays (the layer executor's dims / scalars / pointer tables, the lists of
+    tensors of the optimizer, the column sums and the bf16 weight conversion) get well-formed host arrays whose device
+    pointers are all null, with empty, plausible, negative and unsupported dimensions: every call returns a negative
+    ISG_E* code without touching the device, and the workspace query never wraps around."""
+    script = tmp_path / "host_arrays.py"
+    script.write_text(_HOST_ARRAYS)
+    run = subprocess.run([os.sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=300)
+    calls = re.findall(r"^CALL (\S+)$", run.stdout, flags=re.M)
+    rets = {m[0]: tuple(int(v) for v in m[1:]) for m in re.findall(r"^RET (\S+) (-?\d+) (-?\d+) (-?\d+)$", run.stdout, flags=re.M)}
+    assert run.returncode == 0 and calls and sorted(calls) == sorted(rets), (run.returncode, run.stderr[-400:])
+    for label, (ws, a, b) in rets.items():
+        assert a in (-1, -2, -3) and b in (0, -1, -2, -3), (label, a, b)
+        assert 0 <= ws < 1 << 40, (label, ws)
+    assert rets["zeros"][0] == 0 and rets["negative"][0] == 0 and rets["null_ptrs"][0] > 0
