@@ -214,6 +214,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t isg_csr_workspace_bytes(int64_t N, int64_t E) {
   (void)E;
+  if (N < 0) N = 0;  // (isg_csr_build rejects it; no size wraps around here)
   const int tiles = isg::ceil_div(N > 0 ? N : 1, SCAN_TILE);
   return align256((size_t)2 * (size_t)N * sizeof(int)) + align256((size_t)2 * tiles * sizeof(int));
 }

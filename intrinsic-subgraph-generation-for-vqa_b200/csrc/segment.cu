@@ -1126,6 +1126,7 @@ extern "C" int isg_gelu_bwd(const float* g_y, const float* z, float* g_z, int64_
 }
 
 extern "C" size_t isg_colsum_workspace_bytes(int64_t rows, int cols) {
+  if (cols <= 0) return 0;  // (isg_colsum rejects it; no size wraps around here)
   const int64_t parts = (rows + CS_ROWS - 1) / CS_ROWS;
   return (size_t)(parts > 0 ? parts : 1) * (size_t)cols * sizeof(float);
 }

@@ -106,9 +106,15 @@ _SWEEP = r"""
 import ctypes, sys
 sys.path.insert(0, sys.argv[1])
 FILL = int(sys.argv[2])
+FAKE = ctypes.c_void_p(0x7f0000001000) if len(sys.argv) > 3 else None
+HOST_ARRAYS = {"isg_weights_to_bf16", "isg_colsum_multi", "isg_grad_sq_partials", "isg_adam_update", "isg_opt_blocks",
+               "isg_mgat_layer_fwd", "isg_mgat_layer_bwd", "isg_mgat_layer_bwd_workspace_bytes", "isg_layer_slot",
+               "isg_error_string"}  # these read HOST memory through their pointers: not called with a fake address
 from isg_b200 import lib as L
 lib = L.load()
 for name in sorted(L.SIGNATURES):
+    if FAKE is not None and name in HOST_ARRAYS:
+        continue
     res, args = L.SIGNATURES[name]
     vals = []
     for a in args:
@@ -119,7 +125,7 @@ for name in sorted(L.SIGNATURES):
         elif a in (ctypes.c_int, ctypes.c_int64, ctypes.c_int32):
             vals.append(FILL)
         else:
-            vals.append(None)  # every pointer (and by-value struct slot) null
+            vals.append(FAKE)  # every pointer null — or, third argument "fake", a non-null address that is never mapped
     print("CALL", name, flush=True)
     r = getattr(lib, name)(*vals)
     print("RET", name, r if not isinstance(r, bytes) else r.decode(), flush=True)
@@ -196,3 +202,19 @@ def test_host_array_entry_points_reject_null_device_pointers(tmp_path):
         assert a in (-1, -2, -3) and b in (0, -1, -2, -3), (label, a, b)
         assert 0 <= ws < 1 << 40, (label, ws)
     assert rets["zeros"][0] == 0 and rets["negative"][0] == 0 and rets["null_ptrs"][0] > 0
+
+
+def test_negative_sizes_are_rejected_before_any_pointer_is_used(tmp_path):
+    """Non-null (never mapped) device pointers with every size negative: each entry point answers a negative ISG_E*
+    code (or 0 bytes) — no launch is attempted, nothing is dereferenced on the host."""
+    script = tmp_path / "sweep.py"
+    script.write_text(_SWEEP)
+    run = subprocess.run([os.sys.executable, str(script), ROOT, "-3", "fake"], capture_output=True, text=True, timeout=300)
+    calls = re.findall(r"^CALL (\S+)$", run.stdout, flags=re.M)
+    rets = dict(re.findall(r"^RET (\S+) (.*)$", run.stdout, flags=re.M))
+    assert run.returncode == 0 and len(calls) >= 50 and sorted(calls) == sorted(rets), (run.returncode, run.stderr[-400:])
+    for name, r in rets.items():
+        if name.endswith(("_bytes", "_count", "_npad", "_blocks", "_tensors")) or name == "isg_version":
+            assert -1 <= int(r) < 1 << 20, (name, r)  # a fixed header of a few hundred bytes at most
+        else:
+            assert int(r) in (-1, -2, -3), (name, r)
