@@ -91,3 +91,37 @@ def test_forward_returns_the_reference_arity(reference):
     assert arities(importlib.import_module("ISubGVQA.models.mgat").MGAT.forward) == [4]
     ours_ret = arities(ours.MGAT.forward)
     assert ours_ret and set(ours_ret) == {4}, ours_ret
+
+
+def test_fresh_modules_are_initialised_like_the_reference(reference):
+    """Training from scratch starts from the same distribution: every parameter of a freshly built MGAT has the
+    reference's shape; the constant initialisations (GraphNorm weight / bias / mean_scale, conv bias, ...) are equal
+    bit for bit; every randomly initialised tensor of >= 1024 elements has the reference's spread (uniform bound within
+    3 %, standard deviation within 8 % — PyG glorot for lin_l / lin_r / lin_edge / att, torch's Linear default for the
+    MLPs).  The draws themselves differ (the modules call the RNG in a different order)."""
+    import torch
+
+    from ISubGVQA.models.mgat import MGAT as Ref
+    from isg_b200.isubgvqa import MGAT
+
+    kw = dict(channels=64, num_ins=4, heads=4, use_instr=True, masking_thresholds=[1.0, 1.0, 1.0, 0.1], use_topk=True,
+              interpretable_mode=False, sampler_type="aimle", sample_k=2, nb_samples=1, alpha=1.0, beta=10.0, tau=1.0)
+    with rl.scratch_cwd():
+        torch.manual_seed(123)
+        ref = Ref(**kw).state_dict()
+    torch.manual_seed(123)
+    ours = MGAT(**kw).state_dict()
+    assert set(ref) <= set(ours) and all(k.endswith("aimle_state") for k in set(ours) - set(ref))
+    constant = random = 0
+    for k, r in ref.items():
+        o = ours[k]
+        assert o.shape == r.shape and o.dtype == r.dtype, k
+        if r.numel() > 1 and float(r.float().std()) == 0.0:
+            assert torch.equal(o, r), f"{k}: constant initialisation differs"
+            constant += 1
+        elif r.numel() >= 1024:
+            rb, ob = float(r.abs().max()), float(o.abs().max())
+            rs_, os_ = float(r.std()), float(o.std())
+            assert abs(ob - rb) <= 0.03 * rb and abs(os_ - rs_) <= 0.08 * rs_, (k, rb, ob, rs_, os_)
+            random += 1
+    assert constant >= 12 and random >= 30, (constant, random)
