@@ -125,3 +125,28 @@ def test_fresh_modules_are_initialised_like_the_reference(reference):
             assert abs(ob - rb) <= 0.03 * rb and abs(os_ - rs_) <= 0.08 * rs_, (k, rb, ob, rs_, os_)
             random += 1
     assert constant >= 12 and random >= 30, (constant, random)
+
+
+def test_widened_modules_are_initialised_like_the_reference(reference):
+    """The same for the widened rows: GlobalAttention (f1) and the scene-graph encoding MetaLayer (f2) — state_dict
+    keys and shapes equal the reference's, random tensors have its spread."""
+    import torch
+
+    from ISubGVQA.models.att_pooling import GlobalAttention as RefGA
+    from isg_b200.isubgvqa import GlobalAttention, SceneGraphEncodingLayer
+
+    with rl.scratch_cwd():
+        torch.manual_seed(7)
+        ref_ga = RefGA(num_node_features=256, num_out_features=256).state_dict()
+        ref_layer = rl.load_scene_graph_encoding_layer(256, 256, 256).state_dict()
+    torch.manual_seed(7)
+    our_ga = GlobalAttention(num_node_features=256, num_out_features=256).state_dict()
+    our_layer = SceneGraphEncodingLayer(256, 256, 256).state_dict()
+    for ref, ours, what in ((ref_ga, our_ga, "GlobalAttention"), (ref_layer, our_layer, "SceneGraphEncodingLayer")):
+        assert list(ref) == list(ours), what
+        for k, r in ref.items():
+            o = ours[k]
+            assert o.shape == r.shape and o.dtype == r.dtype, (what, k)
+            if r.numel() >= 1024:
+                rb, ob, rs_, os_ = float(r.abs().max()), float(o.abs().max()), float(r.std()), float(o.std())
+                assert abs(ob - rb) <= 0.03 * rb and abs(os_ - rs_) <= 0.08 * rs_, (what, k, rb, ob, rs_, os_)
