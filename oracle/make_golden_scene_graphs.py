@@ -108,7 +108,7 @@ def main():
             "stoi": stoi, "mappings": MAPPINGS, "records": records, "image_ids": ids,
             "expected": {iid: {k: v.tolist() for k, v in d.items()} for iid, d in want.items()}}
     with open(OUT, "w") as f:
-        json.dump(blob, f, indent=0, sort_keys=True)
+        json.dump(blob, f, sort_keys=True, separators=(",", ":"))
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(ids), "records")
 
 
